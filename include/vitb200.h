@@ -1,0 +1,132 @@
+/* vitb200.h — C ABI of the B200-native Vision Transformer forward engine (libvitb200.so).
+ *
+ * This is the drop-in boundary for the arithmetic behind interactive-vit's server-side node graph.  In the
+ * reference every FLOP of a network node is spent inside
+ *     Model.compute(node_name, pinin) -> sub(x) under torch.no_grad()        main/context.py:79-88
+ * reached from Context.compute (main/context.py:143-147) through ModelNode.compute (main/context.py:119-121).
+ * For a ViT those `sub(x)` calls are torchvision's VisionTransformer stages (an un-vendored dependency of the
+ * reference: torchvision/models/vision_transformer.py, "TV" below).  Each entry point names the reference-side
+ * call it replaces.  The reference has no FFI of its own (it is pure Python); the binding a maintainer would
+ * add is the ctypes stub shown in INTEGRATION.md (shipped as interactive-vit_b200/engine.py).
+ *
+ * Conventions: plain pointers and sizes only; `*_host` pointers are CPU memory (pinned memory makes the
+ * copies asynchronous), `*_dev` pointers are CUDA device memory of the engine's device; all tensors are
+ * dense, row-major, fp32 at the boundary (the reference's wire format is fp32: main/message.py:53-59,
+ * 111-121).  Every function returns VITB200_OK (0) or a negative error code; vitb200_last_error() returns
+ * the message for the calling thread (the Python shim raises it, which the reference turns into HTTP 400,
+ * main/views.py:40-42).  There is no CPU fallback: without a CUDA device vitb200_create fails.
+ */
+#ifndef VITB200_H_
+#define VITB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITB200_OK 0
+#define VITB200_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define VITB200_ERR_CUDA (-2)    /* CUDA runtime or driver error (message has the CUDA string) */
+#define VITB200_ERR_STATE (-3)   /* call out of order (e.g. forward before all weights are loaded) */
+
+/* Output selection flags for vitb200_forward_* (bit-or). */
+#define VITB200_EMIT_AVG 1u     /* head-averaged attention probabilities per layer  [L, B, N, N]    */
+#define VITB200_EMIT_CLS 2u     /* per-head class-token attention rows per layer     [L, B, H, N]    */
+#define VITB200_EMIT_ROLLOUT 4u /* attention rollout of the class token              [B, N-1]        */
+#define VITB200_EMIT_HEADS 8u   /* full per-head probabilities per layer (large)     [L, B, H, N, N] */
+#define VITB200_EMIT_HIDDEN 16u /* residual stream after every layer                 [L, B, N, d]    */
+
+typedef struct vitb200_engine vitb200_engine;
+
+/* Architecture of torchvision.models.vision_transformer.VisionTransformer (TV:160-266). */
+typedef struct vitb200_config {
+  int image_size;  /* S: square input side, multiple of patch_size                    */
+  int patch_size;  /* p: 16 (multiple of 8)                                            */
+  int num_layers;  /* L                                                                */
+  int num_heads;   /* H; head dim hidden_dim / H must be 64                            */
+  int hidden_dim;  /* d: multiple of 128                                               */
+  int mlp_dim;     /* multiple of 64                                                   */
+  int num_classes; /* multiple of 8                                                    */
+  int max_batch;   /* workspace is sized for this many images (grows on demand)        */
+  int device;      /* CUDA device ordinal                                              */
+} vitb200_config;
+
+/* Host-side result pointers for vitb200_forward_host; any pointer may be NULL (output skipped). */
+typedef struct vitb200_host_outputs {
+  float* logits;   /* [B, num_classes]                                  heads(x[:,0])      TV:302-304 */
+  float* avg_maps; /* [L, B, N, N]   mean over heads of softmax(QK^T/sqrt(D))  torch/nn/functional.py:6659 */
+  float* cls_maps; /* [L, B, H, N]   softmax row of query token 0, per head                */
+  float* rollout;  /* [B, N-1]       attention rollout, class-token row (oracle/vit_oracle.py) */
+  float* heads;    /* [L, B, H, N, N] per-head probabilities           torch/nn/functional.py:6645-6653 */
+  float* hidden;   /* [L, B, N, d]   EncoderBlock outputs              TV:110-119          */
+} vitb200_host_outputs;
+
+const char* vitb200_last_error(void);
+int vitb200_version(void);
+
+/* Replaces: constructing the torchvision module in the plugin's __init__ (static/models/vgg16.py:11-14 is the
+ * in-tree template).  Creates the CUDA context objects, the stream and the workspace. */
+int vitb200_create(const vitb200_config* cfg, vitb200_engine** out);
+void vitb200_destroy(vitb200_engine* e);
+
+/* Replaces: nn.Module.load_state_dict.  `name` is the torchvision state-dict key (conv_proj.weight,
+ * class_token, encoder.pos_embedding, encoder.layers.encoder_layer_{i}.{ln_1,ln_2}.{weight,bias},
+ * ...self_attention.in_proj_{weight,bias}, ...self_attention.out_proj.{weight,bias}, ...mlp.{0,3}.{weight,bias},
+ * encoder.ln.{weight,bias}, heads.head.{weight,bias}); `data_host` holds `count` fp32 values in the
+ * state-dict layout.  GEMM weights are packed to bf16 on the device. */
+int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_host, size_t count);
+/* VITB200_OK once every tensor of the architecture has been loaded. */
+int vitb200_weights_ready(vitb200_engine* e);
+
+/* Replaces: VisionTransformer.forward(x) (TV:289-306) for a whole batch, plus attention-map extraction
+ * (need_weights=True in EncoderBlock, TV:113).  images: fp32 [B, 3, S, S].  Host variant: H2D copy, forward,
+ * D2H copies of the requested outputs, synchronous on return.  Device variant: enqueues on `stream`
+ * (a cudaStream_t; NULL = the engine's own stream) and returns without synchronising; results stay in the
+ * engine's device buffers (vitb200_device_output). */
+int vitb200_forward_host(vitb200_engine* e, const float* images_host, int batch, uint32_t flags,
+                         const vitb200_host_outputs* out);
+int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, void* stream);
+
+/* Device-resident results of the last forward/stage call.  which: one of the VITB200_EMIT_* flags, or 0 for
+ * logits.  Returns the base pointer and the row pitch (in floats) of the innermost matrix: attention maps
+ * are stored with their rows padded to `pitch` >= N floats. */
+int vitb200_device_output(vitb200_engine* e, uint32_t which, float** ptr_dev, int* pitch);
+int vitb200_synchronize(vitb200_engine* e);
+
+/* Node-granular entry points: one per block-granular graph node of the ViT plugin (embed / layer.i / head /
+ * rollout), i.e. one per Model.compute call of the reference (main/context.py:79-88).  The token stream
+ * [B, N, d] fp32 lives in the engine between calls; set/get move it across the boundary when a node's input
+ * did not come from (or its output must leave) the engine. */
+int vitb200_stage_embed(vitb200_engine* e, const float* images_host, int batch);         /* TV:268-287,295-296 + pos add TV:155 */
+int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags);        /* TV:110-119 */
+int vitb200_stage_head(vitb200_engine* e, int batch, float* logits_host);                /* TV:157,302-304 */
+int vitb200_stage_rollout(vitb200_engine* e, int batch, float* rollout_host);            /* needs avg maps of all layers */
+int vitb200_set_tokens(vitb200_engine* e, const float* tokens_host, int batch);          /* [B, N, d] */
+int vitb200_get_tokens(vitb200_engine* e, float* tokens_host, int batch);
+int vitb200_set_avg_map(vitb200_engine* e, int layer, const float* map_host, int batch); /* [B, N, N] */
+int vitb200_get_avg_map(vitb200_engine* e, int layer, float* map_host, int batch);
+int vitb200_get_cls_map(vitb200_engine* e, int layer, float* map_host, int batch);       /* [B, H, N] */
+int vitb200_get_head_map(vitb200_engine* e, int layer, float* map_host, int batch);      /* [B, H, N, N] */
+
+/* Counters for the harness: kernels launched by this engine since creation. */
+uint64_t vitb200_launch_count(vitb200_engine* e);
+
+/* Single-kernel entry points (device pointers, `stream` = cudaStream_t or NULL for the default stream).
+ * They exist so the parity tests can check each kernel against the oracle in isolation. */
+int vitb200_op_gemm(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, const float* resid_dev,
+                    void* out_dev, int M, int N, int K, int gelu, int out_f32, void* stream);
+int vitb200_op_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, void* y_bf16_dev,
+                         int rows, int d, float eps, void* stream);
+int vitb200_op_attention(const void* qkv_bf16_dev, void* ctx_bf16_dev, float* avg_dev, float* cls_dev,
+                         float* heads_dev, int batch, int tokens, int heads, int pitch, void* stream);
+int vitb200_op_patchify(const float* images_dev, void* patches_bf16_dev, int batch, int image_size, int patch,
+                        void* stream);
+int vitb200_op_rollout(const float* maps_dev, long layer_stride, int layers, int batch, int tokens, int pitch,
+                       float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITB200_H_ */

@@ -1,0 +1,759 @@
+// libvitb200.so — host side of the B200-native ViT forward engine and its C ABI (include/vitb200.h).
+//
+// The engine owns: bf16 weights, an fp32 residual token stream x [B, N, d], bf16 GEMM operands, fp32
+// attention-map buffers, one CUDA stream.  A forward is the kernel sequence of torchvision's
+// VisionTransformer.forward (vision_transformer.py:289-306; EncoderBlock 110-119), i.e. what the reference
+// would execute inside Model.compute (main/context.py:79-88) for a ViT plugin:
+//   patchify -> GEMM(+bias +pos, scatter behind class token) -> cls rows
+//   L x [ LN1 -> GEMM qkv -> fused attention (+maps) -> GEMM out_proj (+x) -> LN2 -> GEMM fc1 (GELU) -> GEMM fc2 (+x) ]
+//   LN(class rows) -> GEMM head -> logits;   rollout over the head-averaged maps.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vitb200.h"
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "rowwise.cuh"
+
+namespace vitb200 {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                      \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess)                                                                                \
+      return fail(VITB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define VT_TRY(expr)          \
+  do {                        \
+    int _s = (expr);          \
+    if (_s != VITB200_OK) return _s; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ TMA descriptors
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, row pitch ld elements), box = box_cols x box_rows,
+// 128-byte swizzle (box_cols * 2 bytes must be 128), out-of-bounds elements read as zero.
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (box_cols * 2 != 128 || box_rows == 0 || box_rows > 256)
+    return fail(VITB200_ERR_INVALID, "bad TMA box %u x %u", box_rows, box_cols);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(VITB200_ERR_INVALID, "TMA operand must be 16-byte aligned (base %p, pitch %llu B)", base,
+                (unsigned long long)(ld * 2));
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VITB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ launch helpers
+static int g_num_sms = 0;
+
+static int device_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool kGelu, bool kOutF32>
+static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
+                         cudaStream_t st) {
+  using C = gemm_cfg::Cfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, kGelu, kOutF32>;
+  static bool configured = false;
+  if (!configured) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  const int m_tiles = (sh.M + gemm_cfg::BM - 1) / gemm_cfg::BM;
+  const int n_tiles = (sh.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < device_sms() ? tiles : device_sms();
+  kern<<<grid, gemm_cfg::kThreads, C::kSmemBytes, st>>>(ta, tw, sh, ep);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
+// out = epilogue(A[M,K] * W[N,K]^T): picks the tile width and the epilogue instantiation.
+static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int K, const GemmEpilogue& ep, bool gelu,
+                       bool out_f32, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm: empty shape %d x %d x %d", M, N, K);
+  if (N % 8 != 0 || K % 8 != 0) return fail(VITB200_ERR_INVALID, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tw;
+  VT_TRY(make_tmap_bf16(&ta, a, M, K, lda, gemm_cfg::BM, gemm_cfg::BK));
+  VT_TRY(make_tmap_bf16(&tw, w, N, K, K, BN, gemm_cfg::BK));
+  GemmShape sh{M, N, K};
+  if (BN == 256) {
+    if (gelu && !out_f32) return launch_gemm_t<256, true, false>(ta, tw, sh, ep, st);
+    if (!gelu && !out_f32) return launch_gemm_t<256, false, false>(ta, tw, sh, ep, st);
+    if (!gelu && out_f32) return launch_gemm_t<256, false, true>(ta, tw, sh, ep, st);
+  } else {
+    if (gelu && !out_f32) return launch_gemm_t<128, true, false>(ta, tw, sh, ep, st);
+    if (!gelu && !out_f32) return launch_gemm_t<128, false, false>(ta, tw, sh, ep, st);
+    if (!gelu && out_f32) return launch_gemm_t<128, false, true>(ta, tw, sh, ep, st);
+  }
+  return fail(VITB200_ERR_INVALID, "gemm: GELU with fp32 output is not instantiated");
+}
+
+static int launch_layernorm(const float* x, long in_stride, const float* g, const float* b, __nv_bfloat16* y, int rows,
+                            int d, float eps, cudaStream_t st) {
+  if (rows <= 0) return fail(VITB200_ERR_INVALID, "layernorm: no rows");
+  if (d % 128 != 0) return fail(VITB200_ERR_INVALID, "layernorm: width %d must be a multiple of 128", d);
+  const int blocks = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
+#define VT_LN_CASE(V)                                                                                \
+  case V:                                                                                            \
+    layernorm_f32_bf16_kernel<V><<<blocks, 256, 0, st>>>(x, in_stride, g, b, y, rows, eps);          \
+    break;
+  switch (d / 128) {
+    VT_LN_CASE(1) VT_LN_CASE(2) VT_LN_CASE(3) VT_LN_CASE(4) VT_LN_CASE(5) VT_LN_CASE(6) VT_LN_CASE(8) VT_LN_CASE(10)
+    default:
+      return fail(VITB200_ERR_INVALID, "layernorm: width %d not instantiated (multiples of 128 up to 1280)", d);
+  }
+#undef VT_LN_CASE
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
+static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* avg, float* cls, float* heads, int B,
+                            int N, int H, int pitch, cudaStream_t st) {
+  using namespace attn_cfg;
+  const int KP = (N + 15) / 16 * 16;
+  if (KP > KP_MAX) return fail(VITB200_ERR_INVALID, "attention: %d tokens exceed this kernel's limit of %d", N, KP_MAX);
+  if (N > 2 * BM) return fail(VITB200_ERR_INVALID, "attention: more than two query tiles");
+  if ((avg || heads) && (pitch < KP || pitch % 4 != 0))
+    return fail(VITB200_ERR_INVALID, "attention: map pitch %d must be >= %d and a multiple of 4", pitch, KP);
+  const int d = H * D;
+  CUtensorMap tq, tkv;
+  VT_TRY(make_tmap_bf16(&tq, qkv, (uint64_t)B * N, 3 * d, 3 * d, BM, D));
+  VT_TRY(make_tmap_bf16(&tkv, qkv, (uint64_t)B * N, 3 * d, 3 * d, KP / 2, D));
+  static bool configured = false;
+  if (!configured) {
+    CU_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  AttnParams p;
+  p.B = B, p.N = N, p.H = H, p.d = d, p.KP = KP;
+  p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
+  p.ctx = ctx, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
+  p.q_tiles = (N + BM - 1) / BM;
+  attention_kernel<<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, p);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ engine
+struct LayerWeights {
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  __nv_bfloat16 *w_qkv = nullptr, *w_o = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
+  float *b_qkv = nullptr, *b_o = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
+};
+
+struct Buffer {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace vitb200
+
+using namespace vitb200;
+
+struct vitb200_engine {
+  vitb200_config cfg{};
+  int N = 0, n = 0, D = 0, KP = 0, pitch = 0, patch_k = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  uint64_t launches = 0;
+
+  // weights
+  __nv_bfloat16* w_patch = nullptr;
+  float* b_patch = nullptr;
+  float *cls_token = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+  __nv_bfloat16* w_head = nullptr;
+  float* b_head = nullptr;
+  std::vector<LayerWeights> layers;
+  std::map<std::string, bool> loaded;
+  size_t expected_tensors = 0;
+  Buffer stage_f32;  // fp32 staging for weight upload / conversion
+
+  // activations (sized for cap_batch images)
+  int cap_batch = 0;
+  uint32_t cap_flags = 0;
+  Buffer images, patches, x, ln, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout;
+
+  ~vitb200_engine();
+};
+
+namespace vitb200 {
+
+static int ensure(Buffer& b, size_t bytes) {
+  if (b.bytes >= bytes) return VITB200_OK;
+  if (b.p) CU_TRY(cudaFree(b.p));
+  b.p = nullptr, b.bytes = 0;
+  CU_TRY(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return VITB200_OK;
+}
+
+static void release(Buffer& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr, b.bytes = 0;
+}
+
+static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
+  const vitb200_config& c = e->cfg;
+  const size_t M = (size_t)B * e->N;
+  const size_t L = c.num_layers;
+  VT_TRY(ensure(e->images, (size_t)B * 3 * c.image_size * c.image_size * 4));
+  VT_TRY(ensure(e->patches, (size_t)B * e->n * e->patch_k * 2));
+  VT_TRY(ensure(e->x, M * c.hidden_dim * 4));
+  VT_TRY(ensure(e->ln, M * c.hidden_dim * 2));
+  VT_TRY(ensure(e->qkv, M * 3 * c.hidden_dim * 2));
+  VT_TRY(ensure(e->ctx, M * c.hidden_dim * 2));
+  VT_TRY(ensure(e->mlp, M * c.mlp_dim * 2));
+  VT_TRY(ensure(e->cls_ln, (size_t)B * c.hidden_dim * 2));
+  VT_TRY(ensure(e->logits, (size_t)B * c.num_classes * 4));
+  if (flags & (VITB200_EMIT_AVG | VITB200_EMIT_ROLLOUT)) VT_TRY(ensure(e->avg, L * M * e->pitch * 4));
+  if (flags & VITB200_EMIT_ROLLOUT) VT_TRY(ensure(e->rollout, (size_t)B * (e->N - 1) * 4));
+  if (flags & VITB200_EMIT_CLS) VT_TRY(ensure(e->cls, L * B * c.num_heads * e->N * 4));
+  if (flags & VITB200_EMIT_HEADS) VT_TRY(ensure(e->heads, L * M * c.num_heads * e->pitch * 4));
+  if (flags & VITB200_EMIT_HIDDEN) VT_TRY(ensure(e->hidden, L * M * c.hidden_dim * 4));
+  if (B > e->cap_batch) e->cap_batch = B;
+  e->cap_flags |= flags;
+  return VITB200_OK;
+}
+
+// ---- forward stages (all enqueue on `st`, no synchronisation) --------------------------------------
+static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStream_t st) {
+  const vitb200_config& c = e->cfg;
+  const long items = (long)B * 3 * c.image_size * (c.image_size / c.patch_size) * (c.patch_size / 8);
+  patchify_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(images_dev, (__nv_bfloat16*)e->patches.p, B,
+                                                                   c.image_size, c.patch_size);
+  CU_TRY(cudaGetLastError());
+  GemmEpilogue ep;
+  ep.bias = e->b_patch;
+  ep.out = e->x.p, ep.ldo = c.hidden_dim;
+  ep.resid = e->pos, ep.ldr = c.hidden_dim;
+  ep.group_rows = e->n, ep.out_group_stride = e->N, ep.out_row_offset = 1;
+  ep.resid_broadcast = 1, ep.resid_row_offset = 1;
+  VT_TRY(launch_gemm(e->patches.p, e->patch_k, e->w_patch, B * e->n, c.hidden_dim, e->patch_k, ep, false, true, st));
+  const long citems = (long)B * (c.hidden_dim / 4);
+  cls_rows_kernel<<<(unsigned)((citems + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p, B, e->N,
+                                                                    c.hidden_dim);
+  CU_TRY(cudaGetLastError());
+  e->launches += 3;
+  return VITB200_OK;
+}
+
+static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream_t st) {
+  const vitb200_config& c = e->cfg;
+  const LayerWeights& w = e->layers[l];
+  const int M = B * e->N, d = c.hidden_dim;
+  float* x = (float*)e->x.p;
+  __nv_bfloat16* ln = (__nv_bfloat16*)e->ln.p;
+  VT_TRY(launch_layernorm(x, d, w.ln1_g, w.ln1_b, ln, M, d, 1e-6f, st));
+  {
+    GemmEpilogue ep;
+    ep.bias = w.b_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
+    VT_TRY(launch_gemm(ln, d, w.w_qkv, M, 3 * d, d, ep, false, false, st));
+  }
+  const bool want_avg = (flags & (VITB200_EMIT_AVG | VITB200_EMIT_ROLLOUT)) != 0;
+  float* avg = want_avg ? (float*)e->avg.p + (size_t)l * e->cap_batch * e->N * e->pitch : nullptr;
+  float* cls = (flags & VITB200_EMIT_CLS) ? (float*)e->cls.p + (size_t)l * e->cap_batch * c.num_heads * e->N : nullptr;
+  float* hm = (flags & VITB200_EMIT_HEADS)
+                  ? (float*)e->heads.p + (size_t)l * e->cap_batch * c.num_heads * e->N * e->pitch
+                  : nullptr;
+  VT_TRY(launch_attention((const __nv_bfloat16*)e->qkv.p, (__nv_bfloat16*)e->ctx.p, avg, cls, hm, B, e->N, c.num_heads,
+                          e->pitch, st));
+  {
+    GemmEpilogue ep;
+    ep.bias = w.b_o, ep.out = x, ep.ldo = d, ep.resid = x, ep.ldr = d;
+    VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st));
+  }
+  VT_TRY(launch_layernorm(x, d, w.ln2_g, w.ln2_b, ln, M, d, 1e-6f, st));
+  {
+    GemmEpilogue ep;
+    ep.bias = w.b_fc1, ep.out = e->mlp.p, ep.ldo = c.mlp_dim;
+    VT_TRY(launch_gemm(ln, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st));
+  }
+  {
+    GemmEpilogue ep;
+    ep.bias = w.b_fc2, ep.out = x, ep.ldo = d, ep.resid = x, ep.ldr = d;
+    VT_TRY(launch_gemm(e->mlp.p, c.mlp_dim, w.w_fc2, M, d, c.mlp_dim, ep, false, true, st));
+  }
+  e->launches += 7;
+  if (flags & VITB200_EMIT_HIDDEN) {
+    float* hid = (float*)e->hidden.p + (size_t)l * e->cap_batch * e->N * d;
+    CU_TRY(cudaMemcpyAsync(hid, x, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return VITB200_OK;
+}
+
+static int run_head(vitb200_engine* e, int B, cudaStream_t st) {
+  const vitb200_config& c = e->cfg;
+  const int d = c.hidden_dim;
+  VT_TRY(launch_layernorm((const float*)e->x.p, (long)e->N * d, e->lnf_g, e->lnf_b, (__nv_bfloat16*)e->cls_ln.p, B, d,
+                          1e-6f, st));
+  GemmEpilogue ep;
+  ep.bias = e->b_head, ep.out = e->logits.p, ep.ldo = c.num_classes;
+  VT_TRY(launch_gemm(e->cls_ln.p, d, e->w_head, B, c.num_classes, d, ep, false, true, st));
+  e->launches += 2;
+  return VITB200_OK;
+}
+
+static int run_rollout(vitb200_engine* e, int B, cudaStream_t st) {
+  const size_t smem = 3 * (size_t)e->pitch * sizeof(float);
+  rollout_cls_kernel<<<B, 256, smem, st>>>((const float*)e->avg.p, (long)e->cap_batch * e->N * e->pitch,
+                                           e->cfg.num_layers, e->N, e->pitch, (float*)e->rollout.p);
+  CU_TRY(cudaGetLastError());
+  e->launches += 1;
+  return VITB200_OK;
+}
+
+static int check_ready(vitb200_engine* e) {
+  if (e->loaded.size() != e->expected_tensors)
+    return fail(VITB200_ERR_STATE, "weights incomplete: %zu of %zu tensors loaded", e->loaded.size(), e->expected_tensors);
+  return VITB200_OK;
+}
+
+static int check_batch(vitb200_engine* e, int B) {
+  if (B <= 0) return fail(VITB200_ERR_INVALID, "batch must be positive (got %d)", B);
+  (void)e;
+  return VITB200_OK;
+}
+
+static int forward_device_locked(vitb200_engine* e, const float* images_dev, int B, uint32_t flags, cudaStream_t st) {
+  VT_TRY(check_ready(e));
+  VT_TRY(check_batch(e, B));
+  // the layer-strided map buffers are addressed with cap_batch: grow first, then never shrink
+  VT_TRY(ensure_workspace(e, B > e->cap_batch ? B : e->cap_batch, flags | e->cap_flags));
+  VT_TRY(run_embed(e, images_dev, B, st));
+  for (int l = 0; l < e->cfg.num_layers; ++l) VT_TRY(run_layer(e, l, B, flags, st));
+  VT_TRY(run_head(e, B, st));
+  if (flags & VITB200_EMIT_ROLLOUT) VT_TRY(run_rollout(e, B, st));
+  return VITB200_OK;
+}
+
+// dense host <- pitched device rows
+static int copy_rows_to_host(float* dst, const float* src_dev, size_t rows, int width, int pitch, cudaStream_t st) {
+  CU_TRY(cudaMemcpy2DAsync(dst, (size_t)width * 4, src_dev, (size_t)pitch * 4, (size_t)width * 4, rows,
+                           cudaMemcpyDeviceToHost, st));
+  return VITB200_OK;
+}
+
+}  // namespace vitb200
+
+vitb200_engine::~vitb200_engine() {
+  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &ln, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout};
+  for (Buffer* b : bufs) release(*b);
+  auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(w_patch), fr(b_patch), fr(cls_token), fr(pos), fr(lnf_g), fr(lnf_b), fr(w_head), fr(b_head);
+  for (auto& l : layers) {
+    fr(l.ln1_g), fr(l.ln1_b), fr(l.ln2_g), fr(l.ln2_b), fr(l.w_qkv), fr(l.w_o), fr(l.w_fc1), fr(l.w_fc2);
+    fr(l.b_qkv), fr(l.b_o), fr(l.b_fc1), fr(l.b_fc2);
+  }
+  if (stream) cudaStreamDestroy(stream);
+}
+
+// =========================================================================================== C ABI
+extern "C" {
+
+const char* vitb200_last_error(void) { return g_last_error.c_str(); }
+int vitb200_version(void) { return 1; }
+
+int vitb200_create(const vitb200_config* cfg, vitb200_engine** out) {
+  if (!cfg || !out) return fail(VITB200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const vitb200_config& c = *cfg;
+  if (c.patch_size <= 0 || c.patch_size % 8 != 0 || c.image_size % c.patch_size != 0)
+    return fail(VITB200_ERR_INVALID, "image_size %d must be a multiple of patch_size %d (itself a multiple of 8)",
+                c.image_size, c.patch_size);
+  if (c.num_heads <= 0 || c.hidden_dim != c.num_heads * 64)
+    return fail(VITB200_ERR_INVALID, "head dim must be 64 (hidden_dim %d, heads %d)", c.hidden_dim, c.num_heads);
+  if (c.hidden_dim % 128 != 0 || c.mlp_dim % 64 != 0 || c.num_classes % 8 != 0 || c.num_layers <= 0)
+    return fail(VITB200_ERR_INVALID, "unsupported widths: hidden %d mlp %d classes %d layers %d", c.hidden_dim, c.mlp_dim,
+                c.num_classes, c.num_layers);
+  const int n = (c.image_size / c.patch_size) * (c.image_size / c.patch_size);
+  const int N = n + 1;
+  const int KP = (N + 15) / 16 * 16;
+  if (KP > attn_cfg::KP_MAX)
+    return fail(VITB200_ERR_INVALID, "%d tokens per image exceed the fused attention kernel's limit (%d)", N, attn_cfg::KP_MAX);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(VITB200_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  if (c.device < 0 || c.device >= ndev) return fail(VITB200_ERR_INVALID, "device %d out of range (%d devices)", c.device, ndev);
+  CU_TRY(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, c.device));
+  if (prop.major != 10) return fail(VITB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", c.device, prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+
+  vitb200_engine* e = new vitb200_engine();
+  e->cfg = c;
+  e->n = n, e->N = N, e->D = 64, e->KP = KP, e->pitch = KP, e->patch_k = 3 * c.patch_size * c.patch_size;
+  e->layers.resize(c.num_layers);
+  e->expected_tensors = 4 + 12 * (size_t)c.num_layers + 4;
+  cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (err != cudaSuccess) {
+    delete e;
+    return fail(VITB200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(err));
+  }
+  if (c.max_batch > 0) {
+    int s = ensure_workspace(e, c.max_batch, 0);
+    if (s != VITB200_OK) {
+      delete e;
+      return s;
+    }
+  }
+  *out = e;
+  return VITB200_OK;
+}
+
+void vitb200_destroy(vitb200_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_host, size_t count) {
+  if (!e || !name || !data_host) return fail(VITB200_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  const vitb200_config& c = e->cfg;
+  const size_t d = c.hidden_dim;
+  const std::string key(name);
+  void** slot = nullptr;
+  size_t expect = 0;
+  bool to_bf16 = false;
+  auto F = [&](float** p, size_t n) { slot = (void**)p, expect = n, to_bf16 = false; };
+  auto H = [&](__nv_bfloat16** p, size_t n) { slot = (void**)p, expect = n, to_bf16 = true; };
+  if (key == "conv_proj.weight") H(&e->w_patch, d * e->patch_k);
+  else if (key == "conv_proj.bias") F(&e->b_patch, d);
+  else if (key == "class_token") F(&e->cls_token, d);
+  else if (key == "encoder.pos_embedding") F(&e->pos, (size_t)e->N * d);
+  else if (key == "encoder.ln.weight") F(&e->lnf_g, d);
+  else if (key == "encoder.ln.bias") F(&e->lnf_b, d);
+  else if (key == "heads.head.weight") H(&e->w_head, (size_t)c.num_classes * d);
+  else if (key == "heads.head.bias") F(&e->b_head, c.num_classes);
+  else {
+    int li = -1;
+    char rest[128] = {0};
+    if (sscanf(name, "encoder.layers.encoder_layer_%d.%127s", &li, rest) != 2 || li < 0 || li >= c.num_layers)
+      return fail(VITB200_ERR_INVALID, "unknown weight name '%s'", name);
+    LayerWeights& w = e->layers[li];
+    const std::string r(rest);
+    if (r == "ln_1.weight") F(&w.ln1_g, d);
+    else if (r == "ln_1.bias") F(&w.ln1_b, d);
+    else if (r == "ln_2.weight") F(&w.ln2_g, d);
+    else if (r == "ln_2.bias") F(&w.ln2_b, d);
+    else if (r == "self_attention.in_proj_weight") H(&w.w_qkv, 3 * d * d);
+    else if (r == "self_attention.in_proj_bias") F(&w.b_qkv, 3 * d);
+    else if (r == "self_attention.out_proj.weight") H(&w.w_o, d * d);
+    else if (r == "self_attention.out_proj.bias") F(&w.b_o, d);
+    else if (r == "mlp.0.weight") H(&w.w_fc1, (size_t)c.mlp_dim * d);
+    else if (r == "mlp.0.bias") F(&w.b_fc1, c.mlp_dim);
+    else if (r == "mlp.3.weight") H(&w.w_fc2, d * (size_t)c.mlp_dim);
+    else if (r == "mlp.3.bias") F(&w.b_fc2, d);
+    else return fail(VITB200_ERR_INVALID, "unknown weight name '%s'", name);
+  }
+  if (count != expect)
+    return fail(VITB200_ERR_INVALID, "weight '%s': expected %zu values, got %zu", name, expect, count);
+  if (*slot) {
+    CU_TRY(cudaFree(*slot));
+    *slot = nullptr;
+  }
+  if (!to_bf16) {
+    CU_TRY(cudaMalloc(slot, count * 4));
+    CU_TRY(cudaMemcpyAsync(*slot, data_host, count * 4, cudaMemcpyHostToDevice, e->stream));
+  } else {
+    VT_TRY(ensure(e->stage_f32, count * 4));
+    CU_TRY(cudaMalloc(slot, count * 2));
+    CU_TRY(cudaMemcpyAsync(e->stage_f32.p, data_host, count * 4, cudaMemcpyHostToDevice, e->stream));
+    f32_to_bf16_kernel<<<(unsigned)((count / 4 + 256) / 256), 256, 0, e->stream>>>((const float*)e->stage_f32.p,
+                                                                                  (__nv_bfloat16*)*slot, (long)count);
+    CU_TRY(cudaGetLastError());
+  }
+  CU_TRY(cudaStreamSynchronize(e->stream));
+  e->loaded[key] = true;
+  return VITB200_OK;
+}
+
+int vitb200_weights_ready(vitb200_engine* e) {
+  if (!e) return fail(VITB200_ERR_INVALID, "null engine");
+  return check_ready(e);
+}
+
+int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, void* stream) {
+  if (!e || !images_dev) return fail(VITB200_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  return forward_device_locked(e, images_dev, batch, flags, st);
+}
+
+int vitb200_forward_host(vitb200_engine* e, const float* images_host, int batch, uint32_t flags,
+                         const vitb200_host_outputs* out) {
+  if (!e || !images_host || !out) return fail(VITB200_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  const vitb200_config& c = e->cfg;
+  if (out->avg_maps) flags |= VITB200_EMIT_AVG;
+  if (out->cls_maps) flags |= VITB200_EMIT_CLS;
+  if (out->rollout) flags |= VITB200_EMIT_ROLLOUT;
+  if (out->heads) flags |= VITB200_EMIT_HEADS;
+  if (out->hidden) flags |= VITB200_EMIT_HIDDEN;
+  VT_TRY(check_batch(e, batch));
+  VT_TRY(ensure_workspace(e, batch > e->cap_batch ? batch : e->cap_batch, flags | e->cap_flags));
+  cudaStream_t st = e->stream;
+  const size_t img_bytes = (size_t)batch * 3 * c.image_size * c.image_size * 4;
+  CU_TRY(cudaMemcpyAsync(e->images.p, images_host, img_bytes, cudaMemcpyHostToDevice, st));
+  VT_TRY(forward_device_locked(e, (const float*)e->images.p, batch, flags, st));
+  const int B = batch, N = e->N, L = c.num_layers, Hh = c.num_heads, d = c.hidden_dim;
+  if (out->logits)
+    CU_TRY(cudaMemcpyAsync(out->logits, e->logits.p, (size_t)B * c.num_classes * 4, cudaMemcpyDeviceToHost, st));
+  for (int l = 0; l < L; ++l) {
+    if (out->avg_maps)
+      VT_TRY(copy_rows_to_host(out->avg_maps + (size_t)l * B * N * N, (const float*)e->avg.p + (size_t)l * e->cap_batch * N * e->pitch,
+                               (size_t)B * N, N, e->pitch, st));
+    if (out->cls_maps)
+      CU_TRY(cudaMemcpyAsync(out->cls_maps + (size_t)l * B * Hh * N, (const float*)e->cls.p + (size_t)l * e->cap_batch * Hh * N,
+                             (size_t)B * Hh * N * 4, cudaMemcpyDeviceToHost, st));
+    if (out->heads)
+      VT_TRY(copy_rows_to_host(out->heads + (size_t)l * B * Hh * N * N,
+                               (const float*)e->heads.p + (size_t)l * e->cap_batch * Hh * N * e->pitch, (size_t)B * Hh * N, N,
+                               e->pitch, st));
+    if (out->hidden)
+      CU_TRY(cudaMemcpyAsync(out->hidden + (size_t)l * B * N * d, (const float*)e->hidden.p + (size_t)l * e->cap_batch * N * d,
+                             (size_t)B * N * d * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (out->rollout)
+    CU_TRY(cudaMemcpyAsync(out->rollout, e->rollout.p, (size_t)B * (N - 1) * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_device_output(vitb200_engine* e, uint32_t which, float** ptr_dev, int* pitch) {
+  if (!e || !ptr_dev) return fail(VITB200_ERR_INVALID, "null argument");
+  int pt = 0;
+  void* p = nullptr;
+  switch (which) {
+    case 0: p = e->logits.p, pt = e->cfg.num_classes; break;
+    case VITB200_EMIT_AVG: p = e->avg.p, pt = e->pitch; break;
+    case VITB200_EMIT_CLS: p = e->cls.p, pt = e->N; break;
+    case VITB200_EMIT_ROLLOUT: p = e->rollout.p, pt = e->N - 1; break;
+    case VITB200_EMIT_HEADS: p = e->heads.p, pt = e->pitch; break;
+    case VITB200_EMIT_HIDDEN: p = e->hidden.p, pt = e->cfg.hidden_dim; break;
+    default: return fail(VITB200_ERR_INVALID, "unknown output selector %u", which);
+  }
+  if (!p) return fail(VITB200_ERR_STATE, "output %u has not been produced", which);
+  *ptr_dev = (float*)p;
+  if (pitch) *pitch = pt;
+  return VITB200_OK;
+}
+
+int vitb200_synchronize(vitb200_engine* e) {
+  if (!e) return fail(VITB200_ERR_INVALID, "null engine");
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  CU_TRY(cudaStreamSynchronize(e->stream));
+  return VITB200_OK;
+}
+
+uint64_t vitb200_launch_count(vitb200_engine* e) { return e ? e->launches : 0; }
+
+// ---- node-granular stages --------------------------------------------------------------------------
+#define STAGE_PROLOGUE(B, FLAGS)                                                            \
+  if (!e) return fail(VITB200_ERR_INVALID, "null engine");                                  \
+  std::lock_guard<std::mutex> lock(e->mu);                                                  \
+  CU_TRY(cudaSetDevice(e->cfg.device));                                                     \
+  VT_TRY(check_ready(e));                                                                   \
+  VT_TRY(check_batch(e, (B)));                                                              \
+  VT_TRY(ensure_workspace(e, (B) > e->cap_batch ? (B) : e->cap_batch, (FLAGS) | e->cap_flags)); \
+  cudaStream_t st = e->stream;
+
+int vitb200_stage_embed(vitb200_engine* e, const float* images_host, int batch) {
+  if (!images_host) return fail(VITB200_ERR_INVALID, "null images");
+  STAGE_PROLOGUE(batch, 0)
+  const size_t img_bytes = (size_t)batch * 3 * e->cfg.image_size * e->cfg.image_size * 4;
+  CU_TRY(cudaMemcpyAsync(e->images.p, images_host, img_bytes, cudaMemcpyHostToDevice, st));
+  VT_TRY(run_embed(e, (const float*)e->images.p, batch, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags) {
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  STAGE_PROLOGUE(batch, flags)
+  VT_TRY(run_layer(e, layer, batch, flags, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_stage_head(vitb200_engine* e, int batch, float* logits_host) {
+  STAGE_PROLOGUE(batch, 0)
+  VT_TRY(run_head(e, batch, st));
+  if (logits_host)
+    CU_TRY(cudaMemcpyAsync(logits_host, e->logits.p, (size_t)batch * e->cfg.num_classes * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_stage_rollout(vitb200_engine* e, int batch, float* rollout_host) {
+  STAGE_PROLOGUE(batch, VITB200_EMIT_ROLLOUT)
+  VT_TRY(run_rollout(e, batch, st));
+  if (rollout_host)
+    CU_TRY(cudaMemcpyAsync(rollout_host, e->rollout.p, (size_t)batch * (e->N - 1) * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_set_tokens(vitb200_engine* e, const float* tokens_host, int batch) {
+  if (!tokens_host) return fail(VITB200_ERR_INVALID, "null tokens");
+  STAGE_PROLOGUE(batch, 0)
+  CU_TRY(cudaMemcpyAsync(e->x.p, tokens_host, (size_t)batch * e->N * e->cfg.hidden_dim * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_get_tokens(vitb200_engine* e, float* tokens_host, int batch) {
+  if (!tokens_host) return fail(VITB200_ERR_INVALID, "null tokens");
+  STAGE_PROLOGUE(batch, 0)
+  CU_TRY(cudaMemcpyAsync(tokens_host, e->x.p, (size_t)batch * e->N * e->cfg.hidden_dim * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_set_avg_map(vitb200_engine* e, int layer, const float* map_host, int batch) {
+  if (!map_host) return fail(VITB200_ERR_INVALID, "null map");
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  STAGE_PROLOGUE(batch, VITB200_EMIT_AVG)
+  float* dst = (float*)e->avg.p + (size_t)layer * e->cap_batch * e->N * e->pitch;
+  CU_TRY(cudaMemcpy2DAsync(dst, (size_t)e->pitch * 4, map_host, (size_t)e->N * 4, (size_t)e->N * 4, (size_t)batch * e->N,
+                           cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_get_avg_map(vitb200_engine* e, int layer, float* map_host, int batch) {
+  if (!map_host) return fail(VITB200_ERR_INVALID, "null map");
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  STAGE_PROLOGUE(batch, VITB200_EMIT_AVG)
+  const float* src = (const float*)e->avg.p + (size_t)layer * e->cap_batch * e->N * e->pitch;
+  VT_TRY(copy_rows_to_host(map_host, src, (size_t)batch * e->N, e->N, e->pitch, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_get_cls_map(vitb200_engine* e, int layer, float* map_host, int batch) {
+  if (!map_host) return fail(VITB200_ERR_INVALID, "null map");
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  STAGE_PROLOGUE(batch, VITB200_EMIT_CLS)
+  const float* src = (const float*)e->cls.p + (size_t)layer * e->cap_batch * e->cfg.num_heads * e->N;
+  CU_TRY(cudaMemcpyAsync(map_host, src, (size_t)batch * e->cfg.num_heads * e->N * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_get_head_map(vitb200_engine* e, int layer, float* map_host, int batch) {
+  if (!map_host) return fail(VITB200_ERR_INVALID, "null map");
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  STAGE_PROLOGUE(batch, VITB200_EMIT_HEADS)
+  const float* src = (const float*)e->heads.p + (size_t)layer * e->cap_batch * e->cfg.num_heads * e->N * e->pitch;
+  VT_TRY(copy_rows_to_host(map_host, src, (size_t)batch * e->cfg.num_heads * e->N, e->N, e->pitch, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+// ---- single-kernel entry points (parity tests) -----------------------------------------------------
+int vitb200_op_gemm(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N, int K,
+                    int gelu, int out_f32, void* stream) {
+  if (!a || !w || !out) return fail(VITB200_ERR_INVALID, "null argument");
+  GemmEpilogue ep;
+  ep.bias = bias, ep.out = out, ep.ldo = N, ep.resid = resid, ep.ldr = N;
+  return launch_gemm(a, K, w, M, N, K, ep, gelu != 0, out_f32 != 0, (cudaStream_t)stream);
+}
+
+int vitb200_op_layernorm(const float* x, const float* gamma, const float* beta, void* y, int rows, int d, float eps,
+                         void* stream) {
+  if (!x || !gamma || !beta || !y) return fail(VITB200_ERR_INVALID, "null argument");
+  return launch_layernorm(x, d, gamma, beta, (__nv_bfloat16*)y, rows, d, eps, (cudaStream_t)stream);
+}
+
+int vitb200_op_attention(const void* qkv, void* ctx, float* avg, float* cls, float* heads, int batch, int tokens,
+                         int nheads, int pitch, void* stream) {
+  if (!qkv || !ctx) return fail(VITB200_ERR_INVALID, "null argument");
+  return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, avg, cls, heads, batch, tokens, nheads, pitch,
+                          (cudaStream_t)stream);
+}
+
+int vitb200_op_patchify(const float* images, void* patches, int batch, int image_size, int patch, void* stream) {
+  if (!images || !patches) return fail(VITB200_ERR_INVALID, "null argument");
+  if (patch <= 0 || patch % 8 != 0 || image_size % patch != 0) return fail(VITB200_ERR_INVALID, "bad patch geometry");
+  const long items = (long)batch * 3 * image_size * (image_size / patch) * (patch / 8);
+  patchify_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(images, (__nv_bfloat16*)patches,
+                                                                                     batch, image_size, patch);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
+int vitb200_op_rollout(const float* maps, long layer_stride, int layers, int batch, int tokens, int pitch, float* out,
+                       void* stream) {
+  if (!maps || !out) return fail(VITB200_ERR_INVALID, "null argument");
+  rollout_cls_kernel<<<batch, 256, 3 * (size_t)pitch * sizeof(float), (cudaStream_t)stream>>>(maps, layer_stride, layers,
+                                                                                              tokens, pitch, out);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+"""ctypes binding of libvitb200.so (C ABI: include/vitb200.h) — the only way Python reaches the CUDA kernels.
+
+The reference has no FFI (it calls torch modules directly inside ``Model.compute``, main/context.py:79-88);
+this module is the stub a maintainer would add.  There is deliberately no fallback: if the shared library is
+missing or no sm_100 device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvitb200.so")
+
+EMIT_AVG = 1
+EMIT_CLS = 2
+EMIT_ROLLOUT = 4
+EMIT_HEADS = 8
+EMIT_HIDDEN = 16
+
+
+class EngineError(RuntimeError):
+    """Raised for every non-zero status of the C ABI; ``str(e)`` is vitb200_last_error()."""
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("image_size", C.c_int),
+        ("patch_size", C.c_int),
+        ("num_layers", C.c_int),
+        ("num_heads", C.c_int),
+        ("hidden_dim", C.c_int),
+        ("mlp_dim", C.c_int),
+        ("num_classes", C.c_int),
+        ("max_batch", C.c_int),
+        ("device", C.c_int),
+    ]
+
+
+class _HostOutputs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p),
+        ("avg_maps", C.c_void_p),
+        ("cls_maps", C.c_void_p),
+        ("rollout", C.c_void_p),
+        ("heads", C.c_void_p),
+        ("hidden", C.c_void_p),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+# name -> (restype, argtypes); kept in one table so the symbol test can walk it against include/vitb200.h
+_P, _I, _U32, _F, _L = C.c_void_p, C.c_int, C.c_uint32, C.c_float, C.c_long
+SIGNATURES = {
+    "vitb200_last_error": (C.c_char_p, []),
+    "vitb200_version": (_I, []),
+    "vitb200_create": (_I, [C.POINTER(_Config), C.POINTER(_P)]),
+    "vitb200_destroy": (None, [_P]),
+    "vitb200_load_weight": (_I, [_P, C.c_char_p, _P, C.c_size_t]),
+    "vitb200_weights_ready": (_I, [_P]),
+    "vitb200_forward_host": (_I, [_P, _P, _I, _U32, C.POINTER(_HostOutputs)]),
+    "vitb200_forward_device": (_I, [_P, _P, _I, _U32, _P]),
+    "vitb200_device_output": (_I, [_P, _U32, C.POINTER(_P), C.POINTER(_I)]),
+    "vitb200_synchronize": (_I, [_P]),
+    "vitb200_stage_embed": (_I, [_P, _P, _I]),
+    "vitb200_stage_layer": (_I, [_P, _I, _I, _U32]),
+    "vitb200_stage_head": (_I, [_P, _I, _P]),
+    "vitb200_stage_rollout": (_I, [_P, _I, _P]),
+    "vitb200_set_tokens": (_I, [_P, _P, _I]),
+    "vitb200_get_tokens": (_I, [_P, _P, _I]),
+    "vitb200_set_avg_map": (_I, [_P, _I, _P, _I]),
+    "vitb200_get_avg_map": (_I, [_P, _I, _P, _I]),
+    "vitb200_get_cls_map": (_I, [_P, _I, _P, _I]),
+    "vitb200_get_head_map": (_I, [_P, _I, _P, _I]),
+    "vitb200_launch_count": (C.c_uint64, [_P]),
+    "vitb200_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vitb200_op_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
+    "vitb200_op_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "vitb200_op_patchify": (_I, [_P, _P, _I, _I, _I, _P]),
+    "vitb200_op_rollout": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
+}
+
+
+def load_library() -> C.CDLL:
+    """dlopen libvitb200.so (built in-tree by __graft_entry__.build()) and type its entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load_library().vitb200_last_error()
+        raise EngineError(f"vitb200 error {status}: {msg.decode() if msg else '?'}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@dataclass(frozen=True)
+class VitConfig:
+    image_size: int = 224
+    patch_size: int = 16
+    num_layers: int = 12
+    num_heads: int = 12
+    hidden_dim: int = 768
+    mlp_dim: int = 3072
+    num_classes: int = 1000
+
+    @property
+    def tokens(self) -> int:
+        return (self.image_size // self.patch_size) ** 2 + 1
+
+    @property
+    def grid(self) -> int:
+        return self.image_size // self.patch_size
+
+    def gflop_per_image(self) -> float:
+        """Tensor-core FLOPs of one forward (SURVEY.md §8d formula; GEMMs + attention matmuls only)."""
+        n, N, d, m, L = self.grid ** 2, self.tokens, self.hidden_dim, self.mlp_dim, self.num_layers
+        f = 2 * n * (3 * self.patch_size ** 2) * d
+        f += L * (2 * N * d * 3 * d + 4 * N * N * d + 2 * N * d * d + 4 * N * d * m)
+        f += 2 * d * self.num_classes
+        return f / 1e9
+
+
+CONFIGS: Dict[str, VitConfig] = {
+    "vit_s_16": VitConfig(224, 16, 12, 6, 384, 1536),
+    "vit_b_16": VitConfig(224, 16, 12, 12, 768, 3072),
+    "vit_l_16": VitConfig(224, 16, 24, 16, 1024, 4096),
+}
+
+
+class VitEngine:
+    """One engine = one model replica on one GPU.  Thread-safe (the C side serialises calls)."""
+
+    def __init__(self, cfg: VitConfig, device: int = 0, max_batch: int = 1):
+        self.lib = load_library()
+        self.cfg = cfg
+        self.device = device
+        c = _Config(cfg.image_size, cfg.patch_size, cfg.num_layers, cfg.num_heads, cfg.hidden_dim, cfg.mlp_dim,
+                    cfg.num_classes, max_batch, device)
+        h = C.c_void_p()
+        check(self.lib.vitb200_create(C.byref(c), C.byref(h)))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self.lib.vitb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """torchvision VisionTransformer state-dict (fp32) -> device (bf16 GEMM operands, fp32 the rest)."""
+        for name, t in sd.items():
+            t = t.detach().to(torch.float32).contiguous().cpu()
+            check(self.lib.vitb200_load_weight(self._h, name.encode(), t.data_ptr(), t.numel()))
+        check(self.lib.vitb200_weights_ready(self._h))
+
+    # ---- whole forward ---------------------------------------------------------------------------
+    def forward_host(self, images: torch.Tensor, flags: int = 0, out: Optional[Dict[str, torch.Tensor]] = None
+                     ) -> Dict[str, torch.Tensor]:
+        """images: CPU fp32 [B,3,S,S] (pinned for async copies).  Returns CPU fp32 tensors."""
+        assert images.device.type == "cpu" and images.dtype == torch.float32 and images.is_contiguous()
+        cfg = self.cfg
+        B, N, L, H, d = images.shape[0], cfg.tokens, cfg.num_layers, cfg.num_heads, cfg.hidden_dim
+        shapes = {"logits": (B, cfg.num_classes)}
+        if flags & EMIT_AVG:
+            shapes["avg_maps"] = (L, B, N, N)
+        if flags & EMIT_CLS:
+            shapes["cls_maps"] = (L, B, H, N)
+        if flags & EMIT_ROLLOUT:
+            shapes["rollout"] = (B, N - 1)
+        if flags & EMIT_HEADS:
+            shapes["heads"] = (L, B, H, N, N)
+        if flags & EMIT_HIDDEN:
+            shapes["hidden"] = (L, B, N, d)
+        res = {}
+        for k, shp in shapes.items():
+            if out is not None and k in out:
+                assert tuple(out[k].shape) == shp and out[k].dtype == torch.float32 and out[k].is_contiguous()
+                res[k] = out[k]
+            else:
+                res[k] = torch.empty(shp, dtype=torch.float32)
+        ho = _HostOutputs(*[_ptr(res.get(k)) for k in ("logits", "avg_maps", "cls_maps", "rollout", "heads", "hidden")])
+        check(self.lib.vitb200_forward_host(self._h, images.data_ptr(), B, flags, C.byref(ho)))
+        return res
+
+    def forward_device(self, images: torch.Tensor, flags: int = 0, stream: Optional[int] = None) -> None:
+        """images: CUDA fp32 [B,3,S,S] on this engine's device; enqueues on `stream` (raw cudaStream_t)."""
+        assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
+        check(self.lib.vitb200_forward_device(self._h, images.data_ptr(), images.shape[0], flags, stream))
+
+    def device_output(self, which: int, shape, batch_capacity: Optional[int] = None) -> torch.Tensor:
+        """Zero-copy torch view of an engine-owned device buffer (valid until the next growing call)."""
+        p, pitch = C.c_void_p(), C.c_int()
+        check(self.lib.vitb200_device_output(self._h, which, C.byref(p), C.byref(pitch)))
+        return _device_view(p.value, shape, self.device)
+
+    def synchronize(self) -> None:
+        check(self.lib.vitb200_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.vitb200_launch_count(self._h))
+
+    # ---- node-granular stages ----------------------------------------------------------------------
+    def stage_embed(self, images: torch.Tensor) -> None:
+        assert images.device.type == "cpu" and images.dtype == torch.float32 and images.is_contiguous()
+        check(self.lib.vitb200_stage_embed(self._h, images.data_ptr(), images.shape[0]))
+
+    def stage_layer(self, layer: int, batch: int, flags: int) -> None:
+        check(self.lib.vitb200_stage_layer(self._h, layer, batch, flags))
+
+    def stage_head(self, batch: int) -> torch.Tensor:
+        out = torch.empty(batch, self.cfg.num_classes, dtype=torch.float32)
+        check(self.lib.vitb200_stage_head(self._h, batch, out.data_ptr()))
+        return out
+
+    def stage_rollout(self, batch: int) -> torch.Tensor:
+        out = torch.empty(batch, self.cfg.tokens - 1, dtype=torch.float32)
+        check(self.lib.vitb200_stage_rollout(self._h, batch, out.data_ptr()))
+        return out
+
+    def set_tokens(self, tokens: torch.Tensor) -> None:
+        assert tokens.device.type == "cpu" and tokens.dtype == torch.float32 and tokens.is_contiguous()
+        check(self.lib.vitb200_set_tokens(self._h, tokens.data_ptr(), tokens.shape[0]))
+
+    def get_tokens(self, batch: int) -> torch.Tensor:
+        out = torch.empty(batch, self.cfg.tokens, self.cfg.hidden_dim, dtype=torch.float32)
+        check(self.lib.vitb200_get_tokens(self._h, out.data_ptr(), batch))
+        return out
+
+    def set_avg_map(self, layer: int, amap: torch.Tensor) -> None:
+        assert amap.device.type == "cpu" and amap.dtype == torch.float32 and amap.is_contiguous()
+        check(self.lib.vitb200_set_avg_map(self._h, layer, amap.data_ptr(), amap.shape[0]))
+
+    def get_avg_map(self, layer: int, batch: int) -> torch.Tensor:
+        N = self.cfg.tokens
+        out = torch.empty(batch, N, N, dtype=torch.float32)
+        check(self.lib.vitb200_get_avg_map(self._h, layer, out.data_ptr(), batch))
+        return out
+
+    def get_cls_map(self, layer: int, batch: int) -> torch.Tensor:
+        out = torch.empty(batch, self.cfg.num_heads, self.cfg.tokens, dtype=torch.float32)
+        check(self.lib.vitb200_get_cls_map(self._h, layer, out.data_ptr(), batch))
+        return out
+
+    def get_head_map(self, layer: int, batch: int) -> torch.Tensor:
+        N = self.cfg.tokens
+        out = torch.empty(batch, self.cfg.num_heads, N, N, dtype=torch.float32)
+        check(self.lib.vitb200_get_head_map(self._h, layer, out.data_ptr(), batch))
+        return out
+
+
+def _device_view(ptr: int, shape, device: int) -> torch.Tensor:
+    """Wrap a raw device pointer as a torch tensor through __cuda_array_interface__ (no copy)."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {
+        "shape": tuple(int(s) for s in shape),
+        "typestr": "<f4",
+        "data": (int(ptr), False),
+        "version": 2,
+    }
+    return torch.as_tensor(h, device=f"cuda:{device}")
+
+
+# ---- single-kernel wrappers used by the parity tests (device tensors in, device tensors out) ---------
+def op_gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+            gelu: bool = False, out_f32: bool = False) -> torch.Tensor:
+    lib = load_library()
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    check(lib.vitb200_op_gemm(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(resid), out.data_ptr(), M, N, K, int(gelu),
+                              int(out_f32), None))
+    return out
+
+
+def op_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    lib = load_library()
+    rows, d = x.shape
+    y = torch.empty(rows, d, device=x.device, dtype=torch.bfloat16)
+    check(lib.vitb200_op_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), rows, d, eps, None))
+    return y
+
+
+def op_attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, want_avg=True, want_cls=True, want_heads=False):
+    lib = load_library()
+    d = heads * 64
+    pitch = (tokens + 15) // 16 * 16
+    ctx = torch.zeros(batch * tokens, d, device=qkv.device, dtype=torch.bfloat16)
+    avg = torch.zeros(batch, tokens, pitch, device=qkv.device) if want_avg else None
+    cls = torch.zeros(batch, heads, tokens, device=qkv.device) if want_cls else None
+    hm = torch.zeros(batch, heads, tokens, pitch, device=qkv.device) if want_heads else None
+    check(lib.vitb200_op_attention(qkv.data_ptr(), ctx.data_ptr(), _ptr(avg), _ptr(cls), _ptr(hm), batch, tokens, heads,
+                                   pitch, None))
+    return ctx, (avg[..., :tokens] if avg is not None else None), cls, (hm[..., :tokens] if hm is not None else None)
+
+
+def op_patchify(images: torch.Tensor, patch: int) -> torch.Tensor:
+    lib = load_library()
+    B, _, S, _ = images.shape
+    n = (S // patch) ** 2
+    out = torch.empty(B * n, 3 * patch * patch, device=images.device, dtype=torch.bfloat16)
+    check(lib.vitb200_op_patchify(images.data_ptr(), out.data_ptr(), B, S, patch, None))
+    return out
+
+
+def op_rollout(maps: torch.Tensor) -> torch.Tensor:
+    """maps: CUDA fp32 [L, B, N, pitch] -> [B, N-1] (pitch may exceed N)."""
+    lib = load_library()
+    L, B, N, pitch = maps.shape
+    out = torch.empty(B, N - 1, device=maps.device)
+    check(lib.vitb200_op_rollout(maps.data_ptr(), B * N * pitch, L, B, N, pitch, out.data_ptr(), None))
+    return out
