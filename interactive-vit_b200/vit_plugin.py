@@ -1,0 +1,284 @@
+"""The ViT ``Model`` plugin: block-granular graph nodes whose ``compute`` runs on the B200 engine.
+
+It plays the role ``static/models/vgg16.py:10-62`` plays for VGG16 in the reference — a ``Model`` subclass that
+overrides ``list_node_names / compute / io / contents / generate_graph_json`` — because the generic leaf-module
+wrapper cannot express a ViT (it drops nn.MultiheadAttention, the class token, the position
+embedding and both residual adds, and Graph.connect cannot fan a channel out server-side).
+
+Nodes (``<name>`` is the model name, e.g. ``vit_b_16``):
+
+    <name>:embed      ins [o]            outs [o]              [3,S,S] or [B,3,S,S] -> tokens [N,d] / [B,N,d]
+    <name>:layer.<i>  ins [o]            outs [o, attn, cls]   tokens -> tokens, head-averaged map [N,N],
+                                          (+ heads if params["heads"] == "1")   per-head CLS maps [H,g,g], [H,N,N]
+    <name>:head       ins [o]            outs [o]              tokens -> logits [classes]
+    <name>:rollout    ins [a0..a{L-1}]   outs [o]              head-averaged maps -> rollout map [g,g]
+
+Every output is a CPU fp32 tensor (the wire format, main/message.py:111-121).  Between consecutive nodes of
+one request the token stream stays on the GPU: the plugin remembers which tensor object it handed out last and
+skips the upload when that same object comes back as the next node's input.
+
+The class is produced by ``make_vit_model_class(Model, Pinout)`` so that the same code subclasses either this
+package's mirror of the plugin API or the reference's own ``main.context.Model``.
+"""
+from __future__ import annotations
+
+import math
+import os
+import threading
+from typing import Dict, List, Optional
+
+import torch
+
+from . import engine as E
+
+
+def build_torchvision_vit(cfg: E.VitConfig, seed: int = 0) -> torch.nn.Module:
+    """Random-init torchvision ViT (weights cannot be downloaded offline).  The classifier is re-drawn from
+    N(0, 0.02): torchvision zero-inits it (vision_transformer.py:264-266), which would make every logit 0."""
+    from torchvision.models.vision_transformer import VisionTransformer
+
+    torch.manual_seed(seed)
+    m = VisionTransformer(image_size=cfg.image_size, patch_size=cfg.patch_size, num_layers=cfg.num_layers,
+                          num_heads=cfg.num_heads, hidden_dim=cfg.hidden_dim, mlp_dim=cfg.mlp_dim,
+                          num_classes=cfg.num_classes)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        m.heads.head.weight.normal_(0.0, 0.02, generator=g)
+        m.heads.head.bias.normal_(0.0, 0.02, generator=g)
+    return m.eval()
+
+
+def imagenet_categories(num_classes: int) -> List[str]:
+    if num_classes == 1000:
+        try:
+            from torchvision.models import ViT_B_16_Weights
+
+            return list(ViT_B_16_Weights.IMAGENET1K_V1.meta["categories"])
+        except Exception:
+            pass
+    return [f"class {i}" for i in range(num_classes)]
+
+
+def make_vit_model_class(ModelBase, PinoutCls):
+    class VitB200Model(ModelBase):
+        """One ViT replica on one GPU behind the reference's ``Model`` plugin interface."""
+
+        def __init__(self, name: str, cfg: E.VitConfig, module: Optional[torch.nn.Module] = None, device: int = 0,
+                     max_batch: int = 1, engine: Optional[E.VitEngine] = None):
+            module = module if module is not None else build_torchvision_vit(cfg)
+            super().__init__(module, name)  # .eval(), self.name (main/context.py:39-42)
+            self.cfg = cfg
+            self.engine = engine if engine is not None else E.VitEngine(cfg, device, max_batch)
+            self.engine.load_state_dict(module.state_dict())
+            self._lock = threading.Lock()
+            self._tokens_out: Optional[torch.Tensor] = None   # last token tensor handed out (device-resident copy valid)
+            self._tokens_batch = 0
+            self._maps_out: Dict[int, torch.Tensor] = {}      # layer -> avg-map tensor handed out (resident on device)
+            self.node_names = ([self.prefix() + "embed"] + [self.prefix() + f"layer.{i}" for i in range(cfg.num_layers)]
+                               + [self.prefix() + "head", self.prefix() + "rollout"])
+
+        # ---- catalogue ---------------------------------------------------------------------------
+        def list_node_names(self) -> List[str]:
+            return self.node_names
+
+        def _kind(self, node_name: str) -> str:
+            sub = node_name.removeprefix(self.prefix())
+            if sub in ("embed", "head", "rollout"):
+                return sub
+            if sub.startswith("layer."):
+                i = int(sub[len("layer."):])
+                if 0 <= i < self.cfg.num_layers:
+                    return "layer"
+            raise KeyError(node_name)
+
+        def io(self, node_name: str, params: Optional[Dict[str, str]] = None) -> Dict:
+            kind = self._kind(node_name)
+            if kind == "layer":
+                outs = ["o", "attn", "cls"]
+                if params is not None and str(params.get("heads", "0")) == "1":
+                    outs.append("heads")
+                return {"ins": ["o"], "outs": outs}
+            if kind == "rollout":
+                return {"ins": [f"a{i}" for i in range(self.cfg.num_layers)], "outs": ["o"]}
+            return {"ins": ["o"], "outs": ["o"]}
+
+        def contents(self, node_name: str) -> str:
+            kind = self._kind(node_name)
+            c = self.cfg
+            what = {
+                "embed": f"patch {c.patch_size}x{c.patch_size} embedding + class token + position ({c.tokens} tokens x {c.hidden_dim})",
+                "layer": f"EncoderBlock: {c.num_heads}-head attention + MLP {c.mlp_dim} (outs: o, attn, cls)",
+                "head": f"LayerNorm + Linear -> {c.num_classes} logits",
+                "rollout": f"attention rollout over {c.num_layers} layers -> {c.image_size // c.patch_size}x{c.image_size // c.patch_size}",
+            }[kind]
+            return f"<p>{node_name}</p> <p>{what}</p> <p>B200 engine</p>"
+
+        def generate_graph_json(self) -> Dict:
+            """Same file format as Model.generate_graph_json (main/context.py:55-73) and VggModel's category tail
+            (static/models/vgg16.py:16-29): chain embed -> layers -> head -> category, plus attn_i -> rollout."""
+            names = self.list_node_names()
+            L = self.cfg.num_layers
+            w = int(math.sqrt(len(names) + 1))
+            nodes, edges = [], []
+            for i, endpoint in enumerate(names):
+                nodes.append({"instance": {"kind": "net_node", "endpoint": endpoint, "params": {}},
+                              "pos": {"x": (i % w) * 200, "y": int(i / w) * 200}})
+            head_idx, rollout_idx = 1 + L, 2 + L
+            for i in range(1, head_idx + 1):  # embed -> layer.0 -> ... -> head
+                edges.append({"in_port": {"node": i - 1, "channel": "o"}, "out_port": {"node": i, "channel": "o"}})
+            for i in range(L):
+                edges.append({"in_port": {"node": 1 + i, "channel": "attn"},
+                              "out_port": {"node": rollout_idx, "channel": f"a{i}"}})
+            cat_idx = len(nodes)
+            nodes.append({"instance": {"kind": "category", "cats": imagenet_categories(self.cfg.num_classes)},
+                          "pos": {"x": (cat_idx % w) * 200, "y": int(cat_idx / w) * 200}})
+            edges.append({"in_port": {"node": head_idx, "channel": "o"}, "out_port": {"node": cat_idx, "channel": "o"}})
+            return {"nodes": nodes, "edges": edges}
+
+        # ---- compute -----------------------------------------------------------------------------
+        @staticmethod
+        def _need(pinin, ch: str) -> torch.Tensor:
+            t = pinin.get(ch)
+            if t is None:
+                raise Exception(f"missing input: {ch}")
+            if not isinstance(t, torch.Tensor):
+                raise Exception(f"input {ch} is not a tensor")
+            return t
+
+        @staticmethod
+        def _host(t: torch.Tensor) -> torch.Tensor:
+            return t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+
+        def _bind_tokens(self, x: torch.Tensor) -> int:
+            """Make the engine's token stream equal to `x` ([N,d] or [B,N,d]); returns the batch size."""
+            c = self.cfg
+            if x.dim() not in (2, 3) or tuple(x.shape[-2:]) != (c.tokens, c.hidden_dim):
+                raise Exception(f"expected tokens of shape [{c.tokens}, {c.hidden_dim}] (optionally batched), got {list(x.shape)}")
+            batch = 1 if x.dim() == 2 else x.shape[0]
+            if x is self._tokens_out and batch == self._tokens_batch:
+                return batch  # still resident from the previous node of this request
+            self.engine.set_tokens(self._host(x).reshape(batch, c.tokens, c.hidden_dim))
+            return batch
+
+        def _emit_tokens(self, batch: int, batched: bool) -> torch.Tensor:
+            t = self.engine.get_tokens(batch)
+            t = t if batched else t[0]
+            self._tokens_out, self._tokens_batch = t, batch
+            return t
+
+        def compute(self, node_name: str, pinin, params: Optional[Dict[str, str]] = None):
+            kind = self._kind(node_name)
+            c = self.cfg
+            g = c.image_size // c.patch_size
+            out = PinoutCls()
+            with self._lock:
+                if kind == "embed":
+                    x = self._need(pinin, "o")
+                    if x.dim() not in (3, 4) or tuple(x.shape[-3:]) != (3, c.image_size, c.image_size):
+                        raise Exception(f"expected an image of shape [3, {c.image_size}, {c.image_size}] (optionally batched), got {list(x.shape)}")
+                    batched = x.dim() == 4
+                    imgs = self._host(x).reshape(-1, 3, c.image_size, c.image_size)
+                    self.engine.stage_embed(imgs)
+                    out.set("o", self._emit_tokens(imgs.shape[0], batched))
+                elif kind == "layer":
+                    i = int(node_name.removeprefix(self.prefix())[len("layer."):])
+                    x = self._need(pinin, "o")
+                    batched = x.dim() == 3
+                    batch = self._bind_tokens(x)
+                    want_heads = params is not None and str(params.get("heads", "0")) == "1"
+                    flags = E.EMIT_AVG | E.EMIT_CLS | (E.EMIT_HEADS if want_heads else 0)
+                    self.engine.stage_layer(i, batch, flags)
+                    out.set("o", self._emit_tokens(batch, batched))
+                    amap = self.engine.get_avg_map(i, batch)
+                    cls = self.engine.get_cls_map(i, batch)[:, :, 1:].reshape(batch, c.num_heads, g, g)
+                    amap = amap if batched else amap[0]
+                    self._maps_out[i] = amap
+                    out.set("attn", amap)
+                    out.set("cls", cls if batched else cls[0])
+                    if want_heads:
+                        hm = self.engine.get_head_map(i, batch)
+                        out.set("heads", hm if batched else hm[0])
+                elif kind == "head":
+                    x = self._need(pinin, "o")
+                    batched = x.dim() == 3
+                    batch = self._bind_tokens(x)
+                    logits = self.engine.stage_head(batch)
+                    out.set("o", logits if batched else logits[0])
+                else:  # rollout
+                    maps = [self._need(pinin, f"a{i}") for i in range(c.num_layers)]
+                    batched = maps[0].dim() == 3
+                    batch = maps[0].shape[0] if batched else 1
+                    for i, m in enumerate(maps):
+                        if tuple(m.shape[-2:]) != (c.tokens, c.tokens) or (m.dim() == 3) != batched:
+                            raise Exception(f"a{i}: expected a [{c.tokens}, {c.tokens}] map, got {list(m.shape)}")
+                        if m is not self._maps_out.get(i):
+                            self.engine.set_avg_map(i, self._host(m).reshape(batch, c.tokens, c.tokens))
+                    r = self.engine.stage_rollout(batch).reshape(batch, g, g)
+                    out.set("o", r if batched else r[0])
+            return out
+
+        # ---- registration: ModelNode forwards (params are dropped by the reference's ModelNode,
+        #      main/context.py:119-129, so the per-node params variant is wired through our own node class)
+        def register(self, ctx) -> None:
+            super().register(ctx)  # graph json + one ModelNode per name
+            for node_name in self.list_node_names():
+                ctx.register(_ParamNode(self, node_name))
+
+    class _ParamNode:
+        """Same surface as ModelNode (get_name / compute / contents / io / register) but passes ``params`` on."""
+
+        def __init__(self, parent, name: str):
+            self.parent = parent
+            self.name = name
+
+        def get_name(self) -> str:
+            return self.name
+
+        def compute(self, params, inputs):
+            return self.parent.compute(self.name, inputs, params)
+
+        def contents(self, params) -> str:
+            return self.parent.contents(self.name)
+
+        def io(self, params) -> Dict:
+            return self.parent.io(self.name, params)
+
+        def register(self, ctx) -> None:
+            ctx.register(self)
+
+    return VitB200Model
+
+
+def _default_class():
+    from .context import Model
+    from .graph import Pinout
+
+    return make_vit_model_class(Model, Pinout)
+
+
+_cls_cache = None
+
+
+def VitB200Model(*args, **kwargs):
+    """Plugin class bound to this package's mirror of the plugin API."""
+    global _cls_cache
+    if _cls_cache is None:
+        _cls_cache = _default_class()
+    return _cls_cache(*args, **kwargs)
+
+
+def instances() -> list:
+    """Plugin entry point (what scan_nodes calls, main/context.py:154-176).  Models come from the environment:
+    VITB200_MODELS="vit_b_16[,vit_s_16,...]", VITB200_DEVICE, VITB200_MAX_BATCH, VITB200_WEIGHTS_<NAME>=path.pt."""
+    names = [n for n in os.environ.get("VITB200_MODELS", "vit_b_16").split(",") if n]
+    device = int(os.environ.get("VITB200_DEVICE", "0"))
+    max_batch = int(os.environ.get("VITB200_MAX_BATCH", "1"))
+    out = []
+    for n in names:
+        cfg = E.CONFIGS[n]
+        module = build_torchvision_vit(cfg)
+        wpath = os.environ.get(f"VITB200_WEIGHTS_{n.upper()}")
+        if wpath:
+            module.load_state_dict(torch.load(wpath, map_location="cpu"))
+        out.append(VitB200Model(n, cfg, module, device, max_batch))
+    return out
