@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: images/sec of a ViT-B/16 224 px forward with attention-map extraction.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model vit_b_16] [--batch 256]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" is one forward of `batch` synthetic images PER GPU (weak scaling:
+images are independent units, sharded with no data-path collective; the only exchange is the gather of logits /
+CLS maps / rollout to rank 0, which is inside the timed step).
+
+value      whole-job img/s with the images already resident in HBM, CUDA-event timed on the launch stream.
+e2e        the same metric through the public host API (VitEngine.forward_host): pinned-host images in, H2D +
+           forward + D2H of logits, per-head CLS maps and rollout inside the timed region.
+roofline   the dominant kernel (the tcgen05 GEMM; the fc1 instance by FLOPs) timed alone with CUDA events:
+           achieved TFLOP/s = 2*M*N*K / duration, against the measured burst bf16 peak in MEASURED_PEAKS.json.
+cpu_baseline / --impl reference
+           the reference's own path on the host cores: wire request -> Request.decode -> Context.compute over the
+           torchvision-CPU plugin (one unbatched fp32 image per request, main/context.py:79-88,143-147) ->
+           Response.encode.  /root/reference is not on the GPU box: the scheduler/codec are this repo's mirror of
+           it and the arithmetic is torchvision itself (kind = "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec ViT-B/16 224px fwd+attn maps"
+GEMM_FC1 = (3072, 768)  # (N, K) of the dominant GEMM for ViT-B
+
+
+def _peaks():
+    p = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("bf16_tflops", "bf16_tflops_sustained", "hbm_gbs") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons of one GPU while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+class ReferencePath:
+    """The reference's path on the host cores: one unbatched fp32 image per request through
+    wire decode -> Context.compute (torchvision CPU plugin behind the Model API) -> wire encode."""
+
+    def __init__(self, model_name: str):
+        import torch
+        from interactive_vit_b200 import context as C, graph as G, message as M
+        from oracle import oracle_plugin, vit_oracle as O
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.cores = torch.get_num_threads()
+        self.M, self.plugin_mod, self.name = M, oracle_plugin, model_name
+        self.ocfg = O.ORACLE_CONFIGS[model_name]
+        Cls = oracle_plugin.make_oracle_model_class(C.Model, G.Pinout)
+        plug = Cls(model_name, self.ocfg, O.build_vit(self.ocfg, seed=0))
+        self.ctx = C.Context()
+        for n in plug.list_node_names():
+            C.ModelNode(plug, n).register(self.ctx)
+        self.imgs = O.synthetic_images(4, self.ocfg.image_size)
+        self.one(0)  # warm-up (thread pool, allocator)
+
+    def one(self, i: int) -> bytes:
+        nodes, edges, tensors = self.plugin_mod.vit_graph_request(self.name, self.ocfg.num_layers, self.imgs[i % 4])
+        req = self.M.Request()
+        req.decode(self.M.encode_request(nodes, edges, tensors))
+        self.ctx.compute(req.graph)
+        return self.M.Response(req.graph).encode()
+
+    def run(self, seconds: float, max_images: int):
+        """(images done, seconds): stops at max_images or once `seconds` have elapsed."""
+        t0 = time.perf_counter()
+        done = 0
+        while done < max_images and (time.perf_counter() - t0 < seconds or done == 0):
+            self.one(done)
+            done += 1
+        return done, time.perf_counter() - t0
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    ref = ReferencePath(args.model)
+    per_step = 4
+    for _ in range(args.warmup):
+        ref.run(1e9, 1)
+    steps = []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        steps.append(ref.run(1e9, per_step))
+        if time.perf_counter() - t_all > 150:
+            break
+    imgs = sum(d for d, _ in steps)
+    secs = sum(t for _, t in steps)
+    value = imgs / secs
+    sample = f"{imgs} single-image requests ({len(steps)} steps x {per_step}) through decode -> compute -> encode, fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": args.gpus, "steps": len(steps),
+        "warmup": args.warmup, "ms_per_step": secs / len(steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} 224px forward + attention maps, 1 unbatched image per request on CPU"},
+        "cpu_baseline": {"value": value, "unit": "img/s", "cores": ref.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    import interactive_vit_b200.engine as E
+    from interactive_vit_b200 import dist as D, vit_plugin as P
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = E.CONFIGS[args.model]
+    B = args.batch
+    eng = E.VitEngine(cfg, local_rank, B)
+    eng.load_state_dict(P.build_torchvision_vit(cfg, seed=0).state_dict())
+    flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_images = torch.rand(B, 3, cfg.image_size, cfg.image_size, generator=g).pin_memory()
+    images = host_images.cuda(non_blocking=True)
+    stream = torch.cuda.Stream()
+    L, H, N = cfg.num_layers, cfg.num_heads, cfg.tokens
+    total = B * world
+
+    def gather_outputs():
+        if world == 1:
+            return
+        local = {"logits": eng.device_output(0, (B, cfg.num_classes)),
+                 "cls_maps": eng.device_output(E.EMIT_CLS, (L, B, H, N)),
+                 "rollout": eng.device_output(E.EMIT_ROLLOUT, (B, N - 1))}
+        D.gather_results(local, total, D.RESULT_BATCH_DIMS)
+
+    def step():
+        eng.forward_device(images, flags, stream.cuda_stream)
+        gather_outputs()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        launches0 = eng.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            ev0.record(stream)
+            for _ in range(args.steps):
+                step()
+            ev1.record(stream)
+            barrier()
+        ms = ev0.elapsed_time(ev1) / args.steps
+        launches = eng.launch_count() - launches0
+
+        # ---- e2e: public host API, pinned host buffers, H2D + D2H inside the timed region
+        out = {"logits": torch.empty(B, cfg.num_classes).pin_memory(), "cls_maps": torch.empty(L, B, H, N).pin_memory(),
+               "rollout": torch.empty(B, N - 1).pin_memory()}
+        e2e_flags = E.EMIT_CLS | E.EMIT_ROLLOUT
+
+        def e2e_step():
+            eng.forward_host(host_images, e2e_flags, out)
+            gather_outputs()
+            if world > 1:
+                torch.cuda.synchronize()
+
+        for _ in range(max(2, args.warmup // 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+
+        # ---- dominant kernel alone (rank 0): fc1 GEMM + bias + GELU at the step's M
+        roof = None
+        if rank == 0:
+            peaks = _peaks()
+            M_, (N_, K_) = B * N, GEMM_FC1 if args.model == "vit_b_16" else (cfg.mlp_dim, cfg.hidden_dim)
+            a = (torch.randn(M_, K_, device="cuda") * 0.5).bfloat16()
+            w = (torch.randn(N_, K_, device="cuda") * 0.05).bfloat16()
+            bias = torch.randn(N_, device="cuda")
+            outb = torch.empty(M_, N_, device="cuda", dtype=torch.bfloat16)
+            lib = E.load_library()
+            spoil = torch.empty(256 * 1024 * 1024 // 4, device="cuda")  # > L2: flushed between timed launches
+
+            def gemm():
+                E.check(lib.vitb200_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), None, outb.data_ptr(), M_, N_, K_, 1, 0,
+                                            stream.cuda_stream))
+
+            for _ in range(3):
+                gemm()
+            times = []
+            for _ in range(10):
+                spoil.zero_()
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record(stream)
+                gemm()
+                k1.record(stream)
+                k1.synchronize()
+                times.append(k0.elapsed_time(k1))
+            kms = sum(times) / len(times)
+            achieved = 2.0 * M_ * N_ * K_ / (kms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": f"gemm_bf16_kernel<256,gelu> M={M_} N={N_} K={K_}", "achieved": achieved,
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                    "traffic": None, "peak_source": peaks["source"] + " burst", "kernel_ms": kms}
+
+    t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        peaks = _peaks()
+        value = total / ms * 1e3
+        flop = cfg.gflop_per_image()
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            ref = ReferencePath(args.model)
+            done, dt = ref.run(15.0, 64)
+            cpu = {"value": done / dt, "unit": "img/s", "cores": ref.cores, "kind": "port",
+                   "sample": f"{done} single-image requests in {dt:.1f}s through decode -> compute -> encode (torchvision CPU fp32)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.model} {cfg.image_size}px batch {B} per GPU, forward + head-averaged maps + per-head CLS "
+                                   f"maps + rollout for all {L} layers; random-init weights", "global_batch": total,
+                       "l2": f"inputs larger than L2 ({B * 3 * cfg.image_size ** 2 * 4 >> 20} MiB images, "
+                             f"{B * N * cfg.hidden_dim * 4 >> 20} MiB token stream per step)",
+                       "parallelism": f"dp{world}", "gather": "logits + CLS maps + rollout to rank 0 (NCCL)" if world > 1 else "none"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": total / e2e_ms * 1e3, "unit": "img/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2 * 4,
+                    "d2h_bytes_per_step": (B * cfg.num_classes + L * B * H * N + B * (N - 1)) * 4,
+                    "outputs": "logits, per-head CLS maps (all layers), rollout"},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "step_tensor": {"achieved": value * flop / 1e3, "unit": "TFLOP/s", "gflop_per_image": flop,
+                            "frac_of_burst_peak": value * flop / 1e3 / peaks["bf16_tflops"] / world,
+                            "frac_of_sustained_peak": value * flop / 1e3 / peaks["bf16_tflops_sustained"] / world},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="vit_b_16")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

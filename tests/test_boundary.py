@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference boundary (graph / context / message) against the known answers recorded
+from the unmodified reference (tests/golden/graph_kats.json, wire_tiny.*.bin).  CPU only."""
+import json
+import os
+import struct
+
+import pytest
+import torch
+
+from interactive_vit_b200 import context as C
+from interactive_vit_b200 import graph as G
+from interactive_vit_b200 import message as M
+from oracle import oracle_plugin, refhost, vit_oracle as O
+
+
+@pytest.fixture(scope="module")
+def kats(golden_dir):
+    with open(os.path.join(golden_dir, "graph_kats.json")) as f:
+        return json.load(f)
+
+
+def _build(n, edges, inputs):
+    g = G.Graph()
+    ns = [g.add_node(f"n{i}", {}) for i in range(n)]
+    for (a, ach, b, bch) in edges:
+        g.connect(ns[a], ach, ns[b], bch)
+    for (b, bch) in inputs:
+        g.add_input(torch.zeros(1), ns[b], bch)
+    return g
+
+
+def test_order_matches_reference_visit_order(kats):
+    for name, case in kats["order"].items():
+        g = _build(case["n"], case["edges"], case["inputs"])
+        assert [x.index for x in g.order()] == case["order"], name
+
+
+def test_order_raises_on_cycle_instead_of_spinning():
+    g = G.Graph()
+    a, b = g.add_node("a", {}), g.add_node("b", {})
+    g.connect(a, "o", b, "o")
+    g.connect(b, "o", a, "o")
+    with pytest.raises(ValueError):
+        g.order()
+
+
+def test_pinout_and_dangling_outputs():
+    g = G.Graph()
+    a, b = g.add_node("a", {}), g.add_node("b", {})
+    g.connect(a, "o", b, "o")
+    p = G.Pinout()
+    t1, t2 = torch.ones(2), torch.zeros(3)
+    p.set("o", t1)
+    p.set("extra", t2)
+    a.set_pinout(p)
+    assert b.get_pinin().get("o") is t1                      # by reference, no copy
+    assert a.outputs["extra"].output is None                 # dangling edge still carries the tensor
+    assert a.get_pinout().get("extra") is t2
+    assert G.Pinout().get("missing") is None
+    with pytest.raises(AssertionError):
+        g.add_node("c", {}).get_pinin() if False else G.Node._collect({"o": G.Edge(None, None)})
+
+
+def test_fanout_failure_mode_is_preserved(kats):
+    g = G.Graph()
+    a, b, c = g.add_node("a", {}), g.add_node("b", {}), g.add_node("c", {})
+    g.connect(a, "o", b, "o")
+    g.connect(a, "o", c, "o")
+    p = G.Pinout()
+    p.set("o", torch.ones(1))
+    a.set_pinout(p)
+    assert (b.inputs["o"].tensor is not None) == kats["fanout"]["b_has_tensor"]
+    assert (c.inputs["o"].tensor is not None) == kats["fanout"]["c_has_tensor"]
+    if kats["fanout"]["b_get_pinin"] == "AssertionError":
+        with pytest.raises(AssertionError):
+            b.get_pinin()
+
+
+def test_model_wrapper_matches_reference(kats, tmp_path):
+    toy = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.ReLU(), torch.nn.Sequential(torch.nn.Linear(4, 2), torch.nn.Tanh()))
+    m = C.Model(toy, "toy")
+    k = kats["model"]
+    assert m.list_node_names() == k["node_names"]
+    assert m.generate_graph_json() == k["graph_json"]
+    assert m.io("toy:0") == k["io"]
+    assert m.contents("toy:0") == k["contents"]
+    toy.load_state_dict({n: torch.tensor(v) for n, v in k["state"].items()})
+    pin = G.Pinout()
+    pin.set("o", torch.tensor(k["x"]))
+    assert torch.allclose(m.compute("toy:0", pin).get("o"), torch.tensor(k["y_toy0"]), rtol=1e-6, atol=1e-7)
+    assert not toy.training
+    # register(): writes static/graphs/<name>.json once, registers one ModelNode per node name
+    os.makedirs(tmp_path / "static" / "graphs")
+    C.set_base_dir(str(tmp_path))
+    try:
+        ctx = C.Context()
+        m.register(ctx)
+        assert json.load(open(tmp_path / "static" / "graphs" / "toy.json")) == k["graph_json"]
+        assert sorted(ctx.nodes) == sorted(k["node_names"])
+        node = ctx.get_node("toy:0")
+        assert isinstance(node, C.ModelNode) and node.io({}) == k["io"]
+        with pytest.raises(KeyError):
+            ctx.get_node("nope")
+    finally:
+        C.set_base_dir(None)
+
+
+def test_nodekind_defaults_and_plugin_discovery(kats, tmp_path):
+    base = C.NodeKind("x")
+    assert base.contents({"A": "2"}) == "x?A=2"
+    with pytest.raises(Exception, match="TODO: implement Node.io"):
+        base.io({})
+    with pytest.raises(Exception, match="TODO: implement Node.compute"):
+        base.compute({}, G.Pinout())
+    # a cos-like plugin written against the mirror behaves like the reference's main/nodes/cos.py
+    os.makedirs(tmp_path / "main" / "nodes")
+    (tmp_path / "main" / "nodes" / "cosine.py").write_text(
+        "import torch\nfrom interactive_vit_b200.context import NodeKind\nfrom interactive_vit_b200.graph import Pinout\n"
+        "class Cos(NodeKind):\n"
+        "    def __init__(self): super().__init__('cos')\n"
+        "    def io(self, params): return {'ins': ['o'], 'outs': ['o']}\n"
+        "    def compute(self, params, inputs):\n"
+        "        x = inputs.get('o')\n"
+        "        if x is None: raise Exception('missing input: o')\n"
+        "        r = Pinout(); r.set('o', torch.cos(float(params.get('A', 1.0)) * x + float(params.get('b', 0.0)))); return r\n"
+        "def instances(): return [Cos()]\n")
+    (tmp_path / "main" / "nodes" / "broken.py").write_text("raise RuntimeError('boom')\n")
+    C.set_base_dir(str(tmp_path))
+    try:
+        ctx = C.Context()
+        ok = C.scan_nodes(["main/nodes"], ctx)
+        assert len(ok) == 1 and "cos" in ctx.nodes          # broken plugin is logged and skipped, not fatal
+        g = G.Graph()
+        n = g.add_node("cos", {"A": "2", "b": "0.5"})
+        g.add_input(torch.tensor([0.0, 1.0, 2.0]), n, "o")
+        ctx.compute(g)
+        assert torch.allclose(n.get_pinout().get("o"), torch.tensor(kats["cos"]["y"]))
+        g2 = G.Graph()
+        g2.add_node("cos", {})
+        with pytest.raises(Exception, match=kats["cos"]["missing_input_error"]):
+            ctx.compute(g2)
+    finally:
+        C.set_base_dir(None)
+
+
+def test_wire_header_known_answers(golden_dir):
+    req = open(os.path.join(golden_dir, "wire_tiny.request.bin"), "rb").read()
+    size, magic, blocks, jsize = struct.unpack_from("<IIII", req, 0)
+    assert size == len(req) and magic == 0x69BABE69 and blocks == 1
+    resp = open(os.path.join(golden_dir, "wire_tiny.response.bin"), "rb").read()
+    size, magic, blocks, jsize = struct.unpack_from("<IIII", resp, 0)
+    assert size == len(resp) and magic == 0xDEADBEEF
+    assert M.align_next(17, 4) == 20 and M.align_next(16, 4) == 16
+
+
+def test_wire_round_trip_reproduces_reference_bytes(golden_dir):
+    """Browser request bytes -> mirror Request.decode -> mirror Context.compute over the oracle plugin hosted by
+    the mirror Model -> mirror Response.encode == the bytes the unmodified reference produced."""
+    req_bytes = open(os.path.join(golden_dir, "wire_tiny.request.bin"), "rb").read()
+    want = open(os.path.join(golden_dir, "wire_tiny.response.bin"), "rb").read()
+    cfg = O.ORACLE_CONFIGS["vit_tiny_test"]
+    Cls = oracle_plugin.make_oracle_model_class(C.Model, G.Pinout)
+    model = Cls("vit_tiny_test", cfg, O.build_vit(cfg, seed=0, init="stress"))
+    ctx = C.Context()
+    for name in model.list_node_names():
+        C.ModelNode(model, name).register(ctx)
+    req = M.Request()
+    req.decode(req_bytes)
+    assert [n.name for n in req.graph.nodes][:2] == ["vit_tiny_test:embed", "vit_tiny_test:layer.0"]
+    ctx.compute(req.graph)
+    got = M.Response(req.graph).encode()
+    assert len(got) == len(want)
+    js = struct.unpack_from("<I", want, 12)[0]
+    hdr = M.align_next(16 + js, 4)
+    assert got[:hdr] == want[:hdr]                          # header + json index + padding: byte-identical
+    a, b = M.decode_response(got), M.decode_response(want)
+    assert {k: sorted(v) for k, v in a.items()} == {k: sorted(v) for k, v in b.items()}
+    for node in b:
+        for ch in b[node]:
+            assert a[node][ch].shape == b[node][ch].shape
+            assert torch.allclose(a[node][ch], b[node][ch], rtol=1e-4, atol=1e-6), (node, ch)
+    # the client-side encoder of the mirror reproduces the browser's request bytes exactly
+    img = O.synthetic_images(1, cfg.image_size, seed=1234)[0]
+    nodes, edges, tensors = oracle_plugin.vit_graph_request("vit_tiny_test", cfg.num_layers, img)
+    assert M.encode_request(nodes, edges, tensors) == req_bytes
+
+
+def test_codec_edge_cases():
+    # 0-d, empty and non-contiguous tensors; json length not a multiple of 4
+    g = G.Graph()
+    n = g.add_node("x", {})
+    p = G.Pinout()
+    p.set("s", torch.tensor(3.5))
+    p.set("e", torch.zeros(0, 4))
+    p.set("t", torch.arange(6, dtype=torch.float32).reshape(2, 3).t())
+    p.set("d", torch.arange(4, dtype=torch.float64))      # converted instead of mis-encoded
+    n.set_pinout(p)
+    out = M.decode_response(M.Response(g).encode())[0]
+    assert out["s"].shape == () and out["s"].item() == 3.5
+    assert out["e"].shape == (0, 4)
+    assert torch.equal(out["t"], torch.arange(6, dtype=torch.float32).reshape(2, 3).t())
+    assert torch.equal(out["d"], torch.arange(4, dtype=torch.float32))
+    for extra in ("", "a", "ab", "abc"):
+        b = M.encode_request([{"endpoint": "cos" + extra, "params": {}}], [{"tensor": 0, "out_port": {"node": 0, "channel": "o"}}],
+                             [torch.ones(2, 2)])
+        r = M.Request()
+        r.decode(b)
+        assert torch.equal(r.graph.nodes[0].get_pinin().get("o"), torch.ones(2, 2))
+    bad = bytearray(b)
+    bad[4] ^= 0xFF
+    with pytest.raises(AssertionError):
+        M.Request().decode(bytes(bad))
+
+
+@pytest.mark.skipif(not refhost.available(), reason="reference tree only exists in the build container")
+def test_mirror_and_reference_codecs_interoperate():
+    graph, context, message, _ = refhost.load()
+    t = torch.randn(3, 5)
+    b = M.encode_request([{"endpoint": "cos", "params": {"A": "2"}}], [{"tensor": 0, "out_port": {"node": 0, "channel": "o"}}], [t])
+    ref_req = message.Request()
+    ref_req.decode(b)
+    context.context().compute(ref_req.graph)
+    ref_bytes = message.Response(ref_req.graph).encode()
+    mine = M.Request()
+    mine.decode(b)
+    ctx = C.Context()
+
+    class Cos(C.NodeKind):
+        def compute(self, params, inputs):
+            r = G.Pinout()
+            r.set("o", torch.cos(float(params["A"]) * inputs.get("o")))
+            return r
+
+    ctx.register(Cos("cos"))
+    ctx.compute(mine.graph)
+    assert M.Response(mine.graph).encode() == ref_bytes

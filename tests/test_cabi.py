@@ -1,0 +1,65 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/vitb200.h declares, and fails loudly
+(no CPU fallback) when asked to compute without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "vitb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vitb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(built_library):
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(built_library, n), f"{n} declared in include/vitb200.h but not exported"
+
+
+def test_binding_table_covers_header(built_library):
+    import interactive_vit_b200.engine as E
+
+    assert sorted(E.SIGNATURES) == _declared_symbols()
+
+
+def test_no_torch_types_in_the_abi():
+    text = open(os.path.join(ROOT, "include", "vitb200.h")).read()
+    assert "extern \"C\"" in text
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)          # declarations only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "#include <torch" not in text
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour of a box without a GPU")
+def test_create_fails_loudly_without_gpu(built_library):
+    import interactive_vit_b200.engine as E
+
+    with pytest.raises(E.EngineError, match="no CPU fallback"):
+        E.VitEngine(E.CONFIGS["vit_b_16"], 0, 1)
+
+
+def test_bad_arguments_are_rejected_before_touching_cuda(built_library):
+    import interactive_vit_b200.engine as E
+
+    cfg = E._Config(224, 14, 12, 12, 768, 3072, 1000, 1, 0)     # patch 14: not a multiple of 8
+    h = ctypes.c_void_p()
+    assert built_library.vitb200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"patch_size" in built_library.vitb200_last_error()
+    cfg = E._Config(384, 16, 12, 12, 768, 3072, 1000, 1, 0)     # 577 tokens: beyond the fused attention kernel
+    assert built_library.vitb200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"tokens" in built_library.vitb200_last_error()
+    assert built_library.vitb200_create(None, ctypes.byref(h)) == -1
+
+
+def test_flop_model_matches_survey():
+    import interactive_vit_b200.engine as E
+
+    assert abs(E.CONFIGS["vit_b_16"].gflop_per_image() - 35.128) < 1e-2
+    assert abs(E.CONFIGS["vit_s_16"].gflop_per_image() - 9.198) < 1e-2
+    assert abs(E.CONFIGS["vit_l_16"].gflop_per_image() - 123.109) < 1e-2

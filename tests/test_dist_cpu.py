@@ -1,0 +1,73 @@
+"""Data-parallel sharding + gather to rank 0 on CPU (gloo, world_size 2 and 3, uneven shards)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from interactive_vit_b200.dist import RESULT_BATCH_DIMS, gather_results, shard_range
+
+
+def test_shard_range_partitions_every_image_exactly_once():
+    for total in (0, 1, 2, 7, 8, 255, 256, 4096):
+        for world in (1, 2, 3, 4, 8):
+            covered = []
+            for r in range(world):
+                s, c = shard_range(total, world, r)
+                covered += list(range(s, s + c))
+            assert covered == list(range(total))
+            counts = [shard_range(total, world, r)[1] for r in range(world)]
+            assert max(counts) - min(counts) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        start, count = shard_range(total, world, rank)
+        L, N, H, C = 2, 5, 3, 8
+        idx = torch.arange(start, start + count, dtype=torch.float32)
+        local = {
+            "logits": idx[:, None] + torch.arange(C)[None, :] * 0.001,
+            "rollout": idx[:, None].expand(count, N - 1).clone(),
+            "avg_maps": idx[None, :, None, None].expand(L, count, N, N).clone() + torch.arange(L)[:, None, None, None] * 1000,
+            "cls_maps": idx[None, :, None, None].expand(L, count, H, N).clone(),
+        }
+        out = gather_results(local, total, RESULT_BATCH_DIMS)
+        if rank == 0:
+            ok = out["logits"].shape == (total, C) and torch.equal(out["logits"][:, 0], torch.arange(total, dtype=torch.float32))
+            ok = ok and out["avg_maps"].shape == (L, total, N, N)
+            ok = ok and torch.equal(out["avg_maps"][1, :, 0, 0], torch.arange(total, dtype=torch.float32) + 1000)
+            ok = ok and torch.equal(out["cls_maps"][0, :, 2, 4], torch.arange(total, dtype=torch.float32))
+            ok = ok and torch.equal(out["rollout"][:, 0], torch.arange(total, dtype=torch.float32))
+            q.put(bool(ok))
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,total", [(2, 8), (2, 7), (3, 4)])
+def test_gather_results_gloo(world, total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

@@ -1,0 +1,188 @@
+"""Whole-path parity on the B200 through the C ABI: engine vs the CPU oracle on the same seeded weights and
+images, vs the committed golden vectors, through the reference-facing plugin/scheduler/codec, and through
+size-independent properties at the bench size.
+
+Tolerance (north_star): bf16 mode — logits and attention maps within 2e-2 relative (max|diff| / max|ref|),
+top-1 identical."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _rel(got, ref):
+    return ((got.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def E(built_library):
+    import interactive_vit_b200.engine as E
+
+    assert torch.cuda.is_available()
+    return E
+
+
+def _engine_for(E, ocfg, model, batch):
+    cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                      ocfg.num_classes)
+    eng = E.VitEngine(cfg, 0, batch)
+    eng.load_state_dict(model.state_dict())
+    return eng
+
+
+ALL = 1 | 2 | 4 | 8 | 16
+
+
+@pytest.mark.parametrize("name,batch,init", [("vit_tiny_test", 3, "stress"), ("vit_small_test", 2, "stress"),
+                                             ("vit_small_test", 5, "default"), ("vit_s_16", 2, "stress"),
+                                             ("vit_b_16", 2, "default"), ("vit_b_16", 1, "stress")])
+def test_forward_matches_oracle(E, name, batch, init):
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS[name]
+    model = O.build_vit(ocfg, seed=0, init=init)
+    x = O.synthetic_images(batch, ocfg.image_size)
+    ref = O.forward_with_maps(model, x)
+    eng = _engine_for(E, ocfg, model, batch)
+    got = eng.forward_host(x, ALL)
+    for k in ("logits", "avg_maps", "cls_maps", "rollout", "heads", "hidden"):
+        assert got[k].shape == ref[k].shape, k
+        assert torch.isfinite(got[k]).all(), k
+        assert _rel(got[k], ref[k]) < TOL, (k, _rel(got[k], ref[k]))
+    assert torch.equal(got["logits"].argmax(-1), ref["logits"].argmax(-1))
+    assert (got["avg_maps"].sum(-1) - 1).abs().max() < 1e-4
+    eng.close()
+
+
+def test_vit_l_16_with_maps(E):
+    """config 4: ViT-L/16 with rollout / CLS-attention export for every layer."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_l_16"]
+    model = O.build_vit(ocfg, seed=0, init="default")
+    x = O.synthetic_images(1, ocfg.image_size)
+    ref = O.forward_with_maps(model, x)
+    eng = _engine_for(E, ocfg, model, 1)
+    got = eng.forward_host(x, 1 | 2 | 4)
+    for k in ("logits", "avg_maps", "cls_maps", "rollout"):
+        assert _rel(got[k], ref[k]) < TOL, (k, _rel(got[k], ref[k]))
+    assert torch.equal(got["logits"].argmax(-1), ref["logits"].argmax(-1))
+    eng.close()
+
+
+@pytest.mark.parametrize("fname", ["vit_small_b2.pt", "vit_b16_b1.pt"])
+def test_forward_matches_golden_fixture(E, golden_dir, fname):
+    from oracle import vit_oracle as O
+
+    g = torch.load(os.path.join(golden_dir, fname), map_location="cpu")
+    ocfg = O.ORACLE_CONFIGS[g["config"]]
+    model = O.build_vit(ocfg, seed=g["seed"], init=g["init"])
+    x = O.synthetic_images(g["batch"], ocfg.image_size, seed=g["image_seed"])
+    eng = _engine_for(E, ocfg, model, g["batch"])
+    got = eng.forward_host(x, ALL)
+    assert _rel(got["logits"], g["logits"]) < TOL
+    assert torch.equal(got["logits"].argmax(-1), g["logits"].argmax(-1))
+    assert _rel(got["rollout"], g["rollout"]) < TOL
+    assert _rel(got["cls_maps"], g["cls_maps"]) < TOL
+    assert _rel(got["avg_maps"][:, :, ::16, :], g["avg_rows"]) < TOL
+    assert _rel(got["hidden"][:, :, 0, :], g["hidden_cls"]) < TOL
+    eng.close()
+
+
+def test_stage_entry_points_equal_whole_forward(E):
+    """embed -> layer.i -> head -> rollout through the node-granular C ABI == one forward call, bit for bit."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_small_test"]
+    model = O.build_vit(ocfg, seed=0, init="stress")
+    x = O.synthetic_images(2, ocfg.image_size)
+    eng = _engine_for(E, ocfg, model, 2)
+    whole = eng.forward_host(x, ALL)
+    eng.stage_embed(x)
+    for i in range(ocfg.num_layers):
+        eng.stage_layer(i, 2, E.EMIT_AVG | E.EMIT_CLS)
+        assert torch.equal(eng.get_tokens(2), whole["hidden"][i])
+        assert torch.equal(eng.get_avg_map(i, 2), whole["avg_maps"][i])
+        assert torch.equal(eng.get_cls_map(i, 2), whole["cls_maps"][i])
+    assert torch.equal(eng.stage_head(2), whole["logits"])
+    assert torch.equal(eng.stage_rollout(2), whole["rollout"])
+    # tokens round-trip across the boundary
+    t = eng.get_tokens(2)
+    eng.set_tokens(t)
+    assert torch.equal(eng.get_tokens(2), t)
+    eng.close()
+
+
+def test_plugin_through_scheduler_and_wire_codec(E, golden_dir):
+    """The reference-facing path: browser request bytes -> Request.decode -> Context.compute over the B200 plugin
+    -> Response.encode, compared with the response bytes the unmodified reference produced with the CPU oracle."""
+    from interactive_vit_b200 import context as C, message as M, vit_plugin as P
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_tiny_test"]
+    module = O.build_vit(ocfg, seed=0, init="stress")
+    cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                      ocfg.num_classes)
+    plug = P.VitB200Model("vit_tiny_test", cfg, module, 0, 1)
+    ctx = C.Context()
+    for name in plug.list_node_names():
+        C.ModelNode(plug, name).register(ctx)
+    req = M.Request()
+    req.decode(open(os.path.join(golden_dir, "wire_tiny.request.bin"), "rb").read())
+    ctx.compute(req.graph)
+    got = M.decode_response(M.Response(req.graph).encode())
+    want = M.decode_response(open(os.path.join(golden_dir, "wire_tiny.response.bin"), "rb").read())
+    assert {k: sorted(v) for k, v in got.items()} == {k: sorted(v) for k, v in want.items()}
+    for node in want:
+        for ch in want[node]:
+            assert got[node][ch].shape == want[node][ch].shape and got[node][ch].dtype == torch.float32
+            assert _rel(got[node][ch], want[node][ch]) < TOL, (node, ch)
+    head = 1 + ocfg.num_layers
+    assert got[head]["o"].argmax() == want[head]["o"].argmax()
+    # error behaviour of the boundary: wrong shape and missing input raise (the view turns it into HTTP 400)
+    from interactive_vit_b200.graph import Pinout
+
+    bad = Pinout()
+    bad.set("o", torch.zeros(3, 32, 32))
+    with pytest.raises(Exception, match="expected an image"):
+        plug.compute("vit_tiny_test:embed", bad)
+    with pytest.raises(Exception, match="missing input"):
+        plug.compute("vit_tiny_test:head", Pinout())
+    with pytest.raises(KeyError):
+        ctx.get_node("vit_tiny_test:layer.99")
+    # tokens that did not come from the engine (fresh tensor object) are uploaded, same result
+    tok = got[1]["o"].clone()
+    p = Pinout()
+    p.set("o", tok)
+    again = plug.compute("vit_tiny_test:layer.1", p)
+    assert torch.equal(again.get("o"), got[2]["o"])
+    plug.engine.close()
+
+
+def test_bench_size_properties(E):
+    """ViT-B/16, batch 256 (BASELINE config 2) — properties that need no oracle at this size: every image's result
+    is bit-identical to running that image alone (rows never mix), softmax rows sum to one, rollout rows sum to
+    one minus the class column, logits finite."""
+    from interactive_vit_b200 import vit_plugin as P
+
+    cfg = E.CONFIGS["vit_b_16"]
+    module = P.build_torchvision_vit(cfg, seed=0)
+    eng = E.VitEngine(cfg, 0, 256)
+    eng.load_state_dict(module.state_dict())
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(256, 3, 224, 224, generator=g)
+    flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
+    big = eng.forward_host(x, flags)
+    assert torch.isfinite(big["logits"]).all()
+    assert (big["avg_maps"].sum(-1) - 1).abs().max() < 1e-4
+    assert (big["cls_maps"].sum(-1) - 1).abs().max() < 1e-4
+    assert ((big["rollout"].sum(-1) <= 1.0 + 1e-4) & (big["rollout"].min(-1).values >= 0)).all()
+    for i in (0, 127, 255):
+        one = eng.forward_host(x[i:i + 1].contiguous(), flags)
+        assert torch.equal(one["logits"][0], big["logits"][i])
+        assert torch.equal(one["avg_maps"][:, 0], big["avg_maps"][:, i])
+        assert torch.equal(one["rollout"][0], big["rollout"][i])
+    eng.close()

@@ -1,0 +1,147 @@
+"""Per-kernel parity on the B200: every CUDA kernel is called through the C ABI (libvitb200.so) and compared
+with a plain torch fp32 evaluation of the same op on the same seeded inputs.
+
+Tolerances: the GEMM / attention operands are bf16 by design, so outputs that are *stored* as bf16 carry one
+bf16 rounding (2^-9 relative); fp32 outputs of the GEMM differ from the fp32 reference only by summation order.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_EPS = 2.0 ** -8     # one bf16 rounding of an O(ref_max) value, with margin
+F32_EPS = 2e-5
+
+
+def _rel(got, ref):
+    return ((got.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def E(built_library):
+    import interactive_vit_b200.engine as E
+
+    assert torch.cuda.is_available()
+    return E
+
+
+def test_patchify_is_exact(E):
+    x = torch.rand(3, 3, 224, 224, device="cuda")
+    got = E.op_patchify(x, 16)
+    ref = torch.nn.functional.unfold(x, kernel_size=16, stride=16).transpose(1, 2).reshape(3 * 196, 768).bfloat16()
+    assert torch.equal(got, ref)
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    ref = torch.nn.functional.unfold(x, kernel_size=8, stride=8).transpose(1, 2).reshape(2 * 64, 192).bfloat16()
+    assert torch.equal(E.op_patchify(x, 8), ref)
+
+
+@pytest.mark.parametrize("d", [128, 256, 384, 768, 1024, 1280])
+def test_layernorm(E, d):
+    torch.manual_seed(d)
+    x = torch.randn(1001, d, device="cuda") * 3 + 0.7
+    g, b = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
+    got = E.op_layernorm(x, g, b, 1e-6)
+    ref = torch.nn.functional.layer_norm(x, (d,), g, b, 1e-6)
+    assert _rel(got, ref) < BF16_EPS
+
+
+GEMM_CASES = [
+    # M, N, K, bias, resid, gelu, out_f32
+    (128, 128, 64, False, False, False, True),
+    (128, 256, 64, True, False, False, True),
+    (1, 128, 64, True, False, False, True),          # single row, M tail
+    (129, 256, 128, True, True, False, True),        # one row into the second tile
+    (788, 768, 768, True, True, False, True),        # out_proj + residual
+    (788, 2304, 768, True, False, False, False),     # qkv
+    (788, 3072, 768, True, False, True, False),      # fc1 + GELU
+    (788, 768, 3072, True, True, False, True),       # fc2 + residual
+    (7, 1000, 768, True, False, False, True),        # classifier head, N tail (1000 = 7*128 + 104)
+    (591, 1152, 384, True, False, False, False),     # ViT-S qkv (BN=128 path)
+    (591, 1536, 384, True, False, True, False),      # ViT-S fc1
+    (300, 4096, 1024, True, False, True, False),     # ViT-L fc1
+]
+
+
+@pytest.mark.parametrize("M,N,K,bias,resid,gelu,out_f32", GEMM_CASES)
+def test_gemm(E, M, N, K, bias, resid, gelu, out_f32):
+    torch.manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bs = torch.randn(N, device="cuda") if bias else None
+    rs = torch.randn(M, N, device="cuda") if resid else None
+    got = E.op_gemm(a, w, bs, rs, gelu, out_f32)
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + bs
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    if resid:
+        ref = ref + rs
+    assert got.shape == (M, N) and torch.isfinite(got.float()).all()
+    assert _rel(got, ref) < (F32_EPS if out_f32 else BF16_EPS)
+
+
+def test_gemm_full_size_linearity(E):
+    """Size-independent property at the bench shape (M = 256 * 197): GEMM(a1 + a2) == GEMM(a1) + GEMM(a2) when
+    the sum a1 + a2 is exact in bf16, and every row depends only on its own input row."""
+    M, N, K = 256 * 197, 768, 768
+    torch.manual_seed(0)
+    a1 = (torch.randint(-8, 9, (M, K), device="cuda").float() / 8).bfloat16()
+    a2 = (torch.randint(-8, 9, (M, K), device="cuda").float() / 8).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    y1, y2 = E.op_gemm(a1, w, out_f32=True), E.op_gemm(a2, w, out_f32=True)
+    y12 = E.op_gemm((a1.float() + a2.float()).bfloat16(), w, out_f32=True)
+    assert _rel(y12, y1 + y2) < F32_EPS
+    rows = torch.tensor([0, 127, 128, 50431], device="cuda")
+    assert torch.equal(E.op_gemm(a1[rows].contiguous(), w, out_f32=True), y1[rows])   # bit-exact row independence
+
+
+def _attn_ref(qkv, B, N, H):
+    q, k, v = qkv.float().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    p = torch.softmax((q * 0.125) @ k.transpose(-1, -2), dim=-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * N, H * 64)
+    return o, p
+
+
+@pytest.mark.parametrize("B,N,H,scale", [(2, 197, 12, 1.0), (3, 197, 6, 3.0), (2, 64, 2, 1.0), (1, 17, 2, 2.0),
+                                         (1, 128, 1, 1.0), (2, 129, 3, 1.0), (5, 197, 16, 0.5)])
+def test_attention(E, B, N, H, scale):
+    torch.manual_seed(B * 1000 + N)
+    qkv = (torch.randn(B * N, 3 * H * 64, device="cuda") * scale).bfloat16()
+    ctx, avg, cls, hm = E.op_attention(qkv, B, N, H, True, True, True)
+    o, p = _attn_ref(qkv, B, N, H)
+    assert _rel(ctx, o) < 2 * BF16_EPS           # P is rounded to bf16 for the P.V product, the output again
+    assert _rel(hm, p) < 1e-5                    # probabilities are emitted in fp32
+    assert _rel(avg, p.mean(1)) < 1e-5
+    assert _rel(cls, p[:, :, 0, :]) < 1e-5
+    assert (hm.sum(-1) - 1).abs().max() < 1e-5   # rows of a softmax
+    # outputs selected independently give the same context
+    ctx2, _, _, _ = E.op_attention(qkv, B, N, H, False, False, False)
+    assert torch.equal(ctx, ctx2)
+
+
+def test_attention_masks_padded_keys(E):
+    """Keys beyond N come from the next image (or TMA zero fill) and must get probability 0: changing image 1 must
+    not change image 0's outputs."""
+    B, N, H = 2, 197, 4
+    torch.manual_seed(1)
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda").bfloat16()
+    ctx_a, avg_a, _, _ = E.op_attention(qkv, B, N, H)
+    qkv2 = qkv.clone()
+    qkv2[N:] = (torch.randn(N, 3 * H * 64, device="cuda") * 50).bfloat16()
+    ctx_b, avg_b, _, _ = E.op_attention(qkv2, B, N, H)
+    assert torch.equal(ctx_a[:N], ctx_b[:N]) and torch.equal(avg_a[0], avg_b[0])
+
+
+def test_rollout(E):
+    from oracle.vit_oracle import rollout_from_avg
+
+    L, B, N, pitch = 5, 3, 197, 208
+    torch.manual_seed(2)
+    p = torch.softmax(torch.randn(L, B, N, N) * 2, dim=-1)
+    padded = torch.zeros(L, B, N, pitch)
+    padded[..., :N] = p
+    got = E.op_rollout(padded.cuda()).cpu()
+    ref = rollout_from_avg(list(p))
+    assert _rel(got, ref) < 1e-5
+    assert (got.sum(-1) + rollout_from_avg(list(p)).new_zeros(B) - ref.sum(-1)).abs().max() < 1e-5
