@@ -1,5 +1,6 @@
 // Fused multi-head self-attention with attention-map emission (tcgen05 + TMEM), for sequences whose padded
-// key count KP = round_up(N, 16) fits one UMMA N (<= 256): N = 197 (224 px / patch 16) -> KP = 208.
+// key count KP = round_up(N, 16) fits one UMMA N and this kernel's TMEM plan (KP <= 208): N = 197
+// (224 px / patch 16) -> KP = 208.
 //
 // Arithmetic follows torch.nn.functional.multi_head_attention_forward's weights branch
 // (torch/nn/functional.py:6630-6659: q * 1/sqrt(D), bmm(q, k^T), softmax, bmm(P, v), optional head mean)
@@ -8,17 +9,22 @@
 // exact arithmetic; exact in floating point too when D = 64 since the factor is a power of two).
 //
 // One CTA per (image b, 128-row query tile qt); the CTA loops over all H heads so that the head-averaged
-// probabilities can be accumulated on chip (TMEM) and written to HBM exactly once:
+// probabilities can be accumulated on chip (TMEM) and written to HBM exactly once.  384 threads:
 //   warp 0 lane 0 : TMA producer  Q_h [128 x D], K_h [KP x D], V_h [KP x D] tiles of the packed qkv
-//                   activation, 2-stage ring over heads (head h+1 streams in while head h computes)
+//                   activation, 2-stage ring over heads
 //   warp 1 lane 0 : UMMA issuer   S = Q K^T (M=128, N=KP, K=D)   -> TMEM cols [64, 64+KP)
-//                                 O = P V   (M=128, N=D,  K=KP)  -> TMEM cols [0, D), V is the MN-major B
+//                                 O = P V   (M=128, N=D,  K=KP)  -> TMEM cols [0, D), V is the MN-major B.
+//                   Issue order QK(0), QK(1), PV(0), QK(2), PV(1), ...: the S columns are released as soon
+//                   as the softmax warps have copied them to registers, so QK^T of head h+1 and P V of
+//                   head h run on the tensor pipe underneath the softmax of head h.
 //   warp 2        : TMEM allocator (all 512 columns)
-//   warps 4..7    : softmax, one thread per query row (32x32b TMEM loads: no cross-lane reductions):
-//                   pass 1 row max; pass 2 e = exp2(s*c - m*c) -> bf16 P tile in shared memory (128-B
-//                   swizzled K-major A operand for P V) and fp32 e back into the S columns; pass 3
-//                   Pbar += e / (sum * H) in TMEM cols [288, 288+KP), optional per-head rows to HBM;
-//                   then O * 1/sum -> bf16 context rows.
+//   warps 4..11   : softmax.  Two threads per query row: warps 4..7 own the first half of the key columns,
+//                   warps 8..11 the second half (a warp may only touch the TMEM lane quarter warp%4).  The
+//                   half row (<= 112 scores) is read from TMEM ONCE and stays in registers for: row max
+//                   (exchanged with the partner thread through smem) -> e = exp2(s*c - m*c) -> bf16 P tile
+//                   in shared memory (128-B swizzled K-major A operand of P V) -> row sum (exchanged) ->
+//                   Pbar += e / (sum * H) in TMEM cols [288, 288+KP) -> optional per-head rows to HBM.
+//                   Then O * 1/sum -> bf16 context rows (each half owns 32 of the 64 columns).
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -28,7 +34,7 @@ namespace vitb200 {
 struct AttnParams {
   int B, N, H;          // images, tokens per image, heads
   int d;                // model width = H * D
-  int KP;               // keys padded to a multiple of 16 (<= 208 for this kernel's TMEM plan, see below)
+  int KP;               // keys padded to a multiple of 16 (<= 208)
   float scale_log2;     // (1/sqrt(D)) * log2(e)
   __nv_bfloat16* ctx;   // [B*N, d] attention context (input of out_proj)
   float* avg_map;       // [B, N, ldmap] head-averaged probabilities, or nullptr
@@ -39,10 +45,12 @@ struct AttnParams {
 };
 
 namespace attn_cfg {
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;
+constexpr int kSoftmaxThreads = 256;
 constexpr int BM = 128;
 constexpr int D = 64;
 constexpr int KP_MAX = 208;  // TMEM plan: O [0,64) | S [64,64+KP) | Pbar [288,288+KP)  -> KP <= 208
+constexpr int kMaxChunks = 7;                      // 16-column chunks per softmax thread: ceil(13 / 2)
 constexpr int kTmemO = 0;
 constexpr int kTmemS = 64;
 constexpr int kTmemAvg = 288;
@@ -52,27 +60,35 @@ constexpr int kStageBytes = kQBytes + 2 * kKVBytes;
 constexpr int kPBlockBytes = BM * 128;             // one 64-key K-block of P: 128 rows x 128 B
 constexpr int kPBlocks = (KP_MAX + 63) / 64;       // 4
 constexpr int kPBytes = kPBlocks * kPBlockBytes;   // 64 KB
-constexpr int kClsStageBytes = 256 * 4;
-constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kClsStageBytes + 1024 + 256;
+constexpr int kRedBytes = 2 * 2 * BM * 4;          // row max / row sum exchange: [2 kinds][2 halves][128 rows]
+constexpr int kClsStageBytes = 256 * 4;            // normalised probabilities of query row 0
+constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kRedBytes + kClsStageBytes + 256;
 }  // namespace attn_cfg
 
+// kHeads: also write the full per-head probabilities (opt-in; a separate instantiation keeps that code out of
+// the instruction stream of the common variant, which has to stay inside the 32 KB instruction cache).
+template <bool kHeads>
 __global__ void __launch_bounds__(attn_cfg::kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 over qkv [B*N, 3d]
                  const __grid_constant__ CUtensorMap tmap_kv,  // box 64 x (KP/2) over the same tensor
                  AttnParams p) {
   using namespace attn_cfg;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Dynamic smem starts 1024-B aligned (it follows the 1 KB the driver reserves); keeping the array typed lets
+  // the compiler emit LDS/STS instead of generic loads for the exchange buffers.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smem_p = smem + 2 * kStageBytes;
-  float* cls_stage = reinterpret_cast<float*>(smem_p + kPBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + kPBytes + kClsStageBytes);
+  float* red = reinterpret_cast<float*>(smem_p + kPBytes);  // [kind][half][row]
+  float* cls_stage = red + 2 * 2 * BM;                       // [256] normalised probabilities of query row 0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + kPBytes + kRedBytes + kClsStageBytes);
   uint64_t* full_bar = bars;        // [2] Q/K/V of a head landed
   uint64_t* empty_bar = bars + 2;   // [2] Q/K/V stage consumed by the MMAs
   uint64_t* s_full = bars + 4;      // S = QK^T complete
-  uint64_t* p_full = bars + 5;      // bf16 P tile written to smem (128 arrivals)
-  uint64_t* o_full = bars + 6;      // O = PV complete
-  uint64_t* s_free = bars + 7;      // softmax done with S / O / Pbar columns of this head (128 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_free = bars + 5;      // S copied to registers by all softmax threads (256 arrivals)
+  uint64_t* p_full = bars + 6;      // bf16 P tile written to smem (256 arrivals)
+  uint64_t* o_full = bars + 7;      // O = PV complete
+  uint64_t* o_free = bars + 8;      // O columns read by all softmax threads (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,9 +108,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     ptx::mbar_init(&empty_bar[0], 1);
     ptx::mbar_init(&empty_bar[1], 1);
     ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(s_free, kSoftmaxThreads);
+    ptx::mbar_init(p_full, kSoftmaxThreads);
     ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(s_free, 128);
+    ptx::mbar_init(o_free, kSoftmaxThreads);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
@@ -127,24 +144,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     const uint32_t idesc_pv = ptx::make_idesc_bf16(BM, D, 0, 1);  // B (= V) is MN-major
     const uint32_t sp = ptx::smem_u32(smem_p);
     const int ksteps = KP >> 4;
-    for (int h = 0; h < p.H; ++h) {
+    auto issue_qk = [&](int h) {
       const int st = h & 1;
-      const uint32_t ph = (h >> 1) & 1;
-      ptx::mbar_wait(&full_bar[st], ph);
+      ptx::mbar_wait(&full_bar[st], (h >> 1) & 1);
       if (h > 0) ptx::mbar_wait(s_free, (h - 1) & 1);
       ptx::tc_fence_after();
       const uint32_t sq = ptx::smem_u32(smem + st * kStageBytes);
-      const uint32_t sk = sq + kQBytes;
-      const uint32_t sv = sk + kKVBytes;
       const uint64_t dq = ptx::make_smem_desc_sw128(sq, 16, 1024);
-      const uint64_t dk = ptx::make_smem_desc_sw128(sk, 16, 1024);
+      const uint64_t dk = ptx::make_smem_desc_sw128(sq + kQBytes, 16, 1024);
 #pragma unroll
       for (int k = 0; k < D / 16; ++k)
         ptx::umma_bf16_ss(tmem_base + kTmemS, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
       ptx::umma_commit(s_full);
-
+    };
+    issue_qk(0);
+    for (int h = 0; h < p.H; ++h) {
+      if (h + 1 < p.H) issue_qk(h + 1);
+      const int st = h & 1;
       ptx::mbar_wait(p_full, h & 1);
+      if (h > 0) ptx::mbar_wait(o_free, (h - 1) & 1);
       ptx::tc_fence_after();
+      const uint32_t sv = ptx::smem_u32(smem + st * kStageBytes) + kQBytes + kKVBytes;
       for (int ks = 0; ks < ksteps; ++ks) {
         // A: P K-block (ks / 4), +32 B per 16 keys inside the swizzle span.  B: V rows [16 ks, 16 ks + 16),
         // MN-major: 8-key groups 1024 B apart (SBO); the single 64-wide MN group makes LBO irrelevant.
@@ -156,154 +176,208 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       ptx::umma_commit(o_full);
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ softmax / epilogue (thread = query row)
-    const int quarter = warp & 3;
+    // ------------------------------------------------------------ softmax / epilogue
+    const int half = (warp - 4) >> 2;           // which half of the key columns
+    const int quarter = warp & 3;               // TMEM lane quarter
     const int r = quarter * 32 + lane;          // row inside the tile
     const int qrow = qt * BM + r;               // token index inside the image
     const bool row_ok = qrow < p.N;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int nchunks = KP >> 4;
+    const int split = (nchunks + 1) >> 1;       // 16-key chunks [0, split) -> half 0, [split, nchunks) -> half 1
+    const int nmy = half ? nchunks - split : split;
+    // local chunk c <-> global chunk gc: half 0 walks up from 0, half 1 walks DOWN from the last chunk, so the
+    // only chunk that can hold padded keys (>= N) is always local chunk 0 of half 1 (a static register index)
+    const int gc_base = half ? nchunks - 1 : 0;
+    const int gc_step = half ? -1 : 1;
+    const int tail_valid = p.N - (nchunks - 1) * 16;  // valid keys in the last chunk (1..16)
     const float inv_h = 1.0f / static_cast<float>(p.H);
     const bool want_avg = p.avg_map != nullptr;
     const bool want_cls = p.cls_map != nullptr && qt == 0;
+    const bool want_maps = want_avg || want_cls || kHeads;
     const uint32_t p_row = ptx::smem_u32(smem_p) + r * 128;
     const int sw = r & 7;
+    float* red_max = red;                        // [half][row]
+    float* red_sum = red + 2 * BM;
+    const uint32_t t_s = lane_base + kTmemS + gc_base * 16;
+    const uint32_t t_avg = lane_base + kTmemAvg + gc_base * 16;
+    const int t_step = gc_step * 16;
 
     for (int h = 0; h < p.H; ++h) {
+      // ---- S half-row -> registers (single TMEM read), then release the S columns
+      uint32_t s[kMaxChunks][16];
       ptx::mbar_wait(s_full, h & 1);
       ptx::tc_fence_after();
-      // pass 1: row maximum over the valid keys
-      float mx = -INFINITY;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t s[16];
-        ptx::tmem_ld_x16(lane_base + kTmemS + c * 16, s);
-        ptx::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < kMaxChunks; ++c)
+        if (c < nmy) ptx::tmem_ld_x16(t_s + c * t_step, s[c]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(s_free);
+      if (half && tail_valid < 16) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c * 16 + j < p.N) mx = fmaxf(mx, __uint_as_float(s[j]));
+          if (j >= tail_valid) s[0][j] = 0xff800000u;  // -inf: exp2 gives 0, max ignores it
       }
+
+      // ---- row max (own half, then partner's through smem)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kMaxChunks; ++c) {
+        if (c < nmy) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(s[c][j]));
+        }
+      }
+      red_max[half * BM + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, red_max[(half ^ 1) * BM + r]);
       const float mxs = mx * p.scale_log2;
-      // pass 2: e = exp2(s*c - max*c); bf16 P to smem (swizzled K-major), fp32 e back to TMEM
-      float sum = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t s[16];
-        ptx::tmem_ld_x16(lane_base + kTmemS + c * 16, s);
-        ptx::tmem_ld_wait();
-        float e[16];
+
+      // ---- e = exp2(s*c - max*c) in place; bf16 P to smem (swizzled K-major)
+      float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float v = exp2f(fmaf(__uint_as_float(s[j]), p.scale_log2, -mxs));
-          e[j] = (c * 16 + j < p.N) ? v : 0.f;
-          sum += e[j];
-          s[j] = __float_as_uint(e[j]);
-        }
-        ptx::tmem_st_x16(lane_base + kTmemS + c * 16, s);
-        uint32_t pk[8];
+      for (int c = 0; c < kMaxChunks; ++c) {
+        if (c < nmy) {
+          const int gc = gc_base + c * gc_step;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 t = __floats2bfloat162_rn(e[2 * j], e[2 * j + 1]);
-          pk[j] = *reinterpret_cast<uint32_t*>(&t);
+          for (int j = 0; j < 16; j += 4) {
+            const float v0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -mxs));
+            const float v1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 1]), p.scale_log2, -mxs));
+            const float v2 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 2]), p.scale_log2, -mxs));
+            const float v3 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 3]), p.scale_log2, -mxs));
+            ps0 += v0, ps1 += v1, ps2 += v2, ps3 += v3;
+            s[c][j] = __float_as_uint(v0), s[c][j + 1] = __float_as_uint(v1);
+            s[c][j + 2] = __float_as_uint(v2), s[c][j + 3] = __float_as_uint(v3);
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(s[c][2 * j]), __uint_as_float(s[c][2 * j + 1]));
+            pk[j] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          // keys [16 gc, 16 gc + 16): K-block gc/4, 16-byte chunks 2*(gc%4) and 2*(gc%4)+1 of this row
+          const uint32_t blk = p_row + (gc >> 2) * kPBlockBytes;
+          const int ch0 = 2 * (gc & 3);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((ch0 ^ sw) << 4)), "r"(pk[0]),
+                       "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch0 + 1) ^ sw) << 4)), "r"(pk[4]),
+                       "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                       : "memory");
         }
-        // keys [16c, 16c+16): K-block kb = c/4, 16-byte chunks 2*(c%4) and 2*(c%4)+1 of this row
-        const uint32_t blk = p_row + (c >> 2) * kPBlockBytes;
-        const int ch0 = 2 * (c & 3);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((ch0 ^ sw) << 4)), "r"(pk[0]),
-                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                     : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch0 + 1) ^ sw) << 4)), "r"(pk[4]),
-                     "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                     : "memory");
       }
-      ptx::tmem_st_wait();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(p_full);
 
-      // pass 3 (overlaps the P V MMAs): normalised probabilities -> head average / per-head rows
-      const float inv = 1.0f / sum;
-      if (want_avg || want_cls || p.head_map != nullptr) {
+      // ---- row sum exchange
+      float sum = (ps0 + ps1) + (ps2 + ps3);
+      red_sum[half * BM + r] = sum;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      sum += red_sum[(half ^ 1) * BM + r];
+      const float inv = ptx::rcp_approx(sum);
+
+      // ---- normalised probabilities -> head average (TMEM) / per-head rows (HBM); overlaps the P V MMAs
+      if (want_maps) {
         const float wavg = inv * inv_h;
-        for (int c = 0; c < nchunks; ++c) {
-          uint32_t e[16];
-          ptx::tmem_ld_x16(lane_base + kTmemS + c * 16, e);
-          if (want_avg) {
-            uint32_t a[16];
-            if (h > 0) {
-              ptx::tmem_ld_x16(lane_base + kTmemAvg + c * 16, a);
-              ptx::tmem_ld_wait();
+        if (want_avg) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                a[j] = __float_as_uint(fmaf(__uint_as_float(e[j]), wavg, __uint_as_float(a[j])));
-            } else {
-              ptx::tmem_ld_wait();
+          for (int c = 0; c < kMaxChunks; ++c) {
+            if (c < nmy) {
+              uint32_t a[16];
+              if (h > 0) {
+                ptx::tmem_ld_x16(t_avg + c * t_step, a);
+                ptx::tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(e[j]) * wavg);
+                for (int j = 0; j < 16; ++j)
+                  a[j] = __float_as_uint(fmaf(__uint_as_float(s[c][j]), wavg, __uint_as_float(a[j])));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(s[c][j]) * wavg);
+              }
+              ptx::tmem_st_x16(t_avg + c * t_step, a);
             }
-            ptx::tmem_st_x16(lane_base + kTmemAvg + c * 16, a);
-          } else {
-            ptx::tmem_ld_wait();
           }
-          if (want_cls && r == 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) cls_stage[c * 16 + j] = __uint_as_float(e[j]) * inv;
-          }
-          if (p.head_map != nullptr && row_ok) {
-            float* hp = p.head_map + ((static_cast<size_t>(b) * p.H + h) * p.N + qrow) * p.ldmap + c * 16;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(hp + j) =
-                  make_float4(__uint_as_float(e[j]) * inv, __uint_as_float(e[j + 1]) * inv,
-                              __uint_as_float(e[j + 2]) * inv, __uint_as_float(e[j + 3]) * inv);
-          }
+          ptx::tmem_st_wait();
         }
-        if (want_avg) ptx::tmem_st_wait();
-        if (want_cls) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (want_cls && quarter == 0) {
+          // query row 0 lives in lane 0 of warps 4 (first half of the keys) and 8 (second half): it stages its
+          // normalised values, then the whole warp writes that key range out (no cross-warp dependency)
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < kMaxChunks; ++c) {
+              if (c < nmy) {
+                float* dst = cls_stage + (gc_base + c * gc_step) * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) =
+                      make_float4(__uint_as_float(s[c][j]) * inv, __uint_as_float(s[c][j + 1]) * inv,
+                                  __uint_as_float(s[c][j + 2]) * inv, __uint_as_float(s[c][j + 3]) * inv);
+              }
+            }
+          }
+          __syncwarp();
+          const int lo = half ? split * 16 : 0;
+          const int hi = half ? p.N : min(split * 16, p.N);
           float* cp = p.cls_map + (static_cast<size_t>(b) * p.H + h) * p.N;
-          for (int j = threadIdx.x - 128; j < p.N; j += 128) cp[j] = cls_stage[j];
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int j = lo + lane; j < hi; j += 32) cp[j] = cls_stage[j];
+          __syncwarp();
+        }
+        if (kHeads) {
+          if (p.head_map != nullptr && row_ok) {
+            float* hp = p.head_map + ((static_cast<size_t>(b) * p.H + h) * p.N + qrow) * p.ldmap;
+#pragma unroll
+            for (int c = 0; c < kMaxChunks; ++c) {
+              if (c < nmy) {
+                float* dst = hp + (gc_base + c * gc_step) * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) =
+                      make_float4(__uint_as_float(s[c][j]) * inv, __uint_as_float(s[c][j + 1]) * inv,
+                                  __uint_as_float(s[c][j + 2]) * inv, __uint_as_float(s[c][j + 3]) * inv);
+              }
+            }
+          }
         }
       }
 
-      // O epilogue: context rows = (P_unnormalised V) / sum
+      // ---- O epilogue: context rows = (P_unnormalised V) / sum; this half owns 32 of the 64 columns
       ptx::mbar_wait(o_full, h & 1);
       ptx::tc_fence_after();
       {
-        uint32_t o[4][16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ptx::tmem_ld_x16(lane_base + kTmemO + c * 16, o[c]);
+        uint32_t o[32];
+        ptx::tmem_ld_x32(lane_base + kTmemO + half * 32, o);
         ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(o_free);
         if (row_ok) {
-          __nv_bfloat16* op = p.ctx + (static_cast<size_t>(row0) + qrow) * p.d + h * D;
+          __nv_bfloat16* op = p.ctx + (static_cast<size_t>(row0) + qrow) * p.d + h * D + half * 32;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o[c][j]) * inv, __uint_as_float(o[c][j + 1]) * inv);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(o[c][j + 2]) * inv, __uint_as_float(o[c][j + 3]) * inv);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o[c][j + 4]) * inv, __uint_as_float(o[c][j + 5]) * inv);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o[c][j + 6]) * inv, __uint_as_float(o[c][j + 7]) * inv);
-              pk.x = *reinterpret_cast<uint32_t*>(&t0);
-              pk.y = *reinterpret_cast<uint32_t*>(&t1);
-              pk.z = *reinterpret_cast<uint32_t*>(&t2);
-              pk.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(op + c * 16 + j) = pk;
-            }
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0);
+            pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2);
+            pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(op + j) = pk;
           }
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(s_free);
     }
 
     // head-averaged map rows -> HBM, once per (image, query row)
     if (want_avg) {
-      for (int c = 0; c < nchunks; ++c) {
+#pragma unroll 1
+      for (int c = 0; c < nmy; ++c) {
         uint32_t a[16];
-        ptx::tmem_ld_x16(lane_base + kTmemAvg + c * 16, a);
+        ptx::tmem_ld_x16(t_avg + c * t_step, a);
         ptx::tmem_ld_wait();
         if (row_ok) {
-          float* ap = p.avg_map + (static_cast<size_t>(b) * p.N + qrow) * p.ldmap + c * 16;
+          float* ap = p.avg_map + (static_cast<size_t>(b) * p.N + qrow) * p.ldmap + (gc_base + c * gc_step) * 16;
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(ap + j) = make_float4(__uint_as_float(a[j]), __uint_as_float(a[j + 1]),

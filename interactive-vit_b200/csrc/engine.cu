@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -106,23 +107,59 @@ static int device_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool kGelu, bool kOutF32>
+template <int BN, int kPair, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
                          cudaStream_t st) {
-  using C = gemm_cfg::Cfg<BN>;
-  auto kern = gemm_bf16_kernel<BN, kGelu, kOutF32>;
+  using C = gemm_cfg::Cfg<BN, kPair>;
+  auto kern = gemm_bf16_kernel<BN, kPair, kGelu, kOutF32, kResid, kRemap>;
   static bool configured = false;
   if (!configured) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  const int m_tiles = (sh.M + gemm_cfg::BM - 1) / gemm_cfg::BM;
+  const int tile_m = gemm_cfg::BM * kPair;
+  const int m_tiles = (sh.M + tile_m - 1) / tile_m;
   const int n_tiles = (sh.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < device_sms() ? tiles : device_sms();
-  kern<<<grid, gemm_cfg::kThreads, C::kSmemBytes, st>>>(ta, tw, sh, ep);
-  CU_TRY(cudaGetLastError());
+  const int units = device_sms() / kPair;  // persistent: one CTA (or CTA pair) per SM (pair)
+  const int grid = (tiles < units ? tiles : units) * kPair;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(gemm_cfg::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CU_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw, sh, ep));
   return VITB200_OK;
+}
+
+// CTA-pair (cta_group::2) kernels unless VITB200_GEMM_PAIR=1 asks for the single-CTA baseline.
+static int gemm_pair_mode() {
+  static int mode = 0;
+  if (mode == 0) {
+    const char* v = getenv("VITB200_GEMM_PAIR");
+    mode = (v && v[0] == '1') ? 1 : 2;
+  }
+  return mode;
+}
+
+template <int BN, int kPair>
+static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep, bool gelu,
+                          bool out_f32, cudaStream_t st) {
+  const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0;
+  if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, true, false, false, false>(ta, tw, sh, ep, st);
+  if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, false, false, false, false>(ta, tw, sh, ep, st);
+  if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, false, true, false, false>(ta, tw, sh, ep, st);
+  if (!gelu && out_f32 && resid && !remap) return launch_gemm_t<BN, kPair, false, true, true, false>(ta, tw, sh, ep, st);
+  if (!gelu && out_f32 && resid && remap) return launch_gemm_t<BN, kPair, false, true, true, true>(ta, tw, sh, ep, st);
+  return fail(VITB200_ERR_INVALID, "gemm: epilogue combination not instantiated (gelu=%d f32=%d resid=%d remap=%d)", gelu,
+              out_f32, resid, remap);
 }
 
 // out = epilogue(A[M,K] * W[N,K]^T): picks the tile width and the epilogue instantiation.
@@ -131,20 +168,17 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm: empty shape %d x %d x %d", M, N, K);
   if (N % 8 != 0 || K % 8 != 0) return fail(VITB200_ERR_INVALID, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
   const int BN = (N % 256 == 0) ? 256 : 128;
+  const int pair = gemm_pair_mode();
   CUtensorMap ta, tw;
   VT_TRY(make_tmap_bf16(&ta, a, M, K, lda, gemm_cfg::BM, gemm_cfg::BK));
-  VT_TRY(make_tmap_bf16(&tw, w, N, K, K, BN, gemm_cfg::BK));
+  VT_TRY(make_tmap_bf16(&tw, w, N, K, K, BN / pair, gemm_cfg::BK));
   GemmShape sh{M, N, K};
   if (BN == 256) {
-    if (gelu && !out_f32) return launch_gemm_t<256, true, false>(ta, tw, sh, ep, st);
-    if (!gelu && !out_f32) return launch_gemm_t<256, false, false>(ta, tw, sh, ep, st);
-    if (!gelu && out_f32) return launch_gemm_t<256, false, true>(ta, tw, sh, ep, st);
-  } else {
-    if (gelu && !out_f32) return launch_gemm_t<128, true, false>(ta, tw, sh, ep, st);
-    if (!gelu && !out_f32) return launch_gemm_t<128, false, false>(ta, tw, sh, ep, st);
-    if (!gelu && out_f32) return launch_gemm_t<128, false, true>(ta, tw, sh, ep, st);
+    return pair == 2 ? launch_gemm_bn<256, 2>(ta, tw, sh, ep, gelu, out_f32, st)
+                     : launch_gemm_bn<256, 1>(ta, tw, sh, ep, gelu, out_f32, st);
   }
-  return fail(VITB200_ERR_INVALID, "gemm: GELU with fp32 output is not instantiated");
+  return pair == 2 ? launch_gemm_bn<128, 2>(ta, tw, sh, ep, gelu, out_f32, st)
+                   : launch_gemm_bn<128, 1>(ta, tw, sh, ep, gelu, out_f32, st);
 }
 
 static int launch_layernorm(const float* x, long in_stride, const float* g, const float* b, __nv_bfloat16* y, int rows,
@@ -180,7 +214,8 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   VT_TRY(make_tmap_bf16(&tkv, qkv, (uint64_t)B * N, 3 * d, 3 * d, KP / 2, D));
   static bool configured = false;
   if (!configured) {
-    CU_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CU_TRY(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CU_TRY(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
   AttnParams p;
@@ -188,7 +223,8 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
   p.ctx = ctx, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
   p.q_tiles = (N + BM - 1) / BM;
-  attention_kernel<<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, p);
+  if (heads) attention_kernel<true><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, p);
+  else attention_kernel<false><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, p);
   CU_TRY(cudaGetLastError());
   return VITB200_OK;
 }
@@ -353,8 +389,8 @@ static int run_head(vitb200_engine* e, int B, cudaStream_t st) {
 }
 
 static int run_rollout(vitb200_engine* e, int B, cudaStream_t st) {
-  const size_t smem = 3 * (size_t)e->pitch * sizeof(float);
-  rollout_cls_kernel<<<B, 256, smem, st>>>((const float*)e->avg.p, (long)e->cap_batch * e->N * e->pitch,
+  if (e->N > 256) return fail(VITB200_ERR_INVALID, "rollout: at most 256 tokens");
+  rollout_cls_kernel<<<B, kRolloutThreads, 0, st>>>((const float*)e->avg.p, (long)e->cap_batch * e->N * e->pitch,
                                            e->cfg.num_layers, e->N, e->pitch, (float*)e->rollout.p);
   CU_TRY(cudaGetLastError());
   e->launches += 1;
@@ -750,8 +786,8 @@ int vitb200_op_patchify(const float* images, void* patches, int batch, int image
 int vitb200_op_rollout(const float* maps, long layer_stride, int layers, int batch, int tokens, int pitch, float* out,
                        void* stream) {
   if (!maps || !out) return fail(VITB200_ERR_INVALID, "null argument");
-  rollout_cls_kernel<<<batch, 256, 3 * (size_t)pitch * sizeof(float), (cudaStream_t)stream>>>(maps, layer_stride, layers,
-                                                                                              tokens, pitch, out);
+  if (tokens > 256) return fail(VITB200_ERR_INVALID, "rollout: at most 256 tokens");
+  rollout_cls_kernel<<<batch, kRolloutThreads, 0, (cudaStream_t)stream>>>(maps, layer_stride, layers, tokens, pitch, out);
   CU_TRY(cudaGetLastError());
   return VITB200_OK;
 }

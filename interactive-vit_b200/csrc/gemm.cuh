@@ -8,13 +8,22 @@
 //   MLPBlock Linear -> GELU(erf) -> Linear        vision_transformer.py:40-47
 //   heads.head                                    vision_transformer.py:302-304
 //
-// Roles (256 threads, 1 CTA / SM, persistent over output tiles):
-//   warp 0 lane 0 : TMA producer  (A tile 128x64, W tile BNx64, SWIZZLE_128B, kStages-deep mbarrier ring)
-//   warp 1 lane 0 : UMMA issuer   (tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 x4 per stage)
-//   warp 2        : TMEM allocator (2 accumulator buffers of BN fp32 columns -> MMA of tile i+1 overlaps
-//                   the epilogue of tile i)
-//   warps 4..7    : epilogue (tcgen05.ld 32x32b -> +bias [-> GELU] [+ fp32 residual / pos-embedding]
-//                   -> bf16 or fp32 global stores)
+// kPair = 2 (default): a CTA pair (cluster of 2, cta_group::2) computes a 256 x BN output tile with
+// UMMA M = 256: each CTA stages its own 128 rows of A and HALF of the W tile, so the L2 -> SMEM traffic per
+// FLOP is 2/3 of the single-CTA kernel's (the 128 x 256 single-CTA tile is L2-bandwidth bound at ~900 TF/s).
+// kPair = 1: one CTA computes 128 x BN on its own (kept as the A/B baseline).
+//
+// Roles (384 threads, 1 CTA / SM, persistent over output tiles):
+//   warp 0 lane 0 : TMA producer  (A tile 128x64, W tile (BN/kPair)x64, SWIZZLE_128B, mbarrier ring; in a pair both
+//                   CTAs' loads complete_tx on the LEADER's full barrier)
+//   warp 1 lane 0 : UMMA issuer (leader CTA only in a pair): 4 x tcgen05.mma (K = 16) per stage, commit ->
+//                   empty barrier of both CTAs; accumulator-complete commit -> both CTAs' epilogues
+//   warp 2        : TMEM allocator (2 accumulator buffers of BN fp32 columns: MMA of tile i+1 overlaps the
+//                   epilogue of tile i)
+//   warps 4..11   : epilogue, 2 warps per TMEM lane quarter (each owns half of the BN columns).  Per 32-column
+//                   chunk: tcgen05.ld -> warp-private smem slab -> re-read transposed so that a warp store
+//                   covers 4 rows x 128 contiguous bytes -> +bias [-> GELU] [+ fp32 residual / pos-embedding]
+//                   -> coalesced bf16 / fp32 global stores.
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -44,35 +53,62 @@ struct GemmShape {
 };
 
 namespace gemm_cfg {
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle span
-constexpr int kThreads = 256;
+constexpr int BM = 128;  // rows per CTA (a pair covers 256)
+constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle span
+constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
-template <int BN>
+constexpr int kEpiWarps = 8;
+constexpr int kSlabStride = 36;                           // floats per slab row: 32 + 4 pad (16-B bank skew)
+constexpr int kSlabBytes = 32 * kSlabStride * 4;          // one warp's 32 x 32 fp32 transpose slab
+template <int BN, int kPair>
 struct Cfg {
   static constexpr int kStageBytesA = BM * BK * 2;
-  static constexpr int kStageBytesB = BN * BK * 2;
+  static constexpr int kStageBytesB = (BN / kPair) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - kEpiWarps * kSlabBytes;
+  static constexpr int kStagesFit = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kSlabBytes + 256;
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 }  // namespace gemm_cfg
 
-// Exact-erf GELU (torch.nn.GELU default, vision_transformer.py:40-47 MLPBlock).
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (torch.nn.GELU default, vision_transformer.py:40-47 MLPBlock): 0.5 x (1 + erf(x / sqrt 2)).
+// erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32 round-off level) evaluated with one
+// MUFU.RCP and one MUFU.EX2 instead of the ~25-instruction libdevice erff: the fc1 epilogue must keep pace with
+// a 6144-cycle MMA main loop per 128x256 tile.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = ptx::rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = ptx::ex2_approx(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-poly, e, 1.0f);           // erf(|x|/sqrt2)
+  const float half_x = 0.5f * x;
+  return fmaf(copysignf(erf_abs, x), half_x, half_x);   // 0.5 x (1 + erf)
+}
 
-template <int BN, bool kGelu, bool kOutF32>
+// kGelu / kOutF32 / kResid / kRemap select the epilogue at compile time (the fc1 epilogue is issue-bound: every
+// instruction that a runtime flag would leave in its inner loop costs ~1% of the kernel).
+template <int BN, int kPair, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
 __global__ void __launch_bounds__(gemm_cfg::kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  GemmShape shape, GemmEpilogue ep) {
   using namespace gemm_cfg;
-  using C = Cfg<BN>;
+  using C = Cfg<BN, kPair>;
   constexpr int kStages = C::kStages;
+  constexpr int kTileM = BM * kPair;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes);
+  // Dynamic smem starts 1024-B aligned (it follows the 1 KB the driver reserves); keeping the array typed lets
+  // the compiler emit LDS/STS (not generic LD/ST) for the epilogue slabs.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  float* slabs = reinterpret_cast<float*>(smem + kStages * C::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes + kEpiWarps * kSlabBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -80,8 +116,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kPair == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / kPair;       // CTA (kPair=1) or CTA-pair index
+  const int num_units = gridDim.x / kPair;
 
-  const int m_tiles = (shape.M + BM - 1) / BM;
+  const int m_tiles = (shape.M + kTileM - 1) / kTileM;
   const int n_tiles = (shape.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (shape.K + BK - 1) / BK;
@@ -97,45 +137,56 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 128);
+      ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps * kPair);  // one elected lane per epilogue warp (of both CTAs)
     }
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+    if (kPair == 2) ptx::tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+    else ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair == 2) ptx::cluster_sync();  // peer barriers initialised before any multicast commit / remote arrive
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (every CTA)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile % n_tiles;
+      const int a_row = m_blk * kTileM + static_cast<int>(cta_rank) * BM;
+      const int w_row = n_blk * BN + static_cast<int>(cta_rank) * (BN / kPair);
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::kStageBytes;
         uint8_t* sb = sa + C::kStageBytesA;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-        ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-        ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, n_blk * BN);
+        if (kPair == 2) {
+          // one barrier (the leader's) tracks the bytes of both CTAs' halves
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+          ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
+          ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
+        } else {
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+          ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
+          ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
+        }
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ UMMA issuer
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ------------------------------------------------------------ UMMA issuer (leader CTA)
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -151,107 +202,124 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // +32 bytes per K=16 step inside the 128-B swizzle span (descriptor address is in 16-B units)
-          ptx::umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (kPair == 2) ptx::umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          else ptx::umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+        // smem slot reusable (in both CTAs) once these MMAs retire
+        if (kPair == 2) ptx::umma_commit_pair(&empty_bar[stage], 0x3);
+        else ptx::umma_commit(&empty_bar[stage]);
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      // accumulator complete -> epilogue warps (of both CTAs)
+      if (kPair == 2) ptx::umma_commit_pair(&tmem_full_bar[acc], 0x3);
+      else ptx::umma_commit(&tmem_full_bar[acc]);
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int col_half = (warp - kEpiWarp0) >> 2;   // which half of the BN accumulator columns
+    constexpr int kChunks = BN / 2 / 32;            // 32-column chunks per warp
+    float* slab = slabs + (warp - kEpiWarp0) * (32 * kSlabStride);
+    const int trow = lane >> 3;                     // transposed mapping: rows trow + 4 i, 4 columns at 4 * tcol
+    const int tcol = lane & 7;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++local) {
       const int m_blk = tile / n_tiles;
       const int n_blk = tile % n_tiles;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int row = m_blk * BM + quarter * 32 + lane;
-      const bool row_ok = row < shape.M;
-      long out_row = row, resid_row = row;
-      if (ep.group_rows > 0) {
-        const int g = row / ep.group_rows;
-        const int i = row - g * ep.group_rows;
-        out_row = static_cast<long>(g) * ep.out_group_stride + ep.out_row_offset + i;
-        resid_row = ep.resid_broadcast ? (ep.resid_row_offset + i) : out_row;
-      }
+      const int row_base = m_blk * kTileM + static_cast<int>(cta_rank) * BM + quarter * 32;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const uint32_t taddr0 =
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_half * (BN / 2);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n_blk * BN + c * 32;
+      for (int c = 0; c < kChunks; ++c) {
         uint32_t r[32];
         ptx::tmem_ld_x32(taddr0 + c * 32, r);
         ptx::tmem_ld_wait();
+        if (c + 1 == kChunks) {
+          // every TMEM read of this accumulator has landed in registers: hand it back to the MMA issuer
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          }
+        }
+        const int col0 = n_blk * BN + col_half * (BN / 2) + c * 32;
         if (col0 >= shape.N) continue;  // warp-uniform
-        float v[32];
+        // registers (thread = row, 32 columns) -> slab
+        float* srow = slab + lane * kSlabStride;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (ep.bias != nullptr) {
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+        const int col = col0 + 4 * tcol;
+        const bool col_ok = col < shape.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias != nullptr && col_ok) bias4 = *reinterpret_cast<const float4*>(ep.bias + col);
+        // transposed pass: 8 rows (trow + 4 i) x 4 columns per thread, in two batches of 4 rows so that the
+        // residual loads of a batch are all in flight before the first dependent store
+        const float* sl = slab + trow * kSlabStride + 4 * tcol;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 8; i0 += 4) {
+          float4 v[4], q[4];
+          long orow[4];
+          bool ok[4];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < shape.N) {
-              const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
-              v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+          for (int i = 0; i < 4; ++i) {
+            const int row = row_base + trow + 4 * (i0 + i);
+            v[i] = *reinterpret_cast<const float4*>(sl + 4 * (i0 + i) * kSlabStride);
+            ok[i] = row < shape.M && col_ok;
+            long out_row = row, resid_row = row;
+            if (kRemap) {
+              const int g = row / ep.group_rows;
+              const int gi = row - g * ep.group_rows;
+              out_row = static_cast<long>(g) * ep.out_group_stride + ep.out_row_offset + gi;
+              resid_row = ep.resid_broadcast ? (ep.resid_row_offset + gi) : out_row;
+            }
+            orow[i] = out_row;
+            if (kResid) {
+              q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok[i]) q[i] = *reinterpret_cast<const float4*>(ep.resid + resid_row * ep.ldr + col);
             }
           }
-        }
-        if (kGelu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (row_ok) {
-          if (ep.resid != nullptr) {
-            const float* rp = ep.resid + resid_row * ep.ldr + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < shape.N) {
-                const float4 b = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+          for (int i = 0; i < 4; ++i) {
+            float4 t = v[i];
+            t.x += bias4.x, t.y += bias4.y, t.z += bias4.z, t.w += bias4.w;
+            if (kGelu) t.x = gelu_erf(t.x), t.y = gelu_erf(t.y), t.z = gelu_erf(t.z), t.w = gelu_erf(t.w);
+            if (kResid) t.x += q[i].x, t.y += q[i].y, t.z += q[i].z, t.w += q[i].w;
+            if (ok[i]) {
+              if (kOutF32) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow[i] * ep.ldo + col) = t;
+              } else {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(t.z, t.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow[i] * ep.ldo + col) = pk;
               }
             }
           }
-          if (kOutF32) {
-            float* op = reinterpret_cast<float*>(ep.out) + out_row * ep.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < shape.N) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + out_row * ep.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < shape.N) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(op + j) = pk;
-              }
-            }
-          }
         }
+        __syncwarp();  // slab is rewritten by the next chunk
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
 
+  __syncwarp();
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair == 2) ptx::cluster_sync();  // the peer may still be signalling this CTA's barriers / reading its smem
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+    if (kPair == 2) ptx::tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+    else ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 

@@ -127,43 +127,51 @@ f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out
 // Attention rollout, class-token row only.  For layer l with head-averaged map Abar_l [N, N]:
 //     Ahat_l = rownorm(0.5 * Abar_l + 0.5 * I),      R = Ahat_L ... Ahat_1,      out = R[0, 1:]
 // Only row 0 of R is needed, so r <- r * Ahat_l is evaluated right-to-left over layers L, L-1, ..., 1:
-// L vector-matrix products of N x N instead of L matrix-matrix products.  One CTA per image.
-// maps: [L][B, N, ld] fp32 (layer stride given in floats).
-__global__ void __launch_bounds__(256)
+// L vector-matrix products of N x N instead of L matrix-matrix products.  With w_k = r_k / rowsum_k:
+//     (r * Ahat)_j = 0.5 * sum_k w_k Abar[k, j] + 0.5 * w_j
+// One CTA (1024 threads) per image: 32 warps take the row sums (coalesced 128-B row reads), then 4 thread
+// groups split the k range of the vector-matrix product (coalesced across j) and are reduced through smem.
+// maps: [L][B, N, ld] fp32 (layer stride given in floats); N <= 256.
+constexpr int kRolloutThreads = 1024;
+__global__ void __launch_bounds__(kRolloutThreads)
 rollout_cls_kernel(const float* __restrict__ maps, long layer_stride, int L, int N, int ld, float* __restrict__ out /*[B, N-1]*/) {
-  extern __shared__ float sm[];
-  float* r = sm;            // [ld] current row vector (scaled by 1/rowsum below)
-  float* rn = sm + ld;      // [ld] next
-  float* rs = sm + 2 * ld;  // [ld] 1 / rowsum of (0.5 A + 0.5 I)
+  __shared__ float r[256];        // current row vector
+  __shared__ float w[256];        // r_k / rowsum_k
+  __shared__ float part[4][256];  // partial products per k group
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = tid & 255, g = tid >> 8;
+  const int kper = (N + 3) / 4;
   for (int l = L - 1; l >= 0; --l) {
     const float* A = maps + l * layer_stride + static_cast<long>(b) * N * ld;
-    // row sums of 0.5 A + 0.5 I
-    for (int k = warp; k < N; k += nwarps) {
+    // w_k = r_k / (0.5 * rowsum_k + 0.5); for the top layer r = e_0
+    for (int k = warp; k < N; k += 32) {
       float s = 0.f;
-      for (int j = lane; j < N; j += 32) s += 0.5f * A[static_cast<long>(k) * ld + j] + (j == k ? 0.5f : 0.f);
+#pragma unroll 8
+      for (int c = lane; c < N; c += 32) s += A[static_cast<long>(k) * ld + c];
       s = warp_sum(s);
-      if (lane == 0) rs[k] = 1.0f / s;
-    }
-    __syncthreads();
-    if (l == L - 1) {
-      for (int j = tid; j < N; j += blockDim.x) rn[j] = (0.5f * A[j] + (j == 0 ? 0.5f : 0.f)) * rs[0];
-    } else {
-      for (int j = tid; j < N; j += blockDim.x) {
-        float acc = 0.f;
-        for (int k = 0; k < N; ++k) {
-          const float a = 0.5f * A[static_cast<long>(k) * ld + j] + (j == k ? 0.5f : 0.f);
-          acc = fmaf(r[k] * rs[k], a, acc);
-        }
-        rn[j] = acc;
+      if (lane == 0) {
+        const float rk = (l == L - 1) ? (k == 0 ? 1.0f : 0.0f) : r[k];
+        w[k] = rk / (0.5f * s + 0.5f);
       }
     }
     __syncthreads();
-    for (int j = tid; j < N; j += blockDim.x) r[j] = rn[j];
+    float acc = 0.f;
+    if (j < N) {
+      if (l == L - 1) {
+        if (g == 0) acc = w[0] * A[j];  // only k = 0 contributes
+      } else {
+        const int k0 = g * kper, k1 = min(N, k0 + kper);
+#pragma unroll 8
+        for (int k = k0; k < k1; ++k) acc = fmaf(w[k], A[static_cast<long>(k) * ld + j], acc);
+      }
+    }
+    part[g][j] = acc;
+    __syncthreads();
+    if (g == 0 && j < N) r[j] = 0.5f * ((part[0][j] + part[1][j]) + (part[2][j] + part[3][j])) + 0.5f * w[j];
     __syncthreads();
   }
-  for (int j = tid + 1; j < N; j += blockDim.x) out[static_cast<long>(b) * (N - 1) + j - 1] = r[j];
+  if (g == 0 && j >= 1 && j < N) out[static_cast<long>(b) * (N - 1) + j - 1] = r[j];
 }
 
 }  // namespace vitb200

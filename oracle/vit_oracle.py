@@ -96,7 +96,7 @@ def build_vit(cfg: OracleConfig, seed: int = 0, init: str = "default") -> Vision
                     ln.weight.copy_(1.0 + 0.1 * torch.randn(d, generator=g))
                     ln.bias.normal_(0.0, 0.05, generator=g)
                 att = blk.self_attention
-                att.in_proj_weight[: 2 * d].mul_(3.0)  # peakier softmax
+                att.in_proj_weight[: 2 * d].mul_(2.0)  # peakier softmax (4x larger attention logits)
                 att.in_proj_bias.normal_(0.0, 0.02, generator=g)
                 att.out_proj.bias.normal_(0.0, 0.02, generator=g)
                 blk.mlp[0].bias.normal_(0.0, 0.02, generator=g)

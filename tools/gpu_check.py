@@ -98,8 +98,9 @@ def gemm_perf():
     import torch
     from interactive_vit_b200 import engine as E
     M = 256 * 197
-    for (N, K, gelu, f32, resid) in ((2304, 768, False, False, False), (768, 768, False, True, True),
-                                     (3072, 768, True, False, False), (768, 3072, False, True, True)):
+    for (M, N, K, gelu, f32, resid) in ((M, 2304, 768, False, False, False), (M, 768, 768, False, True, True),
+                                        (M, 3072, 768, True, False, False), (M, 768, 3072, False, True, True),
+                                        (74 * 256, 256, 16384, False, False, False), (74 * 256 * 4, 512, 4096, False, False, False)):
         a = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
         w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
         bs = torch.randn(N, device="cuda")
