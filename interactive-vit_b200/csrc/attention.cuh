@@ -108,10 +108,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     ptx::mbar_init(&empty_bar[0], 1);
     ptx::mbar_init(&empty_bar[1], 1);
     ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(s_free, kSoftmaxThreads);
-    ptx::mbar_init(p_full, kSoftmaxThreads);
+    // one arrival per softmax WARP (lane 0 after __syncwarp): 256 lanes arriving on one smem word serialise
+    ptx::mbar_init(s_free, kSoftmaxThreads / 32);
+    ptx::mbar_init(p_full, kSoftmaxThreads / 32);
     ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(o_free, kSoftmaxThreads);
+    ptx::mbar_init(o_free, kSoftmaxThreads / 32);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
@@ -122,7 +123,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 
   const int row0 = b * p.N;  // first token row of this image in the [B*N, 3d] activation
 
-  if (warp == 0 && lane == 0) {
+  // Producer and MMA loops run on whole warps with one elected lane issuing, so that addresses and descriptors
+  // stay in uniform registers (a single-lane loop pays an R2UR chain in front of every UTMALDG / UTCHMMA).
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     for (int h = 0; h < p.H; ++h) {
       const int st = h & 1;
@@ -131,14 +134,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       uint8_t* sq = smem + st * kStageBytes;
       uint8_t* sk = sq + kQBytes;
       uint8_t* sv = sk + kKVBytes;
-      ptx::mbar_arrive_expect_tx(&full_bar[st], stage_tx);
-      ptx::tma_load_2d(sq, &tmap_q, &full_bar[st], h * D, row0 + qt * BM);
-      ptx::tma_load_2d(sk, &tmap_kv, &full_bar[st], p.d + h * D, row0);
-      ptx::tma_load_2d(sk + half_rows * 128, &tmap_kv, &full_bar[st], p.d + h * D, row0 + half_rows);
-      ptx::tma_load_2d(sv, &tmap_kv, &full_bar[st], 2 * p.d + h * D, row0);
-      ptx::tma_load_2d(sv + half_rows * 128, &tmap_kv, &full_bar[st], 2 * p.d + h * D, row0 + half_rows);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&full_bar[st], stage_tx);
+        ptx::tma_load_2d(sq, &tmap_q, &full_bar[st], h * D, row0 + qt * BM);
+        ptx::tma_load_2d(sk, &tmap_kv, &full_bar[st], p.d + h * D, row0);
+        ptx::tma_load_2d(sk + half_rows * 128, &tmap_kv, &full_bar[st], p.d + h * D, row0 + half_rows);
+        ptx::tma_load_2d(sv, &tmap_kv, &full_bar[st], 2 * p.d + h * D, row0);
+        ptx::tma_load_2d(sv + half_rows * 128, &tmap_kv, &full_bar[st], 2 * p.d + h * D, row0 + half_rows);
+      }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
     const uint32_t idesc_qk = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(KP), 0, 0);
     const uint32_t idesc_pv = ptx::make_idesc_bf16(BM, D, 0, 1);  // B (= V) is MN-major
@@ -152,10 +158,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       const uint32_t sq = ptx::smem_u32(smem + st * kStageBytes);
       const uint64_t dq = ptx::make_smem_desc_sw128(sq, 16, 1024);
       const uint64_t dk = ptx::make_smem_desc_sw128(sq + kQBytes, 16, 1024);
+      if (ptx::elect_one()) {
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        ptx::umma_bf16_ss(tmem_base + kTmemS, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-      ptx::umma_commit(s_full);
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16_ss(tmem_base + kTmemS, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        ptx::umma_commit(s_full);
+      }
+      __syncwarp();
     };
     issue_qk(0);
     for (int h = 0; h < p.H; ++h) {
@@ -165,15 +174,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       if (h > 0) ptx::mbar_wait(o_free, (h - 1) & 1);
       ptx::tc_fence_after();
       const uint32_t sv = ptx::smem_u32(smem + st * kStageBytes) + kQBytes + kKVBytes;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        // A: P K-block (ks / 4), +32 B per 16 keys inside the swizzle span.  B: V rows [16 ks, 16 ks + 16),
-        // MN-major: 8-key groups 1024 B apart (SBO); the single 64-wide MN group makes LBO irrelevant.
-        const uint64_t dp = ptx::make_smem_desc_sw128(sp + (ks >> 2) * kPBlockBytes, 16, 1024) + 2 * (ks & 3);
-        const uint64_t dv = ptx::make_smem_desc_sw128(sv + ks * 2048, 1024, 1024);
-        ptx::umma_bf16_ss(tmem_base + kTmemO, dp, dv, idesc_pv, ks != 0 ? 1u : 0u);
+      // A: P K-block (ks / 4), +32 B per 16 keys inside the swizzle span.  B: V rows [16 ks, 16 ks + 16),
+      // MN-major: 8-key groups 1024 B apart (SBO); the single 64-wide MN group makes LBO irrelevant.
+      // Descriptor start addresses are in 16-B units: +2 per 16 keys of P inside a K-block, +1024 (= 16 KB) to the
+      // next K-block, +128 (= 2 KB) per 16 keys of V.
+      const uint64_t dp0 = ptx::make_smem_desc_sw128(sp, 16, 1024);
+      const uint64_t dv0 = ptx::make_smem_desc_sw128(sv, 1024, 1024);
+      if (ptx::elect_one()) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t dp = dp0 + static_cast<uint64_t>((ks >> 2) * (kPBlockBytes >> 4) + 2 * (ks & 3));
+          const uint64_t dv = dv0 + static_cast<uint64_t>(ks * (2048 >> 4));
+          ptx::umma_bf16_ss(tmem_base + kTmemO, dp, dv, idesc_pv, ks != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[st]);
+        ptx::umma_commit(o_full);
       }
-      ptx::umma_commit(&empty_bar[st]);
-      ptx::umma_commit(o_full);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax / epilogue
@@ -213,7 +229,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         if (c < nmy) ptx::tmem_ld_x16(t_s + c * t_step, s[c]);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(s_free);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(s_free);
       if (half && tail_valid < 16) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -268,7 +285,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         }
       }
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
 
       // ---- row sum exchange
       float sum = (ps0 + ps1) + (ps2 + ps3);
@@ -349,7 +367,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         ptx::tmem_ld_x32(lane_base + kTmemO + half * 32, o);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(o_free);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(o_free);
         if (row_ok) {
           __nv_bfloat16* op = p.ctx + (static_cast<size_t>(row0) + qrow) * p.d + h * D + half * 32;
 #pragma unroll

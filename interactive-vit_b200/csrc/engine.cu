@@ -751,6 +751,15 @@ int vitb200_get_head_map(vitb200_engine* e, int layer, float* map_host, int batc
   return VITB200_OK;
 }
 
+#ifdef VITB200_ATTN_TRACE
+// tracing build only (tools/attn_trace.py): copies the clock64() stamps of CTA 0 to the host
+int vitb200_debug_attn_trace(long long* host, int count) {
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(long long) * count));
+  return VITB200_OK;
+}
+#endif
+
 // ---- single-kernel entry points (parity tests) -----------------------------------------------------
 int vitb200_op_gemm(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N, int K,
                     int gelu, int out_f32, void* stream) {

@@ -151,7 +151,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // The producer and MMA loops are executed by WHOLE warps with one elected lane issuing: loop counters, smem
+  // addresses and descriptors then stay warp-uniform (uniform registers), instead of being moved from vector to
+  // uniform registers (R2UR) in front of every UTMALDG / UTCHMMA, which throttles a single-thread issue loop.
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA)
     int stage = 0;
     uint32_t phase = 0;
@@ -164,23 +167,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::kStageBytes;
         uint8_t* sb = sa + C::kStageBytesA;
-        if (kPair == 2) {
-          // one barrier (the leader's) tracks the bytes of both CTAs' halves
-          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-          ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
-          ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
-        } else {
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
-          ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
+        if (ptx::elect_one()) {
+          if (kPair == 2) {
+            // one barrier (the leader's) tracks the bytes of both CTAs' halves
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
+            ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
+            ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
+          }
         }
+        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
+  } else if (warp == 1 && leader) {
     // ------------------------------------------------------------ UMMA issuer (leader CTA)
     constexpr uint32_t idesc = ptx::make_idesc_bf16(kTileM, BN, 0, 0);
     int stage = 0;
@@ -199,23 +205,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t sb = sa + C::kStageBytesA;
         const uint64_t da = ptx::make_smem_desc_sw128(sa, 16, 1024);
         const uint64_t db = ptx::make_smem_desc_sw128(sb, 16, 1024);
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // +32 bytes per K=16 step inside the 128-B swizzle span (descriptor address is in 16-B units)
-          if (kPair == 2) ptx::umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          else ptx::umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-B swizzle span (descriptor address is in 16-B units)
+            if (kPair == 2) ptx::umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else ptx::umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          // smem slot reusable (in both CTAs) once these MMAs retire
+          if (kPair == 2) ptx::umma_commit_pair(&empty_bar[stage], 0x3);
+          else ptx::umma_commit(&empty_bar[stage]);
         }
-        // smem slot reusable (in both CTAs) once these MMAs retire
-        if (kPair == 2) ptx::umma_commit_pair(&empty_bar[stage], 0x3);
-        else ptx::umma_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
       // accumulator complete -> epilogue warps (of both CTAs)
-      if (kPair == 2) ptx::umma_commit_pair(&tmem_full_bar[acc], 0x3);
-      else ptx::umma_commit(&tmem_full_bar[acc]);
+      if (ptx::elect_one()) {
+        if (kPair == 2) ptx::umma_commit_pair(&tmem_full_bar[acc], 0x3);
+        else ptx::umma_commit(&tmem_full_bar[acc]);
+      }
+      __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue

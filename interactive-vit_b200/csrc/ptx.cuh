@@ -158,6 +158,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // ---------------------------------------------------------------- tcgen05: TMEM <-> registers
 // 32x32b shape: the warp reads its own 32-lane quarter (lanes 32*(warp%4)..+31); thread t gets lane
 // base+t, N consecutive 32-bit columns starting at the column in `taddr`.
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "

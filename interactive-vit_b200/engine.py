@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvitb200.so")
+LIB_PATH = os.environ.get("VITB200_LIB", os.path.join(_HERE, "libvitb200.so"))  # override: tracing builds (tools/)
 
 EMIT_AVG = 1
 EMIT_CLS = 2
