@@ -110,7 +110,7 @@ static int device_sms() {
 template <int BN, int kPair, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
                          cudaStream_t st) {
-  using C = gemm_cfg::Cfg<BN, kPair>;
+  using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu)>;
   auto kern = gemm_bf16_kernel<BN, kPair, kGelu, kOutF32, kResid, kRemap>;
   static bool configured = false;
   if (!configured) {
@@ -125,7 +125,7 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape
   const int grid = (tiles < units ? tiles : units) * kPair;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(gemm_cfg::kThreads);
+  cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

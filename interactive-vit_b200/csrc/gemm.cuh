@@ -13,14 +13,14 @@
 // FLOP is 2/3 of the single-CTA kernel's (the 128 x 256 single-CTA tile is L2-bandwidth bound at ~900 TF/s).
 // kPair = 1: one CTA computes 128 x BN on its own (kept as the A/B baseline).
 //
-// Roles (384 threads, 1 CTA / SM, persistent over output tiles):
+// Roles (4 + 8 warps, or 4 + 16 for the GELU epilogue; 1 CTA / SM, persistent over output tiles):
 //   warp 0 lane 0 : TMA producer  (A tile 128x64, W tile (BN/kPair)x64, SWIZZLE_128B, mbarrier ring; in a pair both
 //                   CTAs' loads complete_tx on the LEADER's full barrier)
 //   warp 1 lane 0 : UMMA issuer (leader CTA only in a pair): 4 x tcgen05.mma (K = 16) per stage, commit ->
 //                   empty barrier of both CTAs; accumulator-complete commit -> both CTAs' epilogues
 //   warp 2        : TMEM allocator (2 accumulator buffers of BN fp32 columns: MMA of tile i+1 overlaps the
 //                   epilogue of tile i)
-//   warps 4..11   : epilogue, 2 warps per TMEM lane quarter (each owns half of the BN columns).  Per 32-column
+//   warps 4..     : epilogue, 2 (4 with GELU) warps per TMEM lane quarter, each owning a slice of the BN columns.  Per 32-column
 //                   chunk: tcgen05.ld -> warp-private smem slab -> re-read transposed so that a warp store
 //                   covers 4 rows x 128 contiguous bytes -> +bias [-> GELU] [+ fp32 residual / pos-embedding]
 //                   -> coalesced bf16 / fp32 global stores.
@@ -55,13 +55,15 @@ struct GemmShape {
 namespace gemm_cfg {
 constexpr int BM = 128;  // rows per CTA (a pair covers 256)
 constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle span
-constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 8;
+// Epilogue warps: 2 per TMEM lane quarter normally; the GELU epilogue is issue/latency bound (about 24 instructions
+// per output element against a 6144-cycle main loop per tile), so it gets 4 per quarter = 4 per SM sub-partition.
+__host__ __device__ constexpr int epi_warps(bool gelu) { return gelu ? 16 : 8; }
 constexpr int kSlabStride = 36;                           // floats per slab row: 32 + 4 pad (16-B bank skew)
 constexpr int kSlabBytes = 32 * kSlabStride * 4;          // one warp's 32 x 32 fp32 transpose slab
-template <int BN, int kPair>
+template <int BN, int kPair, int kEpiWarps>
 struct Cfg {
+  static constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = (BN / kPair) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
@@ -95,11 +97,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // kGelu / kOutF32 / kResid / kRemap select the epilogue at compile time (the fc1 epilogue is issue-bound: every
 // instruction that a runtime flag would leave in its inner loop costs ~1% of the kernel).
 template <int BN, int kPair, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
-__global__ void __launch_bounds__(gemm_cfg::kThreads, 1)
+__global__ void __launch_bounds__((gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu)>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  GemmShape shape, GemmEpilogue ep) {
   using namespace gemm_cfg;
-  using C = Cfg<BN, kPair>;
+  constexpr int kEpiWarps = epi_warps(kGelu);
+  constexpr int kColGroups = kEpiWarps / 4;  // warps per TMEM lane quarter; each owns BN / kColGroups columns
+  using C = Cfg<BN, kPair, kEpiWarps>;
   constexpr int kStages = C::kStages;
   constexpr int kTileM = BM * kPair;
 
@@ -232,8 +236,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
-    const int col_half = (warp - kEpiWarp0) >> 2;   // which half of the BN accumulator columns
-    constexpr int kChunks = BN / 2 / 32;            // 32-column chunks per warp
+    const int col_grp = (warp - kEpiWarp0) >> 2;    // which group of the BN accumulator columns
+    constexpr int kGroupCols = BN / kColGroups;
+    constexpr int kChunks = kGroupCols / 32;        // 32-column chunks per warp
+    static_assert(kChunks >= 1, "column group narrower than one 32-column chunk");
     float* slab = slabs + (warp - kEpiWarp0) * (32 * kSlabStride);
     const int trow = lane >> 3;                     // transposed mapping: rows trow + 4 i, 4 columns at 4 * tcol
     const int tcol = lane & 7;
@@ -247,7 +253,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr0 =
-          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_half * (BN / 2);
+          tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_grp * kGroupCols;
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         uint32_t r[32];
@@ -262,7 +268,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             else ptx::mbar_arrive(&tmem_empty_bar[acc]);
           }
         }
-        const int col0 = n_blk * BN + col_half * (BN / 2) + c * 32;
+        const int col0 = n_blk * BN + col_grp * kGroupCols + c * 32;
         if (col0 >= shape.N) continue;  // warp-uniform
         // registers (thread = row, 32 columns) -> slab
         float* srow = slab + lane * kSlabStride;
@@ -273,16 +279,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool col_ok = col < shape.N;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias != nullptr && col_ok) bias4 = *reinterpret_cast<const float4*>(ep.bias + col);
-        // transposed pass: 8 rows (trow + 4 i) x 4 columns per thread, in two batches of 4 rows so that the
-        // residual loads of a batch are all in flight before the first dependent store
+        // transposed pass: 8 rows (trow + 4 i) x 4 columns per thread.  With a residual all 8 rows form one batch so
+        // that 8 independent 16-byte loads per thread are in flight (the out_proj / fc2 epilogues are bound by
+        // HBM latency x outstanding bytes); otherwise two batches of 4 keep the instruction footprint small.
+        constexpr int kRowBatch = kResid ? 8 : 4;
         const float* sl = slab + trow * kSlabStride + 4 * tcol;
 #pragma unroll 1
-        for (int i0 = 0; i0 < 8; i0 += 4) {
-          float4 v[4], q[4];
-          long orow[4];
-          bool ok[4];
+        for (int i0 = 0; i0 < 8; i0 += kRowBatch) {
+          float4 v[kRowBatch], q[kRowBatch];
+          long orow[kRowBatch];
+          bool ok[kRowBatch];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < kRowBatch; ++i) {
             const int row = row_base + trow + 4 * (i0 + i);
             v[i] = *reinterpret_cast<const float4*>(sl + 4 * (i0 + i) * kSlabStride);
             ok[i] = row < shape.M && col_ok;
@@ -300,7 +308,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < kRowBatch; ++i) {
             float4 t = v[i];
             t.x += bias4.x, t.y += bias4.y, t.z += bias4.z, t.w += bias4.w;
             if (kGelu) t.x = gelu_erf(t.x), t.y = gelu_erf(t.y), t.z = gelu_erf(t.z), t.w = gelu_erf(t.w);
