@@ -44,6 +44,15 @@ struct AttnParams {
   int q_tiles;          // 128-row query tiles per image: ceil(N / 128) (1 or 2)
 };
 
+// Optional phase tracing (built only with -DVITB200_ATTN_TRACE into a separate library, tools/attn_trace.py):
+// CTA 0's softmax warp 4 / lane 0 and the MMA warp write clock64() stamps per head to a global buffer.
+#ifdef VITB200_ATTN_TRACE
+__device__ long long g_attn_trace[64 * 32];
+#define ATTN_TS(slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 1)) g_attn_trace[(h) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define ATTN_TS(slot) do { } while (0)
+#endif
+
 namespace attn_cfg {
 constexpr int kThreads = 384;
 constexpr int kSoftmaxThreads = 256;
@@ -170,8 +179,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     for (int h = 0; h < p.H; ++h) {
       if (h + 1 < p.H) issue_qk(h + 1);
       const int st = h & 1;
+      ATTN_TS(16);
       ptx::mbar_wait(p_full, h & 1);
+      ATTN_TS(17);
       if (h > 0) ptx::mbar_wait(o_free, (h - 1) & 1);
+      ATTN_TS(18);
       ptx::tc_fence_after();
       const uint32_t sv = ptx::smem_u32(smem + st * kStageBytes) + kQBytes + kKVBytes;
       // A: P K-block (ks / 4), +32 B per 16 keys inside the swizzle span.  B: V rows [16 ks, 16 ks + 16),
@@ -190,6 +202,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         ptx::umma_commit(o_full);
       }
       __syncwarp();
+      ATTN_TS(19);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ softmax / epilogue
@@ -222,12 +235,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     for (int h = 0; h < p.H; ++h) {
       // ---- S half-row -> registers (single TMEM read), then release the S columns
       uint32_t s[kMaxChunks][16];
+      ATTN_TS(0);
       ptx::mbar_wait(s_full, h & 1);
+      ATTN_TS(1);
       ptx::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < kMaxChunks; ++c)
         if (c < nmy) ptx::tmem_ld_x16(t_s + c * t_step, s[c]);
       ptx::tmem_ld_wait();
+      ATTN_TS(2);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(s_free);
@@ -247,7 +263,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         }
       }
       red_max[half * BM + r] = mx;
+      ATTN_TS(3);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      ATTN_TS(4);
       mx = fmaxf(mx, red_max[(half ^ 1) * BM + r]);
       const float mxs = mx * p.scale_log2;
 
@@ -284,14 +302,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
                        : "memory");
         }
       }
+      ATTN_TS(5);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
+      ATTN_TS(6);
 
       // ---- row sum exchange
       float sum = (ps0 + ps1) + (ps2 + ps3);
       red_sum[half * BM + r] = sum;
       asm volatile("bar.sync 2, 256;" ::: "memory");
+      ATTN_TS(7);
       sum += red_sum[(half ^ 1) * BM + r];
       const float inv = ptx::rcp_approx(sum);
 
@@ -360,12 +381,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       }
 
       // ---- O epilogue: context rows = (P_unnormalised V) / sum; this half owns 32 of the 64 columns
+      ATTN_TS(8);
       ptx::mbar_wait(o_full, h & 1);
+      ATTN_TS(9);
       ptx::tc_fence_after();
       {
         uint32_t o[32];
         ptx::tmem_ld_x32(lane_base + kTmemO + half * 32, o);
         ptx::tmem_ld_wait();
+        ATTN_TS(10);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(o_free);

@@ -234,3 +234,51 @@ def test_mirror_and_reference_codecs_interoperate():
     ctx.register(Cos("cos"))
     ctx.compute(mine.graph)
     assert M.Response(mine.graph).encode() == ref_bytes
+
+
+def test_vit_plugin_catalogue_without_gpu():
+    """io()/contents()/graph-json of the B200 plugin class do not need the device: build the class around a stub
+    engine and compare the catalogue with the oracle plugin (the contract the UI sees)."""
+    from interactive_vit_b200 import engine as E, vit_plugin as P
+
+    class StubEngine:
+        def load_state_dict(self, sd):
+            self.keys = sorted(sd)
+
+    ocfg = O.ORACLE_CONFIGS["vit_tiny_test"]
+    cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                      ocfg.num_classes)
+    plug = P.VitB200Model("vit_tiny_test", cfg, O.build_vit(ocfg), engine=StubEngine())
+    oracle = oracle_plugin.make_oracle_model_class(C.Model, G.Pinout)("vit_tiny_test", ocfg, O.build_vit(ocfg))
+    assert plug.list_node_names() == oracle.list_node_names()
+    for n in plug.list_node_names():
+        assert plug.io(n) == oracle.io(n)
+        assert n in plug.contents(n)
+        assert "/" not in n                                  # node names are URL path segments (main/urls.py:12-13)
+    assert plug.io("vit_tiny_test:layer.0", {"heads": "1"})["outs"] == ["o", "attn", "cls", "heads"]
+    with pytest.raises(KeyError):
+        plug.io("vit_tiny_test:layer.7")
+    assert "encoder.layers.encoder_layer_1.mlp.3.bias" in plug.engine.keys and len(plug.engine.keys) == 4 + 12 * 2 + 4
+    g = plug.generate_graph_json()
+    L = ocfg.num_layers
+    assert [n["instance"].get("endpoint") for n in g["nodes"][:-1]] == plug.list_node_names()
+    assert g["nodes"][-1]["instance"]["kind"] == "category" and len(g["nodes"][-1]["instance"]["cats"]) == ocfg.num_classes
+    chain = [(e["in_port"]["node"], e["in_port"]["channel"], e["out_port"]["node"], e["out_port"]["channel"]) for e in g["edges"]]
+    assert (0, "o", 1, "o") in chain and (L, "o", L + 1, "o") in chain and (L + 1, "o", L + 3, "o") in chain
+    assert all((1 + i, "attn", L + 2, f"a{i}") in chain for i in range(L))
+    # every output channel has at most one server-side consumer (Graph.connect keeps one edge per channel)
+    outs = [(a, ch) for (a, ch, _, _) in chain]
+    assert len(outs) == len(set(outs))
+    # register(): graph json written once, nodes registered under their names, params reach compute()
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "static", "graphs"))
+        C.set_base_dir(d)
+        try:
+            ctx = C.Context()
+            plug.register(ctx)
+            assert sorted(ctx.nodes) == sorted(plug.list_node_names())
+            assert json.load(open(os.path.join(d, "static", "graphs", "vit_tiny_test.json"))) == g
+            assert ctx.get_node("vit_tiny_test:layer.1").io({"heads": "1"})["outs"][-1] == "heads"
+        finally:
+            C.set_base_dir(None)

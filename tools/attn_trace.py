@@ -19,12 +19,12 @@ for maps in ((True, True), (False, False)):
     lib.vitb200_debug_attn_trace.argtypes = [C.c_void_p, C.c_int]
     assert lib.vitb200_debug_attn_trace(buf, 64 * 32) == 0
     t = [[buf[h * 32 + k] for k in range(32)] for h in range(H)]
-    names = {0: "loop top", 1: "S ld done", 2: "max done", 3: "bar1 passed", 4: "exp done", 5: "bar2 passed", 9: "O(h-1) done",
-             6: "P stored", 7: "maps done", 8: "S(h+1) issued"}
+    names = {1: "s_full passed", 2: "S ld done", 3: "max done", 4: "bar1 passed", 5: "exp+P stored", 6: "p_full arrived",
+             7: "bar2 passed", 8: "Pbar+maps done", 9: "o_full passed", 10: "O ld done"}
     print(f"maps={maps}: softmax warp 4 lane 0, cycles since loop top of the head (mean over heads 2..{H - 2})")
-    for k in (1, 2, 3, 4, 5, 9, 6, 7, 8):
+    for k in range(1, 11):
         d = [t[h][k] - t[h][0] for h in range(2, H - 1)]
-        print(f"   {names[k]:14s} {sum(d) / len(d):8.0f}")
+        print(f"   {names[k]:16s} {sum(d) / len(d):8.0f}")
     per_head = [t[h + 1][0] - t[h][0] for h in range(2, H - 2)]
     print(f"   head period    {sum(per_head) / len(per_head):8.0f}")
     print("  MMA thread: p_full wait %.0f, o_free wait %.0f, issue PV(+avg) %.0f, period %.0f" % (
