@@ -89,6 +89,12 @@ int vitb200_forward_host(vitb200_engine* e, const float* images_host, int batch,
                          const vitb200_host_outputs* out);
 int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, void* stream);
 
+/* Measurement aid: one forward on the engine's own stream with a CUDA event in front of every kernel launch.
+ * `report` receives text lines "kernel,launches,total_ms" (event-to-event times, so each kernel's figure
+ * includes the gap to the next launch) and a final "total,<kinds>,<ms>" line.  Synchronous. */
+int vitb200_profile_forward(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, char* report,
+                            size_t report_cap);
+
 /* Device-resident results of the last forward/stage call.  which: one of the VITB200_EMIT_* flags, or 0 for
  * logits.  Returns the base pointer and the row pitch (in floats) of the innermost matrix: attention maps
  * are stored with their rows padded to `pitch` >= N floats. */

@@ -31,6 +31,11 @@
 
 namespace vitb200 {
 
+__device__ __forceinline__ uint32_t pack_bf16x2_u(uint32_t a_f32_bits, uint32_t b_f32_bits) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(a_f32_bits), __uint_as_float(b_f32_bits));
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
 struct AttnParams {
   int B, N, H;          // images, tokens per image, heads
   int d;                // model width = H * D
@@ -54,12 +59,16 @@ __device__ long long g_attn_trace[64 * 32];
 #endif
 
 namespace attn_cfg {
-constexpr int kThreads = 384;
-constexpr int kSoftmaxThreads = 256;
+constexpr int kCtrlWarps = 4;                      // TMA, MMA, TMEM allocator, spare
+constexpr int kColGroups = 4;                      // softmax threads per query row
+constexpr int kSoftmaxWarps = 4 * kColGroups;      // one warp per (TMEM lane quarter, column group)
+constexpr int kSoftmaxThreads = 32 * kSoftmaxWarps;
+constexpr int kThreads = 32 * kCtrlWarps + kSoftmaxThreads;  // 640
 constexpr int BM = 128;
 constexpr int D = 64;
 constexpr int KP_MAX = 208;  // TMEM plan: O [0,64) | S [64,64+KP) | Pbar [288,288+KP)  -> KP <= 208
-constexpr int kMaxChunks = 7;                      // 16-column chunks per softmax thread: ceil(13 / 2)
+constexpr int kMaxGran = 7;                        // 8-key granules per softmax thread: ceil(26 / 4)
+constexpr int kMaxKSteps = KP_MAX / 16;            // 13
 constexpr int kTmemO = 0;
 constexpr int kTmemS = 64;
 constexpr int kTmemAvg = 288;
@@ -69,17 +78,21 @@ constexpr int kStageBytes = kQBytes + 2 * kKVBytes;
 constexpr int kPBlockBytes = BM * 128;             // one 64-key K-block of P: 128 rows x 128 B
 constexpr int kPBlocks = (KP_MAX + 63) / 64;       // 4
 constexpr int kPBytes = kPBlocks * kPBlockBytes;   // 64 KB
-constexpr int kRedBytes = 2 * 2 * BM * 4;          // row max / row sum exchange: [2 kinds][2 halves][128 rows]
-constexpr int kClsStageBytes = 256 * 4;            // normalised probabilities of query row 0
-constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kRedBytes + kClsStageBytes + 256;
+constexpr int kIdentBytes = 16 * 128;              // 16 x 16 bf16 identity in 128-B rows (B operand of the head-average MMAs)
+constexpr int kCtxStageBytes = BM * D * 2;         // 16 KB: bf16 context tile of one head, staged for the TMA store
+constexpr int kRedBytes = 2 * kColGroups * BM * 4; // row max / row sum exchange: [2 kinds][4 groups][128 rows]
+constexpr int kClsStageBytes = 256 * 4;            // normalised probabilities of query row 0 (one head)
+constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kCtxStageBytes + kIdentBytes + kRedBytes + kClsStageBytes + 256;
+static_assert(kSmemBytes <= 227 * 1024, "attention: shared memory budget");
 }  // namespace attn_cfg
 
 // kHeads: also write the full per-head probabilities (opt-in; a separate instantiation keeps that code out of
-// the instruction stream of the common variant, which has to stay inside the 32 KB instruction cache).
+// the instruction stream of the common variant).
 template <bool kHeads>
 __global__ void __launch_bounds__(attn_cfg::kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 over qkv [B*N, 3d]
                  const __grid_constant__ CUtensorMap tmap_kv,  // box 64 x (KP/2) over the same tensor
+                 const __grid_constant__ CUtensorMap tmap_ctx, // box 64 x 32 x 1 over ctx viewed as [B][N][d]: rows >= N clip
                  AttnParams p) {
   using namespace attn_cfg;
   // Dynamic smem starts 1024-B aligned (it follows the 1 KB the driver reserves); keeping the array typed lets
@@ -87,17 +100,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* smem_p = smem + 2 * kStageBytes;
-  float* red = reinterpret_cast<float*>(smem_p + kPBytes);  // [kind][half][row]
-  float* cls_stage = red + 2 * 2 * BM;                       // [256] normalised probabilities of query row 0
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + kPBytes + kRedBytes + kClsStageBytes);
+  uint8_t* smem_ctx = smem_p + kPBytes;      // 4 quarter tiles of 32 rows x 128 B, 128-B swizzle
+  uint8_t* smem_id = smem_ctx + kCtxStageBytes;
+  float* red = reinterpret_cast<float*>(smem_id + kIdentBytes);  // [kind][group][row]
+  float* cls_stage = red + 2 * kColGroups * BM;                   // [256] normalised probabilities of query row 0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_id + kIdentBytes + kRedBytes + kClsStageBytes);
   uint64_t* full_bar = bars;        // [2] Q/K/V of a head landed
   uint64_t* empty_bar = bars + 2;   // [2] Q/K/V stage consumed by the MMAs
   uint64_t* s_full = bars + 4;      // S = QK^T complete
-  uint64_t* s_free = bars + 5;      // S copied to registers by all softmax threads (256 arrivals)
-  uint64_t* p_full = bars + 6;      // bf16 P tile written to smem (256 arrivals)
-  uint64_t* o_full = bars + 7;      // O = PV complete
-  uint64_t* o_free = bars + 8;      // O columns read by all softmax threads (256 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* s_free = bars + 5;      // S copied to registers by all softmax warps
+  uint64_t* p_full = bars + 6;      // bf16 P tile written to smem by all softmax warps
+  uint64_t* o_full = bars + 7;      // O = PV complete (also releases the Q/K/V stage)
+  uint64_t* o_free = bars + 8;      // O columns read by all softmax warps
+  uint64_t* p_free = bars + 9;      // Pbar += P complete as well: the P tile may be overwritten
+  uint64_t* cls_full = bars + 10;   // row 0 of the normalised probabilities staged in smem (4 column-group warps)
+  uint64_t* cls_free = bars + 11;   // ... and copied out by warp 3
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,10 +124,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   const int KP = p.KP;
   const int half_rows = KP >> 1;
   const uint32_t stage_tx = kQBytes + 2 * static_cast<uint32_t>(KP) * D * 2;
+  const bool want_avg = p.avg_map != nullptr;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_q);
     ptx::prefetch_tmap(&tmap_kv);
+    ptx::prefetch_tmap(&tmap_ctx);
   }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(&full_bar[0], 1);
@@ -117,14 +137,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     ptx::mbar_init(&empty_bar[0], 1);
     ptx::mbar_init(&empty_bar[1], 1);
     ptx::mbar_init(s_full, 1);
-    // one arrival per softmax WARP (lane 0 after __syncwarp): 256 lanes arriving on one smem word serialise
-    ptx::mbar_init(s_free, kSoftmaxThreads / 32);
-    ptx::mbar_init(p_full, kSoftmaxThreads / 32);
+    // one arrival per softmax WARP (lane 0 after __syncwarp): 512 lanes arriving on one smem word serialise
+    ptx::mbar_init(s_free, kSoftmaxWarps);
+    ptx::mbar_init(p_full, kSoftmaxWarps);
     ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(o_free, kSoftmaxThreads / 32);
+    ptx::mbar_init(o_free, kSoftmaxWarps);
+    ptx::mbar_init(p_free, 1);
+    ptx::mbar_init(cls_full, kColGroups);
+    ptx::mbar_init(cls_free, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
+  if (warp == 3) {
+    // 16 x 16 bf16 identity, K-major rows of 128 B in the 128-B swizzle: element (n, k) lives in 16-B chunk
+    // (k / 8) ^ (n % 8) of row n.  Pbar[:, 16 ks + n] += sum_k P[:, 16 ks + k] * I[n, k] accumulates the normalised
+    // probabilities over the heads on the tensor pipe (fp32 in TMEM) instead of a TMEM load/add/store pass per head
+    // in the softmax threads.
+    uint4* id = reinterpret_cast<uint4*>(smem_id);
+    for (int i = lane; i < kIdentBytes / 16; i += 32) {
+      const int n = i >> 3, c = (i & 7) ^ (n & 7);  // this physical chunk holds k in [8 c, 8 c + 8)
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if ((n >> 3) == c) {
+        const uint32_t one = 0x3F80u << (16 * (n & 1));  // bf16 1.0 at position n % 8 of the chunk
+        const int w = (n & 7) >> 1;
+        v.x = w == 0 ? one : 0u, v.y = w == 1 ? one : 0u, v.z = w == 2 ? one : 0u, v.w = w == 3 ? one : 0u;
+      }
+      id[i] = v;
+    }
+    ptx::fence_proxy_async_smem();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -159,6 +200,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     const uint32_t idesc_pv = ptx::make_idesc_bf16(BM, D, 0, 1);  // B (= V) is MN-major
     const uint32_t sp = ptx::smem_u32(smem_p);
     const int ksteps = KP >> 4;
+    const uint32_t idesc_avg = ptx::make_idesc_bf16(BM, 16, 0, 0);
+    // A: P K-block (ks / 4), +32 B per 16 keys inside the swizzle span (descriptor addresses are in 16-B units:
+    // +2 per 16 keys, +1024 = 16 KB to the next K-block).
+    const uint64_t dp0 = ptx::make_smem_desc_sw128(sp, 16, 1024);
+    const uint64_t did = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_id), 16, 1024);
     auto issue_qk = [&](int h) {
       const int st = h & 1;
       ptx::mbar_wait(&full_bar[st], (h >> 1) & 1);
@@ -186,97 +232,151 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       ATTN_TS(18);
       ptx::tc_fence_after();
       const uint32_t sv = ptx::smem_u32(smem + st * kStageBytes) + kQBytes + kKVBytes;
-      // A: P K-block (ks / 4), +32 B per 16 keys inside the swizzle span.  B: V rows [16 ks, 16 ks + 16),
-      // MN-major: 8-key groups 1024 B apart (SBO); the single 64-wide MN group makes LBO irrelevant.
-      // Descriptor start addresses are in 16-B units: +2 per 16 keys of P inside a K-block, +1024 (= 16 KB) to the
-      // next K-block, +128 (= 2 KB) per 16 keys of V.
-      const uint64_t dp0 = ptx::make_smem_desc_sw128(sp, 16, 1024);
+      // B = V rows [16 ks, 16 ks + 16), MN-major: 8-key groups 1024 B apart (SBO); the single 64-wide MN group makes
+      // LBO irrelevant; +128 (= 2 KB) per 16 keys.
       const uint64_t dv0 = ptx::make_smem_desc_sw128(sv, 1024, 1024);
       if (ptx::elect_one()) {
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t dp = dp0 + static_cast<uint64_t>((ks >> 2) * (kPBlockBytes >> 4) + 2 * (ks & 3));
-          const uint64_t dv = dv0 + static_cast<uint64_t>(ks * (2048 >> 4));
-          ptx::umma_bf16_ss(tmem_base + kTmemO, dp, dv, idesc_pv, ks != 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < kMaxKSteps; ++ks) {
+          if (ks < ksteps) {
+            const uint64_t dp = dp0 + static_cast<uint64_t>((ks >> 2) * (kPBlockBytes >> 4) + 2 * (ks & 3));
+            ptx::umma_bf16_ss(tmem_base + kTmemO, dp, dv0 + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv,
+                              ks != 0 ? 1u : 0u);
+          }
         }
         ptx::umma_commit(&empty_bar[st]);
         ptx::umma_commit(o_full);
+        if (want_avg) {
+          // Pbar[:, 16 ks + n] += sum_k P[:, 16 ks + k] * I[n, k]: one M = 128, N = 16, K = 16 instruction per 16 keys
+#pragma unroll
+          for (int ks = 0; ks < kMaxKSteps; ++ks) {
+            if (ks < ksteps) {
+              const uint64_t dp = dp0 + static_cast<uint64_t>((ks >> 2) * (kPBlockBytes >> 4) + 2 * (ks & 3));
+              ptx::umma_bf16_ss(tmem_base + kTmemAvg + 16 * ks, dp, did, idesc_avg, h != 0 ? 1u : 0u);
+            }
+          }
+        }
+        ptx::umma_commit(p_free);
       }
       __syncwarp();
       ATTN_TS(19);
     }
-  } else if (warp >= 4) {
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ CLS-row writer
+    // Row 0 of the normalised probabilities (fp32) is staged in smem by the four warps that own it; this otherwise
+    // idle warp streams it to HBM with coalesced stores, off the softmax warps' critical path.
+    if (p.cls_map != nullptr && qt == 0) {
+      for (int h = 0; h < p.H; ++h) {
+        ptx::mbar_wait(cls_full, h & 1);
+        float* cp = p.cls_map + (static_cast<size_t>(b) * p.H + h) * p.N;
+        for (int j = lane; j < p.N; j += 32) cp[j] = cls_stage[j];
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(cls_free);
+      }
+    }
+  } else if (warp >= kCtrlWarps) {
     // ------------------------------------------------------------ softmax / epilogue
-    const int half = (warp - 4) >> 2;           // which half of the key columns
+    const int cg = (warp - kCtrlWarps) >> 2;    // column group: which quarter of the key granules
     const int quarter = warp & 3;               // TMEM lane quarter
     const int r = quarter * 32 + lane;          // row inside the tile
     const int qrow = qt * BM + r;               // token index inside the image
     const bool row_ok = qrow < p.N;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int nchunks = KP >> 4;
-    const int split = (nchunks + 1) >> 1;       // 16-key chunks [0, split) -> half 0, [split, nchunks) -> half 1
-    const int nmy = half ? nchunks - split : split;
-    // local chunk c <-> global chunk gc: half 0 walks up from 0, half 1 walks DOWN from the last chunk, so the
-    // only chunk that can hold padded keys (>= N) is always local chunk 0 of half 1 (a static register index)
-    const int gc_base = half ? nchunks - 1 : 0;
-    const int gc_step = half ? -1 : 1;
-    const int tail_valid = p.N - (nchunks - 1) * 16;  // valid keys in the last chunk (1..16)
+    const int ngran = KP >> 3;                  // 8-key granules in a row
+    const int gbase = ngran / kColGroups, grem = ngran - gbase * kColGroups;
+    const int nmy = gbase + (cg < grem ? 1 : 0);               // granules of this thread
+    const int g0 = cg * gbase + (cg < grem ? cg : grem);       // first granule
     const float inv_h = 1.0f / static_cast<float>(p.H);
-    const bool want_avg = p.avg_map != nullptr;
-    const bool want_cls = p.cls_map != nullptr && qt == 0;
-    const bool want_maps = want_avg || want_cls || kHeads;
+    const bool want_cls = p.cls_map != nullptr && qt == 0 && quarter == 0;
     const uint32_t p_row = ptx::smem_u32(smem_p) + r * 128;
     const int sw = r & 7;
-    float* red_max = red;                        // [half][row]
-    float* red_sum = red + 2 * BM;
-    const uint32_t t_s = lane_base + kTmemS + gc_base * 16;
-    const uint32_t t_avg = lane_base + kTmemAvg + gc_base * 16;
-    const int t_step = gc_step * 16;
+    float* red_max = red;                        // [group][row]
+    float* red_sum = red + kColGroups * BM;
+    const uint32_t t_s = lane_base + kTmemS + g0 * 8;
+    const uint32_t t_avg = lane_base + kTmemAvg + g0 * 8;
+    const uint32_t t_o = lane_base + kTmemO + cg * 16;  // this thread's 16 of the 64 context columns
+
+    // Context columns of head hh: O is final (P was normalised before the MMA) -> bf16 -> smem quarter tile (32 rows x
+    // 128 B, 128-B swizzle) -> one TMA store per quarter.  Direct 32-B-per-thread global stores cost a warp-wide
+    // STG 32 L1 wavefronts (32 different lines); the LSU backlog showed up as ~800 stall samples per head.
+    // The tensor map views ctx as [B][N][d], so rows of the last query tile that lie beyond the image are clipped.
+    uint8_t* ctx_tile = smem_ctx + quarter * (32 * 128);
+    const uint32_t ctx_dst = ptx::smem_u32(ctx_tile) + lane * 128;
+    auto o_epilogue = [&](int hh) {
+      ptx::mbar_wait(o_full, hh & 1);
+      ptx::tc_fence_after();
+      uint32_t o[16];
+      ptx::tmem_ld_x16(t_o, o);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(o_free);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ctx_dst + (((2 * cg) ^ (lane & 7)) << 4)),
+                   "r"(pack_bf16x2_u(o[0], o[1])), "r"(pack_bf16x2_u(o[2], o[3])), "r"(pack_bf16x2_u(o[4], o[5])),
+                   "r"(pack_bf16x2_u(o[6], o[7]))
+                   : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ctx_dst + (((2 * cg + 1) ^ (lane & 7)) << 4)),
+                   "r"(pack_bf16x2_u(o[8], o[9])), "r"(pack_bf16x2_u(o[10], o[11])), "r"(pack_bf16x2_u(o[12], o[13])),
+                   "r"(pack_bf16x2_u(o[14], o[15]))
+                   : "memory");
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + quarter) : "memory");  // the four column-group warps of this quarter
+      if (cg == 0 && ptx::elect_one()) {
+        ptx::tma_store_3d(&tmap_ctx, ctx_tile, hh * D, qt * BM + quarter * 32, b);
+        ptx::tma_store_commit();
+      }
+      __syncwarp();
+    };
 
     for (int h = 0; h < p.H; ++h) {
-      // ---- S half-row -> registers (single TMEM read), then release the S columns
-      uint32_t s[kMaxChunks][16];
+      // ---- this thread's part of the S row -> registers (single TMEM read), then release the S columns
+      uint32_t s[kMaxGran][8];
       ATTN_TS(0);
       ptx::mbar_wait(s_full, h & 1);
       ATTN_TS(1);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < kMaxChunks; ++c)
-        if (c < nmy) ptx::tmem_ld_x16(t_s + c * t_step, s[c]);
+      for (int c = 0; c < kMaxGran; ++c)
+        if (c < nmy) ptx::tmem_ld_x8(t_s + c * 8, s[c]);
       ptx::tmem_ld_wait();
       ATTN_TS(2);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(s_free);
-      if (half && tail_valid < 16) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j >= tail_valid) s[0][j] = 0xff800000u;  // -inf: exp2 gives 0, max ignores it
-      }
 
-      // ---- row max (own half, then partner's through smem)
+      ATTN_TS(3);
+
+      // ---- row max (own granules, then the other three groups' through smem); padded keys (>= N) count as -inf
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < kMaxChunks; ++c) {
+      for (int c = 0; c < kMaxGran; ++c) {
         if (c < nmy) {
+          const int key0 = (g0 + c) * 8;
+          if (key0 + 8 > p.N) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(s[c][j]));
+            for (int j = 0; j < 8; ++j)
+              if (key0 + j >= p.N) s[c][j] = 0xff800000u;  // -inf: exp2 gives 0, max ignores it
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) mx = ptx::fmax3(mx, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
         }
       }
-      red_max[half * BM + r] = mx;
-      ATTN_TS(3);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      red_max[cg * BM + r] = mx;
+      // the context tile of head h-2 has been read out of smem before anyone can restage it (after this barrier);
+      // only the issuing thread has a bulk group outstanding, for everyone else this returns immediately
+      ptx::tma_store_wait_read<0>();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       ATTN_TS(4);
-      mx = fmaxf(mx, red_max[(half ^ 1) * BM + r]);
+      mx = fmaxf(fmaxf(red_max[r], red_max[BM + r]), fmaxf(red_max[2 * BM + r], red_max[3 * BM + r]));
       const float mxs = mx * p.scale_log2;
 
-      // ---- e = exp2(s*c - max*c) in place; bf16 P to smem (swizzled K-major)
+      // ---- e = exp2(s*c - max*c) in place
       float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < kMaxChunks; ++c) {
+      for (int c = 0; c < kMaxGran; ++c) {
         if (c < nmy) {
-          const int gc = gc_base + c * gc_step;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
+          for (int j = 0; j < 8; j += 4) {
             const float v0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -mxs));
             const float v1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 1]), p.scale_log2, -mxs));
             const float v2 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 2]), p.scale_log2, -mxs));
@@ -285,146 +385,93 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
             s[c][j] = __float_as_uint(v0), s[c][j + 1] = __float_as_uint(v1);
             s[c][j + 2] = __float_as_uint(v2), s[c][j + 3] = __float_as_uint(v3);
           }
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(s[c][2 * j]), __uint_as_float(s[c][2 * j + 1]));
-            pk[j] = *reinterpret_cast<uint32_t*>(&t);
-          }
-          // keys [16 gc, 16 gc + 16): K-block gc/4, 16-byte chunks 2*(gc%4) and 2*(gc%4)+1 of this row
-          const uint32_t blk = p_row + (gc >> 2) * kPBlockBytes;
-          const int ch0 = 2 * (gc & 3);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((ch0 ^ sw) << 4)), "r"(pk[0]),
-                       "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                       : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((ch0 + 1) ^ sw) << 4)), "r"(pk[4]),
-                       "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                       : "memory");
         }
       }
       ATTN_TS(5);
+      red_sum[cg * BM + r] = (ps0 + ps1) + (ps2 + ps3);
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      ATTN_TS(6);
+      const float inv = ptx::rcp_approx((red_sum[r] + red_sum[BM + r]) + (red_sum[2 * BM + r] + red_sum[3 * BM + r]));
+
+      // ---- the P tile is about to be overwritten: the previous head's P V and Pbar MMAs (issued a whole softmax
+      //      pass ago) must have retired
+      if (h > 0) ptx::mbar_wait(p_free, (h - 1) & 1);
+
+      // ---- p = e / sum -> bf16 P tile (swizzled K-major A operand of P V and of the head-average MMAs); fp32 copies
+      //      of row 0 / of every row for the CLS / per-head maps
+#pragma unroll
+      for (int c = 0; c < kMaxGran; ++c) {
+        if (c < nmy) {
+          const int g = g0 + c;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[c][j] = __float_as_uint(__uint_as_float(s[c][j]) * inv);
+          // keys [8 g, 8 g + 8): K-block g / 8, 16-byte chunk g % 8 of this row
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (g >> 3) * kPBlockBytes + (((g & 7) ^ sw) << 4)),
+                       "r"(pack_bf16x2_u(s[c][0], s[c][1])), "r"(pack_bf16x2_u(s[c][2], s[c][3])),
+                       "r"(pack_bf16x2_u(s[c][4], s[c][5])), "r"(pack_bf16x2_u(s[c][6], s[c][7]))
+                       : "memory");
+        }
+      }
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
-      ATTN_TS(6);
-
-      // ---- row sum exchange
-      float sum = (ps0 + ps1) + (ps2 + ps3);
-      red_sum[half * BM + r] = sum;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
       ATTN_TS(7);
-      sum += red_sum[(half ^ 1) * BM + r];
-      const float inv = ptx::rcp_approx(sum);
 
-      // ---- normalised probabilities -> head average (TMEM) / per-head rows (HBM); overlaps the P V MMAs
-      if (want_maps) {
-        const float wavg = inv * inv_h;
-        if (want_avg) {
+      // ---- context of the previous head.  Placed AFTER the P tile hand-off: fence.proxy.async is a MEMBAR that
+      //      waits for every global store this thread has in flight, so the stores below get a whole head to drain.
+      if (h > 0) o_epilogue(h - 1);
+
+      if (want_cls && lane == 0) {
+        // query row 0 lives in lane 0 of the quarter-0 warp of every column group
+        if (h > 0) ptx::mbar_wait(cls_free, (h - 1) & 1);
 #pragma unroll
-          for (int c = 0; c < kMaxChunks; ++c) {
+        for (int c = 0; c < kMaxGran; ++c) {
+          if (c < nmy) {
+            float4* dst = reinterpret_cast<float4*>(cls_stage + (g0 + c) * 8);
+            dst[0] = make_float4(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]), __uint_as_float(s[c][2]),
+                                 __uint_as_float(s[c][3]));
+            dst[1] = make_float4(__uint_as_float(s[c][4]), __uint_as_float(s[c][5]), __uint_as_float(s[c][6]),
+                                 __uint_as_float(s[c][7]));
+          }
+        }
+        ptx::mbar_arrive(cls_full);  // release: the staged values are visible to warp 3 once the phase completes
+      }
+      if (kHeads) {
+        if (p.head_map != nullptr && row_ok) {
+          float* hp = p.head_map + ((static_cast<size_t>(b) * p.H + h) * p.N + qrow) * p.ldmap;
+#pragma unroll
+          for (int c = 0; c < kMaxGran; ++c) {
             if (c < nmy) {
-              uint32_t a[16];
-              if (h > 0) {
-                ptx::tmem_ld_x16(t_avg + c * t_step, a);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  a[j] = __float_as_uint(fmaf(__uint_as_float(s[c][j]), wavg, __uint_as_float(a[j])));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(s[c][j]) * wavg);
-              }
-              ptx::tmem_st_x16(t_avg + c * t_step, a);
-            }
-          }
-          ptx::tmem_st_wait();
-        }
-        if (want_cls && quarter == 0) {
-          // query row 0 lives in lane 0 of warps 4 (first half of the keys) and 8 (second half): it stages its
-          // normalised values, then the whole warp writes that key range out (no cross-warp dependency)
-          if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < kMaxChunks; ++c) {
-              if (c < nmy) {
-                float* dst = cls_stage + (gc_base + c * gc_step) * 16;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(dst + j) =
-                      make_float4(__uint_as_float(s[c][j]) * inv, __uint_as_float(s[c][j + 1]) * inv,
-                                  __uint_as_float(s[c][j + 2]) * inv, __uint_as_float(s[c][j + 3]) * inv);
-              }
-            }
-          }
-          __syncwarp();
-          const int lo = half ? split * 16 : 0;
-          const int hi = half ? p.N : min(split * 16, p.N);
-          float* cp = p.cls_map + (static_cast<size_t>(b) * p.H + h) * p.N;
-          for (int j = lo + lane; j < hi; j += 32) cp[j] = cls_stage[j];
-          __syncwarp();
-        }
-        if (kHeads) {
-          if (p.head_map != nullptr && row_ok) {
-            float* hp = p.head_map + ((static_cast<size_t>(b) * p.H + h) * p.N + qrow) * p.ldmap;
-#pragma unroll
-            for (int c = 0; c < kMaxChunks; ++c) {
-              if (c < nmy) {
-                float* dst = hp + (gc_base + c * gc_step) * 16;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  *reinterpret_cast<float4*>(dst + j) =
-                      make_float4(__uint_as_float(s[c][j]) * inv, __uint_as_float(s[c][j + 1]) * inv,
-                                  __uint_as_float(s[c][j + 2]) * inv, __uint_as_float(s[c][j + 3]) * inv);
-              }
+              float4* dst = reinterpret_cast<float4*>(hp + (g0 + c) * 8);
+              dst[0] = make_float4(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]), __uint_as_float(s[c][2]),
+                                   __uint_as_float(s[c][3]));
+              dst[1] = make_float4(__uint_as_float(s[c][4]), __uint_as_float(s[c][5]), __uint_as_float(s[c][6]),
+                                   __uint_as_float(s[c][7]));
             }
           }
         }
       }
-
-      // ---- O epilogue: context rows = (P_unnormalised V) / sum; this half owns 32 of the 64 columns
       ATTN_TS(8);
-      ptx::mbar_wait(o_full, h & 1);
-      ATTN_TS(9);
-      ptx::tc_fence_after();
-      {
-        uint32_t o[32];
-        ptx::tmem_ld_x32(lane_base + kTmemO + half * 32, o);
-        ptx::tmem_ld_wait();
-        ATTN_TS(10);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(o_free);
-        if (row_ok) {
-          __nv_bfloat16* op = p.ctx + (static_cast<size_t>(row0) + qrow) * p.d + h * D + half * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(op + j) = pk;
-          }
-        }
-      }
     }
+    // (restaging needs the previous store's smem reads done; every warp passes through the issuer's wait via bar 3+q)
+    ptx::tma_store_wait_read<0>();
+    asm volatile("bar.sync %0, 128;" ::"r"(3 + quarter) : "memory");
+    o_epilogue(p.H - 1);
+    ptx::tma_store_wait<0>();
 
-    // head-averaged map rows -> HBM, once per (image, query row)
+    // head-averaged map rows -> HBM, once per (image, query row): Pbar holds the SUM over heads
     if (want_avg) {
 #pragma unroll 1
       for (int c = 0; c < nmy; ++c) {
-        uint32_t a[16];
-        ptx::tmem_ld_x16(t_avg + c * t_step, a);
+        uint32_t a[8];
+        ptx::tmem_ld_x8(t_avg + c * 8, a);
         ptx::tmem_ld_wait();
         if (row_ok) {
-          float* ap = p.avg_map + (static_cast<size_t>(b) * p.N + qrow) * p.ldmap + (gc_base + c * gc_step) * 16;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(ap + j) = make_float4(__uint_as_float(a[j]), __uint_as_float(a[j + 1]),
-                                                             __uint_as_float(a[j + 2]), __uint_as_float(a[j + 3]));
+          float4* ap = reinterpret_cast<float4*>(p.avg_map + (static_cast<size_t>(b) * p.N + qrow) * p.ldmap + (g0 + c) * 8);
+          ap[0] = make_float4(__uint_as_float(a[0]) * inv_h, __uint_as_float(a[1]) * inv_h, __uint_as_float(a[2]) * inv_h,
+                              __uint_as_float(a[3]) * inv_h);
+          ap[1] = make_float4(__uint_as_float(a[4]) * inv_h, __uint_as_float(a[5]) * inv_h, __uint_as_float(a[6]) * inv_h,
+                              __uint_as_float(a[7]) * inv_h);
         }
       }
     }

@@ -94,6 +94,28 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint
   return VITB200_OK;
 }
 
+// 3-D bf16 tensor [batch][rows][cols] (cols contiguous, row pitch ld elements, image pitch rows * ld), box =
+// box_cols x box_rows x 1, 128-byte swizzle.  Used for stores that must clip at the end of each image.
+static int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (box_cols * 2 != 128 || box_rows == 0 || box_rows > 256)
+    return fail(VITB200_ERR_INVALID, "bad TMA box %u x %u", box_rows, box_cols);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(VITB200_ERR_INVALID, "TMA operand must be 16-byte aligned (base %p, pitch %llu B)", base,
+                (unsigned long long)(ld * 2));
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld * 2, rows * ld * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return VITB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ launch helpers
 static int g_num_sms = 0;
 
@@ -107,57 +129,74 @@ static int device_sms() {
   return g_num_sms;
 }
 
-template <int BN, int kPair, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
+// Host mirror of GemmWork::num_units (gemm.cuh).
+static int gemm_units(int M, int N, int tile_m, int bn, int pairs) {
+  const int m_tiles = (M + tile_m - 1) / tile_m, n_tiles = (N + bn - 1) / bn;
+  if (pairs == 1) return m_tiles * n_tiles;
+  return (m_tiles / 2) * n_tiles + ((m_tiles & 1) ? (n_tiles + 1) / 2 : 0);
+}
+
+template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
                          cudaStream_t st) {
   using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu)>;
-  auto kern = gemm_bf16_kernel<BN, kPair, kGelu, kOutF32, kResid, kRemap>;
-  static bool configured = false;
-  if (!configured) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
-  }
-  const int tile_m = gemm_cfg::BM * kPair;
-  const int m_tiles = (sh.M + tile_m - 1) / tile_m;
-  const int n_tiles = (sh.N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles;
-  const int units = device_sms() / kPair;  // persistent: one CTA (or CTA pair) per SM (pair)
-  const int grid = (tiles < units ? tiles : units) * kPair;
+  auto kern = gemm_bf16_kernel<BN, kPair, kPairs, kGelu, kOutF32, kResid, kRemap>;
+  constexpr int kClusterCtas = kPair * kPairs;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kPair;
+  attr[0].val.clusterDim.x = kClusterCtas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // persistent: one CTA / pair / 4-CTA cluster per scheduler slot; the slots are what the device can co-schedule
+  // (4-CTA clusters do not tile every GPC: 148 SMs hold fewer than 37 of them)
+  static int slots = 0;
+  if (slots == 0) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    slots = device_sms() / kClusterCtas;
+    if (kClusterCtas > 2) {
+      cfg.gridDim = dim3(device_sms() / kClusterCtas * kClusterCtas);
+      int n = 0;
+      CU_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      if (n <= 0) return fail(VITB200_ERR_CUDA, "gemm: no %d-CTA cluster fits on this device", kClusterCtas);
+      if (n < slots) slots = n;
+      const char* v = getenv("VITB200_GEMM_SLOTS");
+      if (v && atoi(v) > 0 && atoi(v) < slots) slots = atoi(v);
+    }
+  }
+  const int units = gemm_units(sh.M, sh.N, gemm_cfg::BM * kPair, BN, kPairs);
+  cfg.gridDim = dim3((units < slots ? units : slots) * kClusterCtas);
   CU_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw, sh, ep));
   return VITB200_OK;
 }
 
-// CTA-pair (cta_group::2) kernels unless VITB200_GEMM_PAIR=1 asks for the single-CTA baseline.
+// VITB200_GEMM_PAIR: 1 = single-CTA baseline, 2 (default) = CTA pairs, 4 = two pairs per cluster with the shared
+// operand multicast (BN = 256 shapes only; others fall back to pairs).  Measured on B200 (profiles/README.md): the
+// multicast variant is NOT faster (1190 vs 1249 TF/s on the qkv shape): the bound is bytes DELIVERED into the SMs,
+// which multicast does not reduce, and only 33 four-CTA clusters (132 of 148 SMs) are co-resident.
 static int gemm_pair_mode() {
   static int mode = 0;
   if (mode == 0) {
     const char* v = getenv("VITB200_GEMM_PAIR");
-    mode = (v && v[0] == '1') ? 1 : 2;
+    mode = (v && v[0] == '1') ? 1 : (v && v[0] == '4') ? 4 : 2;
   }
   return mode;
 }
 
-template <int BN, int kPair>
+template <int BN, int kPair, int kPairs>
 static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep, bool gelu,
                           bool out_f32, cudaStream_t st) {
   const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0;
-  if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, true, false, false, false>(ta, tw, sh, ep, st);
-  if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, false, false, false, false>(ta, tw, sh, ep, st);
-  if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, false, true, false, false>(ta, tw, sh, ep, st);
-  if (!gelu && out_f32 && resid && !remap) return launch_gemm_t<BN, kPair, false, true, true, false>(ta, tw, sh, ep, st);
-  if (!gelu && out_f32 && resid && remap) return launch_gemm_t<BN, kPair, false, true, true, true>(ta, tw, sh, ep, st);
+  if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false>(ta, tw, sh, ep, st);
+  if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, false, false, false>(ta, tw, sh, ep, st);
+  if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, false, false>(ta, tw, sh, ep, st);
+  if (!gelu && out_f32 && resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, true, false>(ta, tw, sh, ep, st);
+  if (!gelu && out_f32 && resid && remap) return launch_gemm_t<BN, kPair, kPairs, false, true, true, true>(ta, tw, sh, ep, st);
   return fail(VITB200_ERR_INVALID, "gemm: epilogue combination not instantiated (gelu=%d f32=%d resid=%d remap=%d)", gelu,
               out_f32, resid, remap);
 }
@@ -168,17 +207,27 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm: empty shape %d x %d x %d", M, N, K);
   if (N % 8 != 0 || K % 8 != 0) return fail(VITB200_ERR_INVALID, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
   const int BN = (N % 256 == 0) ? 256 : 128;
-  const int pair = gemm_pair_mode();
-  CUtensorMap ta, tw;
-  VT_TRY(make_tmap_bf16(&ta, a, M, K, lda, gemm_cfg::BM, gemm_cfg::BK));
-  VT_TRY(make_tmap_bf16(&tw, w, N, K, K, BN / pair, gemm_cfg::BK));
-  GemmShape sh{M, N, K};
-  if (BN == 256) {
-    return pair == 2 ? launch_gemm_bn<256, 2>(ta, tw, sh, ep, gelu, out_f32, st)
-                     : launch_gemm_bn<256, 1>(ta, tw, sh, ep, gelu, out_f32, st);
+  int mode = gemm_pair_mode();
+  // the multicast clusters pay off once there is more than one wave of tiles; small problems keep the finer pairs
+  // (VITB200_GEMM_CLUSTER_MIN_TILES overrides the threshold: the parity tests force clusters onto small shapes)
+  static int min_tiles = -1;
+  if (min_tiles < 0) {
+    const char* v = getenv("VITB200_GEMM_CLUSTER_MIN_TILES");
+    min_tiles = v ? atoi(v) : device_sms() / 2 + 1;
   }
-  return pair == 2 ? launch_gemm_bn<128, 2>(ta, tw, sh, ep, gelu, out_f32, st)
-                   : launch_gemm_bn<128, 1>(ta, tw, sh, ep, gelu, out_f32, st);
+  if (mode == 4 && (BN != 256 || gemm_units(M, N, 256, 256, 1) < min_tiles)) mode = 2;
+  const int pair = mode == 1 ? 1 : 2;
+  CUtensorMap ta, tw;
+  VT_TRY(make_tmap_bf16(&ta, a, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
+  VT_TRY(make_tmap_bf16(&tw, w, N, K, K, mode == 4 ? 64 : BN / pair, gemm_cfg::BK));
+  GemmShape sh{M, N, K};
+  if (mode == 4) return launch_gemm_bn<256, 2, 2>(ta, tw, sh, ep, gelu, out_f32, st);
+  if (BN == 256) {
+    return pair == 2 ? launch_gemm_bn<256, 2, 1>(ta, tw, sh, ep, gelu, out_f32, st)
+                     : launch_gemm_bn<256, 1, 1>(ta, tw, sh, ep, gelu, out_f32, st);
+  }
+  return pair == 2 ? launch_gemm_bn<128, 2, 1>(ta, tw, sh, ep, gelu, out_f32, st)
+                   : launch_gemm_bn<128, 1, 1>(ta, tw, sh, ep, gelu, out_f32, st);
 }
 
 static int launch_layernorm(const float* x, long in_stride, const float* g, const float* b, __nv_bfloat16* y, int rows,
@@ -209,9 +258,10 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   if ((avg || heads) && (pitch < KP || pitch % 4 != 0))
     return fail(VITB200_ERR_INVALID, "attention: map pitch %d must be >= %d and a multiple of 4", pitch, KP);
   const int d = H * D;
-  CUtensorMap tq, tkv;
+  CUtensorMap tq, tkv, tctx;
   VT_TRY(make_tmap_bf16(&tq, qkv, (uint64_t)B * N, 3 * d, 3 * d, BM, D));
   VT_TRY(make_tmap_bf16(&tkv, qkv, (uint64_t)B * N, 3 * d, 3 * d, KP / 2, D));
+  VT_TRY(make_tmap_bf16_3d(&tctx, ctx, B, N, d, d, 32, D));
   static bool configured = false;
   if (!configured) {
     CU_TRY(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -223,8 +273,8 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
   p.ctx = ctx, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
   p.q_tiles = (N + BM - 1) / BM;
-  if (heads) attention_kernel<true><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, p);
-  else attention_kernel<false><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, p);
+  if (heads) attention_kernel<true><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, p);
+  else attention_kernel<false><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, p);
   CU_TRY(cudaGetLastError());
   return VITB200_OK;
 }
@@ -268,6 +318,11 @@ struct vitb200_engine {
   uint32_t cap_flags = 0;
   Buffer images, patches, x, ln, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout;
 
+  // vitb200_profile_forward: an event in front of every launch (only while `profiling`)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<std::string> prof_names;
+
   ~vitb200_engine();
 };
 
@@ -310,10 +365,21 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   return VITB200_OK;
 }
 
+// In profiling mode: a CUDA event on the launch stream in front of the named kernel.
+static void prof_mark(vitb200_engine* e, const char* name, cudaStream_t st) {
+  if (!e->profiling) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  e->prof_events.push_back(ev);
+  e->prof_names.push_back(name);
+}
+
 // ---- forward stages (all enqueue on `st`, no synchronisation) --------------------------------------
 static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStream_t st) {
   const vitb200_config& c = e->cfg;
   const long items = (long)B * 3 * c.image_size * (c.image_size / c.patch_size) * (c.patch_size / 8);
+  prof_mark(e, "patchify", st);
   patchify_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(images_dev, (__nv_bfloat16*)e->patches.p, B,
                                                                    c.image_size, c.patch_size);
   CU_TRY(cudaGetLastError());
@@ -323,8 +389,10 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
   ep.resid = e->pos, ep.ldr = c.hidden_dim;
   ep.group_rows = e->n, ep.out_group_stride = e->N, ep.out_row_offset = 1;
   ep.resid_broadcast = 1, ep.resid_row_offset = 1;
+  prof_mark(e, "gemm_patch_embed", st);
   VT_TRY(launch_gemm(e->patches.p, e->patch_k, e->w_patch, B * e->n, c.hidden_dim, e->patch_k, ep, false, true, st));
   const long citems = (long)B * (c.hidden_dim / 4);
+  prof_mark(e, "cls_rows", st);
   cls_rows_kernel<<<(unsigned)((citems + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p, B, e->N,
                                                                     c.hidden_dim);
   CU_TRY(cudaGetLastError());
@@ -338,9 +406,11 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
   const int M = B * e->N, d = c.hidden_dim;
   float* x = (float*)e->x.p;
   __nv_bfloat16* ln = (__nv_bfloat16*)e->ln.p;
+  prof_mark(e, "layernorm", st);
   VT_TRY(launch_layernorm(x, d, w.ln1_g, w.ln1_b, ln, M, d, 1e-6f, st));
   {
     GemmEpilogue ep;
+    prof_mark(e, "gemm_qkv", st);
     ep.bias = w.b_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
     VT_TRY(launch_gemm(ln, d, w.w_qkv, M, 3 * d, d, ep, false, false, st));
   }
@@ -350,21 +420,26 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
   float* hm = (flags & VITB200_EMIT_HEADS)
                   ? (float*)e->heads.p + (size_t)l * e->cap_batch * c.num_heads * e->N * e->pitch
                   : nullptr;
+  prof_mark(e, "attention", st);
   VT_TRY(launch_attention((const __nv_bfloat16*)e->qkv.p, (__nv_bfloat16*)e->ctx.p, avg, cls, hm, B, e->N, c.num_heads,
                           e->pitch, st));
   {
     GemmEpilogue ep;
+    prof_mark(e, "gemm_out_proj", st);
     ep.bias = w.b_o, ep.out = x, ep.ldo = d, ep.resid = x, ep.ldr = d;
     VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st));
   }
+  prof_mark(e, "layernorm", st);
   VT_TRY(launch_layernorm(x, d, w.ln2_g, w.ln2_b, ln, M, d, 1e-6f, st));
   {
     GemmEpilogue ep;
+    prof_mark(e, "gemm_fc1_gelu", st);
     ep.bias = w.b_fc1, ep.out = e->mlp.p, ep.ldo = c.mlp_dim;
     VT_TRY(launch_gemm(ln, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st));
   }
   {
     GemmEpilogue ep;
+    prof_mark(e, "gemm_fc2", st);
     ep.bias = w.b_fc2, ep.out = x, ep.ldo = d, ep.resid = x, ep.ldr = d;
     VT_TRY(launch_gemm(e->mlp.p, c.mlp_dim, w.w_fc2, M, d, c.mlp_dim, ep, false, true, st));
   }
@@ -379,10 +454,12 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
 static int run_head(vitb200_engine* e, int B, cudaStream_t st) {
   const vitb200_config& c = e->cfg;
   const int d = c.hidden_dim;
+  prof_mark(e, "layernorm_final", st);
   VT_TRY(launch_layernorm((const float*)e->x.p, (long)e->N * d, e->lnf_g, e->lnf_b, (__nv_bfloat16*)e->cls_ln.p, B, d,
                           1e-6f, st));
   GemmEpilogue ep;
   ep.bias = e->b_head, ep.out = e->logits.p, ep.ldo = c.num_classes;
+  prof_mark(e, "gemm_head", st);
   VT_TRY(launch_gemm(e->cls_ln.p, d, e->w_head, B, c.num_classes, d, ep, false, true, st));
   e->launches += 2;
   return VITB200_OK;
@@ -390,6 +467,7 @@ static int run_head(vitb200_engine* e, int B, cudaStream_t st) {
 
 static int run_rollout(vitb200_engine* e, int B, cudaStream_t st) {
   if (e->N > 256) return fail(VITB200_ERR_INVALID, "rollout: at most 256 tokens");
+  prof_mark(e, "rollout", st);
   rollout_cls_kernel<<<B, kRolloutThreads, 0, st>>>((const float*)e->avg.p, (long)e->cap_batch * e->N * e->pitch,
                                            e->cfg.num_layers, e->N, e->pitch, (float*)e->rollout.p);
   CU_TRY(cudaGetLastError());
@@ -577,6 +655,44 @@ int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch
   CU_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   return forward_device_locked(e, images_dev, batch, flags, st);
+}
+
+int vitb200_profile_forward(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, char* report,
+                            size_t report_cap) {
+  if (!e || !images_dev || !report || report_cap == 0) return fail(VITB200_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = e->stream;
+  e->profiling = true;
+  int rc = forward_device_locked(e, images_dev, batch, flags, st);
+  prof_mark(e, "end", st);
+  e->profiling = false;
+  cudaError_t err = cudaStreamSynchronize(st);
+  // one line per kernel kind: name,launches,total_ms  (event-to-event, i.e. including the gap to the next launch)
+  std::map<std::string, std::pair<int, double>> agg;
+  std::vector<std::string> order;
+  double total = 0;
+  for (size_t i = 0; rc == VITB200_OK && err == cudaSuccess && i + 1 < e->prof_events.size(); ++i) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->prof_events[i], e->prof_events[i + 1]);
+    if (!agg.count(e->prof_names[i])) order.push_back(e->prof_names[i]);
+    agg[e->prof_names[i]].first += 1, agg[e->prof_names[i]].second += ms, total += ms;
+  }
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  e->prof_events.clear(), e->prof_names.clear();
+  if (rc != VITB200_OK) return rc;
+  if (err != cudaSuccess) return fail(VITB200_ERR_CUDA, "profile_forward: %s", cudaGetErrorString(err));
+  std::string out;
+  char line[160];
+  for (const std::string& n : order) {
+    snprintf(line, sizeof(line), "%s,%d,%.6f\n", n.c_str(), agg[n].first, agg[n].second);
+    out += line;
+  }
+  snprintf(line, sizeof(line), "total,%zu,%.6f\n", order.size(), total);
+  out += line;
+  if (out.size() + 1 > report_cap) return fail(VITB200_ERR_INVALID, "profile report needs %zu bytes", out.size() + 1);
+  memcpy(report, out.c_str(), out.size() + 1);
+  return VITB200_OK;
 }
 
 int vitb200_forward_host(vitb200_engine* e, const float* images_host, int batch, uint32_t flags,

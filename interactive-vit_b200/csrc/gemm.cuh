@@ -12,6 +12,12 @@
 // UMMA M = 256: each CTA stages its own 128 rows of A and HALF of the W tile, so the L2 -> SMEM traffic per
 // FLOP is 2/3 of the single-CTA kernel's (the 128 x 256 single-CTA tile is L2-bandwidth bound at ~900 TF/s).
 // kPair = 1: one CTA computes 128 x BN on its own (kept as the A/B baseline).
+// kPairs = 2 (BN = 256 only): a cluster of FOUR CTAs = two pairs.  The pair kernel is bound by the L2 -> SMEM
+// feed (64 B/clk/SM against ~42 B/clk/SM that the L2 delivers to 148 SMs at once: measured 65% tensor-pipe
+// activity), so the two pairs of a cluster compute two tiles that share one operand and fetch the shared 128-row
+// operand block only once: each CTA loads 64 of its rows and TMA-multicasts them to its counterpart in the other
+// pair (48 B/clk/SM).  Normally the pairs take vertically adjacent tiles (same W tile, "share W"); an odd last
+// row of tiles is covered with horizontally adjacent tiles (same A tile, "share A") so that no cluster idles.
 //
 // Roles (4 + 8 warps, or 4 + 16 for the GELU epilogue; 1 CTA / SM, persistent over output tiles):
 //   warp 0 lane 0 : TMA producer  (A tile 128x64, W tile (BN/kPair)x64, SWIZZLE_128B, mbarrier ring; in a pair both
@@ -76,27 +82,58 @@ struct Cfg {
 };
 }  // namespace gemm_cfg
 
-// Exact-erf GELU (torch.nn.GELU default, vision_transformer.py:40-47 MLPBlock): 0.5 x (1 + erf(x / sqrt 2)).
-// erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32 round-off level) evaluated with one
-// MUFU.RCP and one MUFU.EX2 instead of the ~25-instruction libdevice erff: the fc1 epilogue must keep pace with
-// a 6144-cycle MMA main loop per 128x256 tile.
+// Exact-erf GELU (torch.nn.GELU default, vision_transformer.py:40-47 MLPBlock): x * Phi(x), Phi the normal CDF.
+// With u = |x| and e(u) = erfc(u / sqrt 2) = 2 Phi(-u):   gelu(x) = max(x, 0) - 0.5 * u * e(u).
+// e(u) = exp2(-u * q(u)) with q a degree-4 polynomial fitted to -log2(erfc(u / sqrt 2)) / u on [0, 6] (weighted
+// minimax; |abs error of gelu| <= 6e-7 for every x, checked in tests/test_gpu_kernels.py): 4 FFMA + 3 FMUL +
+// 1 FMNMX + 1 FFMA and ONE MUFU.EX2 per element (Abramowitz-Stegun 7.1.26 needed MUFU.RCP + MUFU.EX2 and ~15
+// instructions; the fc1 epilogue has to keep pace with a 6144-cycle MMA main loop per 128x256 tile).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = ptx::rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = ptx::ex2_approx(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-poly, e, 1.0f);           // erf(|x|/sqrt2)
-  const float half_x = 0.5f * x;
-  return fmaf(copysignf(erf_abs, x), half_x, half_x);   // 0.5 x (1 + erf)
+  const float u = fabsf(x);
+  float q = fmaf(-4.881035730e-04f, u, 7.198722885e-03f);
+  q = fmaf(q, u, -5.214662994e-02f);
+  q = fmaf(q, u, -4.595958578e-01f);
+  q = fmaf(q, u, -1.151000535e+00f);
+  const float e = ptx::ex2_approx(q * u);   // erfc(u / sqrt 2); -> 0 for large u (q * u -> -inf)
+  return fmaf(u * e, -0.5f, fmaxf(x, 0.0f));
 }
 
 // kGelu / kOutF32 / kResid / kRemap select the epilogue at compile time (the fc1 epilogue is issue-bound: every
 // instruction that a runtime flag would leave in its inner loop costs ~1% of the kernel).
-template <int BN, int kPair, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
+// Work decomposition shared by the three roles.  A "unit" is what one persistent scheduler slot (CTA, pair, or
+// 4-CTA cluster) processes per iteration.  kPairs == 1: unit i = tile i (m = i / n_tiles, n = i % n_tiles).
+// kPairs == 2: units [0, full_rows * n_tiles) are "share W" (pair p takes m = 2 * (i / n_tiles) + p, n = i % n_tiles);
+// if m_tiles is odd, the last row of tiles follows as "share A" units (m = m_tiles - 1, pair p takes n = 2 j + p;
+// an n beyond the last tile is computed on zero-filled operands and dropped by the epilogue's column check).
+struct GemmWork {
+  int m_tiles, n_tiles, full_rows, w_units, num_units;
+  __device__ GemmWork(int M, int N, int tile_m, int bn, int pairs) {
+    m_tiles = (M + tile_m - 1) / tile_m;
+    n_tiles = (N + bn - 1) / bn;
+    if (pairs == 1) {
+      full_rows = m_tiles, w_units = m_tiles * n_tiles, num_units = w_units;
+    } else {
+      full_rows = m_tiles >> 1, w_units = full_rows * n_tiles;
+      num_units = w_units + ((m_tiles & 1) ? ((n_tiles + 1) >> 1) : 0);
+    }
+  }
+  // returns true when the unit shares A between the pairs (else it shares W, or nothing for pairs == 1)
+  __device__ bool decode(int unit, int pairs, int pair_id, int& m_blk, int& n_blk) const {
+    if (pairs == 1) {
+      m_blk = unit / n_tiles, n_blk = unit - m_blk * n_tiles;
+      return false;
+    }
+    if (unit < w_units) {
+      const int row = unit / n_tiles;
+      m_blk = 2 * row + pair_id, n_blk = unit - row * n_tiles;
+      return false;
+    }
+    m_blk = m_tiles - 1, n_blk = 2 * (unit - w_units) + pair_id;
+    return true;
+  }
+};
+
+template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
 __global__ void __launch_bounds__((gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu)>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  GemmShape shape, GemmEpilogue ep) {
@@ -120,14 +157,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (kPair == 2) ? ptx::cluster_ctarank() : 0u;
+  static_assert(kPairs == 1 || (kPair == 2 && BN == 256), "4-CTA clusters: pair kernels with BN = 256 only");
+  constexpr int kClusterCtas = kPair * kPairs;
+  const uint32_t cluster_rank = (kClusterCtas > 1) ? ptx::cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cluster_rank & (kPair - 1);    // rank inside the CTA pair
+  const int pair_id = static_cast<int>(cluster_rank >> 1);  // which pair of the cluster (0 when kPairs == 1)
   const bool leader = cta_rank == 0;
-  const int unit = blockIdx.x / kPair;       // CTA (kPair=1) or CTA-pair index
-  const int num_units = gridDim.x / kPair;
+  const int slot = blockIdx.x / kClusterCtas;               // persistent scheduler slot: CTA, pair or cluster
+  const int num_slots = gridDim.x / kClusterCtas;
 
-  const int m_tiles = (shape.M + kTileM - 1) / kTileM;
-  const int n_tiles = (shape.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const GemmWork work(shape.M, shape.N, kTileM, BN, kPairs);
+  const int num_units = work.num_units;
   const int num_kb = (shape.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -137,7 +177,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], kPairs);  // a stage is written for both pairs: both pairs' MMAs must release it
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
@@ -150,7 +190,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     else ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
   }
   ptx::tc_fence_before();
-  if (kPair == 2) ptx::cluster_sync();  // peer barriers initialised before any multicast commit / remote arrive
+  if (kClusterCtas > 1) ptx::cluster_sync();  // peer barriers initialised before any multicast commit / remote arrive
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -162,9 +202,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ TMA producer (every CTA)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
-      const int m_blk = tile / n_tiles;
-      const int n_blk = tile % n_tiles;
+    // kPairs == 2: the counterpart of this CTA in the other pair has the same rank-in-pair
+    const uint16_t mc_mask = static_cast<uint16_t>((1u << cta_rank) | (1u << (2 + cta_rank)));
+    for (int unit = slot; unit < num_units; unit += num_slots) {
+      int m_blk, n_blk;
+      const bool share_a = work.decode(unit, kPairs, pair_id, m_blk, n_blk);
       const int a_row = m_blk * kTileM + static_cast<int>(cta_rank) * BM;
       const int w_row = n_blk * BN + static_cast<int>(cta_rank) * (BN / kPair);
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -172,7 +214,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* sa = smem + stage * C::kStageBytes;
         uint8_t* sb = sa + C::kStageBytesA;
         if (ptx::elect_one()) {
-          if (kPair == 2) {
+          if (kPairs == 2) {
+            // 64-row boxes.  Own operand: both halves; shared operand: this pair's half, multicast to the counterpart.
+            constexpr int kHalf = 64 * BK * 2;
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+            if (!share_a) {
+              ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
+              ptx::tma_load_2d_pair(sa + kHalf, &tmap_a, &full_bar[stage], kb * BK, a_row + 64);
+              ptx::tma_load_2d_pair_mc(sb + pair_id * kHalf, &tmap_w, &full_bar[stage], kb * BK, w_row + pair_id * 64,
+                                       mc_mask);
+            } else {
+              ptx::tma_load_2d_pair_mc(sa + pair_id * kHalf, &tmap_a, &full_bar[stage], kb * BK, a_row + pair_id * 64,
+                                       mc_mask);
+              ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
+              ptx::tma_load_2d_pair(sb + kHalf, &tmap_w, &full_bar[stage], kb * BK, w_row + 64);
+            }
+          } else if (kPair == 2) {
             // one barrier (the leader's) tracks the bytes of both CTAs' halves
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
             ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
@@ -196,7 +253,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units, ++local) {
+    // commits: the smem stage is released in every CTA of the cluster, the accumulator goes to this pair's epilogues
+    constexpr uint16_t kEmptyMask = static_cast<uint16_t>((1u << kClusterCtas) - 1);
+    const uint16_t full_mask = static_cast<uint16_t>(0x3u << (2 * pair_id));
+    for (int unit = slot; unit < num_units; unit += num_slots, ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -217,7 +277,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             else ptx::umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // smem slot reusable (in both CTAs) once these MMAs retire
-          if (kPair == 2) ptx::umma_commit_pair(&empty_bar[stage], 0x3);
+          if (kPair == 2) ptx::umma_commit_pair(&empty_bar[stage], kEmptyMask);
           else ptx::umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -228,7 +288,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       // accumulator complete -> epilogue warps (of both CTAs)
       if (ptx::elect_one()) {
-        if (kPair == 2) ptx::umma_commit_pair(&tmem_full_bar[acc], 0x3);
+        if (kPair == 2) ptx::umma_commit_pair(&tmem_full_bar[acc], full_mask);
         else ptx::umma_commit(&tmem_full_bar[acc]);
       }
       __syncwarp();
@@ -244,9 +304,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int trow = lane >> 3;                     // transposed mapping: rows trow + 4 i, 4 columns at 4 * tcol
     const int tcol = lane & 7;
     int local = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units, ++local) {
-      const int m_blk = tile / n_tiles;
-      const int n_blk = tile % n_tiles;
+    for (int unit = slot; unit < num_units; unit += num_slots, ++local) {
+      int m_blk, n_blk;
+      work.decode(unit, kPairs, pair_id, m_blk, n_blk);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int row_base = m_blk * kTileM + static_cast<int>(cta_rank) * BM + quarter * 32;
@@ -264,7 +324,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (kPair == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            if (kPair == 2) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], cluster_rank & ~1u);
             else ptx::mbar_arrive(&tmem_empty_bar[acc]);
           }
         }
@@ -334,7 +394,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   __syncwarp();
   ptx::tc_fence_before();
-  if (kPair == 2) ptx::cluster_sync();  // the peer may still be signalling this CTA's barriers / reading its smem
+  if (kClusterCtas > 1) ptx::cluster_sync();  // the peer may still be signalling this CTA's barriers / reading its smem
   else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vitb200_weights_ready": (_I, [_P]),
     "vitb200_forward_host": (_I, [_P, _P, _I, _U32, C.POINTER(_HostOutputs)]),
     "vitb200_forward_device": (_I, [_P, _P, _I, _U32, _P]),
+    "vitb200_profile_forward": (_I, [_P, _P, _I, _U32, C.c_char_p, C.c_size_t]),
     "vitb200_device_output": (_I, [_P, _U32, C.POINTER(_P), C.POINTER(_I)]),
     "vitb200_synchronize": (_I, [_P]),
     "vitb200_stage_embed": (_I, [_P, _P, _I]),
@@ -214,6 +215,17 @@ class VitEngine:
         """images: CUDA fp32 [B,3,S,S] on this engine's device; enqueues on `stream` (raw cudaStream_t)."""
         assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
         check(self.lib.vitb200_forward_device(self._h, images.data_ptr(), images.shape[0], flags, stream))
+
+    def profile_forward(self, images: torch.Tensor, flags: int = 0) -> Dict[str, tuple]:
+        """One forward with a CUDA event in front of every launch: {kernel: (launches, total_ms)} plus "total"."""
+        assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
+        buf = C.create_string_buffer(8192)
+        check(self.lib.vitb200_profile_forward(self._h, images.data_ptr(), images.shape[0], flags, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split(",")
+            out[name] = (int(n), float(ms))
+        return out
 
     def device_output(self, which: int, shape, batch_capacity: Optional[int] = None) -> torch.Tensor:
         """Zero-copy torch view of an engine-owned device buffer (valid until the next growing call)."""

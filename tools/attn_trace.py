@@ -19,10 +19,10 @@ for maps in ((True, True), (False, False)):
     lib.vitb200_debug_attn_trace.argtypes = [C.c_void_p, C.c_int]
     assert lib.vitb200_debug_attn_trace(buf, 64 * 32) == 0
     t = [[buf[h * 32 + k] for k in range(32)] for h in range(H)]
-    names = {1: "s_full passed", 2: "S ld done", 3: "max done", 4: "bar1 passed", 5: "exp+P stored", 6: "p_full arrived",
-             7: "bar2 passed", 8: "Pbar+maps done", 9: "o_full passed", 10: "O ld done"}
+    names = {1: "s_full passed", 2: "S ld done", 3: "O(h-1) epilogue", 4: "max + bar1", 5: "exp done", 6: "bar2 passed",
+             7: "P stored+arrive", 8: "maps done"}
     print(f"maps={maps}: softmax warp 4 lane 0, cycles since loop top of the head (mean over heads 2..{H - 2})")
-    for k in range(1, 11):
+    for k in range(1, 9):
         d = [t[h][k] - t[h][0] for h in range(2, H - 1)]
         print(f"   {names[k]:16s} {sum(d) / len(d):8.0f}")
     per_head = [t[h + 1][0] - t[h][0] for h in range(2, H - 2)]
@@ -30,4 +30,4 @@ for maps in ((True, True), (False, False)):
     print("  MMA thread: p_full wait %.0f, o_free wait %.0f, issue PV(+avg) %.0f, period %.0f" % (
         sum(t[h][17] - t[h][16] for h in range(2, H - 1)) / (H - 3), sum(t[h][18] - t[h][17] for h in range(2, H - 1)) / (H - 3),
         sum(t[h][19] - t[h][18] for h in range(2, H - 1)) / (H - 3), sum(t[h + 1][16] - t[h][16] for h in range(2, H - 2)) / (H - 4)))
-    print("  softmax P stored -> MMA saw p_full: %.0f" % (sum(t[h][17] - t[h][6] for h in range(2, H - 1)) / (H - 3)))
+    print("  softmax P stored -> MMA saw p_full: %.0f" % (sum(t[h][17] - t[h][7] for h in range(2, H - 1)) / (H - 3)))

@@ -94,6 +94,29 @@ def gemm_shapes():
 
 
 @case
+def gemm_cluster():
+    """4-CTA multicast clusters forced onto small shapes: share-W units, the share-A last row (even and odd n_tiles),
+    M tails, every epilogue."""
+    os.environ["VITB200_GEMM_CLUSTER_MIN_TILES"] = "0"
+    os.environ["VITB200_GEMM_PAIR"] = "4"
+    _gemm_case(512, 256, 64, False, False, False, True)
+    _gemm_case(512, 256, 768, True, False, False, True)
+    _gemm_case(768, 512, 256, True, False, False, True)      # odd m_tiles: one share-W row + one share-A unit
+    _gemm_case(768, 768, 256, True, False, False, True)      # share-A row with odd n_tiles (second pair idle)
+    _gemm_case(256, 768, 128, True, False, False, True)      # share-A only
+    _gemm_case(700, 2304, 768, True, False, True, False)     # M tail, GELU, bf16 out
+    _gemm_case(197 * 9, 768, 3072, True, True, False, True)  # residual epilogue
+    _gemm_case(197 * 64, 2304, 768, True, False, False, False)
+    _gemm_case(197 * 256, 768, 768, True, True, False, True)
+
+
+@case
+def gemm_perf_cluster():
+    os.environ["VITB200_GEMM_PAIR"] = "4"
+    gemm_perf()
+
+
+@case
 def gemm_perf():
     import torch
     from interactive_vit_b200 import engine as E
@@ -247,6 +270,43 @@ def forward_perf():
         ips = B / ms * 1e3
         print(f"    forward vit_b_16 B={B} flags={flags}: {ms:.3f} ms  {ips:.0f} img/s  "
               f"{ips * cfg.gflop_per_image() / 1e3:.1f} TFLOP/s", flush=True)
+
+
+@case
+def forward_profile():
+    """Per-kernel event times inside one real forward (vit_b_16, B=256, all maps): where the step goes."""
+    import torch
+    from interactive_vit_b200 import engine as E
+    from oracle import vit_oracle as O
+    name = os.environ.get("VITB200_PROFILE_MODEL", "vit_b_16")
+    B = int(os.environ.get("VITB200_PROFILE_BATCH", "256"))
+    ocfg = O.ORACLE_CONFIGS[name]
+    model = O.build_vit(ocfg, seed=0)
+    cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                      ocfg.num_classes)
+    eng = E.VitEngine(cfg, 0, B)
+    eng.load_state_dict(model.state_dict())
+    x = torch.rand(B, 3, ocfg.image_size, ocfg.image_size, device="cuda")
+    flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
+    for _ in range(3):
+        eng.forward_device(x, flags)
+    eng.synchronize()
+    runs = [eng.profile_forward(x, flags) for _ in range(5)]
+    keys = list(runs[0])
+    print(f"    {name} B={B}: median of 5 profiled forwards (event-to-event ms, gaps included)")
+    for k in keys:
+        ms = sorted(r[k][1] for r in runs)[2]
+        print(f"    {k:20s} x{runs[0][k][0]:3d}  {ms:8.3f} ms  {1e3 * ms / max(runs[0][k][0], 1):8.1f} us each", flush=True)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.current_stream().cuda_stream
+    eng.forward_device(x, flags, st)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(5):
+        eng.forward_device(x, flags, st)
+    t1.record()
+    torch.cuda.synchronize()
+    print(f"    unprofiled forward: {t0.elapsed_time(t1) / 5:.3f} ms", flush=True)
 
 
 def main():
