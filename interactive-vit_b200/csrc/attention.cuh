@@ -80,9 +80,9 @@ constexpr int kPBlocks = (KP_MAX + 63) / 64;       // 4
 constexpr int kPBytes = kPBlocks * kPBlockBytes;   // 64 KB
 constexpr int kIdentBytes = 16 * 128;              // 16 x 16 bf16 identity in 128-B rows (B operand of the head-average MMAs)
 constexpr int kCtxStageBytes = BM * D * 2;         // 16 KB: bf16 context tile of one head, staged for the TMA store
-constexpr int kRedBytes = 2 * kColGroups * BM * 4; // row max / row sum exchange: [2 kinds][4 groups][128 rows]
-constexpr int kClsStageBytes = 256 * 4;            // normalised probabilities of query row 0 (one head)
-constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kCtxStageBytes + kIdentBytes + kRedBytes + kClsStageBytes + 256;
+constexpr int kRedBytes = 2 * 2 * kColGroups * BM * 4;  // row max / row sum exchange: [head parity][2 kinds][4 groups][128 rows]
+constexpr int kClsStageBytes = KP_MAX * 4;         // normalised probabilities of query row 0 (one head)
+constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kCtxStageBytes + kIdentBytes + kRedBytes + kClsStageBytes + 128;
 static_assert(kSmemBytes <= 227 * 1024, "attention: shared memory budget");
 }  // namespace attn_cfg
 
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(attn_cfg::kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 over qkv [B*N, 3d]
                  const __grid_constant__ CUtensorMap tmap_kv,  // box 64 x (KP/2) over the same tensor
                  const __grid_constant__ CUtensorMap tmap_ctx, // box 64 x 32 x 1 over ctx viewed as [B][N][d]: rows >= N clip
+                 const __grid_constant__ CUtensorMap tmap_avg, // fp32, box 32 x 128 x 1 over avg_map viewed as [B][N][ldmap]
                  AttnParams p) {
   using namespace attn_cfg;
   // Dynamic smem starts 1024-B aligned (it follows the 1 KB the driver reserves); keeping the array typed lets
@@ -103,7 +104,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   uint8_t* smem_ctx = smem_p + kPBytes;      // 4 quarter tiles of 32 rows x 128 B, 128-B swizzle
   uint8_t* smem_id = smem_ctx + kCtxStageBytes;
   float* red = reinterpret_cast<float*>(smem_id + kIdentBytes);  // [kind][group][row]
-  float* cls_stage = red + 2 * kColGroups * BM;                   // [256] normalised probabilities of query row 0
+  float* cls_stage = red + 2 * 2 * kColGroups * BM;               // [KP_MAX] normalised probabilities of query row 0
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_id + kIdentBytes + kRedBytes + kClsStageBytes);
   uint64_t* full_bar = bars;        // [2] Q/K/V of a head landed
   uint64_t* empty_bar = bars + 2;   // [2] Q/K/V stage consumed by the MMAs
@@ -130,6 +131,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     ptx::prefetch_tmap(&tmap_q);
     ptx::prefetch_tmap(&tmap_kv);
     ptx::prefetch_tmap(&tmap_ctx);
+    ptx::prefetch_tmap(&tmap_avg);
   }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(&full_bar[0], 1);
@@ -287,11 +289,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     const int nmy = gbase + (cg < grem ? 1 : 0);               // granules of this thread
     const int g0 = cg * gbase + (cg < grem ? cg : grem);       // first granule
     const float inv_h = 1.0f / static_cast<float>(p.H);
+    const bool has_pad = (g0 + nmy) * 8 > p.N;                 // warp-uniform: this column group owns padded keys
     const bool want_cls = p.cls_map != nullptr && qt == 0 && quarter == 0;
     const uint32_t p_row = ptx::smem_u32(smem_p) + r * 128;
     const int sw = r & 7;
-    float* red_max = red;                        // [group][row]
-    float* red_sum = red + kColGroups * BM;
     const uint32_t t_s = lane_base + kTmemS + g0 * 8;
     const uint32_t t_avg = lane_base + kTmemAvg + g0 * 8;
     const uint32_t t_o = lane_base + kTmemO + cg * 16;  // this thread's 16 of the 64 context columns
@@ -346,31 +347,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 
       ATTN_TS(3);
 
-      // ---- row max (own granules, then the other three groups' through smem); padded keys (>= N) count as -inf
-      float mx = -INFINITY;
+      // ---- padded keys (>= N) count as -inf.  Only the last column group can own any (KP - N < 16): warp-uniform
+      if (has_pad) {
 #pragma unroll
-      for (int c = 0; c < kMaxGran; ++c) {
-        if (c < nmy) {
+        for (int c = 0; c < kMaxGran; ++c) {
           const int key0 = (g0 + c) * 8;
-          if (key0 + 8 > p.N) {
+          if (c < nmy && key0 + 8 > p.N) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (key0 + j >= p.N) s[c][j] = 0xff800000u;  // -inf: exp2 gives 0, max ignores it
           }
+        }
+      }
+
+      // ---- e = exp2((s - m_t) * c) with the maximum m_t of this thread's OWN columns: no exchange is needed before
+      //      the exponentials.  Softmax is invariant to the shift, the four threads of a row reconcile afterwards:
+      //      p = e * f_t,  f_t = exp2((m_t - M) c) / sum_u(sum_u exp2((m_u - M) c)),  M = max_u m_u.
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kMaxGran; ++c) {
+        if (c < nmy) {
 #pragma unroll
           for (int j = 0; j < 8; j += 2) mx = ptx::fmax3(mx, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
         }
       }
-      red_max[cg * BM + r] = mx;
-      // the context tile of head h-2 has been read out of smem before anyone can restage it (after this barrier);
-      // only the issuing thread has a bulk group outstanding, for everyone else this returns immediately
-      ptx::tma_store_wait_read<0>();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // a thread whose columns are all padding (tiny test shapes) must not produce -inf - -inf
+      const float mxs = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
       ATTN_TS(4);
-      mx = fmaxf(fmaxf(red_max[r], red_max[BM + r]), fmaxf(red_max[2 * BM + r], red_max[3 * BM + r]));
-      const float mxs = mx * p.scale_log2;
-
-      // ---- e = exp2(s*c - max*c) in place
       float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
@@ -388,10 +391,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         }
       }
       ATTN_TS(5);
+      // exchange buffers alternate with the head parity: with one barrier per head a fast thread may already write
+      // head h+1's values while a slow one still reads head h's
+      float* red_max = red + (h & 1) * (2 * kColGroups * BM);  // [group][row]
+      float* red_sum = red_max + kColGroups * BM;
+      red_max[cg * BM + r] = (mx == -INFINITY) ? -INFINITY : mxs;   // already in the exp2 domain
       red_sum[cg * BM + r] = (ps0 + ps1) + (ps2 + ps3);
-      asm volatile("bar.sync 2, 512;" ::: "memory");
+      // the context tile of head h-2 has been read out of smem before anyone can restage it (after this barrier);
+      // only the issuing thread has a bulk group outstanding, for everyone else this returns immediately
+      ptx::tma_store_wait_read<0>();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       ATTN_TS(6);
-      const float inv = ptx::rcp_approx((red_sum[r] + red_sum[BM + r]) + (red_sum[2 * BM + r] + red_sum[3 * BM + r]));
+      float inv;
+      {
+        const float m0 = red_max[r], m1 = red_max[BM + r], m2 = red_max[2 * BM + r], m3 = red_max[3 * BM + r];
+        const float M = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        // groups without a valid column have m = -inf and sum = 0: exp2(-inf) = 0 keeps them out
+        const float tot = (red_sum[r] * ptx::ex2_approx(m0 - M) + red_sum[BM + r] * ptx::ex2_approx(m1 - M)) +
+                          (red_sum[2 * BM + r] * ptx::ex2_approx(m2 - M) + red_sum[3 * BM + r] * ptx::ex2_approx(m3 - M));
+        inv = ptx::ex2_approx(mxs - M) * ptx::rcp_approx(tot);
+        if (mx == -INFINITY) inv = 0.f;
+      }
 
       // ---- the P tile is about to be overwritten: the previous head's P V and Pbar MMAs (issued a whole softmax
       //      pass ago) must have retired
@@ -459,21 +479,43 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     o_epilogue(p.H - 1);
     ptx::tma_store_wait<0>();
 
-    // head-averaged map rows -> HBM, once per (image, query row): Pbar holds the SUM over heads
+    // head-averaged map rows -> HBM, once per (image, query tile): Pbar holds the SUM over heads.  The tile goes
+    // through shared memory (the Q/K/V stages are dead by now) as 32-column slabs of 128 rows x 128 B in the 128-B
+    // swizzle and leaves with one TMA store per slab; rows beyond the image and columns beyond ldmap are clipped by
+    // the [B][N][ldmap] tensor map.  (32-B-per-thread global stores from here cost ~14% of the kernel: every
+    // warp-wide STG touched 32 different lines.)
     if (want_avg) {
-#pragma unroll 1
-      for (int c = 0; c < nmy; ++c) {
-        uint32_t a[8];
-        ptx::tmem_ld_x8(t_avg + c * 8, a);
-        ptx::tmem_ld_wait();
-        if (row_ok) {
-          float4* ap = reinterpret_cast<float4*>(p.avg_map + (static_cast<size_t>(b) * p.N + qrow) * p.ldmap + (g0 + c) * 8);
-          ap[0] = make_float4(__uint_as_float(a[0]) * inv_h, __uint_as_float(a[1]) * inv_h, __uint_as_float(a[2]) * inv_h,
-                              __uint_as_float(a[3]) * inv_h);
-          ap[1] = make_float4(__uint_as_float(a[4]) * inv_h, __uint_as_float(a[5]) * inv_h, __uint_as_float(a[6]) * inv_h,
-                              __uint_as_float(a[7]) * inv_h);
+      uint32_t a[kMaxGran][8];
+#pragma unroll
+      for (int c = 0; c < kMaxGran; ++c)
+        if (c < nmy) ptx::tmem_ld_x8(t_avg + c * 8, a[c]);
+      ptx::tmem_ld_wait();
+      const uint32_t slab0 = ptx::smem_u32(smem) + r * 128;
+#pragma unroll
+      for (int c = 0; c < kMaxGran; ++c) {
+        if (c < nmy) {
+          const int g = g0 + c;
+          const uint32_t dst = slab0 + (g >> 2) * (BM * 128);
+          const int ch = 2 * (g & 3);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((ch ^ sw) << 4)),
+                       "f"(__uint_as_float(a[c][0]) * inv_h), "f"(__uint_as_float(a[c][1]) * inv_h),
+                       "f"(__uint_as_float(a[c][2]) * inv_h), "f"(__uint_as_float(a[c][3]) * inv_h)
+                       : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (((ch + 1) ^ sw) << 4)),
+                       "f"(__uint_as_float(a[c][4]) * inv_h), "f"(__uint_as_float(a[c][5]) * inv_h),
+                       "f"(__uint_as_float(a[c][6]) * inv_h), "f"(__uint_as_float(a[c][7]) * inv_h)
+                       : "memory");
         }
       }
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (warp == kCtrlWarps && ptx::elect_one()) {
+        const int nslabs = (KP + 31) >> 5;
+        for (int j = 0; j < nslabs; ++j) ptx::tma_store_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, b);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait<0>();
+      }
+      __syncwarp();
     }
   }
 

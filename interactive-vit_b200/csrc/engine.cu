@@ -116,6 +116,25 @@ static int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t batch, 
   return VITB200_OK;
 }
 
+// 3-D fp32 tensor [batch][rows][cols], box = 32 cols (128 B) x box_rows x 1, 128-byte swizzle (attention-map stores).
+static int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 4) % 16 != 0 || box_rows == 0 || box_rows > 256)
+    return fail(VITB200_ERR_INVALID, "fp32 TMA operand must be 16-byte aligned (base %p, pitch %llu B)", base,
+                (unsigned long long)(ld * 4));
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld * 4, rows * ld * 4};
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 3-D) failed with CUresult %d", (int)r);
+  return VITB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ launch helpers
 static int g_num_sms = 0;
 
@@ -262,6 +281,8 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   VT_TRY(make_tmap_bf16(&tq, qkv, (uint64_t)B * N, 3 * d, 3 * d, BM, D));
   VT_TRY(make_tmap_bf16(&tkv, qkv, (uint64_t)B * N, 3 * d, 3 * d, KP / 2, D));
   VT_TRY(make_tmap_bf16_3d(&tctx, ctx, B, N, d, d, 32, D));
+  CUtensorMap tavg = tctx;  // placeholder when no head-averaged map is requested (never dereferenced)
+  if (avg) VT_TRY(make_tmap_f32_3d(&tavg, avg, B, N, pitch, pitch, BM));
   static bool configured = false;
   if (!configured) {
     CU_TRY(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -273,8 +294,8 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
   p.ctx = ctx, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
   p.q_tiles = (N + BM - 1) / BM;
-  if (heads) attention_kernel<true><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, p);
-  else attention_kernel<false><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, p);
+  if (heads) attention_kernel<true><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
+  else attention_kernel<false><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   CU_TRY(cudaGetLastError());
   return VITB200_OK;
 }

@@ -19,10 +19,10 @@ for maps in ((True, True), (False, False)):
     lib.vitb200_debug_attn_trace.argtypes = [C.c_void_p, C.c_int]
     assert lib.vitb200_debug_attn_trace(buf, 64 * 32) == 0
     t = [[buf[h * 32 + k] for k in range(32)] for h in range(H)]
-    names = {1: "s_full passed", 2: "S ld done", 3: "O(h-1) epilogue", 4: "max + bar1", 5: "exp done", 6: "bar2 passed",
-             7: "P stored+arrive", 8: "maps done"}
+    names = {1: "s_full passed", 2: "S ld done", 4: "mask+max done", 5: "exp done", 6: "bar passed",
+             7: "P stored+arrive", 8: "O epi+maps done"}
     print(f"maps={maps}: softmax warp 4 lane 0, cycles since loop top of the head (mean over heads 2..{H - 2})")
-    for k in range(1, 9):
+    for k in (1, 2, 4, 5, 6, 7, 8):
         d = [t[h][k] - t[h][0] for h in range(2, H - 1)]
         print(f"   {names[k]:16s} {sum(d) / len(d):8.0f}")
     per_head = [t[h + 1][0] - t[h][0] for h in range(2, H - 2)]
@@ -31,3 +31,4 @@ for maps in ((True, True), (False, False)):
         sum(t[h][17] - t[h][16] for h in range(2, H - 1)) / (H - 3), sum(t[h][18] - t[h][17] for h in range(2, H - 1)) / (H - 3),
         sum(t[h][19] - t[h][18] for h in range(2, H - 1)) / (H - 3), sum(t[h + 1][16] - t[h][16] for h in range(2, H - 2)) / (H - 4)))
     print("  softmax P stored -> MMA saw p_full: %.0f" % (sum(t[h][17] - t[h][7] for h in range(2, H - 1)) / (H - 3)))
+    print("  whole CTA 0 (first stamp of head 0 -> last stamp): %.0f cycles" % (max(t[H - 1][8], t[H - 1][19]) - t[0][0]))
