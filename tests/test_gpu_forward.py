@@ -53,7 +53,11 @@ def test_forward_matches_oracle(E, name, batch, init):
         assert torch.isfinite(got[k]).all(), k
         assert _rel(got[k], ref[k]) < TOL, (k, _rel(got[k], ref[k]))
     assert torch.equal(got["logits"].argmax(-1), ref["logits"].argmax(-1))
-    assert (got["avg_maps"].sum(-1) - 1).abs().max() < 1e-4
+    # the head average is accumulated on the tensor pipe from the bf16 probabilities that also feed P V (fp32
+    # accumulation): every row sums to 1 within bf16 rounding (2^-9 per element, partly averaging out), not fp32
+    assert (got["avg_maps"].sum(-1) - 1).abs().max() < 4e-3
+    # the per-head class-token rows are emitted from the fp32 probabilities
+    assert (got["cls_maps"].sum(-1) - 1).abs().max() < 1e-4
     eng.close()
 
 
@@ -177,7 +181,7 @@ def test_bench_size_properties(E):
     flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
     big = eng.forward_host(x, flags)
     assert torch.isfinite(big["logits"]).all()
-    assert (big["avg_maps"].sum(-1) - 1).abs().max() < 1e-4
+    assert (big["avg_maps"].sum(-1) - 1).abs().max() < 4e-3  # bf16 probabilities feed the on-chip head average
     assert (big["cls_maps"].sum(-1) - 1).abs().max() < 1e-4
     assert ((big["rollout"].sum(-1) <= 1.0 + 1e-4) & (big["rollout"].min(-1).values >= 0)).all()
     for i in (0, 127, 255):

@@ -112,7 +112,8 @@ def test_attention(E, B, N, H, scale):
     o, p = _attn_ref(qkv, B, N, H)
     assert _rel(ctx, o) < 2 * BF16_EPS           # P is rounded to bf16 for the P.V product, the output again
     assert _rel(hm, p) < 1e-5                    # probabilities are emitted in fp32
-    assert _rel(avg, p.mean(1)) < 1e-5
+    # the head average is summed on the tensor pipe (fp32 accumulate) from the SAME bf16 probabilities that feed P.V
+    assert _rel(avg, p.mean(1)) < BF16_EPS
     assert _rel(cls, p[:, :, 0, :]) < 1e-5
     assert (hm.sum(-1) - 1).abs().max() < 1e-5   # rows of a softmax
     # outputs selected independently give the same context
