@@ -486,12 +486,27 @@ static int run_head(vitb200_engine* e, int B, cudaStream_t st) {
   return VITB200_OK;
 }
 
-static int run_rollout(vitb200_engine* e, int B, cudaStream_t st) {
-  if (e->N > 256) return fail(VITB200_ERR_INVALID, "rollout: at most 256 tokens");
-  prof_mark(e, "rollout", st);
-  rollout_cls_kernel<<<B, kRolloutThreads, 0, st>>>((const float*)e->avg.p, (long)e->cap_batch * e->N * e->pitch,
-                                           e->cfg.num_layers, e->N, e->pitch, (float*)e->rollout.p);
+// stages: as many as fit two CTAs per SM (the copies in flight are what saturates HBM)
+static int launch_rollout(const float* maps, long layer_stride, int L, int B, int N, int ld, float* out, cudaStream_t st) {
+  if (N > kRolloutThreads * kRolloutMaxCols) return fail(VITB200_ERR_INVALID, "rollout: at most %d tokens", kRolloutThreads * kRolloutMaxCols);
+  if (ld % 4 != 0 || ld < N) return fail(VITB200_ERR_INVALID, "rollout: pitch %d must be >= %d and a multiple of 4", ld, N);
+  int stages = 8;
+  while (stages > 2 && rollout_smem_bytes(ld, stages) > 110 * 1024) --stages;
+  const int smem = rollout_smem_bytes(ld, stages);
+  static int configured = 0;
+  if (configured < smem) {
+    CU_TRY(cudaFuncSetAttribute(rollout_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  rollout_cls_kernel<<<B, kRolloutThreads, smem, st>>>(maps, layer_stride, L, N, ld, stages, out);
   CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
+static int run_rollout(vitb200_engine* e, int B, cudaStream_t st) {
+  prof_mark(e, "rollout", st);
+  VT_TRY(launch_rollout((const float*)e->avg.p, (long)e->cap_batch * e->N * e->pitch, e->cfg.num_layers, B, e->N, e->pitch,
+                        (float*)e->rollout.p, st));
   e->launches += 1;
   return VITB200_OK;
 }
@@ -932,10 +947,7 @@ int vitb200_op_patchify(const float* images, void* patches, int batch, int image
 int vitb200_op_rollout(const float* maps, long layer_stride, int layers, int batch, int tokens, int pitch, float* out,
                        void* stream) {
   if (!maps || !out) return fail(VITB200_ERR_INVALID, "null argument");
-  if (tokens > 256) return fail(VITB200_ERR_INVALID, "rollout: at most 256 tokens");
-  rollout_cls_kernel<<<batch, kRolloutThreads, 0, (cudaStream_t)stream>>>(maps, layer_stride, layers, tokens, pitch, out);
-  CU_TRY(cudaGetLastError());
-  return VITB200_OK;
+  return launch_rollout(maps, layer_stride, layers, batch, tokens, pitch, out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

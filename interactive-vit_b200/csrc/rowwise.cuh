@@ -129,49 +129,172 @@ f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out
 // Only row 0 of R is needed, so r <- r * Ahat_l is evaluated right-to-left over layers L, L-1, ..., 1:
 // L vector-matrix products of N x N instead of L matrix-matrix products.  With w_k = r_k / rowsum_k:
 //     (r * Ahat)_j = 0.5 * sum_k w_k Abar[k, j] + 0.5 * w_j
-// One CTA (1024 threads) per image: 32 warps take the row sums (coalesced 128-B row reads), then 4 thread
-// groups split the k range of the vector-matrix product (coalesced across j) and are reduced through smem.
-// maps: [L][B, N, ld] fp32 (layer stride given in floats); N <= 256.
-constexpr int kRolloutThreads = 1024;
+//
+// HBM-bound: L * N * ld * 4 bytes per image, each byte read ONCE.  One 256-thread CTA per image streams the
+// maps through a ring of shared-memory stages with bulk async copies (cp.async.bulk + mbarrier), kRolloutRows
+// rows per stage; the copies do not depend on r, so they run ahead across layer boundaries while the
+// layer-to-layer dependency (the 197-float vector) stays on chip.  Per stage: every warp reduces the row sums of
+// two rows (coalesced smem reads), then each thread accumulates its column(s) over the stage's rows.
+// For the top layer r = e_0, so only row 0 is fetched.  maps: [L][B, N, ld] fp32; N <= kRolloutThreads * 3.
+constexpr int kRolloutThreads = 256;
+constexpr int kRolloutRows = 16;      // rows per stage
+constexpr int kRolloutMaxCols = 3;    // columns per thread: N <= 768
+__host__ __device__ inline int rollout_stage_bytes(int ld) { return kRolloutRows * ld * 4; }
+__host__ __device__ inline int rollout_smem_bytes(int ld, int stages) {
+  return stages * rollout_stage_bytes(ld) + 2 * kRolloutMaxCols * kRolloutThreads * 4 + kRolloutRows * 4 + 16 * 8 +
+         4 * ld * 4 /* partial-product scratch */;
+}
+
+// one (layer, chunk) cursor of the streaming schedule; the top layer contributes only row 0 (r = e_0 there)
+struct RolloutCursor {
+  int layer, chunk, stage, parity;
+  __device__ void advance(int L, int chunks_per_layer, int stages) {
+    const int n = (layer == L - 1) ? 1 : chunks_per_layer;
+    if (++chunk == n) chunk = 0, --layer;
+    if (++stage == stages) stage = 0, parity ^= 1;
+  }
+};
+
 __global__ void __launch_bounds__(kRolloutThreads)
-rollout_cls_kernel(const float* __restrict__ maps, long layer_stride, int L, int N, int ld, float* __restrict__ out /*[B, N-1]*/) {
-  __shared__ float r[256];        // current row vector
-  __shared__ float w[256];        // r_k / rowsum_k
-  __shared__ float part[4][256];  // partial products per k group
+rollout_cls_kernel(const float* __restrict__ maps, long layer_stride, int L, int N, int ld, int stages,
+                   float* __restrict__ out /*[B, N-1]*/) {
+  extern __shared__ __align__(128) uint8_t rsm[];
+  const int stage_bytes = rollout_stage_bytes(ld);
+  float* r = reinterpret_cast<float*>(rsm + stages * stage_bytes);   // current row vector [<= 768]
+  float* w = r + kRolloutMaxCols * kRolloutThreads;                   // r_k / rowsum_k
+  float* wchunk = w + kRolloutMaxCols * kRolloutThreads;              // the stage's w_k
+  uint64_t* full = reinterpret_cast<uint64_t*>(wchunk + kRolloutRows);   // [<= 16] one mbarrier per stage; scratch follows
+  float4* scratch = reinterpret_cast<float4*>(wchunk + kRolloutRows + 32);  // [4 row groups][ld] partial products
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j = tid & 255, g = tid >> 8;
-  const int kper = (N + 3) / 4;
-  for (int l = L - 1; l >= 0; --l) {
-    const float* A = maps + l * layer_stride + static_cast<long>(b) * N * ld;
-    // w_k = r_k / (0.5 * rowsum_k + 0.5); for the top layer r = e_0
-    for (int k = warp; k < N; k += 32) {
-      float s = 0.f;
-#pragma unroll 8
-      for (int c = lane; c < N; c += 32) s += A[static_cast<long>(k) * ld + c];
-      s = warp_sum(s);
-      if (lane == 0) {
-        const float rk = (l == L - 1) ? (k == 0 ? 1.0f : 0.0f) : r[k];
-        w[k] = rk / (0.5f * s + 0.5f);
-      }
+  const int chunks_per_layer = (N + kRolloutRows - 1) / kRolloutRows;
+  const int ld4 = ld >> 2;
+  const float* img = maps + static_cast<long>(b) * N * ld;
+
+  auto issue = [&](const RolloutCursor& c) {
+    const int row0 = c.chunk * kRolloutRows;
+    const int rows = (c.layer == L - 1) ? 1 : min(kRolloutRows, N - row0);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ld * 4;
+    const float* src = img + c.layer * layer_stride + static_cast<long>(row0) * ld;
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&full[c.stage]));
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(rsm + c.stage * stage_bytes));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+  };
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&full[s]));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     }
-    __syncthreads();
-    float acc = 0.f;
-    if (j < N) {
-      if (l == L - 1) {
-        if (g == 0) acc = w[0] * A[j];  // only k = 0 contributes
-      } else {
-        const int k0 = g * kper, k1 = min(N, k0 + kper);
-#pragma unroll 8
-        for (int k = k0; k < k1; ++k) acc = fmaf(w[k], A[static_cast<long>(k) * ld + j], acc);
-      }
-    }
-    part[g][j] = acc;
-    __syncthreads();
-    if (g == 0 && j < N) r[j] = 0.5f * ((part[0][j] + part[1][j]) + (part[2][j] + part[3][j])) + 0.5f * w[j];
-    __syncthreads();
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (g == 0 && j >= 1 && j < N) out[static_cast<long>(b) * (N - 1) + j - 1] = r[j];
+  for (int j = tid; j < kRolloutMaxCols * kRolloutThreads; j += kRolloutThreads) r[j] = (j == 0) ? 1.0f : 0.0f, w[j] = 0.0f;
+  __syncthreads();
+  RolloutCursor prod{L - 1, 0, 0, 0};   // next chunk to fetch (thread 0)
+  if (tid == 0)
+    for (int q = 0; q < stages && prod.layer >= 0; ++q) issue(prod), prod.advance(L, chunks_per_layer, stages);
+
+  float4 acc4[kRolloutMaxCols];
+#pragma unroll
+  for (int i = 0; i < kRolloutMaxCols; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int g = tid >> 6, t = tid & 63;   // accumulate pass: row group, float4 column
+  RolloutCursor cons{L - 1, 0, 0, 0};
+  while (cons.layer >= 0) {
+    const int row0 = cons.chunk * kRolloutRows;
+    const int rows = (cons.layer == L - 1) ? 1 : min(kRolloutRows, N - row0);
+    const bool layer_end = (cons.layer == L - 1) || (cons.chunk == chunks_per_layer - 1);
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&full[cons.stage]));
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+          : "=r"(ok)
+          : "r"(bar), "r"(cons.parity)
+          : "memory");
+    }
+    const float* A = reinterpret_cast<const float*>(rsm + cons.stage * stage_bytes);
+    // row sums -> w_k = r_k / (0.5 * rowsum_k + 0.5): 8 warps x 2 rows, both rows' 128-bit reads in flight together.
+    // Only the float4 that straddles column N needs masking (pad columns may hold anything).
+    {
+      const int k0 = warp, k1 = warp + kRolloutThreads / 32;
+      const float4* rowa = reinterpret_cast<const float4*>(A + k0 * ld);
+      const float4* rowb = reinterpret_cast<const float4*>(A + k1 * ld);
+      const bool has_b = k1 < rows;
+      float sa = 0.f, sb = 0.f;
+      if (k0 < rows) {
+        for (int c = lane; c < ld4; c += 32) {
+          float4 va = rowa[c];
+          float4 vb = has_b ? rowb[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int j = 4 * c;
+          if (j + 3 >= N) {
+            if (j >= N) va.x = 0.f, vb.x = 0.f;
+            if (j + 1 >= N) va.y = 0.f, vb.y = 0.f;
+            if (j + 2 >= N) va.z = 0.f, vb.z = 0.f;
+            va.w = 0.f, vb.w = 0.f;
+          }
+          sa += (va.x + va.y) + (va.z + va.w);
+          sb += (vb.x + vb.y) + (vb.z + vb.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if (lane == 0) {
+          const float wk = __fdividef(r[row0 + k0], 0.5f * sa + 0.5f);
+          wchunk[k0] = wk, w[row0 + k0] = wk;
+          if (has_b) {
+            const float wk1 = __fdividef(r[row0 + k1], 0.5f * sb + 0.5f);
+            wchunk[k1] = wk1, w[row0 + k1] = wk1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // columns: thread t of row-group g (4 groups of 64 threads) owns columns 4t .. 4t+3 (+256 i) and the stage's
+    // rows k = g, g+4, ...; the four partial sums meet at the end of the layer
+#pragma unroll
+    for (int i = 0; i < kRolloutMaxCols; ++i) {
+      const int c4 = t + 64 * i;
+      if (c4 < ld4) {
+        float4 a = acc4[i];
+#pragma unroll
+        for (int kk = 0; kk < kRolloutRows / 4; ++kk) {
+          const int k = g + 4 * kk;
+          if (k < rows) {
+            const float wk = wchunk[k];
+            const float4 v = reinterpret_cast<const float4*>(A + k * ld)[c4];
+            a.x = fmaf(wk, v.x, a.x), a.y = fmaf(wk, v.y, a.y), a.z = fmaf(wk, v.z, a.z), a.w = fmaf(wk, v.w, a.w);
+          }
+        }
+        acc4[i] = a;
+      }
+    }
+    if (layer_end) {
+#pragma unroll
+      for (int i = 0; i < kRolloutMaxCols; ++i) {
+        const int c4 = t + 64 * i;
+        if (c4 < ld4) scratch[g * ld4 + c4] = acc4[i];
+        acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();  // the stage and wchunk are free again (and the partial products are staged)
+    if (tid == 0 && prod.layer >= 0) issue(prod), prod.advance(L, chunks_per_layer, stages);
+    if (layer_end) {
+      // r <- 0.5 * (sum of the four partial products) + 0.5 * w
+      const float* sc = reinterpret_cast<const float*>(scratch);
+      for (int j = tid; j < N; j += kRolloutThreads) {
+        const float a = (sc[j] + sc[ld + j]) + (sc[2 * ld + j] + sc[3 * ld + j]);
+        r[j] = 0.5f * a + 0.5f * w[j];
+      }
+      __syncthreads();   // (w needs no reset: rows 1.. of the top layer keep their initial 0, later layers rewrite all)
+    }
+    cons.advance(L, chunks_per_layer, stages);
+  }
+  __syncthreads();
+  for (int j = tid + 1; j < N; j += kRolloutThreads) out[static_cast<long>(b) * (N - 1) + j - 1] = r[j];
 }
 
 }  // namespace vitb200
