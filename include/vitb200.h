@@ -45,7 +45,7 @@ typedef struct vitb200_config {
   int image_size;  /* S: square input side, multiple of patch_size                    */
   int patch_size;  /* p: 16 (multiple of 8)                                            */
   int num_layers;  /* L                                                                */
-  int num_heads;   /* H; head dim hidden_dim / H must be 64                            */
+  int num_heads;   /* H; head dim hidden_dim / H in 64..128, multiple of 16 (64 or 80)  */
   int hidden_dim;  /* d: multiple of 128                                               */
   int mlp_dim;     /* multiple of 64                                                   */
   int num_classes; /* multiple of 8                                                    */
@@ -127,6 +127,10 @@ int vitb200_op_layernorm(const float* x_dev, const float* gamma_dev, const float
                          int rows, int d, float eps, void* stream);
 int vitb200_op_attention(const void* qkv_bf16_dev, void* ctx_bf16_dev, float* avg_dev, float* cls_dev,
                          float* heads_dev, int batch, int tokens, int heads, int pitch, void* stream);
+/* Same with an explicit head dimension (64..128 in steps of 16; ViT-H uses 80).  Token counts above 208 or head
+ * dimensions other than 64 take the key-blocked two-kernel path (attention_long.cuh). */
+int vitb200_op_attention_ex(const void* qkv_bf16_dev, void* ctx_bf16_dev, float* avg_dev, float* cls_dev,
+                            float* heads_dev, int batch, int tokens, int heads, int head_dim, int pitch, void* stream);
 int vitb200_op_patchify(const float* images_dev, void* patches_bf16_dev, int batch, int image_size, int patch,
                         void* stream);
 int vitb200_op_rollout(const float* maps_dev, long layer_stride, int layers, int batch, int tokens, int pitch,

@@ -23,6 +23,7 @@
 
 #include "../../include/vitb200.h"
 #include "attention.cuh"
+#include "attention_long.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
 
@@ -268,12 +269,49 @@ static int launch_layernorm(const float* x, long in_stride, const float* g, cons
   return VITB200_OK;
 }
 
+// Long / wide variant (attention_long.cuh): any N, head dims 64..128.  `stats` holds B*H*N float2 (row max, 1/sum).
+static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* avg, float* cls, float* heads, int B,
+                                 int N, int H, int D, int pitch, float2* stats, cudaStream_t st) {
+  using namespace attn_long_cfg;
+  if (D < 64 || D > 128 || D % 16 != 0) return fail(VITB200_ERR_INVALID, "attention: head dim %d not in 64..128 step 16", D);
+  if ((avg || heads) && (pitch < N || pitch % 4 != 0))
+    return fail(VITB200_ERR_INVALID, "attention: map pitch %d must be >= %d and a multiple of 4", pitch, N);
+  if (!stats) return fail(VITB200_ERR_INVALID, "attention: statistics buffer missing");
+  const int d = H * D;
+  CUtensorMap tqkv;
+  VT_TRY(make_tmap_bf16_3d(&tqkv, qkv, B, N, 3 * d, 3 * d, 128, 64));
+  static bool configured = false;
+  if (!configured) {
+    CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtx));
+    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
+    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
+    configured = true;
+  }
+  AttnLongParams p;
+  p.B = B, p.N = N, p.H = H, p.D = D, p.d = d;
+  p.q_tiles = (N + BM - 1) / BM, p.k_blocks = (N + BK - 1) / BK;
+  p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
+  p.ctx = ctx, p.stats = stats, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
+  attention_long_ctx_kernel<<<B * p.q_tiles * H, kThreads, kSmemCtx, st>>>(tqkv, p);
+  CU_TRY(cudaGetLastError());
+  if (avg || cls || heads) {
+    const int grid = B * p.q_tiles * p.k_blocks;
+    if (heads) attention_long_maps_kernel<true><<<grid, kThreads, kSmemMaps, st>>>(tqkv, p);
+    else attention_long_maps_kernel<false><<<grid, kThreads, kSmemMaps, st>>>(tqkv, p);
+    CU_TRY(cudaGetLastError());
+  }
+  return VITB200_OK;
+}
+
+// Row pitch of the attention maps for N tokens: the fused kernel pads keys to 16, the long kernel needs 4.
+static int attention_pitch(int N) { return (N + 15) / 16 * 16; }
+static bool attention_is_fused(int N, int D) { return D == 64 && (N + 15) / 16 * 16 <= attn_cfg::KP_MAX; }
+
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* avg, float* cls, float* heads, int B,
-                            int N, int H, int pitch, cudaStream_t st) {
+                            int N, int H, int D, int pitch, float2* stats, cudaStream_t st) {
   using namespace attn_cfg;
+  if (!attention_is_fused(N, D)) return launch_attention_long(qkv, ctx, avg, cls, heads, B, N, H, D, pitch, stats, st);
   const int KP = (N + 15) / 16 * 16;
-  if (KP > KP_MAX) return fail(VITB200_ERR_INVALID, "attention: %d tokens exceed this kernel's limit of %d", N, KP_MAX);
-  if (N > 2 * BM) return fail(VITB200_ERR_INVALID, "attention: more than two query tiles");
   if ((avg || heads) && (pitch < KP || pitch % 4 != 0))
     return fail(VITB200_ERR_INVALID, "attention: map pitch %d must be >= %d and a multiple of 4", pitch, KP);
   const int d = H * D;
@@ -337,7 +375,7 @@ struct vitb200_engine {
   // activations (sized for cap_batch images)
   int cap_batch = 0;
   uint32_t cap_flags = 0;
-  Buffer images, patches, x, ln, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout;
+  Buffer images, patches, x, ln, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
 
   // vitb200_profile_forward: an event in front of every launch (only while `profiling`)
   bool profiling = false;
@@ -373,6 +411,7 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   VT_TRY(ensure(e->ln, M * c.hidden_dim * 2));
   VT_TRY(ensure(e->qkv, M * 3 * c.hidden_dim * 2));
   VT_TRY(ensure(e->ctx, M * c.hidden_dim * 2));
+  if (!attention_is_fused(e->N, e->D)) VT_TRY(ensure(e->attn_stats, M * c.num_heads * sizeof(float2)));
   VT_TRY(ensure(e->mlp, M * c.mlp_dim * 2));
   VT_TRY(ensure(e->cls_ln, (size_t)B * c.hidden_dim * 2));
   VT_TRY(ensure(e->logits, (size_t)B * c.num_classes * 4));
@@ -443,7 +482,7 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
                   : nullptr;
   prof_mark(e, "attention", st);
   VT_TRY(launch_attention((const __nv_bfloat16*)e->qkv.p, (__nv_bfloat16*)e->ctx.p, avg, cls, hm, B, e->N, c.num_heads,
-                          e->pitch, st));
+                          e->D, e->pitch, (float2*)e->attn_stats.p, st));
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_out_proj", st);
@@ -545,7 +584,7 @@ static int copy_rows_to_host(float* dst, const float* src_dev, size_t rows, int 
 }  // namespace vitb200
 
 vitb200_engine::~vitb200_engine() {
-  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &ln, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout};
+  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &ln, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats};
   for (Buffer* b : bufs) release(*b);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(w_patch), fr(b_patch), fr(cls_token), fr(pos), fr(lnf_g), fr(lnf_b), fr(w_head), fr(b_head);
@@ -569,16 +608,19 @@ int vitb200_create(const vitb200_config* cfg, vitb200_engine** out) {
   if (c.patch_size <= 0 || c.patch_size % 8 != 0 || c.image_size % c.patch_size != 0)
     return fail(VITB200_ERR_INVALID, "image_size %d must be a multiple of patch_size %d (itself a multiple of 8)",
                 c.image_size, c.patch_size);
-  if (c.num_heads <= 0 || c.hidden_dim != c.num_heads * 64)
-    return fail(VITB200_ERR_INVALID, "head dim must be 64 (hidden_dim %d, heads %d)", c.hidden_dim, c.num_heads);
+  if (c.num_heads <= 0 || c.hidden_dim % c.num_heads != 0)
+    return fail(VITB200_ERR_INVALID, "hidden_dim %d must be a multiple of the head count %d", c.hidden_dim, c.num_heads);
+  const int hd = c.hidden_dim / c.num_heads;
+  if (hd < 64 || hd > 128 || hd % 16 != 0)
+    return fail(VITB200_ERR_INVALID, "head dim %d unsupported (64..128 in steps of 16)", hd);
   if (c.hidden_dim % 128 != 0 || c.mlp_dim % 64 != 0 || c.num_classes % 8 != 0 || c.num_layers <= 0)
     return fail(VITB200_ERR_INVALID, "unsupported widths: hidden %d mlp %d classes %d layers %d", c.hidden_dim, c.mlp_dim,
                 c.num_classes, c.num_layers);
   const int n = (c.image_size / c.patch_size) * (c.image_size / c.patch_size);
   const int N = n + 1;
-  const int KP = (N + 15) / 16 * 16;
-  if (KP > attn_cfg::KP_MAX)
-    return fail(VITB200_ERR_INVALID, "%d tokens per image exceed the fused attention kernel's limit (%d)", N, attn_cfg::KP_MAX);
+  const int KP = attention_pitch(N);
+  if (N > kRolloutThreads * kRolloutMaxCols)
+    return fail(VITB200_ERR_INVALID, "%d tokens per image exceed the engine's limit (%d)", N, kRolloutThreads * kRolloutMaxCols);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(VITB200_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
@@ -591,7 +633,7 @@ int vitb200_create(const vitb200_config* cfg, vitb200_engine** out) {
 
   vitb200_engine* e = new vitb200_engine();
   e->cfg = c;
-  e->n = n, e->N = N, e->D = 64, e->KP = KP, e->pitch = KP, e->patch_k = 3 * c.patch_size * c.patch_size;
+  e->n = n, e->N = N, e->D = hd, e->KP = KP, e->pitch = KP, e->patch_k = 3 * c.patch_size * c.patch_size;
   e->layers.resize(c.num_layers);
   e->expected_tensors = 4 + 12 * (size_t)c.num_layers + 4;
   cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
@@ -927,11 +969,33 @@ int vitb200_op_layernorm(const float* x, const float* gamma, const float* beta, 
   return launch_layernorm(x, d, gamma, beta, (__nv_bfloat16*)y, rows, d, eps, (cudaStream_t)stream);
 }
 
+// statistics scratch of the long-sequence attention path for the single-kernel entry point (grown on demand)
+static float2* op_attention_stats(size_t count) {
+  static float2* buf = nullptr;
+  static size_t cap = 0;
+  if (count > cap) {
+    if (buf) cudaFree(buf);
+    buf = nullptr, cap = 0;
+    if (cudaMalloc(&buf, count * sizeof(float2)) == cudaSuccess) cap = count;
+  }
+  return buf;
+}
+
+int vitb200_op_attention_ex(const void* qkv, void* ctx, float* avg, float* cls, float* heads, int batch, int tokens,
+                            int nheads, int head_dim, int pitch, void* stream) {
+  if (!qkv || !ctx) return fail(VITB200_ERR_INVALID, "null argument");
+  float2* stats = nullptr;
+  if (!attention_is_fused(tokens, head_dim)) {
+    stats = op_attention_stats((size_t)batch * nheads * tokens);
+    if (!stats) return fail(VITB200_ERR_CUDA, "attention: cannot allocate the statistics scratch");
+  }
+  return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, avg, cls, heads, batch, tokens, nheads, head_dim,
+                          pitch, stats, (cudaStream_t)stream);
+}
+
 int vitb200_op_attention(const void* qkv, void* ctx, float* avg, float* cls, float* heads, int batch, int tokens,
                          int nheads, int pitch, void* stream) {
-  if (!qkv || !ctx) return fail(VITB200_ERR_INVALID, "null argument");
-  return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, avg, cls, heads, batch, tokens, nheads, pitch,
-                          (cudaStream_t)stream);
+  return vitb200_op_attention_ex(qkv, ctx, avg, cls, heads, batch, tokens, nheads, 64, pitch, stream);
 }
 
 int vitb200_op_patchify(const float* images, void* patches, int batch, int image_size, int patch, void* stream) {

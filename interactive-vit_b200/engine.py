@@ -82,6 +82,7 @@ SIGNATURES = {
     "vitb200_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "vitb200_op_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "vitb200_op_attention_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_patchify": (_I, [_P, _P, _I, _I, _I, _P]),
     "vitb200_op_rollout": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
 }
@@ -147,6 +148,8 @@ CONFIGS: Dict[str, VitConfig] = {
     "vit_s_16": VitConfig(224, 16, 12, 6, 384, 1536),
     "vit_b_16": VitConfig(224, 16, 12, 12, 768, 3072),
     "vit_l_16": VitConfig(224, 16, 24, 16, 1024, 4096),
+    "vit_b_16_384": VitConfig(384, 16, 12, 12, 768, 3072),    # 577 tokens
+    "vit_h_16_384": VitConfig(384, 16, 32, 16, 1280, 5120),   # ViT-H width/depth, head dim 80, 577 tokens
 }
 
 
@@ -324,16 +327,17 @@ def op_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: 
     return y
 
 
-def op_attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, want_avg=True, want_cls=True, want_heads=False):
+def op_attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, want_avg=True, want_cls=True, want_heads=False,
+                 head_dim: int = 64):
     lib = load_library()
-    d = heads * 64
+    d = heads * head_dim
     pitch = (tokens + 15) // 16 * 16
     ctx = torch.zeros(batch * tokens, d, device=qkv.device, dtype=torch.bfloat16)
     avg = torch.zeros(batch, tokens, pitch, device=qkv.device) if want_avg else None
     cls = torch.zeros(batch, heads, tokens, device=qkv.device) if want_cls else None
     hm = torch.zeros(batch, heads, tokens, pitch, device=qkv.device) if want_heads else None
-    check(lib.vitb200_op_attention(qkv.data_ptr(), ctx.data_ptr(), _ptr(avg), _ptr(cls), _ptr(hm), batch, tokens, heads,
-                                   pitch, None))
+    check(lib.vitb200_op_attention_ex(qkv.data_ptr(), ctx.data_ptr(), _ptr(avg), _ptr(cls), _ptr(hm), batch, tokens, heads,
+                                      head_dim, pitch, None))
     return ctx, (avg[..., :tokens] if avg is not None else None), cls, (hm[..., :tokens] if hm is not None else None)
 
 

@@ -57,9 +57,17 @@ ORACLE_CONFIGS: Dict[str, OracleConfig] = {
     "vit_s_16": OracleConfig(224, 16, 12, 6, 384, 1536),
     "vit_b_16": OracleConfig(224, 16, 12, 12, 768, 3072),
     "vit_l_16": OracleConfig(224, 16, 24, 16, 1024, 4096),
+    # 384 px / patch 16 -> 577 tokens (BASELINE.json config 5; SURVEY.md section 8 on the "H/14 384px (577 tokens)" wording):
+    # torchvision ships this geometry as ViT-B/16 SWAG_E2E (vision_transformer.py:374-392); "vit_h_16_384" is ViT-H's
+    # width / depth / heads (1280 / 32 / 16, head dim 80) on the same geometry
+    "vit_b_16_384": OracleConfig(384, 16, 12, 12, 768, 3072),
+    "vit_h_16_384": OracleConfig(384, 16, 32, 16, 1280, 5120),
     # small shapes for fast CPU tests (same code path, same 197-token geometry or smaller)
     "vit_tiny_test": OracleConfig(64, 16, 2, 2, 128, 256, 16),
     "vit_small_test": OracleConfig(224, 16, 3, 4, 256, 512, 40),
+    # ViT-H's layer shape (head dim 80, 577 tokens) at 2 layers: the key-blocked attention path end to end in seconds
+    "vit_h_test": OracleConfig(384, 16, 2, 16, 1280, 5120, 40),
+    "vit_577_test": OracleConfig(384, 16, 2, 4, 256, 512, 40),
 }
 
 

@@ -51,9 +51,12 @@ def test_bad_arguments_are_rejected_before_touching_cuda(built_library):
     h = ctypes.c_void_p()
     assert built_library.vitb200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"patch_size" in built_library.vitb200_last_error()
-    cfg = E._Config(384, 16, 12, 12, 768, 3072, 1000, 1, 0)     # 577 tokens: beyond the fused attention kernel
+    cfg = E._Config(512, 16, 12, 12, 768, 3072, 1000, 1, 0)     # 1025 tokens: beyond the engine's limit of 768
     assert built_library.vitb200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
     assert b"tokens" in built_library.vitb200_last_error()
+    cfg = E._Config(224, 16, 12, 16, 768, 3072, 1000, 1, 0)     # head dim 48
+    assert built_library.vitb200_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert b"head dim" in built_library.vitb200_last_error()
     assert built_library.vitb200_create(None, ctypes.byref(h)) == -1
 
 
@@ -63,3 +66,5 @@ def test_flop_model_matches_survey():
     assert abs(E.CONFIGS["vit_b_16"].gflop_per_image() - 35.128) < 1e-2
     assert abs(E.CONFIGS["vit_s_16"].gflop_per_image() - 9.198) < 1e-2
     assert abs(E.CONFIGS["vit_l_16"].gflop_per_image() - 123.109) < 1e-2
+    assert abs(E.CONFIGS["vit_h_16_384"].gflop_per_image() - 781.716) < 1e-2
+    assert abs(E.CONFIGS["vit_b_16_384"].gflop_per_image() - 110.969) < 1e-2

@@ -38,7 +38,10 @@ ALL = 1 | 2 | 4 | 8 | 16
 
 @pytest.mark.parametrize("name,batch,init", [("vit_tiny_test", 3, "stress"), ("vit_small_test", 2, "stress"),
                                              ("vit_small_test", 5, "default"), ("vit_s_16", 2, "stress"),
-                                             ("vit_b_16", 2, "default"), ("vit_b_16", 1, "stress")])
+                                             ("vit_b_16", 2, "default"), ("vit_b_16", 1, "stress"),
+                                             # 577 tokens / head dim 80: the key-blocked attention path (config 5)
+                                             ("vit_577_test", 2, "stress"), ("vit_h_test", 1, "default"),
+                                             ("vit_h_test", 2, "stress")])
 def test_forward_matches_oracle(E, name, batch, init):
     from oracle import vit_oracle as O
 
@@ -72,6 +75,23 @@ def test_vit_l_16_with_maps(E):
     eng = _engine_for(E, ocfg, model, 1)
     got = eng.forward_host(x, 1 | 2 | 4)
     for k in ("logits", "avg_maps", "cls_maps", "rollout"):
+        assert _rel(got[k], ref[k]) < TOL, (k, _rel(got[k], ref[k]))
+    assert torch.equal(got["logits"].argmax(-1), ref["logits"].argmax(-1))
+    eng.close()
+
+
+def test_vit_b_16_384_full_depth(E):
+    """config 5 geometry at full depth: ViT-B/16 at 384 px (577 tokens), logits + every map against the oracle."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_b_16_384"]
+    model = O.build_vit(ocfg, seed=0, init="default")
+    x = O.synthetic_images(1, ocfg.image_size)
+    ref = O.forward_with_maps(model, x)
+    eng = _engine_for(E, ocfg, model, 1)
+    got = eng.forward_host(x, 1 | 2 | 4)
+    for k in ("logits", "avg_maps", "cls_maps", "rollout"):
+        assert got[k].shape == ref[k].shape, k
         assert _rel(got[k], ref[k]) < TOL, (k, _rel(got[k], ref[k]))
     assert torch.equal(got["logits"].argmax(-1), ref["logits"].argmax(-1))
     eng.close()

@@ -96,10 +96,10 @@ def test_gemm_full_size_linearity(E):
     assert torch.equal(E.op_gemm(a1[rows].contiguous(), w, out_f32=True), y1[rows])   # bit-exact row independence
 
 
-def _attn_ref(qkv, B, N, H):
-    q, k, v = qkv.float().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
-    p = torch.softmax((q * 0.125) @ k.transpose(-1, -2), dim=-1)
-    o = (p @ v).permute(0, 2, 1, 3).reshape(B * N, H * 64)
+def _attn_ref(qkv, B, N, H, D=64):
+    q, k, v = qkv.float().reshape(B, N, 3, H, D).permute(2, 0, 3, 1, 4)
+    p = torch.softmax((q * D ** -0.5) @ k.transpose(-1, -2), dim=-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * N, H * D)
     return o, p
 
 
@@ -118,6 +118,25 @@ def test_attention(E, B, N, H, scale):
     assert (hm.sum(-1) - 1).abs().max() < 1e-5   # rows of a softmax
     # outputs selected independently give the same context
     ctx2, _, _, _ = E.op_attention(qkv, B, N, H, False, False, False)
+    assert torch.equal(ctx, ctx2)
+
+
+@pytest.mark.parametrize("B,N,H,D,scale", [(2, 577, 12, 64, 1.0), (2, 577, 16, 80, 1.0), (1, 257, 4, 80, 2.0),
+                                           (3, 197, 6, 80, 1.0), (1, 300, 2, 96, 1.0), (1, 129, 2, 128, 1.0),
+                                           (2, 209, 3, 64, 3.0), (1, 768, 1, 64, 1.0)])
+def test_attention_long(E, B, N, H, D, scale):
+    """Key-blocked two-kernel path: more than 208 tokens and / or head dims other than 64 (ViT-H: 80).  Every map is
+    formed from fp32 probabilities here (the head average accumulates in registers)."""
+    torch.manual_seed(B * 1000 + N + D)
+    qkv = (torch.randn(B * N, 3 * H * D, device="cuda") * scale).bfloat16()
+    ctx, avg, cls, hm = E.op_attention(qkv, B, N, H, True, True, True, head_dim=D)
+    o, p = _attn_ref(qkv, B, N, H, D)
+    assert _rel(ctx, o) < 2 * BF16_EPS
+    assert _rel(hm, p) < 1e-5
+    assert _rel(avg, p.mean(1)) < 1e-5
+    assert _rel(cls, p[:, :, 0, :]) < 1e-5
+    assert (hm.sum(-1) - 1).abs().max() < 1e-5
+    ctx2, _, _, _ = E.op_attention(qkv, B, N, H, False, False, False, head_dim=D)
     assert torch.equal(ctx, ctx2)
 
 

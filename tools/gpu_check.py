@@ -148,11 +148,11 @@ def gemm_perf():
         print(f"    cublas same shape: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
-def _attn_ref(qkv, B, N, H):
+def _attn_ref(qkv, B, N, H, D=64):
     import torch
-    d = H * 64
-    q, k, v = qkv.float().reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
-    s = (q * 0.125) @ k.transpose(-1, -2)
+    d = H * D
+    q, k, v = qkv.float().reshape(B, N, 3, H, D).permute(2, 0, 3, 1, 4)
+    s = (q * D ** -0.5) @ k.transpose(-1, -2)
     p = torch.softmax(s, dim=-1)
     o = (p @ v).permute(0, 2, 1, 3).reshape(B * N, d)
     return o, p
@@ -173,6 +173,27 @@ def attention():
         _err("avg", avg, p.mean(1))
         _err("cls", cls, p[:, :, 0, :])
         _err("heads", hm, p)
+
+
+@case
+def attention_long():
+    """Key-blocked path: 577 tokens (384 px / patch 16), head dims 64 and 80, odd sizes."""
+    import torch
+    from interactive_vit_b200 import engine as E
+    for (B, N, H, D, scale) in ((2, 577, 12, 64, 1.0), (2, 577, 16, 80, 1.0), (1, 257, 4, 80, 2.0), (3, 197, 6, 80, 1.0),
+                                (1, 300, 2, 96, 1.0), (1, 129, 2, 128, 1.0), (2, 209, 3, 64, 3.0)):
+        torch.manual_seed(B * N)
+        qkv = (torch.randn(B * N, 3 * H * D, device="cuda") * scale).bfloat16()
+        ctx, avg, cls, hm = E.op_attention(qkv, B, N, H, True, True, True, head_dim=D)
+        torch.cuda.synchronize()
+        o, p = _attn_ref(qkv, B, N, H, D)
+        print(f"  attention_long B={B} N={N} H={H} D={D} scale={scale}")
+        _err("ctx", ctx, o)
+        _err("avg", avg, p.mean(1))
+        _err("cls", cls, p[:, :, 0, :])
+        _err("heads", hm, p)
+        ctx2, _, _, _ = E.op_attention(qkv, B, N, H, False, False, False, head_dim=D)
+        print("    ctx identical without maps:", bool(torch.equal(ctx, ctx2)), flush=True)
 
 
 @case
@@ -307,6 +328,46 @@ def forward_profile():
     t1.record()
     torch.cuda.synchronize()
     print(f"    unprofiled forward: {t0.elapsed_time(t1) / 5:.3f} ms", flush=True)
+
+
+@case
+def forward_graph():
+    """Eager launches vs one CUDA-graph replay of the same forward: what the launch gaps cost."""
+    import torch
+    from interactive_vit_b200 import engine as E
+    from oracle import vit_oracle as O
+    ocfg = O.ORACLE_CONFIGS["vit_b_16"]
+    model = O.build_vit(ocfg, seed=0)
+    cfg = E.CONFIGS["vit_b_16"]
+    B = 256
+    eng = E.VitEngine(cfg, 0, B)
+    eng.load_state_dict(model.state_dict())
+    x = torch.rand(B, 3, 224, 224, device="cuda")
+    flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            eng.forward_device(x, flags, s.cuda_stream)
+        s.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(s)
+        for _ in range(10):
+            eng.forward_device(x, flags, s.cuda_stream)
+        t1.record(s)
+        s.synchronize()
+        print(f"    eager: {t0.elapsed_time(t1) / 10:.3f} ms", flush=True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            eng.forward_device(x, flags, s.cuda_stream)
+        for _ in range(3):
+            g.replay()
+        s.synchronize()
+        t0.record(s)
+        for _ in range(10):
+            g.replay()
+        t1.record(s)
+        s.synchronize()
+        print(f"    graph: {t0.elapsed_time(t1) / 10:.3f} ms", flush=True)
 
 
 def main():
