@@ -89,6 +89,19 @@ int vitb200_forward_host(vitb200_engine* e, const float* images_host, int batch,
                          const vitb200_host_outputs* out);
 int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, void* stream);
 
+/* Pipelined variant of vitb200_forward_host for request streams: returns once the work is enqueued.  Up to two
+ * requests are in flight; the host-to-device copy of request i+1 and the device-to-host copies of request i-1
+ * overlap the forward of request i (separate copy streams, double-buffered device inputs, per-request staging of
+ * logits / CLS maps / rollout / head-averaged maps).  `images_host` and the `out` pointers must stay valid (and should
+ * be pinned) until vitb200_wait(ticket) returns; per-head maps and hidden states are not available on this path.
+ * vitb200_staged_output: device copy of one output of an in-flight or just-completed ticket (for a device-side
+ * gather): which = 0 (logits) or VITB200_EMIT_{AVG,CLS,ROLLOUT}; dense layouts [B,classes] / [L,B,N,N] / [L,B,H,N] /
+ * [B,N-1]. */
+int vitb200_submit_host(vitb200_engine* e, const float* images_host, int batch, uint32_t flags,
+                        const vitb200_host_outputs* out, uint64_t* ticket);
+int vitb200_wait(vitb200_engine* e, uint64_t ticket);
+int vitb200_staged_output(vitb200_engine* e, uint64_t ticket, uint32_t which, float** ptr_dev);
+
 /* Measurement aid: one forward on the engine's own stream with a CUDA event in front of every kernel launch.
  * `report` receives text lines "kernel,launches,total_ms" (event-to-event times, so each kernel's figure
  * includes the gap to the next launch) and a final "total,<kinds>,<ms>" line.  Synchronous. */

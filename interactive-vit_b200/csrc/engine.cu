@@ -377,6 +377,18 @@ struct vitb200_engine {
   uint32_t cap_flags = 0;
   Buffer images, patches, x, ln, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
 
+  // vitb200_submit_host / vitb200_wait: two requests in flight.  H2D of request i+1 (copy_in stream) and D2H of
+  // request i-1 (copy_out stream, from per-slot staging copies of the small outputs) overlap the forward of request i.
+  struct Slot {
+    Buffer images, logits, cls, rollout, avg;
+    cudaEvent_t in_done = nullptr, compute_done = nullptr, out_done = nullptr;
+    bool busy = false;
+    int batch = 0;
+    uint32_t flags = 0;
+  } slots[2];
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  uint64_t submitted = 0;  // tickets are submission indices; slot = ticket % 2
+
   // vitb200_profile_forward: an event in front of every launch (only while `profiling`)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -592,6 +604,15 @@ vitb200_engine::~vitb200_engine() {
     fr(l.ln1_g), fr(l.ln1_b), fr(l.ln2_g), fr(l.ln2_b), fr(l.w_qkv), fr(l.w_o), fr(l.w_fc1), fr(l.w_fc2);
     fr(l.b_qkv), fr(l.b_o), fr(l.b_fc1), fr(l.b_fc2);
   }
+  for (Slot& sl : slots) {
+    Buffer* sb[] = {&sl.images, &sl.logits, &sl.cls, &sl.rollout, &sl.avg};
+    for (Buffer* b : sb) release(*b);
+    if (sl.in_done) cudaEventDestroy(sl.in_done);
+    if (sl.compute_done) cudaEventDestroy(sl.compute_done);
+    if (sl.out_done) cudaEventDestroy(sl.out_done);
+  }
+  if (copy_in) cudaStreamDestroy(copy_in);
+  if (copy_out) cudaStreamDestroy(copy_out);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -811,6 +832,103 @@ int vitb200_forward_host(vitb200_engine* e, const float* images_host, int batch,
   if (out->rollout)
     CU_TRY(cudaMemcpyAsync(out->rollout, e->rollout.p, (size_t)B * (N - 1) * 4, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+static int wait_slot_locked(vitb200_engine* e, vitb200_engine::Slot& sl) {
+  if (!sl.busy) return VITB200_OK;
+  CU_TRY(cudaEventSynchronize(sl.out_done));
+  sl.busy = false;
+  return VITB200_OK;
+}
+
+int vitb200_submit_host(vitb200_engine* e, const float* images_host, int batch, uint32_t flags,
+                        const vitb200_host_outputs* out, uint64_t* ticket) {
+  if (!e || !images_host || !out || !ticket) return fail(VITB200_ERR_INVALID, "null argument");
+  if (out->heads || out->hidden) return fail(VITB200_ERR_INVALID, "submit_host: per-head maps / hidden states are only available synchronously");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  const vitb200_config& c = e->cfg;
+  if (out->avg_maps) flags |= VITB200_EMIT_AVG;
+  if (out->cls_maps) flags |= VITB200_EMIT_CLS;
+  if (out->rollout) flags |= VITB200_EMIT_ROLLOUT;
+  VT_TRY(check_ready(e));
+  VT_TRY(check_batch(e, batch));
+  VT_TRY(ensure_workspace(e, batch > e->cap_batch ? batch : e->cap_batch, flags | e->cap_flags));
+  if (!e->copy_in) {
+    CU_TRY(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
+    for (auto& sl : e->slots) {
+      CU_TRY(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    }
+  }
+  vitb200_engine::Slot& sl = e->slots[e->submitted & 1];
+  VT_TRY(wait_slot_locked(e, sl));  // third request in flight: the oldest one has to drain first
+  const int B = batch, N = e->N, L = c.num_layers, Hh = c.num_heads;
+  const size_t img_bytes = (size_t)B * 3 * c.image_size * c.image_size * 4;
+  const size_t logit_bytes = (size_t)B * c.num_classes * 4, cls_bytes = (size_t)B * Hh * N * 4;
+  VT_TRY(ensure(sl.images, img_bytes));
+  VT_TRY(ensure(sl.logits, logit_bytes));
+  if (out->cls_maps) VT_TRY(ensure(sl.cls, cls_bytes * L));
+  if (out->rollout) VT_TRY(ensure(sl.rollout, (size_t)B * (N - 1) * 4));
+  if (out->avg_maps) VT_TRY(ensure(sl.avg, (size_t)L * B * N * N * 4));
+  // H2D on the copy stream; the slot's previous forward has finished (wait_slot above)
+  CU_TRY(cudaMemcpyAsync(sl.images.p, images_host, img_bytes, cudaMemcpyHostToDevice, e->copy_in));
+  CU_TRY(cudaEventRecord(sl.in_done, e->copy_in));
+  cudaStream_t st = e->stream;
+  CU_TRY(cudaStreamWaitEvent(st, sl.in_done, 0));
+  VT_TRY(forward_device_locked(e, (const float*)sl.images.p, B, flags, st));
+  // staging copies of the outputs (device to device, tens of MB): the next forward may overwrite the engine's buffers
+  CU_TRY(cudaMemcpyAsync(sl.logits.p, e->logits.p, logit_bytes, cudaMemcpyDeviceToDevice, st));
+  for (int l = 0; l < L; ++l) {
+    if (out->cls_maps)
+      CU_TRY(cudaMemcpyAsync((char*)sl.cls.p + l * cls_bytes, (const float*)e->cls.p + (size_t)l * e->cap_batch * Hh * N, cls_bytes,
+                             cudaMemcpyDeviceToDevice, st));
+    if (out->avg_maps)
+      CU_TRY(cudaMemcpy2DAsync((float*)sl.avg.p + (size_t)l * B * N * N, (size_t)N * 4,
+                               (const float*)e->avg.p + (size_t)l * e->cap_batch * N * e->pitch, (size_t)e->pitch * 4, (size_t)N * 4,
+                               (size_t)B * N, cudaMemcpyDeviceToDevice, st));
+  }
+  if (out->rollout) CU_TRY(cudaMemcpyAsync(sl.rollout.p, e->rollout.p, (size_t)B * (N - 1) * 4, cudaMemcpyDeviceToDevice, st));
+  CU_TRY(cudaEventRecord(sl.compute_done, st));
+  // D2H on the second copy stream
+  CU_TRY(cudaStreamWaitEvent(e->copy_out, sl.compute_done, 0));
+  if (out->logits) CU_TRY(cudaMemcpyAsync(out->logits, sl.logits.p, logit_bytes, cudaMemcpyDeviceToHost, e->copy_out));
+  if (out->cls_maps) CU_TRY(cudaMemcpyAsync(out->cls_maps, sl.cls.p, cls_bytes * L, cudaMemcpyDeviceToHost, e->copy_out));
+  if (out->rollout) CU_TRY(cudaMemcpyAsync(out->rollout, sl.rollout.p, (size_t)B * (N - 1) * 4, cudaMemcpyDeviceToHost, e->copy_out));
+  if (out->avg_maps) CU_TRY(cudaMemcpyAsync(out->avg_maps, sl.avg.p, (size_t)L * B * N * N * 4, cudaMemcpyDeviceToHost, e->copy_out));
+  CU_TRY(cudaEventRecord(sl.out_done, e->copy_out));
+  sl.busy = true, sl.batch = B, sl.flags = flags;
+  *ticket = e->submitted++;
+  return VITB200_OK;
+}
+
+int vitb200_wait(vitb200_engine* e, uint64_t ticket) {
+  if (!e) return fail(VITB200_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  if (ticket >= e->submitted) return fail(VITB200_ERR_STATE, "wait: ticket %llu was never issued", (unsigned long long)ticket);
+  // a ticket whose slot has been taken again was drained when the newer request claimed the slot
+  if (ticket + 2 < e->submitted) return VITB200_OK;
+  return wait_slot_locked(e, e->slots[ticket & 1]);
+}
+
+int vitb200_staged_output(vitb200_engine* e, uint64_t ticket, uint32_t which, float** ptr_dev) {
+  if (!e || !ptr_dev) return fail(VITB200_ERR_INVALID, "null argument");
+  if (ticket >= e->submitted || ticket + 2 < e->submitted) return fail(VITB200_ERR_STATE, "staged_output: ticket not in flight");
+  vitb200_engine::Slot& sl = e->slots[ticket & 1];
+  void* p = nullptr;
+  switch (which) {
+    case 0: p = sl.logits.p; break;
+    case VITB200_EMIT_AVG: p = sl.avg.p; break;
+    case VITB200_EMIT_CLS: p = sl.cls.p; break;
+    case VITB200_EMIT_ROLLOUT: p = sl.rollout.p; break;
+    default: return fail(VITB200_ERR_INVALID, "unknown staged output selector %u", which);
+  }
+  if (!p) return fail(VITB200_ERR_STATE, "output %u was not requested for this ticket", which);
+  *ptr_dev = (float*)p;
   return VITB200_OK;
 }
 

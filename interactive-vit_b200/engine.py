@@ -65,6 +65,9 @@ SIGNATURES = {
     "vitb200_weights_ready": (_I, [_P]),
     "vitb200_forward_host": (_I, [_P, _P, _I, _U32, C.POINTER(_HostOutputs)]),
     "vitb200_forward_device": (_I, [_P, _P, _I, _U32, _P]),
+    "vitb200_submit_host": (_I, [_P, _P, _I, _U32, C.POINTER(_HostOutputs), C.POINTER(C.c_uint64)]),
+    "vitb200_wait": (_I, [_P, C.c_uint64]),
+    "vitb200_staged_output": (_I, [_P, C.c_uint64, _U32, C.POINTER(_P)]),
     "vitb200_profile_forward": (_I, [_P, _P, _I, _U32, C.c_char_p, C.c_size_t]),
     "vitb200_device_output": (_I, [_P, _U32, C.POINTER(_P), C.POINTER(_I)]),
     "vitb200_synchronize": (_I, [_P]),
@@ -213,6 +216,33 @@ class VitEngine:
         ho = _HostOutputs(*[_ptr(res.get(k)) for k in ("logits", "avg_maps", "cls_maps", "rollout", "heads", "hidden")])
         check(self.lib.vitb200_forward_host(self._h, images.data_ptr(), B, flags, C.byref(ho)))
         return res
+
+    def submit_host(self, images: torch.Tensor, flags: int, out: Dict[str, torch.Tensor]) -> int:
+        """Pipelined forward_host: enqueue H2D + forward + D2H into the caller's (pinned) `out` tensors and return a
+        ticket; up to two requests are in flight.  `out` keys: logits, cls_maps, rollout, avg_maps."""
+        assert images.device.type == "cpu" and images.dtype == torch.float32 and images.is_contiguous()
+        cfg = self.cfg
+        B, N, L, H = images.shape[0], cfg.tokens, cfg.num_layers, cfg.num_heads
+        shapes = {"logits": (B, cfg.num_classes), "avg_maps": (L, B, N, N), "cls_maps": (L, B, H, N), "rollout": (B, N - 1)}
+        for k, t in out.items():
+            assert tuple(t.shape) == shapes[k] and t.dtype == torch.float32 and t.is_contiguous() and t.device.type == "cpu", k
+        ho = _HostOutputs(_ptr(out.get("logits")), _ptr(out.get("avg_maps")), _ptr(out.get("cls_maps")), _ptr(out.get("rollout")),
+                          None, None)
+        ticket = C.c_uint64()
+        check(self.lib.vitb200_submit_host(self._h, images.data_ptr(), B, flags, C.byref(ho), C.byref(ticket)))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[ticket.value] = (images, out)   # keep the host buffers alive until wait()
+        return ticket.value
+
+    def wait(self, ticket: int) -> None:
+        check(self.lib.vitb200_wait(self._h, ticket))
+        getattr(self, "_inflight", {}).pop(ticket, None)
+
+    def staged_output(self, ticket: int, which: int, shape) -> torch.Tensor:
+        """Device view of one staged output of an in-flight / just-completed ticket (dense layout)."""
+        p = C.c_void_p()
+        check(self.lib.vitb200_staged_output(self._h, ticket, which, C.byref(p)))
+        return _device_view(p.value, shape, self.device)
 
     def forward_device(self, images: torch.Tensor, flags: int = 0, stream: Optional[int] = None) -> None:
         """images: CUDA fp32 [B,3,S,S] on this engine's device; enqueues on `stream` (raw cudaStream_t)."""

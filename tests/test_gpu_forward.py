@@ -140,6 +140,34 @@ def test_stage_entry_points_equal_whole_forward(E):
     eng.close()
 
 
+def test_pipelined_host_api_equals_synchronous(E):
+    """submit_host / wait (two requests in flight, copies on their own streams) returns bit-identical results to
+    forward_host for every request, in order, including when a third request reclaims a slot."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_small_test"]
+    model = O.build_vit(ocfg, seed=0, init="stress")
+    eng = _engine_for(E, ocfg, model, 3)
+    flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
+    xs = [O.synthetic_images(3, ocfg.image_size, seed=100 + i).pin_memory() for i in range(5)]
+    want = [eng.forward_host(x, flags) for x in xs]
+    L, H, N = ocfg.num_layers, ocfg.num_heads, ocfg.tokens
+    outs = [{"logits": torch.empty(3, ocfg.num_classes).pin_memory(), "avg_maps": torch.empty(L, 3, N, N).pin_memory(),
+             "cls_maps": torch.empty(L, 3, H, N).pin_memory(), "rollout": torch.empty(3, N - 1).pin_memory()}
+            for _ in xs]
+    tickets = [eng.submit_host(x, flags, o) for x, o in zip(xs, outs)]    # the 3rd submit drains the 1st, ...
+    for t in reversed(tickets):                                           # waiting out of order is allowed
+        eng.wait(t)
+    for w, o in zip(want, outs):
+        for k in ("logits", "avg_maps", "cls_maps", "rollout"):
+            assert torch.equal(o[k], w[k]), k
+    # staged device copies of the last ticket stay readable after wait()
+    assert torch.equal(eng.staged_output(tickets[-1], 0, (3, ocfg.num_classes)).cpu(), want[-1]["logits"])
+    with pytest.raises(E.EngineError):
+        eng.wait(99)
+    eng.close()
+
+
 def test_plugin_through_scheduler_and_wire_codec(E, golden_dir):
     """The reference-facing path: browser request bytes -> Request.decode -> Context.compute over the B200 plugin
     -> Response.encode, compared with the response bytes the unmodified reference produced with the CPU oracle."""
