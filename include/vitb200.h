@@ -136,6 +136,16 @@ uint64_t vitb200_launch_count(vitb200_engine* e);
  * They exist so the parity tests can check each kernel against the oracle in isolation. */
 int vitb200_op_gemm(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, const float* resid_dev,
                     void* out_dev, int M, int N, int K, int gelu, int out_f32, void* stream);
+/* GEMM with the LayerNorm-folding epilogues (see the header comment of csrc/engine.cu).  Producer side (needs resid_dev):
+ * xb_out_dev receives the bf16 copy of the fp32 result and stats_out_dev [M, N/32, 2] the per-32-column partial sums
+ * (sum, sum of squares) of every row.  Consumer side: stats_in_dev [M, K/32, 2] + colsum_dev [N] turn the GEMM into
+ * LayerNorm(x) W^T + b for weights prepared by vitb200_op_fold_ln.  Unused pointers are NULL. */
+int vitb200_op_gemm_ex(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, const float* resid_dev,
+                       void* out_dev, int M, int N, int K, int gelu, int out_f32, void* xb_out_dev, float* stats_out_dev,
+                       const float* stats_in_dev, const float* colsum_dev, float ln_eps, void* stream);
+/* W'[n,k] = bf16(gamma[k] W[n,k]); colsum[n] = sum_k W'[n,k]; bias_out[n] = bias[n] + sum_k beta[k] W[n,k]. */
+int vitb200_op_fold_ln(const float* w_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev,
+                       void* wq_bf16_dev, float* colsum_dev, float* bias_out_dev, int N, int K, void* stream);
 int vitb200_op_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, void* y_bf16_dev,
                          int rows, int d, float eps, void* stream);
 int vitb200_op_attention(const void* qkv_bf16_dev, void* ctx_bf16_dev, float* avg_dev, float* cls_dev,

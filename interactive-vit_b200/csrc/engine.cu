@@ -5,8 +5,15 @@
 // VisionTransformer.forward (vision_transformer.py:289-306; EncoderBlock 110-119), i.e. what the reference
 // would execute inside Model.compute (main/context.py:79-88) for a ViT plugin:
 //   patchify -> GEMM(+bias +pos, scatter behind class token) -> cls rows
-//   L x [ LN1 -> GEMM qkv -> fused attention (+maps) -> GEMM out_proj (+x) -> LN2 -> GEMM fc1 (GELU) -> GEMM fc2 (+x) ]
+//   L x [ GEMM qkv (LN1 folded) -> fused attention (+maps) -> GEMM out_proj (+x) -> GEMM fc1 (LN2 folded, GELU) -> GEMM fc2 (+x) ]
 //   LN(class rows) -> GEMM head -> logits;   rollout over the head-averaged maps.
+//
+// LayerNorm is folded into the GEMMs.  LN(x) W^T + b = rstd * (x W'^T - mean * colsum) + b' with W' = gamma o W,
+// colsum[n] = sum_k W'[n, k], b' = b + W beta (fold_ln_weight_kernel, once after the weights are loaded).  Every GEMM
+// that updates the fp32 residual stream x (patch embedding, out_proj, fc2) also writes the bf16 copy xb of its
+// result -- the A operand of the next GEMM -- and per row the partial sums (sum, sum of squares) of each 32-column
+// chunk into fixed slots of `stats`; the consuming GEMM's epilogue reduces them to mean / rstd and applies the
+// affine correction per element.  This removes the 24 LayerNorm launches per forward (232 MB of HBM traffic each).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -156,11 +163,11 @@ static int gemm_units(int M, int N, int tile_m, int bn, int pairs) {
   return (m_tiles / 2) * n_tiles + ((m_tiles & 1) ? (n_tiles + 1) / 2 : 0);
 }
 
-template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
+template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
                          cudaStream_t st) {
   using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu)>;
-  auto kern = gemm_bf16_kernel<BN, kPair, kPairs, kGelu, kOutF32, kResid, kRemap>;
+  auto kern = gemm_bf16_kernel<BN, kPair, kPairs, kGelu, kOutF32, kResid, kRemap, kLnIn>;
   constexpr int kClusterCtas = kPair * kPairs;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(C::kThreads);
@@ -211,7 +218,15 @@ static int gemm_pair_mode() {
 template <int BN, int kPair, int kPairs>
 static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep, bool gelu,
                           bool out_f32, cudaStream_t st) {
-  const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0;
+  const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0, ln_in = ep.row_stats_in != nullptr;
+  if (ln_in) {
+    if (ep.colsum == nullptr || ep.stats_slots <= 0 || ep.ln_width <= 0 || out_f32 || resid || remap)
+      return fail(VITB200_ERR_INVALID, "gemm: folded-LayerNorm epilogue needs colsum / slots / width and a bf16 output");
+    if (gelu) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false, true>(ta, tw, sh, ep, st);
+    return launch_gemm_t<BN, kPair, kPairs, false, false, false, false, true>(ta, tw, sh, ep, st);
+  }
+  if (ep.xb != nullptr && (!resid || ep.row_stats_out == nullptr || ep.stats_slots <= 0))
+    return fail(VITB200_ERR_INVALID, "gemm: the bf16 copy + row statistics are produced by residual epilogues only");
   if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false>(ta, tw, sh, ep, st);
   if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, false, false, false>(ta, tw, sh, ep, st);
   if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, false, false>(ta, tw, sh, ep, st);
@@ -343,6 +358,10 @@ struct LayerWeights {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   __nv_bfloat16 *w_qkv = nullptr, *w_o = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
   float *b_qkv = nullptr, *b_o = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
+  // LayerNorm folding: fp32 originals of the two weights that consume a LayerNorm (w_qkv / w_fc1 above hold the
+  // gamma-scaled bf16 versions), their column sums and beta-folded biases
+  float *w_qkv_f32 = nullptr, *w_fc1_f32 = nullptr;
+  float *s_qkv = nullptr, *s_fc1 = nullptr, *bf_qkv = nullptr, *bf_fc1 = nullptr;
 };
 
 struct Buffer {
@@ -370,12 +389,13 @@ struct vitb200_engine {
   std::vector<LayerWeights> layers;
   std::map<std::string, bool> loaded;
   size_t expected_tensors = 0;
+  bool folded = false;  // fold_ln_weight_kernel has run for the current weights
   Buffer stage_f32;  // fp32 staging for weight upload / conversion
 
   // activations (sized for cap_batch images)
   int cap_batch = 0;
   uint32_t cap_flags = 0;
-  Buffer images, patches, x, ln, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
+  Buffer images, patches, x, xb, ln_stats, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
 
   // vitb200_submit_host / vitb200_wait: two requests in flight.  H2D of request i+1 (copy_in stream) and D2H of
   // request i-1 (copy_out stream, from per-slot staging copies of the small outputs) overlap the forward of request i.
@@ -420,7 +440,8 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   VT_TRY(ensure(e->images, (size_t)B * 3 * c.image_size * c.image_size * 4));
   VT_TRY(ensure(e->patches, (size_t)B * e->n * e->patch_k * 2));
   VT_TRY(ensure(e->x, M * c.hidden_dim * 4));
-  VT_TRY(ensure(e->ln, M * c.hidden_dim * 2));
+  VT_TRY(ensure(e->xb, M * c.hidden_dim * 2));
+  VT_TRY(ensure(e->ln_stats, M * (c.hidden_dim / 32) * sizeof(float2)));
   VT_TRY(ensure(e->qkv, M * 3 * c.hidden_dim * 2));
   VT_TRY(ensure(e->ctx, M * c.hidden_dim * 2));
   if (!attention_is_fused(e->N, e->D)) VT_TRY(ensure(e->attn_stats, M * c.num_heads * sizeof(float2)));
@@ -461,12 +482,15 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
   ep.resid = e->pos, ep.ldr = c.hidden_dim;
   ep.group_rows = e->n, ep.out_group_stride = e->N, ep.out_row_offset = 1;
   ep.resid_broadcast = 1, ep.resid_row_offset = 1;
+  ep.xb = (__nv_bfloat16*)e->xb.p, ep.ldxb = c.hidden_dim;
+  ep.row_stats_out = (float2*)e->ln_stats.p, ep.stats_slots = c.hidden_dim / 32;
   prof_mark(e, "gemm_patch_embed", st);
   VT_TRY(launch_gemm(e->patches.p, e->patch_k, e->w_patch, B * e->n, c.hidden_dim, e->patch_k, ep, false, true, st));
-  const long citems = (long)B * (c.hidden_dim / 4);
+  const long cthreads = (long)B * (c.hidden_dim / 32) * 32;
   prof_mark(e, "cls_rows", st);
-  cls_rows_kernel<<<(unsigned)((citems + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p, B, e->N,
-                                                                    c.hidden_dim);
+  cls_rows_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p,
+                                                                      (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B,
+                                                                      e->N, c.hidden_dim);
   CU_TRY(cudaGetLastError());
   e->launches += 3;
   return VITB200_OK;
@@ -477,14 +501,15 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
   const LayerWeights& w = e->layers[l];
   const int M = B * e->N, d = c.hidden_dim;
   float* x = (float*)e->x.p;
-  __nv_bfloat16* ln = (__nv_bfloat16*)e->ln.p;
-  prof_mark(e, "layernorm", st);
-  VT_TRY(launch_layernorm(x, d, w.ln1_g, w.ln1_b, ln, M, d, 1e-6f, st));
+  __nv_bfloat16* xb = (__nv_bfloat16*)e->xb.p;
+  float2* stats = (float2*)e->ln_stats.p;
+  const int slots = d / 32;
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_qkv", st);
-    ep.bias = w.b_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
-    VT_TRY(launch_gemm(ln, d, w.w_qkv, M, 3 * d, d, ep, false, false, st));
+    ep.bias = w.bf_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
+    ep.row_stats_in = stats, ep.colsum = w.s_qkv, ep.stats_slots = slots, ep.ln_width = d, ep.ln_eps = 1e-6f;
+    VT_TRY(launch_gemm(xb, d, w.w_qkv, M, 3 * d, d, ep, false, false, st));
   }
   const bool want_avg = (flags & (VITB200_EMIT_AVG | VITB200_EMIT_ROLLOUT)) != 0;
   float* avg = want_avg ? (float*)e->avg.p + (size_t)l * e->cap_batch * e->N * e->pitch : nullptr;
@@ -499,23 +524,24 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
     GemmEpilogue ep;
     prof_mark(e, "gemm_out_proj", st);
     ep.bias = w.b_o, ep.out = x, ep.ldo = d, ep.resid = x, ep.ldr = d;
+    ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots;
     VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st));
   }
-  prof_mark(e, "layernorm", st);
-  VT_TRY(launch_layernorm(x, d, w.ln2_g, w.ln2_b, ln, M, d, 1e-6f, st));
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_fc1_gelu", st);
-    ep.bias = w.b_fc1, ep.out = e->mlp.p, ep.ldo = c.mlp_dim;
-    VT_TRY(launch_gemm(ln, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st));
+    ep.bias = w.bf_fc1, ep.out = e->mlp.p, ep.ldo = c.mlp_dim;
+    ep.row_stats_in = stats, ep.colsum = w.s_fc1, ep.stats_slots = slots, ep.ln_width = d, ep.ln_eps = 1e-6f;
+    VT_TRY(launch_gemm(xb, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st));
   }
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_fc2", st);
     ep.bias = w.b_fc2, ep.out = x, ep.ldo = d, ep.resid = x, ep.ldr = d;
+    ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots;
     VT_TRY(launch_gemm(e->mlp.p, c.mlp_dim, w.w_fc2, M, d, c.mlp_dim, ep, false, true, st));
   }
-  e->launches += 7;
+  e->launches += 5;
   if (flags & VITB200_EMIT_HIDDEN) {
     float* hid = (float*)e->hidden.p + (size_t)l * e->cap_batch * e->N * d;
     CU_TRY(cudaMemcpyAsync(hid, x, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, st));
@@ -565,6 +591,26 @@ static int run_rollout(vitb200_engine* e, int B, cudaStream_t st) {
 static int check_ready(vitb200_engine* e) {
   if (e->loaded.size() != e->expected_tensors)
     return fail(VITB200_ERR_STATE, "weights incomplete: %zu of %zu tensors loaded", e->loaded.size(), e->expected_tensors);
+  if (!e->folded) {
+    // LayerNorm folding, weight side (see the header comment): once per set of weights, on the engine's stream
+    const int d = e->cfg.hidden_dim, mlp = e->cfg.mlp_dim;
+    for (LayerWeights& w : e->layers) {
+      auto alloc = [](auto** p, size_t bytes) { return *p ? cudaSuccess : cudaMalloc((void**)p, bytes); };
+      CU_TRY(alloc(&w.w_qkv, (size_t)3 * d * d * 2));
+      CU_TRY(alloc(&w.s_qkv, (size_t)3 * d * 4));
+      CU_TRY(alloc(&w.bf_qkv, (size_t)3 * d * 4));
+      CU_TRY(alloc(&w.w_fc1, (size_t)mlp * d * 2));
+      CU_TRY(alloc(&w.s_fc1, (size_t)mlp * 4));
+      CU_TRY(alloc(&w.bf_fc1, (size_t)mlp * 4));
+      fold_ln_weight_kernel<<<(3 * d * 32 + 255) / 256, 256, 0, e->stream>>>(w.w_qkv_f32, w.ln1_g, w.ln1_b, w.b_qkv, w.w_qkv,
+                                                                             w.s_qkv, w.bf_qkv, 3 * d, d);
+      fold_ln_weight_kernel<<<(mlp * 32 + 255) / 256, 256, 0, e->stream>>>(w.w_fc1_f32, w.ln2_g, w.ln2_b, w.b_fc1, w.w_fc1,
+                                                                           w.s_fc1, w.bf_fc1, mlp, d);
+      CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    e->folded = true;
+  }
   return VITB200_OK;
 }
 
@@ -596,13 +642,14 @@ static int copy_rows_to_host(float* dst, const float* src_dev, size_t rows, int 
 }  // namespace vitb200
 
 vitb200_engine::~vitb200_engine() {
-  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &ln, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats};
+  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats};
   for (Buffer* b : bufs) release(*b);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(w_patch), fr(b_patch), fr(cls_token), fr(pos), fr(lnf_g), fr(lnf_b), fr(w_head), fr(b_head);
   for (auto& l : layers) {
     fr(l.ln1_g), fr(l.ln1_b), fr(l.ln2_g), fr(l.ln2_b), fr(l.w_qkv), fr(l.w_o), fr(l.w_fc1), fr(l.w_fc2);
     fr(l.b_qkv), fr(l.b_o), fr(l.b_fc1), fr(l.b_fc2);
+    fr(l.w_qkv_f32), fr(l.w_fc1_f32), fr(l.s_qkv), fr(l.s_fc1), fr(l.bf_qkv), fr(l.bf_fc1);
   }
   for (Slot& sl : slots) {
     Buffer* sb[] = {&sl.images, &sl.logits, &sl.cls, &sl.rollout, &sl.avg};
@@ -711,11 +758,11 @@ int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_h
     else if (r == "ln_1.bias") F(&w.ln1_b, d);
     else if (r == "ln_2.weight") F(&w.ln2_g, d);
     else if (r == "ln_2.bias") F(&w.ln2_b, d);
-    else if (r == "self_attention.in_proj_weight") H(&w.w_qkv, 3 * d * d);
+    else if (r == "self_attention.in_proj_weight") F(&w.w_qkv_f32, 3 * d * d);   // folded with ln_1 later
     else if (r == "self_attention.in_proj_bias") F(&w.b_qkv, 3 * d);
     else if (r == "self_attention.out_proj.weight") H(&w.w_o, d * d);
     else if (r == "self_attention.out_proj.bias") F(&w.b_o, d);
-    else if (r == "mlp.0.weight") H(&w.w_fc1, (size_t)c.mlp_dim * d);
+    else if (r == "mlp.0.weight") F(&w.w_fc1_f32, (size_t)c.mlp_dim * d);        // folded with ln_2 later
     else if (r == "mlp.0.bias") F(&w.b_fc1, c.mlp_dim);
     else if (r == "mlp.3.weight") H(&w.w_fc2, d * (size_t)c.mlp_dim);
     else if (r == "mlp.3.bias") F(&w.b_fc2, d);
@@ -740,6 +787,7 @@ int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_h
   }
   CU_TRY(cudaStreamSynchronize(e->stream));
   e->loaded[key] = true;
+  e->folded = false;  // any new tensor invalidates the folded LayerNorm weights
   return VITB200_OK;
 }
 
@@ -1010,6 +1058,11 @@ int vitb200_set_tokens(vitb200_engine* e, const float* tokens_host, int batch) {
   if (!tokens_host) return fail(VITB200_ERR_INVALID, "null tokens");
   STAGE_PROLOGUE(batch, 0)
   CU_TRY(cudaMemcpyAsync(e->x.p, tokens_host, (size_t)batch * e->N * e->cfg.hidden_dim * 4, cudaMemcpyHostToDevice, st));
+  // what the folded LayerNorm of the next GEMM reads: bf16 copy + per-chunk partial sums of every row
+  const long rows = (long)batch * e->N;
+  rows_bf16_stats_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const float*)e->x.p, (__nv_bfloat16*)e->xb.p,
+                                                                              (float2*)e->ln_stats.p, rows, e->cfg.hidden_dim);
+  CU_TRY(cudaGetLastError());
   CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
@@ -1079,6 +1132,32 @@ int vitb200_op_gemm(const void* a, const void* w, const float* bias, const float
   GemmEpilogue ep;
   ep.bias = bias, ep.out = out, ep.ldo = N, ep.resid = resid, ep.ldr = N;
   return launch_gemm(a, K, w, M, N, K, ep, gelu != 0, out_f32 != 0, (cudaStream_t)stream);
+}
+
+int vitb200_op_gemm_ex(const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N, int K,
+                       int gelu, int out_f32, void* xb_out, float* stats_out, const float* stats_in, const float* colsum,
+                       float ln_eps, void* stream) {
+  if (!a || !w || !out) return fail(VITB200_ERR_INVALID, "null argument");
+  GemmEpilogue ep;
+  ep.bias = bias, ep.out = out, ep.ldo = N, ep.resid = resid, ep.ldr = N;
+  if (xb_out) {
+    if (N % 32 != 0) return fail(VITB200_ERR_INVALID, "gemm: row statistics need N to be a multiple of 32");
+    ep.xb = (__nv_bfloat16*)xb_out, ep.ldxb = N, ep.row_stats_out = (float2*)stats_out, ep.stats_slots = N / 32;
+  }
+  if (stats_in) {
+    if (K % 32 != 0) return fail(VITB200_ERR_INVALID, "gemm: folded LayerNorm needs K to be a multiple of 32");
+    ep.row_stats_in = (const float2*)stats_in, ep.colsum = colsum, ep.stats_slots = K / 32, ep.ln_width = K, ep.ln_eps = ln_eps;
+  }
+  return launch_gemm(a, K, w, M, N, K, ep, gelu != 0, out_f32 != 0, (cudaStream_t)stream);
+}
+
+int vitb200_op_fold_ln(const float* w, const float* gamma, const float* beta, const float* bias, void* wq, float* colsum,
+                       float* bias_out, int N, int K, void* stream) {
+  if (!w || !gamma || !beta || !bias || !wq || !colsum || !bias_out) return fail(VITB200_ERR_INVALID, "null argument");
+  fold_ln_weight_kernel<<<(N * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, gamma, beta, bias, (__nv_bfloat16*)wq, colsum,
+                                                                              bias_out, N, K);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
 }
 
 int vitb200_op_layernorm(const float* x, const float* gamma, const float* beta, void* y, int rows, int d, float eps,

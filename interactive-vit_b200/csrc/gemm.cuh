@@ -52,6 +52,22 @@ struct GemmEpilogue {
   int out_row_offset = 0;
   int resid_broadcast = 0;
   int resid_row_offset = 0;
+  // LayerNorm folding (see engine.cu, "LayerNorm is folded into the GEMMs"):
+  //  * producer side (kResid epilogues, optional): besides the fp32 result also write its bf16 copy `xb` (the A
+  //    operand of the next GEMM) and, per row and 32-column chunk, the partial sums (sum x, sum x^2) into
+  //    row_stats_out[out_row * stats_slots + col / 32] -- fixed slots, no atomics, so the statistics are
+  //    bit-reproducible.
+  //  * consumer side (kLnIn epilogues): out = rstd_m * (acc - mean_m * colsum[n]) + bias[n], with mean / rstd of row m
+  //    from the stats_slots partial sums in row_stats_in (LayerNorm over ln_width columns, eps ln_eps); the weight
+  //    operand holds gamma-scaled weights, `bias` the beta-folded bias, colsum[n] = sum_k W'[n, k].
+  __nv_bfloat16* xb = nullptr;
+  int ldxb = 0;
+  float2* row_stats_out = nullptr;
+  const float2* row_stats_in = nullptr;
+  const float* colsum = nullptr;
+  int stats_slots = 0;
+  int ln_width = 0;
+  float ln_eps = 0.f;
 };
 
 struct GemmShape {
@@ -81,6 +97,11 @@ struct Cfg {
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 }  // namespace gemm_cfg
+
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 
 // Exact-erf GELU (torch.nn.GELU default, vision_transformer.py:40-47 MLPBlock): x * Phi(x), Phi the normal CDF.
 // With u = |x| and e(u) = erfc(u / sqrt 2) = 2 Phi(-u):   gelu(x) = max(x, 0) - 0.5 * u * e(u).
@@ -133,7 +154,7 @@ struct GemmWork {
   }
 };
 
-template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap>
+template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false>
 __global__ void __launch_bounds__((gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu)>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  GemmShape shape, GemmEpilogue ep) {
@@ -314,6 +335,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_grp * kGroupCols;
+      // folded LayerNorm: scale a = rstd and offset c = -rstd * mean of this thread's 8 rows (trow + 4 i).  Lane l
+      // reduces the partial sums of row row_base + l in slot order (bit-reproducible), the rows are then exchanged.
+      float ln_a[8], ln_c[8];
+      if (kLnIn) {
+        float s1 = 0.f, s2 = 0.f;
+        const int row = row_base + lane;
+        if (row < shape.M) {
+          const float2* sp = ep.row_stats_in + static_cast<long>(row) * ep.stats_slots;
+          for (int j = 0; j < ep.stats_slots; ++j) {
+            const float2 v = sp[j];
+            s1 += v.x, s2 += v.y;
+          }
+        }
+        const float inv_w = 1.0f / static_cast<float>(ep.ln_width);
+        const float mean = s1 * inv_w;
+        const float rstd = rsqrtf(fmaxf(s2 * inv_w - mean * mean, 0.f) + ep.ln_eps);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ln_a[i] = __shfl_sync(0xffffffffu, rstd, trow + 4 * i);
+          ln_c[i] = -ln_a[i] * __shfl_sync(0xffffffffu, mean, trow + 4 * i);
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         uint32_t r[32];
@@ -339,12 +382,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool col_ok = col < shape.N;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias != nullptr && col_ok) bias4 = *reinterpret_cast<const float4*>(ep.bias + col);
+        float4 csum4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kLnIn && col_ok) csum4 = *reinterpret_cast<const float4*>(ep.colsum + col);
         // transposed pass: 8 rows (trow + 4 i) x 4 columns per thread.  With a residual all 8 rows form one batch so
         // that 8 independent 16-byte loads per thread are in flight (the out_proj / fc2 epilogues are bound by
         // HBM latency x outstanding bytes); otherwise two batches of 4 keep the instruction footprint small.
         constexpr int kRowBatch = kResid ? 8 : 4;
         const float* sl = slab + trow * kSlabStride + 4 * tcol;
-#pragma unroll 1
+        // (unrolled for the folded-LayerNorm epilogue: its per-row scale / offset arrays need static indices)
+        constexpr int kBatchUnroll = kLnIn ? 8 / kRowBatch : 1;
+#pragma unroll kBatchUnroll
         for (int i0 = 0; i0 < 8; i0 += kRowBatch) {
           float4 v[kRowBatch], q[kRowBatch];
           long orow[kRowBatch];
@@ -370,9 +417,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int i = 0; i < kRowBatch; ++i) {
             float4 t = v[i];
-            t.x += bias4.x, t.y += bias4.y, t.z += bias4.z, t.w += bias4.w;
+            if (kLnIn) {
+              const float a = ln_a[i0 + i], cc = ln_c[i0 + i];
+              t.x = fmaf(t.x, a, fmaf(cc, csum4.x, bias4.x)), t.y = fmaf(t.y, a, fmaf(cc, csum4.y, bias4.y));
+              t.z = fmaf(t.z, a, fmaf(cc, csum4.z, bias4.z)), t.w = fmaf(t.w, a, fmaf(cc, csum4.w, bias4.w));
+            } else {
+              t.x += bias4.x, t.y += bias4.y, t.z += bias4.z, t.w += bias4.w;
+            }
             if (kGelu) t.x = gelu_erf(t.x), t.y = gelu_erf(t.y), t.z = gelu_erf(t.z), t.w = gelu_erf(t.w);
             if (kResid) t.x += q[i].x, t.y += q[i].y, t.z += q[i].z, t.w += q[i].w;
+            if (kResid && ep.xb != nullptr) {
+              // bf16 copy for the next GEMM + this 32-column chunk's partial sums of the row (the 8 lanes that share
+              // the row are consecutive: xor-shuffles over 1, 2, 4 stay inside the group; every lane takes part)
+              float p1 = ok[i] ? (t.x + t.y) + (t.z + t.w) : 0.f;
+              float p2 = ok[i] ? (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w) : 0.f;
+#pragma unroll
+              for (int o = 1; o < 8; o <<= 1) {
+                p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+              }
+              // a row whose chunk is only partly inside N (never the case for the widths in use) still gets its slot
+              const bool row_in = row_base + trow + 4 * (i0 + i) < shape.M;
+              if (tcol == 0 && row_in) ep.row_stats_out[orow[i] * ep.stats_slots + (col0 >> 5)] = make_float2(p1, p2);
+              if (ok[i]) {
+                uint2 pk;
+                pk.x = pack2_bf16(t.x, t.y), pk.y = pack2_bf16(t.z, t.w);
+                *reinterpret_cast<uint2*>(ep.xb + orow[i] * ep.ldxb + col) = pk;
+              }
+            }
             if (ok[i]) {
               if (kOutF32) {
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow[i] * ep.ldo + col) = t;

@@ -95,17 +95,66 @@ patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, 
   *reinterpret_cast<uint4*>(out + row * (3L * p * p) + col) = o;
 }
 
-// Class-token rows of the token stream: x[b, 0, :] = class_token + pos_embedding[0]  (fp32).
+// Class-token rows of the token stream: x[b, 0, :] = class_token + pos_embedding[0]  (fp32), plus what the folded
+// LayerNorm of the next GEMM needs for these rows: the bf16 copy and the per-32-column partial sums (sum, sum of
+// squares).  One warp per (image, 32-column chunk), one column per lane.
 __global__ void __launch_bounds__(256)
-cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x, int B, int N,
-                int d) {
-  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int d4 = d / 4;
-  if (idx >= static_cast<long>(B) * d4) return;
-  const int b = idx / d4, j = idx % d4;
-  const float4 c = reinterpret_cast<const float4*>(cls)[j];
-  const float4 q = reinterpret_cast<const float4*>(pos)[j];
-  reinterpret_cast<float4*>(x + static_cast<long>(b) * N * d)[j] = make_float4(c.x + q.x, c.y + q.y, c.z + q.z, c.w + q.w);
+cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
+                __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int B, int N, int d) {
+  const int slots = d >> 5;
+  const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= static_cast<long>(B) * slots) return;
+  const int b = static_cast<int>(warp / slots), chunk = static_cast<int>(warp % slots);
+  const int col = chunk * 32 + lane;
+  const float v = cls[col] + pos[col];
+  const long row = static_cast<long>(b) * N;
+  x[row * d + col] = v;
+  if (xb != nullptr) {
+    xb[row * d + col] = __float2bfloat16_rn(v);
+    const float p1 = warp_sum(v), p2 = warp_sum(v * v);
+    if (lane == 0) stats[row * slots + chunk] = make_float2(p1, p2);
+  }
+}
+
+// bf16 copy + partial LayerNorm sums of arbitrary fp32 rows (token streams that enter through the boundary,
+// vitb200_set_tokens): one warp per row.
+__global__ void __launch_bounds__(256)
+rows_bf16_stats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, long rows,
+                       int d) {
+  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int slots = d >> 5;
+  for (int chunk = 0; chunk < slots; ++chunk) {
+    const float v = x[row * d + chunk * 32 + lane];
+    xb[row * d + chunk * 32 + lane] = __float2bfloat16_rn(v);
+    const float p1 = warp_sum(v), p2 = warp_sum(v * v);
+    if (lane == 0) stats[row * slots + chunk] = make_float2(p1, p2);
+  }
+}
+
+// LayerNorm folding, weight side (once, after the weights are loaded).  For a Linear that consumes LayerNorm(x):
+//     W'[n, k] = bf16(gamma[k] * W[n, k]),   colsum[n] = sum_k float(W'[n, k]),   bias'[n] = bias[n] + sum_k beta[k] W[n, k]
+// so that LN(x) W^T + bias = rstd * (x W'^T - mean * colsum) + bias'.  colsum is taken over the ROUNDED weights: the
+// identity then holds exactly for what the tensor cores accumulate.  One warp per output row n.
+__global__ void __launch_bounds__(256)
+fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ Wq, float* __restrict__ colsum,
+                      float* __restrict__ bias_out, int N, int K) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float s = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[static_cast<long>(n) * K + k];
+    const __nv_bfloat16 wq = __float2bfloat16_rn(w * gamma[k]);
+    Wq[static_cast<long>(n) * K + k] = wq;
+    s += __bfloat162float(wq);
+    bb = fmaf(beta[k], w, bb);
+  }
+  s = warp_sum(s), bb = warp_sum(bb);
+  if (lane == 0) colsum[n] = s, bias_out[n] = bias[n] + bb;
 }
 
 // fp32 -> bf16 (weights at load time; also activations arriving from the wire).

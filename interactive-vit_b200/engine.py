@@ -83,6 +83,8 @@ SIGNATURES = {
     "vitb200_get_head_map": (_I, [_P, _I, _P, _I]),
     "vitb200_launch_count": (C.c_uint64, [_P]),
     "vitb200_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vitb200_op_gemm_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P]),
+    "vitb200_op_fold_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "vitb200_op_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "vitb200_op_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vitb200_op_attention_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
@@ -355,6 +357,43 @@ def op_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: 
     y = torch.empty(rows, d, device=x.device, dtype=torch.bfloat16)
     check(lib.vitb200_op_layernorm(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), rows, d, eps, None))
     return y
+
+
+def op_gemm_residual_stats(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, resid: torch.Tensor):
+    """Residual GEMM with the LayerNorm-folding producer epilogue: (x fp32 [M,N], bf16 copy, partial sums [M,N/32,2])."""
+    lib = load_library()
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=a.device)
+    xb = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    stats = torch.zeros(M, N // 32, 2, device=a.device)
+    check(lib.vitb200_op_gemm_ex(a.data_ptr(), w.data_ptr(), bias.data_ptr(), resid.data_ptr(), out.data_ptr(), M, N, K, 0, 1,
+                                 xb.data_ptr(), stats.data_ptr(), None, None, 0.0, None))
+    return out, xb, stats
+
+
+def op_fold_ln(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: torch.Tensor):
+    """(W' bf16, colsum, bias') of a Linear that consumes LayerNorm(x; gamma, beta)."""
+    lib = load_library()
+    N, K = w.shape
+    wq = torch.empty(N, K, device=w.device, dtype=torch.bfloat16)
+    colsum = torch.empty(N, device=w.device)
+    bias_out = torch.empty(N, device=w.device)
+    check(lib.vitb200_op_fold_ln(w.data_ptr(), gamma.data_ptr(), beta.data_ptr(), bias.data_ptr(), wq.data_ptr(),
+                                 colsum.data_ptr(), bias_out.data_ptr(), N, K, None))
+    return wq, colsum, bias_out
+
+
+def op_gemm_ln(xb: torch.Tensor, stats: torch.Tensor, wq: torch.Tensor, colsum: torch.Tensor, bias: torch.Tensor,
+               gelu: bool = False, eps: float = 1e-6) -> torch.Tensor:
+    """LayerNorm(x) W^T + b [-> GELU] from the bf16 copy of x, its partial sums and folded weights; bf16 result."""
+    lib = load_library()
+    M, K = xb.shape
+    N = wq.shape[0]
+    out = torch.empty(M, N, device=xb.device, dtype=torch.bfloat16)
+    check(lib.vitb200_op_gemm_ex(xb.data_ptr(), wq.data_ptr(), bias.data_ptr(), None, out.data_ptr(), M, N, K, int(gelu), 0,
+                                 None, None, stats.data_ptr(), colsum.data_ptr(), eps, None))
+    return out
 
 
 def op_attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, want_avg=True, want_cls=True, want_heads=False,

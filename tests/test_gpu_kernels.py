@@ -96,6 +96,41 @@ def test_gemm_full_size_linearity(E):
     assert torch.equal(E.op_gemm(a1[rows].contiguous(), w, out_f32=True), y1[rows])   # bit-exact row independence
 
 
+@pytest.mark.parametrize("M,d,n_out,gelu", [(788, 768, 2304, False), (788, 768, 3072, True), (300, 384, 1152, False),
+                                             (257, 1280, 5120, True), (50432, 768, 2304, False)])
+def test_layernorm_folded_into_gemms(E, M, d, n_out, gelu):
+    """The residual GEMM's producer epilogue (bf16 copy + per-chunk partial sums) and the consumer epilogue
+    (rstd * (acc - mean * colsum) + bias') together reproduce Linear(LayerNorm(x)) [-> GELU] of the reference
+    (EncoderBlock, vision_transformer.py:110-119) for a residual stream with a non-zero mean and uneven scales."""
+    torch.manual_seed(M + d)
+    a = (torch.randn(M, d, device="cuda") * 0.5).bfloat16()
+    w0 = (torch.randn(d, d, device="cuda") * 0.05).bfloat16()
+    b0 = torch.randn(d, device="cuda")
+    resid = torch.randn(M, d, device="cuda") * torch.linspace(0.5, 3.0, d, device="cuda") + 0.7
+    x, xb, stats = E.op_gemm_residual_stats(a, w0, b0, resid)
+    x_ref = a.float() @ w0.float().t() + b0 + resid
+    assert _rel(x, x_ref) < F32_EPS
+    assert torch.equal(xb, x.bfloat16())                                     # the copy is the rounded fp32 result
+    chunks = x.reshape(M, d // 32, 32)
+    assert _rel(stats[..., 0], chunks.sum(-1)) < 1e-5 and _rel(stats[..., 1], (chunks * chunks).sum(-1)) < 1e-5
+    # consumer
+    gamma = 1.0 + 0.1 * torch.randn(d, device="cuda")
+    beta = 0.05 * torch.randn(d, device="cuda")
+    w1 = torch.randn(n_out, d, device="cuda") * 0.05
+    b1 = torch.randn(n_out, device="cuda") * 0.02
+    wq, colsum, bias_f = E.op_fold_ln(w1, gamma, beta, b1)
+    assert torch.equal(wq, (w1 * gamma).bfloat16())
+    assert _rel(colsum, wq.float().sum(-1)) < 1e-5 and _rel(bias_f, b1 + w1 @ beta) < 1e-5
+    got = E.op_gemm_ln(xb, stats, wq, colsum, bias_f, gelu)
+    ref = torch.nn.functional.layer_norm(x_ref, (d,), gamma, beta, 1e-6) @ w1.t() + b1
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    assert _rel(got, ref) < 2 * BF16_EPS      # bf16 operands (x and gamma * W) and a bf16 result
+    # deterministic: fixed statistics slots, no atomics
+    x2, xb2, stats2 = E.op_gemm_residual_stats(a, w0, b0, resid)
+    assert torch.equal(stats, stats2) and torch.equal(E.op_gemm_ln(xb2, stats2, wq, colsum, bias_f, gelu), got)
+
+
 def _attn_ref(qkv, B, N, H, D=64):
     q, k, v = qkv.float().reshape(B, N, 3, H, D).permute(2, 0, 3, 1, 4)
     p = torch.softmax((q * D ** -0.5) @ k.transpose(-1, -2), dim=-1)
