@@ -166,7 +166,7 @@ static int gemm_units(int M, int N, int tile_m, int bn, int pairs) {
 template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
                          cudaStream_t st) {
-  using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu)>;
+  using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu || kLnIn)>;
   auto kern = gemm_bf16_kernel<BN, kPair, kPairs, kGelu, kOutF32, kResid, kRemap, kLnIn>;
   constexpr int kClusterCtas = kPair * kPairs;
   cudaLaunchConfig_t cfg = {};
@@ -218,10 +218,10 @@ static int gemm_pair_mode() {
 template <int BN, int kPair, int kPairs>
 static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep, bool gelu,
                           bool out_f32, cudaStream_t st) {
-  const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0, ln_in = ep.row_stats_in != nullptr;
+  const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0, ln_in = ep.row_affine_in != nullptr;
   if (ln_in) {
-    if (ep.colsum == nullptr || ep.stats_slots <= 0 || ep.ln_width <= 0 || out_f32 || resid || remap)
-      return fail(VITB200_ERR_INVALID, "gemm: folded-LayerNorm epilogue needs colsum / slots / width and a bf16 output");
+    if (ep.colsum == nullptr || out_f32 || resid || remap)
+      return fail(VITB200_ERR_INVALID, "gemm: folded-LayerNorm epilogue needs colsum and a bf16 output");
     if (gelu) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false, true>(ta, tw, sh, ep, st);
     return launch_gemm_t<BN, kPair, kPairs, false, false, false, false, true>(ta, tw, sh, ep, st);
   }
@@ -395,7 +395,7 @@ struct vitb200_engine {
   // activations (sized for cap_batch images)
   int cap_batch = 0;
   uint32_t cap_flags = 0;
-  Buffer images, patches, x, xb, ln_stats, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
+  Buffer images, patches, x, xb, ln_stats, ln_affine, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
 
   // vitb200_submit_host / vitb200_wait: two requests in flight.  H2D of request i+1 (copy_in stream) and D2H of
   // request i-1 (copy_out stream, from per-slot staging copies of the small outputs) overlap the forward of request i.
@@ -442,6 +442,7 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   VT_TRY(ensure(e->x, M * c.hidden_dim * 4));
   VT_TRY(ensure(e->xb, M * c.hidden_dim * 2));
   VT_TRY(ensure(e->ln_stats, M * (c.hidden_dim / 32) * sizeof(float2)));
+  VT_TRY(ensure(e->ln_affine, M * sizeof(float2)));
   VT_TRY(ensure(e->qkv, M * 3 * c.hidden_dim * 2));
   VT_TRY(ensure(e->ctx, M * c.hidden_dim * 2));
   if (!attention_is_fused(e->N, e->D)) VT_TRY(ensure(e->attn_stats, M * c.num_heads * sizeof(float2)));
@@ -503,12 +504,16 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
   float* x = (float*)e->x.p;
   __nv_bfloat16* xb = (__nv_bfloat16*)e->xb.p;
   float2* stats = (float2*)e->ln_stats.p;
+  float2* affine = (float2*)e->ln_affine.p;
   const int slots = d / 32;
+  prof_mark(e, "ln_row_stats", st);
+  row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
+  CU_TRY(cudaGetLastError());
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_qkv", st);
     ep.bias = w.bf_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
-    ep.row_stats_in = stats, ep.colsum = w.s_qkv, ep.stats_slots = slots, ep.ln_width = d, ep.ln_eps = 1e-6f;
+    ep.row_affine_in = affine, ep.colsum = w.s_qkv;
     VT_TRY(launch_gemm(xb, d, w.w_qkv, M, 3 * d, d, ep, false, false, st));
   }
   const bool want_avg = (flags & (VITB200_EMIT_AVG | VITB200_EMIT_ROLLOUT)) != 0;
@@ -527,11 +532,14 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
     ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots;
     VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st));
   }
+  prof_mark(e, "ln_row_stats", st);
+  row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
+  CU_TRY(cudaGetLastError());
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_fc1_gelu", st);
     ep.bias = w.bf_fc1, ep.out = e->mlp.p, ep.ldo = c.mlp_dim;
-    ep.row_stats_in = stats, ep.colsum = w.s_fc1, ep.stats_slots = slots, ep.ln_width = d, ep.ln_eps = 1e-6f;
+    ep.row_affine_in = affine, ep.colsum = w.s_fc1;
     VT_TRY(launch_gemm(xb, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st));
   }
   {
@@ -541,7 +549,7 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
     ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots;
     VT_TRY(launch_gemm(e->mlp.p, c.mlp_dim, w.w_fc2, M, d, c.mlp_dim, ep, false, true, st));
   }
-  e->launches += 5;
+  e->launches += 7;
   if (flags & VITB200_EMIT_HIDDEN) {
     float* hid = (float*)e->hidden.p + (size_t)l * e->cap_batch * e->N * d;
     CU_TRY(cudaMemcpyAsync(hid, x, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, st));
@@ -642,7 +650,7 @@ static int copy_rows_to_host(float* dst, const float* src_dev, size_t rows, int 
 }  // namespace vitb200
 
 vitb200_engine::~vitb200_engine() {
-  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats};
+  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &ln_affine, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats};
   for (Buffer* b : bufs) release(*b);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(w_patch), fr(b_patch), fr(cls_token), fr(pos), fr(lnf_g), fr(lnf_b), fr(w_head), fr(b_head);
@@ -1145,8 +1153,19 @@ int vitb200_op_gemm_ex(const void* a, const void* w, const float* bias, const fl
     ep.xb = (__nv_bfloat16*)xb_out, ep.ldxb = N, ep.row_stats_out = (float2*)stats_out, ep.stats_slots = N / 32;
   }
   if (stats_in) {
-    if (K % 32 != 0) return fail(VITB200_ERR_INVALID, "gemm: folded LayerNorm needs K to be a multiple of 32");
-    ep.row_stats_in = (const float2*)stats_in, ep.colsum = colsum, ep.stats_slots = K / 32, ep.ln_width = K, ep.ln_eps = ln_eps;
+    if (K % 128 != 0) return fail(VITB200_ERR_INVALID, "gemm: folded LayerNorm needs K to be a multiple of 128");
+    static float2* affine = nullptr;
+    static int cap = 0;
+    if (M > cap) {
+      if (affine) cudaFree(affine);
+      affine = nullptr, cap = 0;
+      CU_TRY(cudaMalloc(&affine, (size_t)M * sizeof(float2)));
+      cap = M;
+    }
+    row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float2*)stats_in, affine, M, K / 32, K,
+                                                                               ln_eps);
+    CU_TRY(cudaGetLastError());
+    ep.row_affine_in = affine, ep.colsum = colsum;
   }
   return launch_gemm(a, K, w, M, N, K, ep, gelu != 0, out_f32 != 0, (cudaStream_t)stream);
 }

@@ -57,17 +57,16 @@ struct GemmEpilogue {
   //    operand of the next GEMM) and, per row and 32-column chunk, the partial sums (sum x, sum x^2) into
   //    row_stats_out[out_row * stats_slots + col / 32] -- fixed slots, no atomics, so the statistics are
   //    bit-reproducible.
-  //  * consumer side (kLnIn epilogues): out = rstd_m * (acc - mean_m * colsum[n]) + bias[n], with mean / rstd of row m
-  //    from the stats_slots partial sums in row_stats_in (LayerNorm over ln_width columns, eps ln_eps); the weight
-  //    operand holds gamma-scaled weights, `bias` the beta-folded bias, colsum[n] = sum_k W'[n, k].
+  //  * consumer side (kLnIn epilogues): out = rstd_m * (acc - mean_m * colsum[n]) + bias[n]; row_affine_in[m] =
+  //    (rstd_m, -rstd_m * mean_m) comes from row_stats_finalize_kernel (rowwise.cuh), which reduces the partial sums
+  //    in slot order; the weight operand holds gamma-scaled weights, `bias` the beta-folded bias,
+  //    colsum[n] = sum_k W'[n, k].
   __nv_bfloat16* xb = nullptr;
   int ldxb = 0;
   float2* row_stats_out = nullptr;
-  const float2* row_stats_in = nullptr;
+  const float2* row_affine_in = nullptr;
   const float* colsum = nullptr;
   int stats_slots = 0;
-  int ln_width = 0;
-  float ln_eps = 0.f;
 };
 
 struct GemmShape {
@@ -89,11 +88,13 @@ struct Cfg {
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = (BN / kPair) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - kEpiWarps * kSlabBytes;
+  static constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - 2 * BM * 8 /*LN rows*/ - kEpiWarps * kSlabBytes;
   static constexpr int kStagesFit = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kSlabBytes + 256;
+  static constexpr int kLnBytes = 2 * BM * 8;  // folded LayerNorm: (rstd, -rstd * mean) of the tile's rows, double-buffered
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kSlabBytes + 256 + kLnBytes;
+  static_assert(kSmemBytes <= 227 * 1024, "gemm: shared memory budget");
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 }  // namespace gemm_cfg
@@ -155,11 +156,11 @@ struct GemmWork {
 };
 
 template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false>
-__global__ void __launch_bounds__((gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu)>::kThreads), 1)
+__global__ void __launch_bounds__((gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu || kLnIn)>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  GemmShape shape, GemmEpilogue ep) {
   using namespace gemm_cfg;
-  constexpr int kEpiWarps = epi_warps(kGelu);
+  constexpr int kEpiWarps = epi_warps(kGelu || kLnIn);  // the folded-LayerNorm epilogue is as issue-bound as the GELU one
   constexpr int kColGroups = kEpiWarps / 4;  // warps per TMEM lane quarter; each owns BN / kColGroups columns
   using C = Cfg<BN, kPair, kEpiWarps>;
   constexpr int kStages = C::kStages;
@@ -174,7 +175,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* ln_full_bar = tmem_empty_bar + 2;   // [2] (rstd, -rstd * mean) of a tile's rows staged by warp 3
+  uint64_t* ln_empty_bar = ln_full_bar + 2;     // [2] ... and read by every epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_empty_bar + 2);
+  float2* ln_rows = reinterpret_cast<float2*>(smem + kStages * C::kStageBytes + kEpiWarps * kSlabBytes + 256);  // [2][BM]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -203,6 +207,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps * kPair);  // one elected lane per epilogue warp (of both CTAs)
+      ptx::mbar_init(&ln_full_bar[a], 1);
+      ptx::mbar_init(&ln_empty_bar[a], kEpiWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -314,6 +320,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       __syncwarp();
     }
+  } else if (kLnIn && warp == 3) {
+    // ------------------------------------------------------------ LayerNorm row statistics (folded-LN GEMMs)
+    // Runs one tile ahead of the epilogue: fetches (rstd, -rstd * mean) of the tile's 128 rows (this CTA's) from the
+    // array row_stats_finalize_kernel wrote and stages them in smem, so that the epilogue never waits for an L2
+    // round trip (exposed, that latency cost ~2,000 cycles per tile).
+    int local = 0;
+    for (int unit = slot; unit < num_units; unit += num_slots, ++local) {
+      int m_blk, n_blk;
+      work.decode(unit, kPairs, pair_id, m_blk, n_blk);
+      const int buf = local & 1;
+      ptx::mbar_wait(&ln_empty_bar[buf], ((local >> 1) & 1) ^ 1);
+      const int row0 = m_blk * kTileM + static_cast<int>(cta_rank) * BM;
+      float2 v[BM / 32];
+#pragma unroll
+      for (int rr = 0; rr < BM / 32; ++rr) {   // all four loads in flight: one L2 round trip per tile
+        const int row = row0 + rr * 32 + lane;
+        v[rr] = row < shape.M ? ep.row_affine_in[row] : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int rr = 0; rr < BM / 32; ++rr) ln_rows[buf * BM + rr * 32 + lane] = v[rr];
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ln_full_bar[buf]);
+    }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------ epilogue
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
@@ -331,33 +360,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int row_base = m_blk * kTileM + static_cast<int>(cta_rank) * BM + quarter * 32;
+      // folded LayerNorm: scale a = rstd and offset c = -rstd * mean of this thread's 8 rows (trow + 4 i), staged by warp 3
+      float ln_a[8], ln_c[8];
+      if (kLnIn) {
+        ptx::mbar_wait(&ln_full_bar[acc], acc_phase);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 v = ln_rows[acc * BM + quarter * 32 + trow + 4 * i];
+          ln_a[i] = v.x, ln_c[i] = v.y;
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ln_empty_bar[acc]);
+      }
+      // bias (and folded-LayerNorm column sums) of every chunk of this tile, fetched before the accumulator wait: loaded
+      // inside the chunk loop their L2 latency was exposed once per chunk (9 % of the epilogue's stall samples)
+      float4 bias_c[kChunks], csum_c[kChunks];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = n_blk * BN + col_grp * kGroupCols + c * 32 + 4 * tcol;
+        bias_c[c] = make_float4(0.f, 0.f, 0.f, 0.f), csum_c[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < shape.N) {
+          if (ep.bias != nullptr) bias_c[c] = *reinterpret_cast<const float4*>(ep.bias + col);
+          if (kLnIn) csum_c[c] = *reinterpret_cast<const float4*>(ep.colsum + col);
+        }
+      }
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr0 =
           tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_grp * kGroupCols;
-      // folded LayerNorm: scale a = rstd and offset c = -rstd * mean of this thread's 8 rows (trow + 4 i).  Lane l
-      // reduces the partial sums of row row_base + l in slot order (bit-reproducible), the rows are then exchanged.
-      float ln_a[8], ln_c[8];
-      if (kLnIn) {
-        float s1 = 0.f, s2 = 0.f;
-        const int row = row_base + lane;
-        if (row < shape.M) {
-          const float2* sp = ep.row_stats_in + static_cast<long>(row) * ep.stats_slots;
-          for (int j = 0; j < ep.stats_slots; ++j) {
-            const float2 v = sp[j];
-            s1 += v.x, s2 += v.y;
-          }
-        }
-        const float inv_w = 1.0f / static_cast<float>(ep.ln_width);
-        const float mean = s1 * inv_w;
-        const float rstd = rsqrtf(fmaxf(s2 * inv_w - mean * mean, 0.f) + ep.ln_eps);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          ln_a[i] = __shfl_sync(0xffffffffu, rstd, trow + 4 * i);
-          ln_c[i] = -ln_a[i] * __shfl_sync(0xffffffffu, mean, trow + 4 * i);
-        }
-      }
-#pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         uint32_t r[32];
         ptx::tmem_ld_x32(taddr0 + c * 32, r);
@@ -380,10 +411,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         __syncwarp();
         const int col = col0 + 4 * tcol;
         const bool col_ok = col < shape.N;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ep.bias != nullptr && col_ok) bias4 = *reinterpret_cast<const float4*>(ep.bias + col);
-        float4 csum4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kLnIn && col_ok) csum4 = *reinterpret_cast<const float4*>(ep.colsum + col);
+        const float4 bias4 = bias_c[c], csum4 = csum_c[c];
         // transposed pass: 8 rows (trow + 4 i) x 4 columns per thread.  With a residual all 8 rows form one batch so
         // that 8 independent 16-byte loads per thread are in flight (the out_proj / fc2 epilogues are bound by
         // HBM latency x outstanding bytes); otherwise two batches of 4 keep the instruction footprint small.

@@ -134,6 +134,28 @@ rows_bf16_stats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ 
   }
 }
 
+// LayerNorm folding, statistics side: partial sums [rows][slots] (sum, sum of squares per 32-column chunk, written by
+// the GEMM epilogues that produce the row) -> (rstd, -rstd * mean) per row, summed in slot order (bit-reproducible).
+// One thread per row; slots is a multiple of 4.  Runs once per LayerNorm instead of once per consuming output tile.
+__global__ void __launch_bounds__(256)
+row_stats_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ affine, long rows, int slots, int width,
+                          float eps) {
+  const long row = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const float4* sp = reinterpret_cast<const float4*>(partial + row * slots);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 6
+  for (int j = 0; j < (slots >> 1); j += 2) {
+    const float4 v0 = sp[j], v1 = sp[j + 1];
+    s1 += v0.x, s2 += v0.y, s1 += v0.z, s2 += v0.w;
+    s1 += v1.x, s2 += v1.y, s1 += v1.z, s2 += v1.w;
+  }
+  const float inv_w = 1.0f / static_cast<float>(width);
+  const float mean = s1 * inv_w;
+  const float rstd = rsqrtf(fmaxf(s2 * inv_w - mean * mean, 0.f) + eps);
+  affine[row] = make_float2(rstd, -rstd * mean);
+}
+
 // LayerNorm folding, weight side (once, after the weights are loaded).  For a Linear that consumes LayerNorm(x):
 //     W'[n, k] = bf16(gamma[k] * W[n, k]),   colsum[n] = sum_k float(W'[n, k]),   bias'[n] = bias[n] + sum_k beta[k] W[n, k]
 // so that LN(x) W^T + bias = rstd * (x W'^T - mean * colsum) + bias'.  colsum is taken over the ROUNDED weights: the

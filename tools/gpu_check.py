@@ -111,6 +111,42 @@ def gemm_cluster():
 
 
 @case
+def gemm_ln_perf():
+    """Plain bias epilogue vs the folded-LayerNorm consumer epilogue, and plain residual vs the producer epilogue."""
+    import torch
+    from interactive_vit_b200 import engine as E
+    M, d = 256 * 197, 768
+
+    def timeit(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / n
+
+    a = (torch.randn(M, d, device="cuda") * 0.5).bfloat16()
+    x = torch.randn(M, d, device="cuda")
+    stats = torch.stack([x.reshape(M, d // 32, 32).sum(-1), (x * x).reshape(M, d // 32, 32).sum(-1)], -1).contiguous()
+    for (N, gelu) in ((2304, False), (3072, True)):
+        w = (torch.randn(N, d, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda")
+        cs = w.float().sum(-1).contiguous()
+        t_plain = timeit(lambda: E.op_gemm(a, w, b, None, gelu, False))
+        t_ln = timeit(lambda: E.op_gemm_ln(a, stats, w, cs, b, gelu))
+        print(f"    N={N} gelu={gelu}: plain {t_plain * 1e3:.1f} us   folded-LN {t_ln * 1e3:.1f} us", flush=True)
+    w = (torch.randn(d, d, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(d, device="cuda")
+    t_plain = timeit(lambda: E.op_gemm(a, w, b, x, False, True))
+    t_st = timeit(lambda: E.op_gemm_residual_stats(a, w, b, x))
+    print(f"    out_proj: plain residual {t_plain * 1e3:.1f} us   + bf16 copy + stats {t_st * 1e3:.1f} us (incl. torch allocs)", flush=True)
+
+
+@case
 def gemm_perf_cluster():
     os.environ["VITB200_GEMM_PAIR"] = "4"
     gemm_perf()
