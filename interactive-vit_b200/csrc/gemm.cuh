@@ -424,6 +424,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           float4 v[kRowBatch], q[kRowBatch];
           long orow[kRowBatch];
           bool ok[kRowBatch];
+          float p1[kRowBatch], p2[kRowBatch];  // producer side of the LayerNorm folding: per-row partial sums
 #pragma unroll
           for (int i = 0; i < kRowBatch; ++i) {
             const int row = row_base + trow + 4 * (i0 + i);
@@ -455,18 +456,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (kGelu) t.x = gelu_erf(t.x), t.y = gelu_erf(t.y), t.z = gelu_erf(t.z), t.w = gelu_erf(t.w);
             if (kResid) t.x += q[i].x, t.y += q[i].y, t.z += q[i].z, t.w += q[i].w;
             if (kResid && ep.xb != nullptr) {
-              // bf16 copy for the next GEMM + this 32-column chunk's partial sums of the row (the 8 lanes that share
-              // the row are consecutive: xor-shuffles over 1, 2, 4 stay inside the group; every lane takes part)
-              float p1 = ok[i] ? (t.x + t.y) + (t.z + t.w) : 0.f;
-              float p2 = ok[i] ? (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w) : 0.f;
-#pragma unroll
-              for (int o = 1; o < 8; o <<= 1) {
-                p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-                p2 += __shfl_xor_sync(0xffffffffu, p2, o);
-              }
-              // a row whose chunk is only partly inside N (never the case for the widths in use) still gets its slot
-              const bool row_in = row_base + trow + 4 * (i0 + i) < shape.M;
-              if (tcol == 0 && row_in) ep.row_stats_out[orow[i] * ep.stats_slots + (col0 >> 5)] = make_float2(p1, p2);
+              // bf16 copy for the next GEMM; this thread's share of the row's partial sums (reduced after the loop)
+              p1[i] = ok[i] ? (t.x + t.y) + (t.z + t.w) : 0.f;
+              p2[i] = ok[i] ? (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w) : 0.f;
               if (ok[i]) {
                 uint2 pk;
                 pk.x = pack2_bf16(t.x, t.y), pk.y = pack2_bf16(t.z, t.w);
@@ -484,6 +476,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow[i] * ep.ldo + col) = pk;
               }
+            }
+          }
+          if (kResid && ep.xb != nullptr) {
+            // The 8 lanes that share a row group (tcol = 0..7, consecutive lanes) hold 8 rows x (sum, sum of squares)
+            // each.  Recursive halving: exchange the half of the rows the partner keeps (xor 4, 2, 1), add, so that
+            // lane tcol ends with the complete sums of row trow + 4 * tcol: 14 shuffles instead of 48.
+            static_assert(!kResid || kRowBatch == 8, "the residual epilogue reduces all 8 rows of a chunk at once");
+            float a1[4], a2[4];
+            const bool b2 = (tcol & 4) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float s1 = b2 ? p1[i] : p1[i + 4], s2 = b2 ? p2[i] : p2[i + 4];   // rows the partner keeps
+              const float k1 = b2 ? p1[i + 4] : p1[i], k2 = b2 ? p2[i + 4] : p2[i];
+              a1[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, 4);
+              a2[i] = k2 + __shfl_xor_sync(0xffffffffu, s2, 4);
+            }
+            float c1[2], c2[2];
+            const bool b1 = (tcol & 2) != 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float s1 = b1 ? a1[i] : a1[i + 2], s2 = b1 ? a2[i] : a2[i + 2];
+              const float k1 = b1 ? a1[i + 2] : a1[i], k2 = b1 ? a2[i + 2] : a2[i];
+              c1[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+              c2[i] = k2 + __shfl_xor_sync(0xffffffffu, s2, 2);
+            }
+            const bool b0 = (tcol & 1) != 0;
+            const float f1 = (b0 ? c1[1] : c1[0]) + __shfl_xor_sync(0xffffffffu, b0 ? c1[0] : c1[1], 1);
+            const float f2 = (b0 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? c2[0] : c2[1], 1);
+            // this lane now owns row index tcol of the batch (bit 2 chose rows 4..7, bit 1 rows +2, bit 0 rows +1)
+            const int row = row_base + trow + 4 * tcol;
+            if (row < shape.M) {
+              long out_row = row;
+              if (kRemap) {
+                const int g = row / ep.group_rows;
+                out_row = static_cast<long>(g) * ep.out_group_stride + ep.out_row_offset + (row - g * ep.group_rows);
+              }
+              ep.row_stats_out[out_row * ep.stats_slots + (col0 >> 5)] = make_float2(f1, f2);
             }
           }
         }
