@@ -174,7 +174,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the communicator comes up; stdout carries exactly one JSON line,
+        # so the file descriptor points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = E.CONFIGS[args.model]
     B = args.batch
     eng = E.VitEngine(cfg, local_rank, B)
