@@ -303,7 +303,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     // The tensor map views ctx as [B][N][d], so rows of the last query tile that lie beyond the image are clipped.
     uint8_t* ctx_tile = smem_ctx + quarter * (32 * 128);
     const uint32_t ctx_dst = ptx::smem_u32(ctx_tile) + lane * 128;
-    auto o_epilogue = [&](int hh) {
+    // stage: TMEM -> bf16 -> smem tile (generic-proxy writes: the caller issues ONE fence.proxy.async for these and for
+    // the P tile); store: the quarter's four warps meet, one thread issues the TMA store.
+    auto o_stage = [&](int hh) {
       ptx::mbar_wait(o_full, hh & 1);
       ptx::tc_fence_after();
       uint32_t o[16];
@@ -320,7 +322,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
                    "r"(pack_bf16x2_u(o[8], o[9])), "r"(pack_bf16x2_u(o[10], o[11])), "r"(pack_bf16x2_u(o[12], o[13])),
                    "r"(pack_bf16x2_u(o[14], o[15]))
                    : "memory");
-      ptx::fence_proxy_async_smem();
+    };
+    auto o_store = [&](int hh) {
       asm volatile("bar.sync %0, 128;" ::"r"(3 + quarter) : "memory");  // the four column-group warps of this quarter
       if (cg == 0 && ptx::elect_one()) {
         ptx::tma_store_3d(&tmap_ctx, ctx_tile, hh * D, qt * BM + quarter * 32, b);
@@ -415,7 +418,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 
       // ---- the P tile is about to be overwritten: the previous head's P V and Pbar MMAs (issued a whole softmax
       //      pass ago) must have retired
-      if (h > 0) ptx::mbar_wait(p_free, (h - 1) & 1);
+      if (h > 0) {
+        ptx::mbar_wait(p_free, (h - 1) & 1);
+        // context of the previous head (its P V retired long ago): TMEM -> smem now, so that the fence below covers it
+        // and P V of THIS head finds the O columns free as soon as the P tile is handed over
+        o_stage(h - 1);
+      }
 
       // ---- p = e / sum -> bf16 P tile (swizzled K-major A operand of P V and of the head-average MMAs); fp32 copies
       //      of row 0 / of every row for the CLS / per-head maps
@@ -437,9 +445,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       if (lane == 0) ptx::mbar_arrive(p_full);
       ATTN_TS(7);
 
-      // ---- context of the previous head.  Placed AFTER the P tile hand-off: fence.proxy.async is a MEMBAR that
-      //      waits for every global store this thread has in flight, so the stores below get a whole head to drain.
-      if (h > 0) o_epilogue(h - 1);
+      // ---- context of the previous head: staged above, ordered by the same fence as the P tile
+      if (h > 0) o_store(h - 1);
 
       if (want_cls && lane == 0) {
         // query row 0 lives in lane 0 of the quarter-0 warp of every column group
@@ -476,7 +483,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     // (restaging needs the previous store's smem reads done; every warp passes through the issuer's wait via bar 3+q)
     ptx::tma_store_wait_read<0>();
     asm volatile("bar.sync %0, 128;" ::"r"(3 + quarter) : "memory");
-    o_epilogue(p.H - 1);
+    o_stage(p.H - 1);
+    ptx::fence_proxy_async_smem();
+    o_store(p.H - 1);
     ptx::tma_store_wait<0>();
 
     // head-averaged map rows -> HBM, once per (image, query tile): Pbar holds the SUM over heads.  The tile goes
