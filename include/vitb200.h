@@ -119,6 +119,14 @@ int vitb200_synchronize(vitb200_engine* e);
  * [B, N, d] fp32 lives in the engine between calls; set/get move it across the boundary when a node's input
  * did not come from (or its output must leave) the engine. */
 int vitb200_stage_embed(vitb200_engine* e, const float* images_host, int batch);         /* TV:268-287,295-296 + pos add TV:155 */
+/* `<model>:transform` node: torchvision's ImageClassification preset (transforms/_presets.py:58-65; the reference's
+ * VggModel runs weights.transforms() on the CPU, static/models/vgg16.py:40-42): antialiased bilinear resize of the
+ * shorter side to `resize`, centre crop to the model's image_size, ImageNet normalisation.  images_host: fp32
+ * [B,3,H,W] in [0,1]; out_host (may be NULL): fp32 [B,3,S,S].  The result also stays in the engine's image buffer:
+ * vitb200_stage_embed_resident embeds it without another upload. */
+int vitb200_stage_transform(vitb200_engine* e, const float* images_host, int batch, int H, int W, int resize,
+                            float* out_host);
+int vitb200_stage_embed_resident(vitb200_engine* e, int batch);
 int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags);        /* TV:110-119 */
 int vitb200_stage_head(vitb200_engine* e, int batch, float* logits_host);                /* TV:157,302-304 */
 int vitb200_stage_rollout(vitb200_engine* e, int batch, float* rollout_host);            /* needs avg maps of all layers */
@@ -154,6 +162,8 @@ int vitb200_op_attention(const void* qkv_bf16_dev, void* ctx_bf16_dev, float* av
  * dimensions other than 64 take the key-blocked two-kernel path (attention_long.cuh). */
 int vitb200_op_attention_ex(const void* qkv_bf16_dev, void* ctx_bf16_dev, float* avg_dev, float* cls_dev,
                             float* heads_dev, int batch, int tokens, int heads, int head_dim, int pitch, void* stream);
+int vitb200_op_preprocess(const float* images_dev, float* out_dev, int batch, int H, int W, int resize, int crop,
+                          void* stream);
 int vitb200_op_patchify(const float* images_dev, void* patches_bf16_dev, int batch, int image_size, int patch,
                         void* stream);
 int vitb200_op_rollout(const float* maps_dev, long layer_stride, int layers, int batch, int tokens, int pitch,

@@ -507,7 +507,7 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
   float2* affine = (float2*)e->ln_affine.p;
   const int slots = d / 32;
   prof_mark(e, "ln_row_stats", st);
-  row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
+  row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
   CU_TRY(cudaGetLastError());
   {
     GemmEpilogue ep;
@@ -533,7 +533,7 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
     VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st));
   }
   prof_mark(e, "ln_row_stats", st);
-  row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
+  row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
   CU_TRY(cudaGetLastError());
   {
     GemmEpilogue ep;
@@ -673,6 +673,8 @@ vitb200_engine::~vitb200_engine() {
 
 // =========================================================================================== C ABI
 extern "C" {
+
+static int preprocess_params(int B, int H, int W, int resize, int crop, PreprocessParams* p);
 
 const char* vitb200_last_error(void) { return g_last_error.c_str(); }
 int vitb200_version(void) { return 1; }
@@ -1036,6 +1038,31 @@ int vitb200_stage_embed(vitb200_engine* e, const float* images_host, int batch) 
   return VITB200_OK;
 }
 
+int vitb200_stage_transform(vitb200_engine* e, const float* images_host, int batch, int H, int W, int resize,
+                            float* out_host) {
+  if (!images_host) return fail(VITB200_ERR_INVALID, "null images");
+  STAGE_PROLOGUE(batch, 0)
+  const int S = e->cfg.image_size;
+  PreprocessParams p;
+  VT_TRY(preprocess_params(batch, H, W, resize, S, &p));
+  const size_t in_bytes = (size_t)batch * 3 * H * W * 4, out_bytes = (size_t)batch * 3 * S * S * 4;
+  VT_TRY(ensure(e->stage_f32, in_bytes));
+  CU_TRY(cudaMemcpyAsync(e->stage_f32.p, images_host, in_bytes, cudaMemcpyHostToDevice, st));
+  preprocess_kernel<<<(unsigned)((out_bytes / 4 + 255) / 256), 256, 0, st>>>((const float*)e->stage_f32.p, (float*)e->images.p, p);
+  CU_TRY(cudaGetLastError());
+  e->launches += 1;
+  if (out_host) CU_TRY(cudaMemcpyAsync(out_host, e->images.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_stage_embed_resident(vitb200_engine* e, int batch) {
+  STAGE_PROLOGUE(batch, 0)
+  VT_TRY(run_embed(e, (const float*)e->images.p, batch, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
 int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags) {
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)
@@ -1162,7 +1189,7 @@ int vitb200_op_gemm_ex(const void* a, const void* w, const float* bias, const fl
       CU_TRY(cudaMalloc(&affine, (size_t)M * sizeof(float2)));
       cap = M;
     }
-    row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float2*)stats_in, affine, M, K / 32, K,
+    row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float2*)stats_in, affine, M, K / 32, K,
                                                                                ln_eps);
     CU_TRY(cudaGetLastError());
     ep.row_affine_in = affine, ep.colsum = colsum;
@@ -1212,6 +1239,31 @@ int vitb200_op_attention_ex(const void* qkv, void* ctx, float* avg, float* cls, 
 int vitb200_op_attention(const void* qkv, void* ctx, float* avg, float* cls, float* heads, int batch, int tokens,
                          int nheads, int pitch, void* stream) {
   return vitb200_op_attention_ex(qkv, ctx, avg, cls, heads, batch, tokens, nheads, 64, pitch, stream);
+}
+
+// torchvision F.resize with a single int (shorter side -> resize, longer = int(resize * long / short)) followed by
+// F.center_crop (offsets = round-half-even((size - crop) / 2)), ImageNet mean / std.
+static int preprocess_params(int B, int H, int W, int resize, int crop, PreprocessParams* p) {
+  if (B <= 0 || H <= 0 || W <= 0 || resize <= 0 || crop <= 0) return fail(VITB200_ERR_INVALID, "preprocess: bad geometry");
+  p->B = B, p->H = H, p->W = W;
+  if (H <= W) p->RH = resize, p->RW = (int)((long)resize * W / H);
+  else p->RW = resize, p->RH = (int)((long)resize * H / W);
+  if (p->RH < crop || p->RW < crop) return fail(VITB200_ERR_INVALID, "preprocess: crop %d larger than the resized image %dx%d", crop, p->RH, p->RW);
+  p->crop = crop;
+  p->top = (int)nearbyint((p->RH - crop) / 2.0), p->left = (int)nearbyint((p->RW - crop) / 2.0);  // ties to even, like Python's round
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (int c = 0; c < 3; ++c) p->mean[c] = mean[c], p->inv_std[c] = 1.0f / stdv[c];
+  return VITB200_OK;
+}
+
+int vitb200_op_preprocess(const float* images_dev, float* out_dev, int batch, int H, int W, int resize, int crop, void* stream) {
+  if (!images_dev || !out_dev) return fail(VITB200_ERR_INVALID, "null argument");
+  PreprocessParams p;
+  VT_TRY(preprocess_params(batch, H, W, resize, crop, &p));
+  const long total = (long)batch * 3 * crop * crop;
+  preprocess_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(images_dev, out_dev, p);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
 }
 
 int vitb200_op_patchify(const float* images, void* patches, int batch, int image_size, int patch, void* stream) {

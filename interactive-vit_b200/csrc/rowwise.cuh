@@ -65,6 +65,64 @@ layernorm_f32_bf16_kernel(const float* __restrict__ x, long in_row_stride, const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Preprocessing node (`<model>:transform`; the reference's VggModel applies weights.transforms() on the CPU,
+// static/models/vgg16.py:40-42): torchvision's ImageClassification preset (transforms/_presets.py:58-65) =
+// antialiased bilinear resize (shorter side -> `resize`), centre crop, normalise.  The resize follows ATen's
+// _upsample_bilinear2d_aa (aten/src/ATen/native/cpu/UpSampleKernel.cpp, _compute_indices_min_size_weights_aa):
+//     scale = in / out, support = max(scale, 1), centre = scale * (i + 0.5),
+//     taps [int(centre - support + 0.5), int(centre + support + 0.5)) clipped to the image,
+//     weight = max(0, 1 - |(j - centre + 0.5) / max(scale, 1)|), normalised to sum 1,
+// horizontal taps accumulated first, then vertical (the order of ATen's two separable passes).
+// One thread per output pixel (crop x crop x 3 x B); in: fp32 [B, 3, H, W] in [0, 1]; out: fp32 [B, 3, crop, crop].
+struct PreprocessParams {
+  int B, H, W;            // input
+  int RH, RW;             // resized image
+  int crop, top, left;    // centre crop window inside the resized image
+  float mean[3], inv_std[3];
+};
+
+__device__ __forceinline__ void aa_taps(int i, float scale, int in_size, int& lo, int& n, float& centre, float& invscale,
+                                        float& total) {
+  const float support = scale >= 1.0f ? scale : 1.0f;
+  centre = scale * (static_cast<float>(i) + 0.5f);
+  invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  lo = max(static_cast<int>(centre - support + 0.5f), 0);
+  n = min(static_cast<int>(centre + support + 0.5f), in_size) - lo;
+  total = 0.f;
+  for (int j = 0; j < n; ++j) total += fmaxf(0.f, 1.0f - fabsf((static_cast<float>(j + lo) - centre + 0.5f) * invscale));
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const float* __restrict__ in, float* __restrict__ out, PreprocessParams p) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total_px = static_cast<long>(p.B) * 3 * p.crop * p.crop;
+  if (idx >= total_px) return;
+  const int x = idx % p.crop;
+  const int y = (idx / p.crop) % p.crop;
+  const int c = (idx / (static_cast<long>(p.crop) * p.crop)) % 3;
+  const int b = idx / (3L * p.crop * p.crop);
+  const float sx = static_cast<float>(p.W) / static_cast<float>(p.RW);
+  const float sy = static_cast<float>(p.H) / static_cast<float>(p.RH);
+  int x0, nx, y0, ny;
+  float cx, ix, tx, cy, iy, ty;
+  aa_taps(x + p.left, sx, p.W, x0, nx, cx, ix, tx);
+  aa_taps(y + p.top, sy, p.H, y0, ny, cy, iy, ty);
+  const float* plane = in + (static_cast<long>(b) * 3 + c) * p.H * p.W;
+  float acc = 0.f;
+  for (int j = 0; j < ny; ++j) {
+    const float wy = fmaxf(0.f, 1.0f - fabsf((static_cast<float>(j + y0) - cy + 0.5f) * iy)) / ty;
+    const float* row = plane + static_cast<long>(y0 + j) * p.W + x0;
+    float h = 0.f;
+    for (int i = 0; i < nx; ++i) {
+      const float wx = fmaxf(0.f, 1.0f - fabsf((static_cast<float>(i + x0) - cx + 0.5f) * ix)) / tx;
+      h = fmaf(row[i], wx, h);
+    }
+    acc = fmaf(h, wy, acc);
+  }
+  out[idx] = (acc - p.mean[c]) * p.inv_std[c];
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Patch gather: images fp32 [B, 3, S, S] -> patch matrix bf16 [B * n, 3 * p * p] with
 // column = c * p * p + ky * p + kx (the flattening of conv_proj.weight [d, 3, p, p]), row = b * n + py * np + px.
 // One thread moves 8 consecutive kx: two float4 reads, one 16-byte write.
@@ -136,24 +194,33 @@ rows_bf16_stats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ 
 
 // LayerNorm folding, statistics side: partial sums [rows][slots] (sum, sum of squares per 32-column chunk, written by
 // the GEMM epilogues that produce the row) -> (rstd, -rstd * mean) per row, summed in slot order (bit-reproducible).
-// One thread per row; slots is a multiple of 4.  Runs once per LayerNorm instead of once per consuming output tile.
+// Four lanes per row (each sums every fourth 16-byte pair of slots, then two xor-shuffles): a warp instruction reads
+// 8 rows x 64 contiguous bytes.  The order of the additions is fixed, so the result is bit-reproducible.  Runs once
+// per LayerNorm instead of once per consuming output tile.
 __global__ void __launch_bounds__(256)
 row_stats_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ affine, long rows, int slots, int width,
                           float eps) {
-  const long row = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (row >= rows) return;
-  const float4* sp = reinterpret_cast<const float4*>(partial + row * slots);
+  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 2;
+  const int q = threadIdx.x & 3;
+  const bool row_ok = row < rows;
+  const int n4 = slots >> 1;  // float4 = two slots
   float s1 = 0.f, s2 = 0.f;
-#pragma unroll 6
-  for (int j = 0; j < (slots >> 1); j += 2) {
-    const float4 v0 = sp[j], v1 = sp[j + 1];
-    s1 += v0.x, s2 += v0.y, s1 += v0.z, s2 += v0.w;
-    s1 += v1.x, s2 += v1.y, s1 += v1.z, s2 += v1.w;
+  if (row_ok) {
+    const float4* sp = reinterpret_cast<const float4*>(partial + row * slots);
+#pragma unroll 4
+    for (int j = q; j < n4; j += 4) {
+      const float4 v = sp[j];
+      s1 += v.x, s2 += v.y, s1 += v.z, s2 += v.w;
+    }
   }
-  const float inv_w = 1.0f / static_cast<float>(width);
-  const float mean = s1 * inv_w;
-  const float rstd = rsqrtf(fmaxf(s2 * inv_w - mean * mean, 0.f) + eps);
-  affine[row] = make_float2(rstd, -rstd * mean);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1), s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 2), s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+  if (row_ok && q == 0) {
+    const float inv_w = 1.0f / static_cast<float>(width);
+    const float mean = s1 * inv_w;
+    const float rstd = rsqrtf(fmaxf(s2 * inv_w - mean * mean, 0.f) + eps);
+    affine[row] = make_float2(rstd, -rstd * mean);
+  }
 }
 
 // LayerNorm folding, weight side (once, after the weights are loaded).  For a Linear that consumes LayerNorm(x):

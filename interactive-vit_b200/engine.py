@@ -72,6 +72,8 @@ SIGNATURES = {
     "vitb200_device_output": (_I, [_P, _U32, C.POINTER(_P), C.POINTER(_I)]),
     "vitb200_synchronize": (_I, [_P]),
     "vitb200_stage_embed": (_I, [_P, _P, _I]),
+    "vitb200_stage_transform": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "vitb200_stage_embed_resident": (_I, [_P, _I]),
     "vitb200_stage_layer": (_I, [_P, _I, _I, _U32]),
     "vitb200_stage_head": (_I, [_P, _I, _P]),
     "vitb200_stage_rollout": (_I, [_P, _I, _P]),
@@ -88,6 +90,7 @@ SIGNATURES = {
     "vitb200_op_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "vitb200_op_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vitb200_op_attention_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vitb200_op_preprocess": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_patchify": (_I, [_P, _P, _I, _I, _I, _P]),
     "vitb200_op_rollout": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
 }
@@ -279,6 +282,18 @@ class VitEngine:
         assert images.device.type == "cpu" and images.dtype == torch.float32 and images.is_contiguous()
         check(self.lib.vitb200_stage_embed(self._h, images.data_ptr(), images.shape[0]))
 
+    def stage_transform(self, images: torch.Tensor, resize: int) -> torch.Tensor:
+        """`<model>:transform`: images CPU fp32 [B,3,H,W] in [0,1] -> preprocessed CPU fp32 [B,3,S,S]; the result also
+        stays on the device for stage_embed_resident."""
+        assert images.device.type == "cpu" and images.dtype == torch.float32 and images.is_contiguous() and images.dim() == 4
+        B, _, H, W = images.shape
+        out = torch.empty(B, 3, self.cfg.image_size, self.cfg.image_size)
+        check(self.lib.vitb200_stage_transform(self._h, images.data_ptr(), B, H, W, resize, out.data_ptr()))
+        return out
+
+    def stage_embed_resident(self, batch: int) -> None:
+        check(self.lib.vitb200_stage_embed_resident(self._h, batch))
+
     def stage_layer(self, layer: int, batch: int, flags: int) -> None:
         check(self.lib.vitb200_stage_layer(self._h, layer, batch, flags))
 
@@ -408,6 +423,14 @@ def op_attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, want_av
     check(lib.vitb200_op_attention_ex(qkv.data_ptr(), ctx.data_ptr(), _ptr(avg), _ptr(cls), _ptr(hm), batch, tokens, heads,
                                       head_dim, pitch, None))
     return ctx, (avg[..., :tokens] if avg is not None else None), cls, (hm[..., :tokens] if hm is not None else None)
+
+
+def op_preprocess(images: torch.Tensor, resize: int, crop: int) -> torch.Tensor:
+    lib = load_library()
+    B, _, H, W = images.shape
+    out = torch.empty(B, 3, crop, crop, device=images.device)
+    check(lib.vitb200_op_preprocess(images.data_ptr(), out.data_ptr(), B, H, W, resize, crop, None))
+    return out
 
 
 def op_patchify(images: torch.Tensor, patch: int) -> torch.Tensor:

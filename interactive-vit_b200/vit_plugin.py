@@ -75,7 +75,8 @@ def make_vit_model_class(ModelBase, PinoutCls):
             self._tokens_batch = 0
             self._maps_out: Dict[int, torch.Tensor] = {}      # layer -> avg-map tensor handed out (resident on device)
             self.node_names = ([self.prefix() + "embed"] + [self.prefix() + f"layer.{i}" for i in range(cfg.num_layers)]
-                               + [self.prefix() + "head", self.prefix() + "rollout"])
+                               + [self.prefix() + "head", self.prefix() + "rollout", self.prefix() + "transform"])
+            self._images_out: Optional[torch.Tensor] = None   # last preprocessed image tensor handed out (still on the device)
 
         # ---- catalogue ---------------------------------------------------------------------------
         def list_node_names(self) -> List[str]:
@@ -83,7 +84,7 @@ def make_vit_model_class(ModelBase, PinoutCls):
 
         def _kind(self, node_name: str) -> str:
             sub = node_name.removeprefix(self.prefix())
-            if sub in ("embed", "head", "rollout"):
+            if sub in ("embed", "head", "rollout", "transform"):
                 return sub
             if sub.startswith("layer."):
                 i = int(sub[len("layer."):])
@@ -110,6 +111,7 @@ def make_vit_model_class(ModelBase, PinoutCls):
                 "layer": f"EncoderBlock: {c.num_heads}-head attention + MLP {c.mlp_dim} (outs: o, attn, cls)",
                 "head": f"LayerNorm + Linear -> {c.num_classes} logits",
                 "rollout": f"attention rollout over {c.num_layers} layers -> {c.image_size // c.patch_size}x{c.image_size // c.patch_size}",
+                "transform": f"resize (antialiased bilinear) + centre crop {c.image_size} + ImageNet normalisation",
             }[kind]
             return f"<p>{node_name}</p> <p>{what}</p> <p>B200 engine</p>"
 
@@ -129,6 +131,9 @@ def make_vit_model_class(ModelBase, PinoutCls):
             for i in range(L):
                 edges.append({"in_port": {"node": 1 + i, "channel": "attn"},
                               "out_port": {"node": rollout_idx, "channel": f"a{i}"}})
+            # preprocessing in front of the chain, as VggModel's `transform` pseudo-node (static/models/vgg16.py:31-35)
+            edges.append({"in_port": {"node": names.index(self.prefix() + "transform"), "channel": "o"},
+                          "out_port": {"node": 0, "channel": "o"}})
             cat_idx = len(nodes)
             nodes.append({"instance": {"kind": "category", "cats": imagenet_categories(self.cfg.num_classes)},
                           "pos": {"x": (cat_idx % w) * 200, "y": int(cat_idx / w) * 200}})
@@ -172,14 +177,29 @@ def make_vit_model_class(ModelBase, PinoutCls):
             g = c.image_size // c.patch_size
             out = PinoutCls()
             with self._lock:
-                if kind == "embed":
+                if kind == "transform":
+                    x = self._need(pinin, "o")
+                    if x.dim() not in (3, 4) or x.shape[-3] != 3:
+                        raise Exception(f"expected an image of shape [3, H, W] (optionally batched), got {list(x.shape)}")
+                    batched = x.dim() == 4
+                    imgs = self._host(x).reshape(-1, 3, x.shape[-2], x.shape[-1])
+                    resize = int(params["resize"]) if params and str(params.get("resize", "")).strip() else (256 if c.image_size == 224 else c.image_size)
+                    y = self.engine.stage_transform(imgs, resize)
+                    y = y if batched else y[0]
+                    self._images_out = y
+                    out.set("o", y)
+                elif kind == "embed":
                     x = self._need(pinin, "o")
                     if x.dim() not in (3, 4) or tuple(x.shape[-3:]) != (3, c.image_size, c.image_size):
                         raise Exception(f"expected an image of shape [3, {c.image_size}, {c.image_size}] (optionally batched), got {list(x.shape)}")
                     batched = x.dim() == 4
-                    imgs = self._host(x).reshape(-1, 3, c.image_size, c.image_size)
-                    self.engine.stage_embed(imgs)
-                    out.set("o", self._emit_tokens(imgs.shape[0], batched))
+                    nimg = x.shape[0] if batched else 1
+                    if x is self._images_out:
+                        self.engine.stage_embed_resident(nimg)   # preprocessed by the transform node: still on the device
+                    else:
+                        self.engine.stage_embed(self._host(x).reshape(-1, 3, c.image_size, c.image_size))
+                    self._images_out = None
+                    out.set("o", self._emit_tokens(nimg, batched))
                 elif kind == "layer":
                     i = int(node_name.removeprefix(self.prefix())[len("layer."):])
                     x = self._need(pinin, "o")

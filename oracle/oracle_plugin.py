@@ -25,7 +25,7 @@ def make_oracle_model_class(ModelBase, PinoutCls):
             super().__init__(module, name)
             self.cfg = cfg
             self.node_names = ([self.prefix() + "embed"] + [self.prefix() + f"layer.{i}" for i in range(cfg.num_layers)]
-                               + [self.prefix() + "head", self.prefix() + "rollout"])
+                               + [self.prefix() + "head", self.prefix() + "rollout", self.prefix() + "transform"])
 
         def list_node_names(self) -> List[str]:
             return self.node_names
@@ -41,7 +41,7 @@ def make_oracle_model_class(ModelBase, PinoutCls):
         def contents(self, node_name: str) -> str:
             return f"<p>{node_name}</p> <p>torchvision CPU oracle</p>"
 
-        def compute(self, node_name: str, pinin):
+        def compute(self, node_name: str, pinin, params=None):
             sub = node_name.removeprefix(self.prefix())
             c = self.cfg
             g = c.image_size // c.patch_size
@@ -77,6 +77,12 @@ def make_oracle_model_class(ModelBase, PinoutCls):
                     r = O.rollout_from_avg([m if batched else m[None] for m in maps])
                     r = r.reshape(r.shape[0], g, g)
                     out.set("o", r if batched else r[0])
+                elif sub == "transform":
+                    # what VggModel does for its `transform` pseudo-node (static/models/vgg16.py:40-42): the weights'
+                    # torchvision preset on the CPU
+                    x = pinin.get("o")
+                    assert x is not None
+                    out.set("o", O.preprocess(x, c.image_size, O.default_resize(c.image_size, params)))
                 else:
                     raise KeyError(node_name)
             return out

@@ -122,6 +122,21 @@ def synthetic_images(batch: int, image_size: int, seed: int = 1234) -> torch.Ten
     return torch.rand(batch, 3, image_size, image_size, generator=g)
 
 
+def default_resize(image_size: int, params=None) -> int:
+    """Resize target of the `transform` node: the node's `resize` param, else torchvision's preset for the geometry
+    (ViT_B_16_Weights.IMAGENET1K_V1: resize 256 / crop 224, vision_transformer.py:354; SWAG 384: resize = crop)."""
+    if params is not None and str(params.get("resize", "")).strip():
+        return int(params["resize"])
+    return 256 if image_size == 224 else image_size
+
+
+def preprocess(x: torch.Tensor, crop: int, resize: int) -> torch.Tensor:
+    """torchvision's ImageClassification preset (transforms/_presets.py:58-65) on [3,H,W] or [B,3,H,W] in [0,1]."""
+    from torchvision.transforms._presets import ImageClassification
+
+    return ImageClassification(crop_size=crop, resize_size=resize)(x)
+
+
 # ---- node-granular stages (each follows the torchvision lines cited) -----------------------------------
 @torch.no_grad()
 def embed(model: VisionTransformer, images: torch.Tensor) -> torch.Tensor:

@@ -264,7 +264,8 @@ def test_vit_plugin_catalogue_without_gpu():
     assert [n["instance"].get("endpoint") for n in g["nodes"][:-1]] == plug.list_node_names()
     assert g["nodes"][-1]["instance"]["kind"] == "category" and len(g["nodes"][-1]["instance"]["cats"]) == ocfg.num_classes
     chain = [(e["in_port"]["node"], e["in_port"]["channel"], e["out_port"]["node"], e["out_port"]["channel"]) for e in g["edges"]]
-    assert (0, "o", 1, "o") in chain and (L, "o", L + 1, "o") in chain and (L + 1, "o", L + 3, "o") in chain
+    assert (0, "o", 1, "o") in chain and (L, "o", L + 1, "o") in chain and (L + 1, "o", L + 4, "o") in chain
+    assert (L + 3, "o", 0, "o") in chain                  # transform -> embed (VggModel's transform pseudo-node)
     assert all((1 + i, "attn", L + 2, f"a{i}") in chain for i in range(L))
     # every output channel has at most one server-side consumer (Graph.connect keeps one edge per channel)
     outs = [(a, ch) for (a, ch, _, _) in chain]

@@ -140,6 +140,44 @@ def test_stage_entry_points_equal_whole_forward(E):
     eng.close()
 
 
+def test_transform_node_feeds_embed_through_the_scheduler(E):
+    """transform -> embed -> head through Context.compute: the preprocessing node's output matches torchvision's preset,
+    and the embed node that follows consumes the device-resident copy (same logits as uploading the preprocessed image)."""
+    from interactive_vit_b200 import context as C, graph as G, vit_plugin as P
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_small_test"]
+    module = O.build_vit(ocfg, seed=0, init="stress")
+    cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                      ocfg.num_classes)
+    plug = P.VitB200Model("vs", cfg, module, 0, 1)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "static", "graphs"))
+        C.set_base_dir(d)
+        try:
+            ctx = C.Context()
+            plug.register(ctx)
+        finally:
+            C.set_base_dir(None)
+    img = torch.rand(3, 300, 380, generator=torch.Generator().manual_seed(5))
+    names = ["vs:transform", "vs:embed"] + [f"vs:layer.{i}" for i in range(ocfg.num_layers)] + ["vs:head"]
+    g = G.Graph()
+    nodes = [g.add_node(n, {}) for n in names]
+    g.add_input(img, nodes[0], "o")
+    for a, b in zip(nodes[:-1], nodes[1:]):
+        g.connect(a, "o", b, "o")
+    ctx.compute(g)
+    pre = g.nodes[0].get_pinout().get("o")
+    ref_pre = O.preprocess(img, ocfg.image_size, 256)
+    assert (pre - ref_pre).abs().max() < 1e-4
+    logits = g.nodes[-1].get_pinout().get("o")
+    ref = O.forward_with_maps(module, ref_pre[None])
+    assert _rel(logits[None], ref["logits"]) < TOL
+    assert torch.equal(logits.argmax(-1), ref["logits"][0].argmax(-1))
+    plug.engine.close()
+
+
 def test_pipelined_host_api_equals_synchronous(E):
     """submit_host / wait (two requests in flight, copies on their own streams) returns bit-identical results to
     forward_host for every request, in order, including when a third request reclaims a slot."""

@@ -131,6 +131,22 @@ def test_layernorm_folded_into_gemms(E, M, d, n_out, gelu):
     assert torch.equal(stats, stats2) and torch.equal(E.op_gemm_ln(xb2, stats2, wq, colsum, bias_f, gelu), got)
 
 
+@pytest.mark.parametrize("B,H,W,resize,crop", [(2, 300, 400, 256, 224), (1, 512, 512, 256, 224), (1, 224, 224, 256, 224),
+                                               (3, 100, 80, 256, 224), (1, 683, 1024, 256, 224), (1, 480, 640, 384, 384),
+                                               (1, 341, 256, 256, 224)])
+def test_preprocess_matches_torchvision_preset(E, B, H, W, resize, crop):
+    """`<model>:transform`: antialiased bilinear resize + centre crop + normalise == torchvision's ImageClassification
+    preset on the CPU (what the reference's VggModel runs for its transform node, static/models/vgg16.py:40-42)."""
+    from oracle import vit_oracle as O
+
+    torch.manual_seed(H * W)
+    x = torch.rand(B, 3, H, W)
+    ref = O.preprocess(x, crop, resize)
+    got = E.op_preprocess(x.cuda(), resize, crop).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 2e-5
+
+
 def _attn_ref(qkv, B, N, H, D=64):
     q, k, v = qkv.float().reshape(B, N, 3, H, D).permute(2, 0, 3, 1, 4)
     p = torch.softmax((q * D ** -0.5) @ k.transpose(-1, -2), dim=-1)
