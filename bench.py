@@ -164,6 +164,47 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+def plugin_request_latency(model_name, cfg, eng, P, n=20):
+    """ms per single-image request through decode -> scheduler -> B200 plugin nodes -> encode (median of n)."""
+    import tempfile
+
+    import torch
+    from interactive_vit_b200 import context as C, message as M
+    from oracle import oracle_plugin, vit_oracle as O   # only the request builder and the synthetic image (checker side)
+
+    plug = P.VitB200Model(model_name, cfg, P.build_torchvision_vit(cfg, seed=0), engine=eng)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "static", "graphs"))
+        C.set_base_dir(d)
+        try:
+            ctx = C.Context()
+            plug.register(ctx)
+        finally:
+            C.set_base_dir(None)
+    img = O.synthetic_images(1, cfg.image_size)[0]
+    nodes, edges, tensors = oracle_plugin.vit_graph_request(model_name, cfg.num_layers, img)
+    body = M.encode_request(nodes, edges, tensors)
+
+    def one():
+        req = M.Request()
+        req.decode(body)
+        ctx.compute(req.graph)
+        return M.Response(req.graph).encode()
+
+    for _ in range(3):
+        one()
+    times = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        resp = one()
+        times.append((time.perf_counter() - t0) * 1e3)
+    times.sort()
+    return {"ms_per_request": times[len(times) // 2], "img_per_s": 1e3 / times[len(times) // 2], "requests": n,
+            "response_bytes": len(resp),
+            "path": "wire request -> Request.decode -> Context.compute (embed, layer.0.., head, rollout nodes on the GPU) -> "
+                    "Response.encode; every node output returned as CPU fp32 like the reference's"}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, rank: int, local_rank: int, world: int):
     import torch
@@ -297,6 +338,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     "peak_source": peaks["source"] + " sustained (kernel timed inside the step)", "kernel_ms": kms,
                     "timing": "CUDA events on the launch stream around every launch of 5 profiled forwards, median"}
 
+        # ---- BASELINE config 1 beside it: ONE unbatched image through the reference-facing path (wire request ->
+        # Request.decode -> Context.compute over the B200 plugin's nodes -> Response.encode), i.e. what the reference's
+        # UI would wait for; same request bytes as the CPU arm below
+        interactive = None
+        if rank == 0 and not args.no_cpu_baseline:
+            try:
+                interactive = plugin_request_latency(args.model, cfg, eng, P)
+            except Exception as ex:  # reported, never fatal for the headline
+                interactive = {"error": str(ex)[:200]}
+
     t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,6 +385,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                             "frac_of_burst_peak": value * flop / 1e3 / peaks["bf16_tflops"] / world,
                             "frac_of_sustained_peak": value * flop / 1e3 / peaks["bf16_tflops_sustained"] / world},
             "cpu_baseline": cpu,
+            "interactive": interactive,
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -163,11 +163,12 @@ static int gemm_units(int M, int N, int tile_m, int bn, int pairs) {
   return (m_tiles / 2) * n_tiles + ((m_tiles & 1) ? (n_tiles + 1) / 2 : 0);
 }
 
-template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false>
+template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false,
+          bool kPrefetch = false>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
                          cudaStream_t st) {
-  using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu || kLnIn)>;
-  auto kern = gemm_bf16_kernel<BN, kPair, kPairs, kGelu, kOutF32, kResid, kRemap, kLnIn>;
+  using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu || kLnIn), kPrefetch>;
+  auto kern = gemm_bf16_kernel<BN, kPair, kPairs, kGelu, kOutF32, kResid, kRemap, kLnIn, kPrefetch>;
   constexpr int kClusterCtas = kPair * kPairs;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(C::kThreads);
@@ -230,7 +231,11 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, GemmShap
   if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false>(ta, tw, sh, ep, st);
   if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, false, false, false>(ta, tw, sh, ep, st);
   if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, false, false>(ta, tw, sh, ep, st);
-  if (!gelu && out_f32 && resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, true, false>(ta, tw, sh, ep, st);
+  if (!gelu && out_f32 && resid && !remap) {
+    // short K: the epilogue (fp32 residual read + write) is the bound -> prefetch the addend; long K: keep the smem stage
+    if (sh.K <= 1024) return launch_gemm_t<BN, kPair, kPairs, false, true, true, false, false, true>(ta, tw, sh, ep, st);
+    return launch_gemm_t<BN, kPair, kPairs, false, true, true, false>(ta, tw, sh, ep, st);
+  }
   if (!gelu && out_f32 && resid && remap) return launch_gemm_t<BN, kPair, kPairs, false, true, true, true>(ta, tw, sh, ep, st);
   return fail(VITB200_ERR_INVALID, "gemm: epilogue combination not instantiated (gelu=%d f32=%d resid=%d remap=%d)", gelu,
               out_f32, resid, remap);

@@ -82,18 +82,20 @@ constexpr int kEpiWarp0 = 4;
 __host__ __device__ constexpr int epi_warps(bool gelu) { return gelu ? 16 : 8; }
 constexpr int kSlabStride = 36;                           // floats per slab row: 32 + 4 pad (16-B bank skew)
 constexpr int kSlabBytes = 32 * kSlabStride * 4;          // one warp's 32 x 32 fp32 transpose slab
-template <int BN, int kPair, int kEpiWarps>
+constexpr int kResidStageBytes = 32 * 8 * 16;             // one warp's residual prefetch buffer: 8 x 16 B per lane
+template <int BN, int kPair, int kEpiWarps, bool kResidStage = false>
 struct Cfg {
   static constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
   static constexpr int kStageBytesA = BM * BK * 2;
   static constexpr int kStageBytesB = (BN / kPair) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - 2 * BM * 8 /*LN rows*/ - kEpiWarps * kSlabBytes;
+  static constexpr int kResidBytes = kResidStage ? kEpiWarps * kResidStageBytes : 0;
+  static constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - 2 * BM * 8 /*LN rows*/ - kEpiWarps * kSlabBytes - kResidBytes;
   static constexpr int kStagesFit = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
   static constexpr int kLnBytes = 2 * BM * 8;  // folded LayerNorm: (rstd, -rstd * mean) of the tile's rows, double-buffered
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kSlabBytes + 256 + kLnBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kSlabBytes + 256 + kLnBytes + kResidBytes;
   static_assert(kSmemBytes <= 227 * 1024, "gemm: shared memory budget");
   static_assert(kStages >= 3, "pipeline too shallow");
 };
@@ -155,14 +157,16 @@ struct GemmWork {
   }
 };
 
-template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false>
-__global__ void __launch_bounds__((gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu || kLnIn)>::kThreads), 1)
+template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false,
+          bool kPrefetch = false>
+__global__ void __launch_bounds__((gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu || kLnIn), kPrefetch>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  GemmShape shape, GemmEpilogue ep) {
   using namespace gemm_cfg;
   constexpr int kEpiWarps = epi_warps(kGelu || kLnIn);  // the folded-LayerNorm epilogue is as issue-bound as the GELU one
   constexpr int kColGroups = kEpiWarps / 4;  // warps per TMEM lane quarter; each owns BN / kColGroups columns
-  using C = Cfg<BN, kPair, kEpiWarps>;
+  static_assert(!kPrefetch || kResid, "the residual prefetch belongs to residual epilogues");
+  using C = Cfg<BN, kPair, kEpiWarps, kPrefetch>;
   constexpr int kStages = C::kStages;
   constexpr int kTileM = BM * kPair;
 
@@ -179,6 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* ln_empty_bar = ln_full_bar + 2;     // [2] ... and read by every epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_empty_bar + 2);
   float2* ln_rows = reinterpret_cast<float2*>(smem + kStages * C::kStageBytes + kEpiWarps * kSlabBytes + 256);  // [2][BM]
+  float4* resid_stage = reinterpret_cast<float4*>(smem + kStages * C::kStageBytes + kEpiWarps * kSlabBytes + 256 + C::kLnBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -353,6 +358,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float* slab = slabs + (warp - kEpiWarp0) * (32 * kSlabStride);
     const int trow = lane >> 3;                     // transposed mapping: rows trow + 4 i, 4 columns at 4 * tcol
     const int tcol = lane & 7;
+    // Residual epilogues of short-K GEMMs (kPrefetch; out_proj): the fp32 addend of chunk c+1 (or of the next tile's
+    // first chunk) is fetched with cp.async into a per-thread staging area while chunk c is processed.  (Long-K GEMMs
+    // such as fc2 hide the load behind their main loop already and prefer the extra smem stage: measured.)  Loading it at the point of use left one HBM round
+    // trip exposed per chunk: 4 KB in flight per warp bounded out_proj at 4.3 TB/s.  Every thread reads back only
+    // what it staged itself, so no warp synchronisation is involved.
+    float4* rstage = resid_stage + (warp - kEpiWarp0) * (kResidStageBytes / 16);
+    auto prefetch_resid = [&](int unit2, int c2) {
+      if (unit2 < num_units) {
+        int m2, n2;
+        work.decode(unit2, kPairs, pair_id, m2, n2);
+        const int col = n2 * BN + col_grp * kGroupCols + c2 * 32 + 4 * tcol;
+        const int rb = m2 * kTileM + static_cast<int>(cta_rank) * BM + quarter * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rb + trow + 4 * i;
+          if (row < shape.M && col < shape.N) {
+            long resid_row = row;
+            if (kRemap) {
+              const int g = row / ep.group_rows;
+              const int gi = row - g * ep.group_rows;
+              resid_row = ep.resid_broadcast ? (ep.resid_row_offset + gi)
+                                             : static_cast<long>(g) * ep.out_group_stride + ep.out_row_offset + gi;
+            }
+            ptx::cp_async_16(&rstage[i * 32 + lane], ep.resid + resid_row * ep.ldr + col);
+          }
+        }
+      }
+      ptx::cp_async_commit();
+    };
+    if (kPrefetch) prefetch_resid(slot, 0);
     int local = 0;
     for (int unit = slot; unit < num_units; unit += num_slots, ++local) {
       int m_blk, n_blk;
@@ -403,7 +438,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         const int col0 = n_blk * BN + col_grp * kGroupCols + c * 32;
-        if (col0 >= shape.N) continue;  // warp-uniform
+        if (col0 >= shape.N) {  // warp-uniform
+          if (kPrefetch) {  // keep the prefetch chain going
+            ptx::cp_async_wait_all();
+            prefetch_resid(c + 1 < kChunks ? unit : unit + num_slots, c + 1 < kChunks ? c + 1 : 0);
+          }
+          continue;
+        }
         // registers (thread = row, 32 columns) -> slab
         float* srow = slab + lane * kSlabStride;
 #pragma unroll
@@ -438,10 +479,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               resid_row = ep.resid_broadcast ? (ep.resid_row_offset + gi) : out_row;
             }
             orow[i] = out_row;
-            if (kResid) {
+            if (kResid && !kPrefetch) {
               q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (ok[i]) q[i] = *reinterpret_cast<const float4*>(ep.resid + resid_row * ep.ldr + col);
             }
+          }
+          if (kPrefetch) {
+            ptx::cp_async_wait_all();
+#pragma unroll
+            for (int i = 0; i < kRowBatch; ++i) q[i] = ok[i] ? rstage[(i0 + i) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            prefetch_resid(c + 1 < kChunks ? unit : unit + num_slots, c + 1 < kChunks ? c + 1 : 0);
           }
 #pragma unroll
           for (int i = 0; i < kRowBatch; ++i) {
