@@ -167,7 +167,7 @@ template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, 
           bool kPrefetch = false>
 static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
                          cudaStream_t st) {
-  using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu || kLnIn), kPrefetch>;
+  using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu), kPrefetch>;
   auto kern = gemm_bf16_kernel<BN, kPair, kPairs, kGelu, kOutF32, kResid, kRemap, kLnIn, kPrefetch>;
   constexpr int kClusterCtas = kPair * kPairs;
   cudaLaunchConfig_t cfg = {};
