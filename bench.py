@@ -170,7 +170,6 @@ def plugin_request_latency(model_name, cfg, eng, P, n=20):
 
     import torch
     from interactive_vit_b200 import context as C, message as M
-    from oracle import oracle_plugin, vit_oracle as O   # only the request builder and the synthetic image (checker side)
 
     plug = P.VitB200Model(model_name, cfg, P.build_torchvision_vit(cfg, seed=0), engine=eng)
     with tempfile.TemporaryDirectory() as d:
@@ -181,8 +180,8 @@ def plugin_request_latency(model_name, cfg, eng, P, n=20):
             plug.register(ctx)
         finally:
             C.set_base_dir(None)
-    img = O.synthetic_images(1, cfg.image_size)[0]
-    nodes, edges, tensors = oracle_plugin.vit_graph_request(model_name, cfg.num_layers, img)
+    img = torch.rand(3, cfg.image_size, cfg.image_size, generator=torch.Generator().manual_seed(1234))
+    nodes, edges, tensors = P.vit_graph_request(model_name, cfg.num_layers, img)
     body = M.encode_request(nodes, edges, tensors)
 
     def one():

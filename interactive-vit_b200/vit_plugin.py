@@ -59,6 +59,21 @@ def imagenet_categories(num_classes: int) -> List[str]:
     return [f"class {i}" for i in range(num_classes)]
 
 
+def vit_graph_request(name: str, num_layers: int, image: torch.Tensor):
+    """(nodes, edges, tensors) of the request a browser POSTs for the full ViT graph (the wire JSON of
+    main/message.py:61-73): image -> embed -> layer.0.. -> head, layer.i `attn` -> rollout."""
+    nodes = [{"endpoint": f"{name}:embed", "params": {}}]
+    nodes += [{"endpoint": f"{name}:layer.{i}", "params": {}} for i in range(num_layers)]
+    nodes += [{"endpoint": f"{name}:head", "params": {}}, {"endpoint": f"{name}:rollout", "params": {}}]
+    head_idx, rollout_idx = 1 + num_layers, 2 + num_layers
+    edges = [{"tensor": 0, "out_port": {"node": 0, "channel": "o"}}]
+    for i in range(1, head_idx + 1):
+        edges.append({"in_port": {"node": i - 1, "channel": "o"}, "out_port": {"node": i, "channel": "o"}})
+    for i in range(num_layers):
+        edges.append({"in_port": {"node": 1 + i, "channel": "attn"}, "out_port": {"node": rollout_idx, "channel": f"a{i}"}})
+    return nodes, edges, [image]
+
+
 def make_vit_model_class(ModelBase, PinoutCls):
     class VitB200Model(ModelBase):
         """One ViT replica on one GPU behind the reference's ``Model`` plugin interface."""
