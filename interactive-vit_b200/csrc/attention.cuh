@@ -47,6 +47,10 @@ struct AttnParams {
   float* cls_map;       // [B, H, N] per-head probabilities of query token 0, or nullptr
   int ldmap;            // row stride of avg_map/head_map in floats (>= KP, multiple of 4)
   int q_tiles;          // 128-row query tiles per image: ceil(N / 128) (1 or 2)
+  // Tail balancing: work items (image, query tile) [0, full_items) get one CTA each; every later item is split over
+  // TWO CTAs by heads ([0, H/2) and [H/2, H)) whose head-average tiles are combined with a TMA reduce-add into rows the
+  // host zeroed.  512 equal items on 148 SMs otherwise leave 80 SMs idle for the whole last round.
+  int full_items;
 };
 
 // Optional phase tracing (built only with -DVITB200_ATTN_TRACE into a separate library, tools/attn_trace.py):
@@ -122,8 +126,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   // the lowest; role % 4 == hardware warp % 4 (TMEM lane quarters)
   const int warp = static_cast<int>((threadIdx.x >> 5) + kCtrlWarps) % (kThreads / 32);
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x / p.q_tiles;
-  const int qt = blockIdx.x - b * p.q_tiles;
+  int item = blockIdx.x, h0 = 0, nh = p.H;
+  bool split_cta = false;
+  if (item >= p.full_items) {
+    const int r = item - p.full_items;
+    item = p.full_items + (r >> 1);
+    const int first = p.H >> 1;
+    h0 = (r & 1) ? first : 0;
+    nh = (r & 1) ? p.H - first : first;
+    split_cta = true;
+  }
+  const int b = item / p.q_tiles;
+  const int qt = item - b * p.q_tiles;
   const int KP = p.KP;
   const int half_rows = KP >> 1;
   const uint32_t stage_tx = kQBytes + 2 * static_cast<uint32_t>(KP) * D * 2;
@@ -181,7 +195,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   // stay in uniform registers (a single-lane loop pays an R2UR chain in front of every UTMALDG / UTCHMMA).
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    for (int h = 0; h < p.H; ++h) {
+    for (int h = 0; h < nh; ++h) {   // h: head index local to this CTA (absolute head h0 + h)
       const int st = h & 1;
       const uint32_t ph = (h >> 1) & 1;
       ptx::mbar_wait(&empty_bar[st], ph ^ 1);
@@ -190,11 +204,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       uint8_t* sv = sk + kKVBytes;
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&full_bar[st], stage_tx);
-        ptx::tma_load_2d(sq, &tmap_q, &full_bar[st], h * D, row0 + qt * BM);
-        ptx::tma_load_2d(sk, &tmap_kv, &full_bar[st], p.d + h * D, row0);
-        ptx::tma_load_2d(sk + half_rows * 128, &tmap_kv, &full_bar[st], p.d + h * D, row0 + half_rows);
-        ptx::tma_load_2d(sv, &tmap_kv, &full_bar[st], 2 * p.d + h * D, row0);
-        ptx::tma_load_2d(sv + half_rows * 128, &tmap_kv, &full_bar[st], 2 * p.d + h * D, row0 + half_rows);
+        ptx::tma_load_2d(sq, &tmap_q, &full_bar[st], (h0 + h) * D, row0 + qt * BM);
+        ptx::tma_load_2d(sk, &tmap_kv, &full_bar[st], p.d + (h0 + h) * D, row0);
+        ptx::tma_load_2d(sk + half_rows * 128, &tmap_kv, &full_bar[st], p.d + (h0 + h) * D, row0 + half_rows);
+        ptx::tma_load_2d(sv, &tmap_kv, &full_bar[st], 2 * p.d + (h0 + h) * D, row0);
+        ptx::tma_load_2d(sv + half_rows * 128, &tmap_kv, &full_bar[st], 2 * p.d + (h0 + h) * D, row0 + half_rows);
       }
       __syncwarp();
     }
@@ -226,8 +240,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       __syncwarp();
     };
     issue_qk(0);
-    for (int h = 0; h < p.H; ++h) {
-      if (h + 1 < p.H) issue_qk(h + 1);
+    for (int h = 0; h < nh; ++h) {
+      if (h + 1 < nh) issue_qk(h + 1);
       const int st = h & 1;
       ATTN_TS(16);
       ptx::mbar_wait(p_full, h & 1);
@@ -270,9 +284,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     // Row 0 of the normalised probabilities (fp32) is staged in smem by the four warps that own it; this otherwise
     // idle warp streams it to HBM with coalesced stores, off the softmax warps' critical path.
     if (p.cls_map != nullptr && qt == 0) {
-      for (int h = 0; h < p.H; ++h) {
+      for (int h = 0; h < nh; ++h) {
         ptx::mbar_wait(cls_full, h & 1);
-        float* cp = p.cls_map + (static_cast<size_t>(b) * p.H + h) * p.N;
+        float* cp = p.cls_map + (static_cast<size_t>(b) * p.H + h0 + h) * p.N;
         for (int j = lane; j < p.N; j += 32) cp[j] = cls_stage[j];
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(cls_free);
@@ -328,13 +342,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     auto o_store = [&](int hh) {
       asm volatile("bar.sync %0, 128;" ::"r"(3 + quarter) : "memory");  // the four column-group warps of this quarter
       if (cg == 0 && ptx::elect_one()) {
-        ptx::tma_store_3d(&tmap_ctx, ctx_tile, hh * D, qt * BM + quarter * 32, b);
+        ptx::tma_store_3d(&tmap_ctx, ctx_tile, (h0 + hh) * D, qt * BM + quarter * 32, b);
         ptx::tma_store_commit();
       }
       __syncwarp();
     };
 
-    for (int h = 0; h < p.H; ++h) {
+    for (int h = 0; h < nh; ++h) {
       // ---- this thread's part of the S row -> registers (single TMEM read), then release the S columns
       uint32_t s[kMaxGran][8];
       ATTN_TS(0);
@@ -467,7 +481,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       }
       if (kHeads) {
         if (p.head_map != nullptr && row_ok) {
-          float* hp = p.head_map + ((static_cast<size_t>(b) * p.H + h) * p.N + qrow) * p.ldmap;
+          float* hp = p.head_map + ((static_cast<size_t>(b) * p.H + h0 + h) * p.N + qrow) * p.ldmap;
 #pragma unroll
           for (int c = 0; c < kMaxGran; ++c) {
             if (c < nmy) {
@@ -485,9 +499,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     // (restaging needs the previous store's smem reads done; every warp passes through the issuer's wait via bar 3+q)
     ptx::tma_store_wait_read<0>();
     asm volatile("bar.sync %0, 128;" ::"r"(3 + quarter) : "memory");
-    o_stage(p.H - 1);
+    o_stage(nh - 1);
     ptx::fence_proxy_async_smem();
-    o_store(p.H - 1);
+    o_store(nh - 1);
     ptx::tma_store_wait<0>();
 
     // head-averaged map rows -> HBM, once per (image, query tile): Pbar holds the SUM over heads.  The tile goes
@@ -522,7 +536,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       asm volatile("bar.sync 1, 512;" ::: "memory");
       if (warp == kCtrlWarps && ptx::elect_one()) {
         const int nslabs = (KP + 31) >> 5;
-        for (int j = 0; j < nslabs; ++j) ptx::tma_store_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, b);
+        for (int j = 0; j < nslabs; ++j) {
+          if (split_cta) ptx::tma_reduce_add_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, b);
+          else ptx::tma_store_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, b);
+        }
         ptx::tma_store_commit();
         ptx::tma_store_wait<0>();
       }

@@ -352,8 +352,25 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
   p.ctx = ctx, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
   p.q_tiles = (N + BM - 1) / BM;
-  if (heads) attention_kernel<true><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
-  else attention_kernel<false><<<B * p.q_tiles, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
+  // Tail balancing (see AttnParams::full_items): the items of a last, at most half-full round are split by heads.
+  const int items = B * p.q_tiles, sms = device_sms();
+  const int rem = items % sms;
+  static int split_mode = -1;
+  if (split_mode < 0) {
+    const char* v = getenv("VITB200_ATTN_SPLIT");
+    split_mode = (v && v[0] == '0') ? 0 : 1;
+  }
+  p.full_items = items;
+  if (split_mode && H >= 2 && items > sms && rem > 0 && 2 * rem <= sms) p.full_items = items - rem;
+  const int grid = p.full_items + 2 * (items - p.full_items);
+  if (avg && p.full_items < items) {
+    // the split CTAs reduce-add their halves of the head average: zero the images they touch first (a full CTA of
+    // the first such image simply stores over the zeros)
+    const int b0 = p.full_items / p.q_tiles;
+    CU_TRY(cudaMemsetAsync(avg + (size_t)b0 * N * pitch, 0, (size_t)(B - b0) * N * pitch * sizeof(float), st));
+  }
+  if (heads) attention_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
+  else attention_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   CU_TRY(cudaGetLastError());
   return VITB200_OK;
 }

@@ -273,6 +273,17 @@ def test_bench_size_properties(E):
     for i in (0, 127, 255):
         one = eng.forward_host(x[i:i + 1].contiguous(), flags)
         assert torch.equal(one["logits"][0], big["logits"][i])
-        assert torch.equal(one["avg_maps"][:, 0], big["avg_maps"][:, i])
-        assert torch.equal(one["rollout"][0], big["rollout"][i])
+        assert torch.equal(one["cls_maps"][:, 0], big["cls_maps"][:, i])
+        if i < 222:
+            assert torch.equal(one["avg_maps"][:, 0], big["avg_maps"][:, i])
+            assert torch.equal(one["rollout"][0], big["rollout"][i])
+        else:
+            # images of the attention kernel's last, short round (work items 444.. of 512 on 148 SMs) are handled by
+            # two CTAs that each sum half of the heads: the head average is (a + b) instead of one running sum, which
+            # differs in the last fp32 bit; everything else about the image is bit-identical
+            assert (one["avg_maps"][:, 0] - big["avg_maps"][:, i]).abs().max() < 1e-6
+            assert (one["rollout"][0] - big["rollout"][i]).abs().max() < 1e-7
+    # run-to-run the batched result is bit-reproducible (the two halves are combined by a commutative add)
+    again = eng.forward_host(x, flags)
+    assert torch.equal(again["avg_maps"], big["avg_maps"]) and torch.equal(again["rollout"], big["rollout"])
     eng.close()

@@ -155,7 +155,10 @@ def _attn_ref(qkv, B, N, H, D=64):
 
 
 @pytest.mark.parametrize("B,N,H,scale", [(2, 197, 12, 1.0), (3, 197, 6, 3.0), (2, 64, 2, 1.0), (1, 17, 2, 2.0),
-                                         (1, 128, 1, 1.0), (2, 129, 3, 1.0), (5, 197, 16, 0.5)])
+                                         (1, 128, 1, 1.0), (2, 129, 3, 1.0), (5, 197, 16, 0.5),
+                                         # more work items than SMs with a short last round: its items are split over
+                                         # two CTAs by heads and the head average is combined with a TMA reduce-add
+                                         (100, 197, 4, 1.0), (90, 197, 3, 1.0), (180, 100, 2, 1.0)])
 def test_attention(E, B, N, H, scale):
     torch.manual_seed(B * 1000 + N)
     qkv = (torch.randn(B * N, 3 * H * 64, device="cuda") * scale).bfloat16()
