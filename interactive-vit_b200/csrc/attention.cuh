@@ -9,22 +9,31 @@
 // exact arithmetic; exact in floating point too when D = 64 since the factor is a power of two).
 //
 // One CTA per (image b, 128-row query tile qt); the CTA loops over all H heads so that the head-averaged
-// probabilities can be accumulated on chip (TMEM) and written to HBM exactly once.  384 threads:
-//   warp 0 lane 0 : TMA producer  Q_h [128 x D], K_h [KP x D], V_h [KP x D] tiles of the packed qkv
+// probabilities can be accumulated on chip (TMEM) and written to HBM exactly once.  640 threads; roles (the four
+// control roles sit on the highest hardware warp ids):
+//   role 0 (one elected lane) : TMA producer  Q_h [128 x D], K_h [KP x D], V_h [KP x D] tiles of the packed qkv
 //                   activation, 2-stage ring over heads
-//   warp 1 lane 0 : UMMA issuer   S = Q K^T (M=128, N=KP, K=D)   -> TMEM cols [64, 64+KP)
-//                                 O = P V   (M=128, N=D,  K=KP)  -> TMEM cols [0, D), V is the MN-major B.
-//                   Issue order QK(0), QK(1), PV(0), QK(2), PV(1), ...: the S columns are released as soon
-//                   as the softmax warps have copied them to registers, so QK^T of head h+1 and P V of
-//                   head h run on the tensor pipe underneath the softmax of head h.
-//   warp 2        : TMEM allocator (all 512 columns)
-//   warps 4..11   : softmax.  Two threads per query row: warps 4..7 own the first half of the key columns,
-//                   warps 8..11 the second half (a warp may only touch the TMEM lane quarter warp%4).  The
-//                   half row (<= 112 scores) is read from TMEM ONCE and stays in registers for: row max
-//                   (exchanged with the partner thread through smem) -> e = exp2(s*c - m*c) -> bf16 P tile
-//                   in shared memory (128-B swizzled K-major A operand of P V) -> row sum (exchanged) ->
-//                   Pbar += e / (sum * H) in TMEM cols [288, 288+KP) -> optional per-head rows to HBM.
-//                   Then O * 1/sum -> bf16 context rows (each half owns 32 of the 64 columns).
+//   role 1 (one elected lane) : UMMA issuer   S = Q K^T (M=128, N=KP, K=D)   -> TMEM cols [64, 64+KP)
+//                                 O = P V   (M=128, N=D,  K=KP)  -> TMEM cols [0, D), V is the MN-major B
+//                                 Pbar += P I16 (M=128, N=16 per 16 keys)      -> TMEM cols [288, 288+KP)
+//                   Issue order QK(0), QK(1), PV(0)+AVG(0), QK(2), ...: the S columns are released as soon as the
+//                   softmax warps have copied them to registers, so QK^T of head h+1 and P V of head h run on the
+//                   tensor pipe underneath the softmax of head h.
+//   role 2        : TMEM allocator (all 512 columns)
+//   role 3        : writes the 16 x 16 identity operand, then streams the class-token rows (row 0 of P, fp32) that
+//                   the softmax warps stage in smem to HBM
+//   roles 4..19   : softmax, FOUR threads per query row (one warp per TMEM lane quarter and column group; a warp may
+//                   only touch the lane quarter warp % 4).  Each thread reads its <= 56 scores from TMEM ONCE and keeps
+//                   them in registers: thread-local max -> e = exp2((s - m_t) c) on the MUFU -> ONE exchange of
+//                   (m_t, sum_t) through smem and a named barrier -> p = e f_t normalised -> bf16 P tile in shared
+//                   memory (128-B swizzled K-major A operand of P V and of the head-average MMAs).  The context tile
+//                   of the previous head goes TMEM -> bf16 -> smem -> TMA store in the same pass; one
+//                   fence.proxy.async per head covers both tiles.  After the last head the head-average tile leaves
+//                   through smem slabs and TMA stores (reduce-add for CTAs that share an item, see AttnParams).
+//
+// History of the design (measured, profiles/README.md): two threads per row with the head average added in TMEM by the
+// softmax threads took 7,285 cycles per head; four threads per row, the head average on the tensor pipe, TMA-stored
+// tiles, thread-local maxima and the class rows on a spare warp brought it to ~5,400.
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"

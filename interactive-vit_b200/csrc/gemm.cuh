@@ -12,24 +12,29 @@
 // UMMA M = 256: each CTA stages its own 128 rows of A and HALF of the W tile, so the L2 -> SMEM traffic per
 // FLOP is 2/3 of the single-CTA kernel's (the 128 x 256 single-CTA tile is L2-bandwidth bound at ~900 TF/s).
 // kPair = 1: one CTA computes 128 x BN on its own (kept as the A/B baseline).
-// kPairs = 2 (BN = 256 only): a cluster of FOUR CTAs = two pairs.  The pair kernel is bound by the L2 -> SMEM
-// feed (64 B/clk/SM against ~42 B/clk/SM that the L2 delivers to 148 SMs at once: measured 65% tensor-pipe
-// activity), so the two pairs of a cluster compute two tiles that share one operand and fetch the shared 128-row
-// operand block only once: each CTA loads 64 of its rows and TMA-multicasts them to its counterpart in the other
-// pair (48 B/clk/SM).  Normally the pairs take vertically adjacent tiles (same W tile, "share W"); an odd last
-// row of tiles is covered with horizontally adjacent tiles (same A tile, "share A") so that no cluster idles.
+// kPairs = 2 (BN = 256 only, opt-in: VITB200_GEMM_PAIR=4): a cluster of FOUR CTAs = two pairs computing two tiles that
+// share one operand; each CTA loads 64 rows of the shared 128-row block and TMA-multicasts them to its counterpart
+// in the other pair.  Normally the pairs take vertically adjacent tiles (same W tile, "share W"); an odd last row of
+// tiles is covered with horizontally adjacent tiles (same A tile, "share A").  Built on the hypothesis that the pair
+// kernel was bound by the L2 -> SMEM feed; measured, it is NOT faster (multicast does not reduce the bytes delivered
+// into each SM, and only 33 four-CTA clusters are co-resident on 148 SMs) -- kept as a correct, tested negative result.
 //
-// Roles (4 + 8 warps, or 4 + 16 for the GELU epilogue; 1 CTA / SM, persistent over output tiles):
-//   warp 0 lane 0 : TMA producer  (A tile 128x64, W tile (BN/kPair)x64, SWIZZLE_128B, mbarrier ring; in a pair both
-//                   CTAs' loads complete_tx on the LEADER's full barrier)
-//   warp 1 lane 0 : UMMA issuer (leader CTA only in a pair): 4 x tcgen05.mma (K = 16) per stage, commit ->
+// Roles (4 + 8 warps, or 4 + 16 for the GELU epilogues; 1 CTA / SM, persistent over output tiles; role = hardware warp
+// rotated so that the control roles own the highest warp ids):
+//   role 0 (elected lane) : TMA producer  (A tile 128x64, W tile (BN/kPair)x64, SWIZZLE_128B, mbarrier ring; in a pair
+//                   both CTAs' loads complete_tx on the LEADER's full barrier)
+//   role 1 (elected lane) : UMMA issuer (leader CTA only in a pair): 4 x tcgen05.mma (K = 16) per stage, commit ->
 //                   empty barrier of both CTAs; accumulator-complete commit -> both CTAs' epilogues
-//   warp 2        : TMEM allocator (2 accumulator buffers of BN fp32 columns: MMA of tile i+1 overlaps the
+//   role 2        : TMEM allocator (2 accumulator buffers of BN fp32 columns: MMA of tile i+1 overlaps the
 //                   epilogue of tile i)
-//   warps 4..     : epilogue, 2 (4 with GELU) warps per TMEM lane quarter, each owning a slice of the BN columns.  Per 32-column
-//                   chunk: tcgen05.ld -> warp-private smem slab -> re-read transposed so that a warp store
-//                   covers 4 rows x 128 contiguous bytes -> +bias [-> GELU] [+ fp32 residual / pos-embedding]
-//                   -> coalesced bf16 / fp32 global stores.
+//   role 3        : folded-LayerNorm GEMMs only: stages (rstd, -rstd * mean) of the next tile's rows in smem
+//   roles 4..     : epilogue, 2 (4 with GELU) warps per TMEM lane quarter, each owning a slice of the BN columns.  Per
+//                   32-column chunk: tcgen05.ld -> warp-private smem slab -> re-read transposed so that a warp store
+//                   covers 4 rows x 128 contiguous bytes -> +bias | folded-LayerNorm affine [-> GELU] [+ fp32 residual
+//                   (cp.async-prefetched for short-K GEMMs) / pos-embedding] -> coalesced bf16 / fp32 global stores
+//                   [+ bf16 copy and per-row partial LayerNorm sums for the next GEMM].
+//                   The accumulator is handed back with a RELAXED cluster-scope arrive: a release there compiled to
+//                   MEMBAR + ERRBAR and waited for every global store in flight (65% -> 82.7% tensor-pipe activity).
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -79,7 +84,10 @@ constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle span
 constexpr int kEpiWarp0 = 4;
 // Epilogue warps: 2 per TMEM lane quarter normally; the GELU epilogue is issue/latency bound (about 24 instructions
 // per output element against a 6144-cycle main loop per tile), so it gets 4 per quarter = 4 per SM sub-partition.
-__host__ __device__ constexpr int epi_warps(bool gelu) { return gelu ? 16 : 8; }
+#ifndef VITB200_GELU_EPI_WARPS
+#define VITB200_GELU_EPI_WARPS 16
+#endif
+__host__ __device__ constexpr int epi_warps(bool gelu) { return gelu ? VITB200_GELU_EPI_WARPS : 8; }
 constexpr int kSlabStride = 36;                           // floats per slab row: 32 + 4 pad (16-B bank skew)
 constexpr int kSlabBytes = 32 * kSlabStride * 4;          // one warp's 32 x 32 fp32 transpose slab
 constexpr int kResidStageBytes = 32 * 8 * 16;             // one warp's residual prefetch buffer: 8 x 16 B per lane
