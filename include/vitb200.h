@@ -51,6 +51,9 @@ typedef struct vitb200_config {
   int num_classes; /* multiple of 8                                                    */
   int max_batch;   /* workspace is sized for this many images (grows on demand)        */
   int device;      /* CUDA device ordinal                                              */
+  int precision;   /* 0: bf16 operands, fp32 accumulation (<= 2e-2 of the fp32 reference)
+                      1: "fp32x3": every matmul operand is carried as hi + lo bf16 and multiplied as
+                         hi*hi + lo*hi + hi*lo with fp32 accumulation (<= 1e-3; head dim 64 only; ~3x tensor work) */
 } vitb200_config;
 
 /* Host-side result pointers for vitb200_forward_host; any pointer may be NULL (output skipped). */
@@ -151,6 +154,13 @@ int vitb200_op_gemm(const void* a_bf16_dev, const void* w_bf16_dev, const float*
 int vitb200_op_gemm_ex(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, const float* resid_dev,
                        void* out_dev, int M, int N, int K, int gelu, int out_f32, void* xb_out_dev, float* stats_out_dev,
                        const float* stats_in_dev, const float* colsum_dev, float ln_eps, void* stream);
+/* fp32x3 precision mode building blocks: split an fp32 array into hi = bf16(x), lo = bf16(x - hi); GEMM over split
+ * operands (A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulate).  out_lo_dev (bf16 outputs only, may be NULL) receives
+ * the low half of the result. */
+int vitb200_op_split_bf16(const float* in_dev, void* hi_dev, void* lo_dev, size_t count, void* stream);
+int vitb200_op_gemm_split(const void* a_hi_dev, const void* a_lo_dev, const void* w_hi_dev, const void* w_lo_dev,
+                          const float* bias_dev, const float* resid_dev, void* out_dev, void* out_lo_dev, int M, int N, int K,
+                          int gelu, int out_f32, void* stream);
 /* W'[n,k] = bf16(gamma[k] W[n,k]); colsum[n] = sum_k W'[n,k]; bias_out[n] = bias[n] + sum_k beta[k] W[n,k]. */
 int vitb200_op_fold_ln(const float* w_dev, const float* gamma_dev, const float* beta_dev, const float* bias_dev,
                        void* wq_bf16_dev, float* colsum_dev, float* bias_out_dev, int N, int K, void* stream);

@@ -32,6 +32,7 @@ struct AttnLongParams {
   int q_tiles, k_blocks;  // ceil(N / 128) each
   float scale_log2;     // (1 / sqrt(D)) * log2(e)
   __nv_bfloat16* ctx;   // [B*N, d]
+  __nv_bfloat16* ctx_lo;  // fp32x3 mode: low halves of the context (nullptr otherwise)
   float2* stats;        // [B, H, N] (max * scale_log2, 1 / sum)
   float* avg_map;       // [B, N, ldmap] or nullptr
   float* head_map;      // [B, H, N, ldmap] or nullptr
@@ -49,6 +50,8 @@ constexpr int kTmemS = 0;                   // two S buffers of 128 fp32 columns
 constexpr int kTmemO = 256;                 // O: up to 128 columns
 // ctx kernel: Q + 2 K stages + 2 V stages + P = 32 * 6 = 192 KB; maps kernel: 2 Q stages + 2 K stages = 128 KB
 constexpr int kSmemCtx = 6 * kTileBytes + 2 * 2 * BM * 4 + 256;
+// fp32x3 mode (head dim 64 only): every 32 KB operand slot holds [hi box | lo box]; one more 32 KB tile for P_lo
+constexpr int kSmemCtxSplit = 7 * kTileBytes + 2 * 2 * BM * 4 + 256;
 constexpr int kSmemMaps = 4 * kTileBytes + 256;
 }  // namespace attn_long_cfg
 
@@ -74,9 +77,27 @@ __device__ __forceinline__ void issue_qk_long(uint32_t tmem_s, uint32_t sq, uint
   }
 }
 
+// fp32x3 mode, D = 64: operand slots are [hi box | lo box]; S = Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T.
+__device__ __forceinline__ void issue_qk_long_split(uint32_t tmem_s, uint32_t sq, uint32_t sk) {
+  using namespace attn_long_cfg;
+  const uint32_t idesc = ptx::make_idesc_bf16(BM, BK, 0, 0);
+  const uint64_t dq = ptx::make_smem_desc_sw128(sq, 16, 1024);
+  const uint64_t dk = ptx::make_smem_desc_sw128(sk, 16, 1024);
+  constexpr uint64_t kLo = kBoxBytes >> 4;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const uint64_t oq = g == 1 ? kLo : 0, ok = g == 2 ? kLo : 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      ptx::umma_bf16_ss(tmem_s, dq + oq + 2 * k, dk + ok + 2 * k, idesc, (g | k) != 0 ? 1u : 0u);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
+template <bool kSplit>
 __global__ void __launch_bounds__(attn_long_cfg::kThreads, 1)
 attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 64 x 128 over qkv viewed as [B][N][3d]
+                          const __grid_constant__ CUtensorMap tmap_qkv_lo,  // kSplit: the low halves, same geometry
                           AttnLongParams p) {
   using namespace attn_long_cfg;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -85,7 +106,8 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
   uint8_t* s_k = smem + kTileBytes;          // 2 stages
   uint8_t* s_v = smem + 3 * kTileBytes;      // 2 stages
   uint8_t* s_p = smem + 5 * kTileBytes;      // 2 K-blocks of 64 keys: [128 rows x 128 B] each
-  float* red = reinterpret_cast<float*>(smem + 6 * kTileBytes);  // [2 kinds][2 halves][128 rows]
+  uint8_t* s_p_lo = smem + 6 * kTileBytes;   // kSplit only
+  float* red = reinterpret_cast<float*>(smem + (kSplit ? 7 : 6) * kTileBytes);  // [2 kinds][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * 2 * BM);
   uint64_t* q_full = bars;          // Q landed
   uint64_t* k_full = bars + 1;      // [2]
@@ -105,8 +127,8 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
   const int b = blockIdx.x / (p.H * p.q_tiles);
   const int nb = p.k_blocks;
   const int D = p.D;
-  const bool two_box = D > 64;
-  const uint32_t tile_tx = two_box ? kTileBytes : kBoxBytes;
+  const bool two_box = !kSplit && D > 64;
+  const uint32_t tile_tx = (kSplit || two_box) ? kTileBytes : kBoxBytes;
 
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_qkv);
   if (warp == 1 && lane == 0) {
@@ -131,7 +153,8 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
     auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
       ptx::mbar_arrive_expect_tx(bar, tile_tx);
       ptx::tma_load_3d(dst, &tmap_qkv, bar, col, row, b);
-      if (two_box) ptx::tma_load_3d(dst + kBoxBytes, &tmap_qkv, bar, col + 64, row, b);
+      if (kSplit) ptx::tma_load_3d(dst + kBoxBytes, &tmap_qkv_lo, bar, col, row, b);
+      else if (two_box) ptx::tma_load_3d(dst + kBoxBytes, &tmap_qkv, bar, col + 64, row, b);
     };
     if (ptx::elect_one()) load_tile(s_q, q_full, h * D, qt * BM);
     __syncwarp();
@@ -160,7 +183,8 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
       if (it >= 2) ptx::mbar_wait(&s_free[st], ((it - 2) >> 1) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        issue_qk_long(tmem_base + kTmemS + st * BK, sq, ptx::smem_u32(s_k + st * kTileBytes), D);
+        if (kSplit) issue_qk_long_split(tmem_base + kTmemS + st * BK, sq, ptx::smem_u32(s_k + st * kTileBytes));
+        else issue_qk_long(tmem_base + kTmemS + st * BK, sq, ptx::smem_u32(s_k + st * kTileBytes), D);
         ptx::umma_commit(&k_empty[st]);
         ptx::umma_commit(&s_full[st]);
       }
@@ -188,7 +212,13 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
           const uint64_t dv = dv0 + static_cast<uint64_t>(ks * (2048 >> 4));
           const uint32_t acc = (blk | ks) != 0 ? 1u : 0u;
           ptx::umma_bf16_ss(tmem_base + kTmemO, dp, dv, idesc_pv0, acc);
-          if (two_box) ptx::umma_bf16_ss(tmem_base + kTmemO + 64, dp, dv + (kBoxBytes >> 4), idesc_pv1, acc);
+          if (kSplit) {
+            // + P_lo V_hi + P_hi V_lo (the P_lo tile sits one 32 KB slot after P_hi, V_lo one box after V_hi)
+            ptx::umma_bf16_ss(tmem_base + kTmemO, dp + (kTileBytes >> 4), dv, idesc_pv0, 1u);
+            ptx::umma_bf16_ss(tmem_base + kTmemO, dp, dv + (kBoxBytes >> 4), idesc_pv0, 1u);
+          } else if (two_box) {
+            ptx::umma_bf16_ss(tmem_base + kTmemO + 64, dp, dv + (kBoxBytes >> 4), idesc_pv1, acc);
+          }
         }
         ptx::umma_commit(&v_empty[vs]);
         ptx::umma_commit(p_free);
@@ -204,6 +234,7 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
     const bool row_ok = qrow < p.N;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t p_row = ptx::smem_u32(s_p) + half * kBoxBytes + r * 128;
+    const uint32_t p_row_lo = ptx::smem_u32(s_p_lo) + half * kBoxBytes + r * 128;
     const int sw = r & 7;
     float* red_max = red;
     float* red_sum = red + 2 * BM;
@@ -267,6 +298,19 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
                      "r"(pack_bf16x2_f(e[8], e[9])), "r"(pack_bf16x2_f(e[10], e[11])), "r"(pack_bf16x2_f(e[12], e[13])),
                      "r"(pack_bf16x2_f(e[14], e[15]))
                      : "memory");
+        if (kSplit) {
+          float l[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) l[j] = e[j] - __bfloat162float(__float2bfloat16_rn(e[j]));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row_lo + (((2 * c) ^ sw) << 4)),
+                       "r"(pack_bf16x2_f(l[0], l[1])), "r"(pack_bf16x2_f(l[2], l[3])), "r"(pack_bf16x2_f(l[4], l[5])),
+                       "r"(pack_bf16x2_f(l[6], l[7]))
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row_lo + (((2 * c + 1) ^ sw) << 4)),
+                       "r"(pack_bf16x2_f(l[8], l[9])), "r"(pack_bf16x2_f(l[10], l[11])), "r"(pack_bf16x2_f(l[12], l[13])),
+                       "r"(pack_bf16x2_f(l[14], l[15]))
+                       : "memory");
+        }
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
@@ -293,6 +337,15 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
         v.z = pack_bf16x2_f(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
         v.w = pack_bf16x2_f(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
         *reinterpret_cast<uint4*>(op + c0) = v;
+        if (kSplit) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+          uint4 l;
+          l.x = pack_bf16x2_f(__uint_as_float(o[0]) * inv - __low2float(h[0]), __uint_as_float(o[1]) * inv - __high2float(h[0]));
+          l.y = pack_bf16x2_f(__uint_as_float(o[2]) * inv - __low2float(h[1]), __uint_as_float(o[3]) * inv - __high2float(h[1]));
+          l.z = pack_bf16x2_f(__uint_as_float(o[4]) * inv - __low2float(h[2]), __uint_as_float(o[5]) * inv - __high2float(h[2]));
+          l.w = pack_bf16x2_f(__uint_as_float(o[6]) * inv - __low2float(h[3]), __uint_as_float(o[7]) * inv - __high2float(h[3]));
+          *reinterpret_cast<uint4*>(p.ctx_lo + (op - p.ctx) + c0) = l;
+        }
       }
     }
   }
@@ -306,9 +359,10 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool kHeads>
+template <bool kHeads, bool kSplit>
 __global__ void __launch_bounds__(attn_long_cfg::kThreads, 1)
-attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, AttnLongParams p) {
+attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_qkv_lo,
+                           AttnLongParams p) {
   using namespace attn_long_cfg;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -326,8 +380,8 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, AttnLon
   const int qt = (blockIdx.x / p.k_blocks) % p.q_tiles;
   const int b = blockIdx.x / (p.k_blocks * p.q_tiles);
   const int D = p.D;
-  const bool two_box = D > 64;
-  const uint32_t stage_tx = 2 * (two_box ? kTileBytes : kBoxBytes);
+  const bool two_box = !kSplit && D > 64;
+  const uint32_t stage_tx = 2 * ((kSplit || two_box) ? kTileBytes : kBoxBytes);
 
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_qkv);
   if (warp == 1 && lane == 0) {
@@ -353,7 +407,10 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, AttnLon
         ptx::mbar_arrive_expect_tx(&full[st], stage_tx);
         ptx::tma_load_3d(q, &tmap_qkv, &full[st], h * D, qt * BM, b);
         ptx::tma_load_3d(k, &tmap_qkv, &full[st], p.d + h * D, kb * BK, b);
-        if (two_box) {
+        if (kSplit) {
+          ptx::tma_load_3d(q + kBoxBytes, &tmap_qkv_lo, &full[st], h * D, qt * BM, b);
+          ptx::tma_load_3d(k + kBoxBytes, &tmap_qkv_lo, &full[st], p.d + h * D, kb * BK, b);
+        } else if (two_box) {
           ptx::tma_load_3d(q + kBoxBytes, &tmap_qkv, &full[st], h * D + 64, qt * BM, b);
           ptx::tma_load_3d(k + kBoxBytes, &tmap_qkv, &full[st], p.d + h * D + 64, kb * BK, b);
         }
@@ -367,7 +424,8 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, AttnLon
       if (h >= 2) ptx::mbar_wait(&s_free[st], ((h - 2) >> 1) & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        issue_qk_long(tmem_base + st * BK, ptx::smem_u32(s_q + st * kTileBytes), ptx::smem_u32(s_k + st * kTileBytes), D);
+        if (kSplit) issue_qk_long_split(tmem_base + st * BK, ptx::smem_u32(s_q + st * kTileBytes), ptx::smem_u32(s_k + st * kTileBytes));
+        else issue_qk_long(tmem_base + st * BK, ptx::smem_u32(s_q + st * kTileBytes), ptx::smem_u32(s_k + st * kTileBytes), D);
         ptx::umma_commit(&empty[st]);
         ptx::umma_commit(&s_full[st]);
       }

@@ -165,8 +165,8 @@ static int gemm_units(int M, int N, int tile_m, int bn, int pairs) {
 
 template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, bool kRemap, bool kLnIn = false,
           bool kPrefetch = false>
-static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep,
-                         cudaStream_t st) {
+static int launch_gemm_t(const CUtensorMap* maps, GemmShape sh, const GemmEpilogue& ep, cudaStream_t st) {
+  const CUtensorMap &ta = maps[0], &tw = maps[1], &ta_lo = maps[2], &tw_lo = maps[3];
   using C = gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu), kPrefetch>;
   auto kern = gemm_bf16_kernel<BN, kPair, kPairs, kGelu, kOutF32, kResid, kRemap, kLnIn, kPrefetch>;
   constexpr int kClusterCtas = kPair * kPairs;
@@ -199,7 +199,7 @@ static int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape
   }
   const int units = gemm_units(sh.M, sh.N, gemm_cfg::BM * kPair, BN, kPairs);
   cfg.gridDim = dim3((units < slots ? units : slots) * kClusterCtas);
-  CU_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw, sh, ep));
+  CU_TRY(cudaLaunchKernelEx(&cfg, kern, ta, tw, ta_lo, tw_lo, sh, ep));
   return VITB200_OK;
 }
 
@@ -217,33 +217,33 @@ static int gemm_pair_mode() {
 }
 
 template <int BN, int kPair, int kPairs>
-static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tw, GemmShape sh, const GemmEpilogue& ep, bool gelu,
-                          bool out_f32, cudaStream_t st) {
+static int launch_gemm_bn(const CUtensorMap* maps, GemmShape sh, const GemmEpilogue& ep, bool gelu, bool out_f32,
+                          cudaStream_t st) {
   const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0, ln_in = ep.row_affine_in != nullptr;
   if (ln_in) {
     if (ep.colsum == nullptr || out_f32 || resid || remap)
       return fail(VITB200_ERR_INVALID, "gemm: folded-LayerNorm epilogue needs colsum and a bf16 output");
-    if (gelu) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false, true>(ta, tw, sh, ep, st);
-    return launch_gemm_t<BN, kPair, kPairs, false, false, false, false, true>(ta, tw, sh, ep, st);
+    if (gelu) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false, true>(maps, sh, ep, st);
+    return launch_gemm_t<BN, kPair, kPairs, false, false, false, false, true>(maps, sh, ep, st);
   }
   if (ep.xb != nullptr && (!resid || ep.row_stats_out == nullptr || ep.stats_slots <= 0))
     return fail(VITB200_ERR_INVALID, "gemm: the bf16 copy + row statistics are produced by residual epilogues only");
-  if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false>(ta, tw, sh, ep, st);
-  if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, false, false, false>(ta, tw, sh, ep, st);
-  if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, false, false>(ta, tw, sh, ep, st);
+  if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false>(maps, sh, ep, st);
+  if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, false, false, false>(maps, sh, ep, st);
+  if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, false, false>(maps, sh, ep, st);
   if (!gelu && out_f32 && resid && !remap) {
     // short K: the epilogue (fp32 residual read + write) is the bound -> prefetch the addend; long K: keep the smem stage
-    if (sh.K <= 1024) return launch_gemm_t<BN, kPair, kPairs, false, true, true, false, false, true>(ta, tw, sh, ep, st);
-    return launch_gemm_t<BN, kPair, kPairs, false, true, true, false>(ta, tw, sh, ep, st);
+    if (sh.K <= 1024) return launch_gemm_t<BN, kPair, kPairs, false, true, true, false, false, true>(maps, sh, ep, st);
+    return launch_gemm_t<BN, kPair, kPairs, false, true, true, false>(maps, sh, ep, st);
   }
-  if (!gelu && out_f32 && resid && remap) return launch_gemm_t<BN, kPair, kPairs, false, true, true, true>(ta, tw, sh, ep, st);
+  if (!gelu && out_f32 && resid && remap) return launch_gemm_t<BN, kPair, kPairs, false, true, true, true>(maps, sh, ep, st);
   return fail(VITB200_ERR_INVALID, "gemm: epilogue combination not instantiated (gelu=%d f32=%d resid=%d remap=%d)", gelu,
               out_f32, resid, remap);
 }
 
 // out = epilogue(A[M,K] * W[N,K]^T): picks the tile width and the epilogue instantiation.
 static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int K, const GemmEpilogue& ep, bool gelu,
-                       bool out_f32, cudaStream_t st) {
+                       bool out_f32, cudaStream_t st, const void* a_lo = nullptr, const void* w_lo = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(VITB200_ERR_INVALID, "gemm: empty shape %d x %d x %d", M, N, K);
   if (N % 8 != 0 || K % 8 != 0) return fail(VITB200_ERR_INVALID, "gemm: N and K must be multiples of 8 (N=%d K=%d)", N, K);
   const int BN = (N % 256 == 0) ? 256 : 128;
@@ -257,27 +257,34 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
   }
   if (mode == 4 && (BN != 256 || gemm_units(M, N, 256, 256, 1) < min_tiles)) mode = 2;
   const int pair = mode == 1 ? 1 : 2;
-  CUtensorMap ta, tw;
-  VT_TRY(make_tmap_bf16(&ta, a, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
-  VT_TRY(make_tmap_bf16(&tw, w, N, K, K, mode == 4 ? 64 : BN / pair, gemm_cfg::BK));
+  if ((a_lo == nullptr) != (w_lo == nullptr)) return fail(VITB200_ERR_INVALID, "gemm: split-bf16 needs both low operands");
+  CUtensorMap maps[4];  // A, W, A_lo, W_lo (the low maps alias the high ones when the operands are plain bf16)
+  VT_TRY(make_tmap_bf16(&maps[0], a, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
+  VT_TRY(make_tmap_bf16(&maps[1], w, N, K, K, mode == 4 ? 64 : BN / pair, gemm_cfg::BK));
+  maps[2] = maps[0], maps[3] = maps[1];
   GemmShape sh{M, N, K};
-  if (mode == 4) return launch_gemm_bn<256, 2, 2>(ta, tw, sh, ep, gelu, out_f32, st);
-  if (BN == 256) {
-    return pair == 2 ? launch_gemm_bn<256, 2, 1>(ta, tw, sh, ep, gelu, out_f32, st)
-                     : launch_gemm_bn<256, 1, 1>(ta, tw, sh, ep, gelu, out_f32, st);
+  if (a_lo != nullptr) {
+    VT_TRY(make_tmap_bf16(&maps[2], a_lo, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
+    VT_TRY(make_tmap_bf16(&maps[3], w_lo, N, K, K, mode == 4 ? 64 : BN / pair, gemm_cfg::BK));
+    sh.split = 3;
   }
-  return pair == 2 ? launch_gemm_bn<128, 2, 1>(ta, tw, sh, ep, gelu, out_f32, st)
-                   : launch_gemm_bn<128, 1, 1>(ta, tw, sh, ep, gelu, out_f32, st);
+  if (mode == 4) return launch_gemm_bn<256, 2, 2>(maps, sh, ep, gelu, out_f32, st);
+  if (BN == 256) {
+    return pair == 2 ? launch_gemm_bn<256, 2, 1>(maps, sh, ep, gelu, out_f32, st)
+                     : launch_gemm_bn<256, 1, 1>(maps, sh, ep, gelu, out_f32, st);
+  }
+  return pair == 2 ? launch_gemm_bn<128, 2, 1>(maps, sh, ep, gelu, out_f32, st)
+                   : launch_gemm_bn<128, 1, 1>(maps, sh, ep, gelu, out_f32, st);
 }
 
 static int launch_layernorm(const float* x, long in_stride, const float* g, const float* b, __nv_bfloat16* y, int rows,
-                            int d, float eps, cudaStream_t st) {
+                            int d, float eps, cudaStream_t st, __nv_bfloat16* y_lo = nullptr) {
   if (rows <= 0) return fail(VITB200_ERR_INVALID, "layernorm: no rows");
   if (d % 128 != 0) return fail(VITB200_ERR_INVALID, "layernorm: width %d must be a multiple of 128", d);
   const int blocks = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
 #define VT_LN_CASE(V)                                                                                \
   case V:                                                                                            \
-    layernorm_f32_bf16_kernel<V><<<blocks, 256, 0, st>>>(x, in_stride, g, b, y, rows, eps);          \
+    layernorm_f32_bf16_kernel<V><<<blocks, 256, 0, st>>>(x, in_stride, g, b, y, rows, eps, y_lo);    \
     break;
   switch (d / 128) {
     VT_LN_CASE(1) VT_LN_CASE(2) VT_LN_CASE(3) VT_LN_CASE(4) VT_LN_CASE(5) VT_LN_CASE(6) VT_LN_CASE(8) VT_LN_CASE(10)
@@ -291,33 +298,48 @@ static int launch_layernorm(const float* x, long in_stride, const float* g, cons
 
 // Long / wide variant (attention_long.cuh): any N, head dims 64..128.  `stats` holds B*H*N float2 (row max, 1/sum).
 static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* avg, float* cls, float* heads, int B,
-                                 int N, int H, int D, int pitch, float2* stats, cudaStream_t st) {
+                                 int N, int H, int D, int pitch, float2* stats, cudaStream_t st,
+                                 const __nv_bfloat16* qkv_lo = nullptr, __nv_bfloat16* ctx_lo = nullptr) {
   using namespace attn_long_cfg;
   if (D < 64 || D > 128 || D % 16 != 0) return fail(VITB200_ERR_INVALID, "attention: head dim %d not in 64..128 step 16", D);
   if ((avg || heads) && (pitch < N || pitch % 4 != 0))
     return fail(VITB200_ERR_INVALID, "attention: map pitch %d must be >= %d and a multiple of 4", pitch, N);
   if (!stats) return fail(VITB200_ERR_INVALID, "attention: statistics buffer missing");
   const int d = H * D;
-  CUtensorMap tqkv;
+  const bool split = qkv_lo != nullptr;
+  if (split && (D != 64 || ctx_lo == nullptr))
+    return fail(VITB200_ERR_INVALID, "attention: the fp32x3 mode supports head dim 64 only (got %d)", D);
+  CUtensorMap tqkv, tqkv_lo;
   VT_TRY(make_tmap_bf16_3d(&tqkv, qkv, B, N, 3 * d, 3 * d, 128, 64));
+  tqkv_lo = tqkv;
+  if (split) VT_TRY(make_tmap_bf16_3d(&tqkv_lo, qkv_lo, B, N, 3 * d, 3 * d, 128, 64));
   static bool configured = false;
   if (!configured) {
-    CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtx));
-    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
-    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
+    CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtx));
+    CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtxSplit));
+    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
+    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
+    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
+    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
     configured = true;
   }
   AttnLongParams p;
   p.B = B, p.N = N, p.H = H, p.D = D, p.d = d;
   p.q_tiles = (N + BM - 1) / BM, p.k_blocks = (N + BK - 1) / BK;
   p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
-  p.ctx = ctx, p.stats = stats, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
-  attention_long_ctx_kernel<<<B * p.q_tiles * H, kThreads, kSmemCtx, st>>>(tqkv, p);
+  p.ctx = ctx, p.ctx_lo = ctx_lo, p.stats = stats, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
+  if (split) attention_long_ctx_kernel<true><<<B * p.q_tiles * H, kThreads, kSmemCtxSplit, st>>>(tqkv, tqkv_lo, p);
+  else attention_long_ctx_kernel<false><<<B * p.q_tiles * H, kThreads, kSmemCtx, st>>>(tqkv, tqkv_lo, p);
   CU_TRY(cudaGetLastError());
   if (avg || cls || heads) {
     const int grid = B * p.q_tiles * p.k_blocks;
-    if (heads) attention_long_maps_kernel<true><<<grid, kThreads, kSmemMaps, st>>>(tqkv, p);
-    else attention_long_maps_kernel<false><<<grid, kThreads, kSmemMaps, st>>>(tqkv, p);
+    if (split) {
+      if (heads) attention_long_maps_kernel<true, true><<<grid, kThreads, kSmemMaps, st>>>(tqkv, tqkv_lo, p);
+      else attention_long_maps_kernel<false, true><<<grid, kThreads, kSmemMaps, st>>>(tqkv, tqkv_lo, p);
+    } else {
+      if (heads) attention_long_maps_kernel<true, false><<<grid, kThreads, kSmemMaps, st>>>(tqkv, tqkv_lo, p);
+      else attention_long_maps_kernel<false, false><<<grid, kThreads, kSmemMaps, st>>>(tqkv, tqkv_lo, p);
+    }
     CU_TRY(cudaGetLastError());
   }
   return VITB200_OK;
@@ -328,9 +350,11 @@ static int attention_pitch(int N) { return (N + 15) / 16 * 16; }
 static bool attention_is_fused(int N, int D) { return D == 64 && (N + 15) / 16 * 16 <= attn_cfg::KP_MAX; }
 
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* avg, float* cls, float* heads, int B,
-                            int N, int H, int D, int pitch, float2* stats, cudaStream_t st) {
+                            int N, int H, int D, int pitch, float2* stats, cudaStream_t st,
+                            const __nv_bfloat16* qkv_lo = nullptr, __nv_bfloat16* ctx_lo = nullptr) {
   using namespace attn_cfg;
-  if (!attention_is_fused(N, D)) return launch_attention_long(qkv, ctx, avg, cls, heads, B, N, H, D, pitch, stats, st);
+  if (qkv_lo != nullptr || !attention_is_fused(N, D))
+    return launch_attention_long(qkv, ctx, avg, cls, heads, B, N, H, D, pitch, stats, st, qkv_lo, ctx_lo);
   const int KP = (N + 15) / 16 * 16;
   if ((avg || heads) && (pitch < KP || pitch % 4 != 0))
     return fail(VITB200_ERR_INVALID, "attention: map pitch %d must be >= %d and a multiple of 4", pitch, KP);
@@ -379,6 +403,7 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
 struct LayerWeights {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   __nv_bfloat16 *w_qkv = nullptr, *w_o = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
+  __nv_bfloat16 *w_qkv_lo = nullptr, *w_o_lo = nullptr, *w_fc1_lo = nullptr, *w_fc2_lo = nullptr;  // fp32x3 mode
   float *b_qkv = nullptr, *b_o = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
   // LayerNorm folding: fp32 originals of the two weights that consume a LayerNorm (w_qkv / w_fc1 above hold the
   // gamma-scaled bf16 versions), their column sums and beta-folded biases
@@ -403,7 +428,9 @@ struct vitb200_engine {
   uint64_t launches = 0;
 
   // weights
+  bool precise = false;  // fp32x3 mode: every GEMM / attention operand is carried as hi + lo bf16 (cfg.precision == 1)
   __nv_bfloat16* w_patch = nullptr;
+  __nv_bfloat16 *w_patch_lo = nullptr, *w_head_lo = nullptr;
   float* b_patch = nullptr;
   float *cls_token = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
   __nv_bfloat16* w_head = nullptr;
@@ -418,6 +445,7 @@ struct vitb200_engine {
   int cap_batch = 0;
   uint32_t cap_flags = 0;
   Buffer images, patches, x, xb, ln_stats, ln_affine, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
+  Buffer patches_lo, xb_lo, qkv_lo, ctx_lo, mlp_lo, cls_ln_lo;  // fp32x3 mode: low halves of the bf16 operands
 
   // vitb200_submit_host / vitb200_wait: two requests in flight.  H2D of request i+1 (copy_in stream) and D2H of
   // request i-1 (copy_out stream, from per-slot staging copies of the small outputs) overlap the forward of request i.
@@ -467,7 +495,15 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   VT_TRY(ensure(e->ln_affine, M * sizeof(float2)));
   VT_TRY(ensure(e->qkv, M * 3 * c.hidden_dim * 2));
   VT_TRY(ensure(e->ctx, M * c.hidden_dim * 2));
-  if (!attention_is_fused(e->N, e->D)) VT_TRY(ensure(e->attn_stats, M * c.num_heads * sizeof(float2)));
+  if (e->precise || !attention_is_fused(e->N, e->D)) VT_TRY(ensure(e->attn_stats, M * c.num_heads * sizeof(float2)));
+  if (e->precise) {
+    VT_TRY(ensure(e->patches_lo, (size_t)B * e->n * e->patch_k * 2));
+    VT_TRY(ensure(e->xb_lo, M * c.hidden_dim * 2));
+    VT_TRY(ensure(e->qkv_lo, M * 3 * c.hidden_dim * 2));
+    VT_TRY(ensure(e->ctx_lo, M * c.hidden_dim * 2));
+    VT_TRY(ensure(e->mlp_lo, M * c.mlp_dim * 2));
+    VT_TRY(ensure(e->cls_ln_lo, (size_t)B * c.hidden_dim * 2));
+  }
   VT_TRY(ensure(e->mlp, M * c.mlp_dim * 2));
   VT_TRY(ensure(e->cls_ln, (size_t)B * c.hidden_dim * 2));
   VT_TRY(ensure(e->logits, (size_t)B * c.num_classes * 4));
@@ -497,7 +533,8 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
   const long items = (long)B * 3 * c.image_size * (c.image_size / c.patch_size) * (c.patch_size / 8);
   prof_mark(e, "patchify", st);
   patchify_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(images_dev, (__nv_bfloat16*)e->patches.p, B,
-                                                                   c.image_size, c.patch_size);
+                                                                   c.image_size, c.patch_size,
+                                                                   (__nv_bfloat16*)e->patches_lo.p);
   CU_TRY(cudaGetLastError());
   GemmEpilogue ep;
   ep.bias = e->b_patch;
@@ -507,13 +544,15 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
   ep.resid_broadcast = 1, ep.resid_row_offset = 1;
   ep.xb = (__nv_bfloat16*)e->xb.p, ep.ldxb = c.hidden_dim;
   ep.row_stats_out = (float2*)e->ln_stats.p, ep.stats_slots = c.hidden_dim / 32;
+  ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
   prof_mark(e, "gemm_patch_embed", st);
-  VT_TRY(launch_gemm(e->patches.p, e->patch_k, e->w_patch, B * e->n, c.hidden_dim, e->patch_k, ep, false, true, st));
+  VT_TRY(launch_gemm(e->patches.p, e->patch_k, e->w_patch, B * e->n, c.hidden_dim, e->patch_k, ep, false, true, st,
+                     e->patches_lo.p, e->w_patch_lo));
   const long cthreads = (long)B * (c.hidden_dim / 32) * 32;
   prof_mark(e, "cls_rows", st);
   cls_rows_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p,
                                                                       (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B,
-                                                                      e->N, c.hidden_dim);
+                                                                      e->N, c.hidden_dim, (__nv_bfloat16*)e->xb_lo.p);
   CU_TRY(cudaGetLastError());
   e->launches += 3;
   return VITB200_OK;
@@ -535,8 +574,8 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
     GemmEpilogue ep;
     prof_mark(e, "gemm_qkv", st);
     ep.bias = w.bf_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
-    ep.row_affine_in = affine, ep.colsum = w.s_qkv;
-    VT_TRY(launch_gemm(xb, d, w.w_qkv, M, 3 * d, d, ep, false, false, st));
+    ep.row_affine_in = affine, ep.colsum = w.s_qkv, ep.out_lo = (__nv_bfloat16*)e->qkv_lo.p;
+    VT_TRY(launch_gemm(xb, d, w.w_qkv, M, 3 * d, d, ep, false, false, st, e->xb_lo.p, w.w_qkv_lo));
   }
   const bool want_avg = (flags & (VITB200_EMIT_AVG | VITB200_EMIT_ROLLOUT)) != 0;
   float* avg = want_avg ? (float*)e->avg.p + (size_t)l * e->cap_batch * e->N * e->pitch : nullptr;
@@ -546,13 +585,14 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
                   : nullptr;
   prof_mark(e, "attention", st);
   VT_TRY(launch_attention((const __nv_bfloat16*)e->qkv.p, (__nv_bfloat16*)e->ctx.p, avg, cls, hm, B, e->N, c.num_heads,
-                          e->D, e->pitch, (float2*)e->attn_stats.p, st));
+                          e->D, e->pitch, (float2*)e->attn_stats.p, st, (const __nv_bfloat16*)e->qkv_lo.p,
+                          (__nv_bfloat16*)e->ctx_lo.p));
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_out_proj", st);
     ep.bias = w.b_o, ep.out = x, ep.ldo = d, ep.resid = x, ep.ldr = d;
-    ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots;
-    VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st));
+    ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots, ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
+    VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st, e->ctx_lo.p, w.w_o_lo));
   }
   prof_mark(e, "ln_row_stats", st);
   row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
@@ -561,15 +601,15 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
     GemmEpilogue ep;
     prof_mark(e, "gemm_fc1_gelu", st);
     ep.bias = w.bf_fc1, ep.out = e->mlp.p, ep.ldo = c.mlp_dim;
-    ep.row_affine_in = affine, ep.colsum = w.s_fc1;
-    VT_TRY(launch_gemm(xb, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st));
+    ep.row_affine_in = affine, ep.colsum = w.s_fc1, ep.out_lo = (__nv_bfloat16*)e->mlp_lo.p;
+    VT_TRY(launch_gemm(xb, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st, e->xb_lo.p, w.w_fc1_lo));
   }
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_fc2", st);
     ep.bias = w.b_fc2, ep.out = x, ep.ldo = d, ep.resid = x, ep.ldr = d;
-    ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots;
-    VT_TRY(launch_gemm(e->mlp.p, c.mlp_dim, w.w_fc2, M, d, c.mlp_dim, ep, false, true, st));
+    ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots, ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
+    VT_TRY(launch_gemm(e->mlp.p, c.mlp_dim, w.w_fc2, M, d, c.mlp_dim, ep, false, true, st, e->mlp_lo.p, w.w_fc2_lo));
   }
   e->launches += 7;
   if (flags & VITB200_EMIT_HIDDEN) {
@@ -584,11 +624,11 @@ static int run_head(vitb200_engine* e, int B, cudaStream_t st) {
   const int d = c.hidden_dim;
   prof_mark(e, "layernorm_final", st);
   VT_TRY(launch_layernorm((const float*)e->x.p, (long)e->N * d, e->lnf_g, e->lnf_b, (__nv_bfloat16*)e->cls_ln.p, B, d,
-                          1e-6f, st));
+                          1e-6f, st, (__nv_bfloat16*)e->cls_ln_lo.p));
   GemmEpilogue ep;
   ep.bias = e->b_head, ep.out = e->logits.p, ep.ldo = c.num_classes;
   prof_mark(e, "gemm_head", st);
-  VT_TRY(launch_gemm(e->cls_ln.p, d, e->w_head, B, c.num_classes, d, ep, false, true, st));
+  VT_TRY(launch_gemm(e->cls_ln.p, d, e->w_head, B, c.num_classes, d, ep, false, true, st, e->cls_ln_lo.p, e->w_head_lo));
   e->launches += 2;
   return VITB200_OK;
 }
@@ -632,10 +672,14 @@ static int check_ready(vitb200_engine* e) {
       CU_TRY(alloc(&w.w_fc1, (size_t)mlp * d * 2));
       CU_TRY(alloc(&w.s_fc1, (size_t)mlp * 4));
       CU_TRY(alloc(&w.bf_fc1, (size_t)mlp * 4));
+      if (e->precise) {
+        CU_TRY(alloc(&w.w_qkv_lo, (size_t)3 * d * d * 2));
+        CU_TRY(alloc(&w.w_fc1_lo, (size_t)mlp * d * 2));
+      }
       fold_ln_weight_kernel<<<(3 * d * 32 + 255) / 256, 256, 0, e->stream>>>(w.w_qkv_f32, w.ln1_g, w.ln1_b, w.b_qkv, w.w_qkv,
-                                                                             w.s_qkv, w.bf_qkv, 3 * d, d);
+                                                                             w.s_qkv, w.bf_qkv, 3 * d, d, w.w_qkv_lo);
       fold_ln_weight_kernel<<<(mlp * 32 + 255) / 256, 256, 0, e->stream>>>(w.w_fc1_f32, w.ln2_g, w.ln2_b, w.b_fc1, w.w_fc1,
-                                                                           w.s_fc1, w.bf_fc1, mlp, d);
+                                                                           w.s_fc1, w.bf_fc1, mlp, d, w.w_fc1_lo);
       CU_TRY(cudaGetLastError());
     }
     CU_TRY(cudaStreamSynchronize(e->stream));
@@ -672,13 +716,16 @@ static int copy_rows_to_host(float* dst, const float* src_dev, size_t rows, int 
 }  // namespace vitb200
 
 vitb200_engine::~vitb200_engine() {
-  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &ln_affine, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats};
+  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &ln_affine, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats,
+                    &patches_lo, &xb_lo, &qkv_lo, &ctx_lo, &mlp_lo, &cls_ln_lo};
   for (Buffer* b : bufs) release(*b);
   auto fr = [](void* p) { if (p) cudaFree(p); };
+  fr(w_patch_lo), fr(w_head_lo);
   fr(w_patch), fr(b_patch), fr(cls_token), fr(pos), fr(lnf_g), fr(lnf_b), fr(w_head), fr(b_head);
   for (auto& l : layers) {
     fr(l.ln1_g), fr(l.ln1_b), fr(l.ln2_g), fr(l.ln2_b), fr(l.w_qkv), fr(l.w_o), fr(l.w_fc1), fr(l.w_fc2);
     fr(l.b_qkv), fr(l.b_o), fr(l.b_fc1), fr(l.b_fc2);
+    fr(l.w_qkv_lo), fr(l.w_o_lo), fr(l.w_fc1_lo), fr(l.w_fc2_lo);
     fr(l.w_qkv_f32), fr(l.w_fc1_f32), fr(l.s_qkv), fr(l.s_fc1), fr(l.bf_qkv), fr(l.bf_fc1);
   }
   for (Slot& sl : slots) {
@@ -721,6 +768,8 @@ int vitb200_create(const vitb200_config* cfg, vitb200_engine** out) {
   const int KP = attention_pitch(N);
   if (N > kRolloutThreads * kRolloutMaxCols)
     return fail(VITB200_ERR_INVALID, "%d tokens per image exceed the engine's limit (%d)", N, kRolloutThreads * kRolloutMaxCols);
+  if (c.precision != 0 && c.precision != 1) return fail(VITB200_ERR_INVALID, "precision must be 0 (bf16) or 1 (fp32x3), got %d", c.precision);
+  if (c.precision == 1 && hd != 64) return fail(VITB200_ERR_INVALID, "the fp32x3 precision mode supports head dim 64 only (got %d)", hd);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(VITB200_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
@@ -733,6 +782,7 @@ int vitb200_create(const vitb200_config* cfg, vitb200_engine** out) {
 
   vitb200_engine* e = new vitb200_engine();
   e->cfg = c;
+  e->precise = c.precision == 1;
   e->n = n, e->N = N, e->D = hd, e->KP = KP, e->pitch = KP, e->patch_k = 3 * c.patch_size * c.patch_size;
   e->layers.resize(c.num_layers);
   e->expected_tensors = 4 + 12 * (size_t)c.num_layers + 4;
@@ -767,17 +817,20 @@ int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_h
   const size_t d = c.hidden_dim;
   const std::string key(name);
   void** slot = nullptr;
+  void** slot_lo = nullptr;  // fp32x3 mode: where the low halves of a bf16 weight go
   size_t expect = 0;
   bool to_bf16 = false;
   auto F = [&](float** p, size_t n) { slot = (void**)p, expect = n, to_bf16 = false; };
-  auto H = [&](__nv_bfloat16** p, size_t n) { slot = (void**)p, expect = n, to_bf16 = true; };
-  if (key == "conv_proj.weight") H(&e->w_patch, d * e->patch_k);
+  auto H = [&](__nv_bfloat16** p, size_t n, __nv_bfloat16** plo) {
+    slot = (void**)p, expect = n, to_bf16 = true, slot_lo = (void**)plo;
+  };
+  if (key == "conv_proj.weight") H(&e->w_patch, d * e->patch_k, &e->w_patch_lo);
   else if (key == "conv_proj.bias") F(&e->b_patch, d);
   else if (key == "class_token") F(&e->cls_token, d);
   else if (key == "encoder.pos_embedding") F(&e->pos, (size_t)e->N * d);
   else if (key == "encoder.ln.weight") F(&e->lnf_g, d);
   else if (key == "encoder.ln.bias") F(&e->lnf_b, d);
-  else if (key == "heads.head.weight") H(&e->w_head, (size_t)c.num_classes * d);
+  else if (key == "heads.head.weight") H(&e->w_head, (size_t)c.num_classes * d, &e->w_head_lo);
   else if (key == "heads.head.bias") F(&e->b_head, c.num_classes);
   else {
     int li = -1;
@@ -792,11 +845,11 @@ int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_h
     else if (r == "ln_2.bias") F(&w.ln2_b, d);
     else if (r == "self_attention.in_proj_weight") F(&w.w_qkv_f32, 3 * d * d);   // folded with ln_1 later
     else if (r == "self_attention.in_proj_bias") F(&w.b_qkv, 3 * d);
-    else if (r == "self_attention.out_proj.weight") H(&w.w_o, d * d);
+    else if (r == "self_attention.out_proj.weight") H(&w.w_o, d * d, &w.w_o_lo);
     else if (r == "self_attention.out_proj.bias") F(&w.b_o, d);
     else if (r == "mlp.0.weight") F(&w.w_fc1_f32, (size_t)c.mlp_dim * d);        // folded with ln_2 later
     else if (r == "mlp.0.bias") F(&w.b_fc1, c.mlp_dim);
-    else if (r == "mlp.3.weight") H(&w.w_fc2, d * (size_t)c.mlp_dim);
+    else if (r == "mlp.3.weight") H(&w.w_fc2, d * (size_t)c.mlp_dim, &w.w_fc2_lo);
     else if (r == "mlp.3.bias") F(&w.b_fc2, d);
     else return fail(VITB200_ERR_INVALID, "unknown weight name '%s'", name);
   }
@@ -813,8 +866,16 @@ int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_h
     VT_TRY(ensure(e->stage_f32, count * 4));
     CU_TRY(cudaMalloc(slot, count * 2));
     CU_TRY(cudaMemcpyAsync(e->stage_f32.p, data_host, count * 4, cudaMemcpyHostToDevice, e->stream));
-    f32_to_bf16_kernel<<<(unsigned)((count / 4 + 256) / 256), 256, 0, e->stream>>>((const float*)e->stage_f32.p,
-                                                                                  (__nv_bfloat16*)*slot, (long)count);
+    if (e->precise) {
+      if (*slot_lo) CU_TRY(cudaFree(*slot_lo));
+      *slot_lo = nullptr;
+      CU_TRY(cudaMalloc(slot_lo, count * 2));
+      f32_to_bf16_split_kernel<<<(unsigned)((count + 255) / 256), 256, 0, e->stream>>>(
+          (const float*)e->stage_f32.p, (__nv_bfloat16*)*slot, (__nv_bfloat16*)*slot_lo, (long)count);
+    } else {
+      f32_to_bf16_kernel<<<(unsigned)((count / 4 + 256) / 256), 256, 0, e->stream>>>((const float*)e->stage_f32.p,
+                                                                                    (__nv_bfloat16*)*slot, (long)count);
+    }
     CU_TRY(cudaGetLastError());
   }
   CU_TRY(cudaStreamSynchronize(e->stream));
@@ -1118,7 +1179,8 @@ int vitb200_set_tokens(vitb200_engine* e, const float* tokens_host, int batch) {
   // what the folded LayerNorm of the next GEMM reads: bf16 copy + per-chunk partial sums of every row
   const long rows = (long)batch * e->N;
   rows_bf16_stats_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const float*)e->x.p, (__nv_bfloat16*)e->xb.p,
-                                                                              (float2*)e->ln_stats.p, rows, e->cfg.hidden_dim);
+                                                                              (float2*)e->ln_stats.p, rows, e->cfg.hidden_dim,
+                                                                              (__nv_bfloat16*)e->xb_lo.p);
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
@@ -1217,6 +1279,23 @@ int vitb200_op_gemm_ex(const void* a, const void* w, const float* bias, const fl
     ep.row_affine_in = affine, ep.colsum = colsum;
   }
   return launch_gemm(a, K, w, M, N, K, ep, gelu != 0, out_f32 != 0, (cudaStream_t)stream);
+}
+
+int vitb200_op_split_bf16(const float* in_dev, void* hi_dev, void* lo_dev, size_t count, void* stream) {
+  if (!in_dev || !hi_dev || !lo_dev) return fail(VITB200_ERR_INVALID, "null argument");
+  f32_to_bf16_split_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in_dev, (__nv_bfloat16*)hi_dev,
+                                                                                            (__nv_bfloat16*)lo_dev, (long)count);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
+int vitb200_op_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                          const float* resid, void* out, void* out_lo, int M, int N, int K, int gelu, int out_f32, void* stream) {
+  if (!a_hi || !a_lo || !w_hi || !w_lo || !out) return fail(VITB200_ERR_INVALID, "null argument");
+  GemmEpilogue ep;
+  ep.bias = bias, ep.out = out, ep.ldo = N, ep.resid = resid, ep.ldr = N;
+  ep.out_lo = (__nv_bfloat16*)out_lo;
+  return launch_gemm(a_hi, K, w_hi, M, N, K, ep, gelu != 0, out_f32 != 0, (cudaStream_t)stream, a_lo, w_lo);
 }
 
 int vitb200_op_fold_ln(const float* w, const float* gamma, const float* beta, const float* bias, void* wq, float* colsum,

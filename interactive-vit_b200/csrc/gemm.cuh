@@ -68,6 +68,10 @@ struct GemmEpilogue {
   //    colsum[n] = sum_k W'[n, k].
   __nv_bfloat16* xb = nullptr;
   int ldxb = 0;
+  // split-bf16 mode: low halves of the bf16 outputs (out for bf16 epilogues, xb for residual epilogues):
+  // lo = bf16(value - float(bf16(value)))
+  __nv_bfloat16* out_lo = nullptr;
+  __nv_bfloat16* xb_lo = nullptr;
   float2* row_stats_out = nullptr;
   const float2* row_affine_in = nullptr;
   const float* colsum = nullptr;
@@ -76,6 +80,10 @@ struct GemmEpilogue {
 
 struct GemmShape {
   int M, N, K;
+  // 1: bf16 operands.  3: split-bf16 ("fp32x3") operands: every fp32 operand value is carried as hi + lo (two bf16
+  // matrices), and the product as A_hi W_hi + A_lo W_hi + A_hi W_lo -- the main loop runs three K passes over the
+  // (hi, hi), (lo, hi), (hi, lo) operand pairs into the same fp32 accumulator (relative error ~2^-17 per product).
+  int split = 1;
 };
 
 namespace gemm_cfg {
@@ -169,6 +177,7 @@ template <int BN, int kPair, int kPairs, bool kGelu, bool kOutF32, bool kResid, 
           bool kPrefetch = false>
 __global__ void __launch_bounds__((gemm_cfg::Cfg<BN, kPair, gemm_cfg::epi_warps(kGelu), kPrefetch>::kThreads), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_a_lo, const __grid_constant__ CUtensorMap tmap_w_lo,
                  GemmShape shape, GemmEpilogue ep) {
   using namespace gemm_cfg;
   constexpr int kEpiWarps = epi_warps(kGelu);
@@ -215,6 +224,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
+    if (shape.split > 1) {
+      ptx::prefetch_tmap(&tmap_a_lo);
+      ptx::prefetch_tmap(&tmap_w_lo);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -253,6 +266,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool share_a = work.decode(unit, kPairs, pair_id, m_blk, n_blk);
       const int a_row = m_blk * kTileM + static_cast<int>(cta_rank) * BM;
       const int w_row = n_blk * BN + static_cast<int>(cta_rank) * (BN / kPair);
+      for (int pass = 0; pass < shape.split; ++pass) {
+      // operand pair of this K pass: (hi, hi), (lo, hi), (hi, lo)
+      const CUtensorMap* ta = pass == 1 ? &tmap_a_lo : &tmap_a;
+      const CUtensorMap* tw = pass == 2 ? &tmap_w_lo : &tmap_w;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::kStageBytes;
@@ -263,25 +280,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             constexpr int kHalf = 64 * BK * 2;
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
             if (!share_a) {
-              ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
-              ptx::tma_load_2d_pair(sa + kHalf, &tmap_a, &full_bar[stage], kb * BK, a_row + 64);
-              ptx::tma_load_2d_pair_mc(sb + pair_id * kHalf, &tmap_w, &full_bar[stage], kb * BK, w_row + pair_id * 64,
+              ptx::tma_load_2d_pair(sa, ta, &full_bar[stage], kb * BK, a_row);
+              ptx::tma_load_2d_pair(sa + kHalf, ta, &full_bar[stage], kb * BK, a_row + 64);
+              ptx::tma_load_2d_pair_mc(sb + pair_id * kHalf, tw, &full_bar[stage], kb * BK, w_row + pair_id * 64,
                                        mc_mask);
             } else {
-              ptx::tma_load_2d_pair_mc(sa + pair_id * kHalf, &tmap_a, &full_bar[stage], kb * BK, a_row + pair_id * 64,
+              ptx::tma_load_2d_pair_mc(sa + pair_id * kHalf, ta, &full_bar[stage], kb * BK, a_row + pair_id * 64,
                                        mc_mask);
-              ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
-              ptx::tma_load_2d_pair(sb + kHalf, &tmap_w, &full_bar[stage], kb * BK, w_row + 64);
+              ptx::tma_load_2d_pair(sb, tw, &full_bar[stage], kb * BK, w_row);
+              ptx::tma_load_2d_pair(sb + kHalf, tw, &full_bar[stage], kb * BK, w_row + 64);
             }
           } else if (kPair == 2) {
             // one barrier (the leader's) tracks the bytes of both CTAs' halves
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-            ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
-            ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
+            ptx::tma_load_2d_pair(sa, ta, &full_bar[stage], kb * BK, a_row);
+            ptx::tma_load_2d_pair(sb, tw, &full_bar[stage], kb * BK, w_row);
           } else {
             ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
-            ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * BK, w_row);
+            ptx::tma_load_2d(sa, ta, &full_bar[stage], kb * BK, a_row);
+            ptx::tma_load_2d(sb, tw, &full_bar[stage], kb * BK, w_row);
           }
         }
         __syncwarp();
@@ -290,6 +307,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           phase ^= 1;
         }
       }
+      }  // K passes
     }
   } else if (warp == 1 && leader) {
     // ------------------------------------------------------------ UMMA issuer (leader CTA)
@@ -306,7 +324,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int total_kb = num_kb * shape.split;  // split-bf16: three K passes into the same accumulator
+      for (int kb = 0; kb < total_kb; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
@@ -519,9 +538,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               p1[i] = ok[i] ? (t.x + t.y) + (t.z + t.w) : 0.f;
               p2[i] = ok[i] ? (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w) : 0.f;
               if (ok[i]) {
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(t.x, t.y), h23 = __floats2bfloat162_rn(t.z, t.w);
                 uint2 pk;
-                pk.x = pack2_bf16(t.x, t.y), pk.y = pack2_bf16(t.z, t.w);
+                pk.x = *reinterpret_cast<const uint32_t*>(&h01), pk.y = *reinterpret_cast<const uint32_t*>(&h23);
                 *reinterpret_cast<uint2*>(ep.xb + orow[i] * ep.ldxb + col) = pk;
+                if (ep.xb_lo != nullptr) {
+                  uint2 pl;
+                  pl.x = pack2_bf16(t.x - __low2float(h01), t.y - __high2float(h01));
+                  pl.y = pack2_bf16(t.z - __low2float(h23), t.w - __high2float(h23));
+                  *reinterpret_cast<uint2*>(ep.xb_lo + orow[i] * ep.ldxb + col) = pl;
+                }
               }
             }
             if (ok[i]) {
@@ -534,6 +560,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 pk.x = *reinterpret_cast<uint32_t*>(&lo);
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
                 *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow[i] * ep.ldo + col) = pk;
+                if (ep.out_lo != nullptr) {  // split-bf16: the rounding residue as a second bf16 matrix
+                  uint2 pl;
+                  pl.x = pack2_bf16(t.x - __low2float(lo), t.y - __high2float(lo));
+                  pl.y = pack2_bf16(t.z - __low2float(hi), t.w - __high2float(hi));
+                  *reinterpret_cast<uint2*>(ep.out_lo + orow[i] * ep.ldo + col) = pl;
+                }
               }
             }
           }

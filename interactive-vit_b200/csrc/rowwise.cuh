@@ -30,7 +30,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 template <int kVec>
 __global__ void __launch_bounds__(256)
 layernorm_f32_bf16_kernel(const float* __restrict__ x, long in_row_stride, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, float eps) {
+                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, float eps,
+                          __nv_bfloat16* __restrict__ y_lo = nullptr /* fp32x3 mode: low halves */) {
   constexpr int d = kVec * 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -57,10 +58,18 @@ layernorm_f32_bf16_kernel(const float* __restrict__ x, long in_row_stride, const
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
     const float4 g = g4[lane + 32 * i], bb = b4[lane + 32 * i];
+    const float r0 = (v[i].x - mean) * rstd * g.x + bb.x, r1 = (v[i].y - mean) * rstd * g.y + bb.y;
+    const float r2 = (v[i].z - mean) * rstd * g.z + bb.z, r3 = (v[i].w - mean) * rstd * g.w + bb.w;
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(r0, r1), h23 = __floats2bfloat162_rn(r2, r3);
     uint2 o;
-    o.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
-    o.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+    o.x = *reinterpret_cast<const uint32_t*>(&h01), o.y = *reinterpret_cast<const uint32_t*>(&h23);
     yr[lane + 32 * i] = o;
+    if (y_lo != nullptr) {
+      uint2 l;
+      l.x = pack_bf16x2(r0 - __low2float(h01), r1 - __high2float(h01));
+      l.y = pack_bf16x2(r2 - __low2float(h23), r3 - __high2float(h23));
+      reinterpret_cast<uint2*>(y_lo + static_cast<long>(warp) * d)[lane + 32 * i] = l;
+    }
   }
 }
 
@@ -127,7 +136,8 @@ preprocess_kernel(const float* __restrict__ in, float* __restrict__ out, Preproc
 // column = c * p * p + ky * p + kx (the flattening of conv_proj.weight [d, 3, p, p]), row = b * n + py * np + px.
 // One thread moves 8 consecutive kx: two float4 reads, one 16-byte write.
 __global__ void __launch_bounds__(256)
-patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int p) {
+patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int p,
+                __nv_bfloat16* __restrict__ out_lo = nullptr /* fp32x3 mode: low halves */) {
   const int np = S / p;
   const int kx8 = p / 8;                                 // 16-byte groups per patch row
   const long total = static_cast<long>(B) * 3 * S * np * kx8;  // one item per (b, c, y, px, g)
@@ -151,6 +161,15 @@ patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, 
   const long row = static_cast<long>(b) * np * np + py * np + px;
   const long col = static_cast<long>(c) * p * p + ky * p + g * 8;
   *reinterpret_cast<uint4*>(out + row * (3L * p * p) + col) = o;
+  if (out_lo != nullptr) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&o);
+    uint4 l;
+    l.x = pack_bf16x2(a.x - __low2float(h[0]), a.y - __high2float(h[0]));
+    l.y = pack_bf16x2(a.z - __low2float(h[1]), a.w - __high2float(h[1]));
+    l.z = pack_bf16x2(bb.x - __low2float(h[2]), bb.y - __high2float(h[2]));
+    l.w = pack_bf16x2(bb.z - __low2float(h[3]), bb.w - __high2float(h[3]));
+    *reinterpret_cast<uint4*>(out_lo + row * (3L * p * p) + col) = l;
+  }
 }
 
 // Class-token rows of the token stream: x[b, 0, :] = class_token + pos_embedding[0]  (fp32), plus what the folded
@@ -158,7 +177,8 @@ patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, 
 // squares).  One warp per (image, 32-column chunk), one column per lane.
 __global__ void __launch_bounds__(256)
 cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
-                __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int B, int N, int d) {
+                __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int B, int N, int d,
+                __nv_bfloat16* __restrict__ xb_lo = nullptr) {
   const int slots = d >> 5;
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,7 +189,9 @@ cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, fl
   const long row = static_cast<long>(b) * N;
   x[row * d + col] = v;
   if (xb != nullptr) {
-    xb[row * d + col] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+    xb[row * d + col] = hb;
+    if (xb_lo != nullptr) xb_lo[row * d + col] = __float2bfloat16_rn(v - __bfloat162float(hb));
     const float p1 = warp_sum(v), p2 = warp_sum(v * v);
     if (lane == 0) stats[row * slots + chunk] = make_float2(p1, p2);
   }
@@ -179,14 +201,16 @@ cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, fl
 // vitb200_set_tokens): one warp per row.
 __global__ void __launch_bounds__(256)
 rows_bf16_stats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, long rows,
-                       int d) {
+                       int d, __nv_bfloat16* __restrict__ xb_lo = nullptr) {
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int slots = d >> 5;
   for (int chunk = 0; chunk < slots; ++chunk) {
     const float v = x[row * d + chunk * 32 + lane];
-    xb[row * d + chunk * 32 + lane] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+    xb[row * d + chunk * 32 + lane] = hb;
+    if (xb_lo != nullptr) xb_lo[row * d + chunk * 32 + lane] = __float2bfloat16_rn(v - __bfloat162float(hb));
     const float p1 = warp_sum(v), p2 = warp_sum(v * v);
     if (lane == 0) stats[row * slots + chunk] = make_float2(p1, p2);
   }
@@ -230,16 +254,23 @@ row_stats_finalize_kernel(const float2* __restrict__ partial, float2* __restrict
 __global__ void __launch_bounds__(256)
 fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ Wq, float* __restrict__ colsum,
-                      float* __restrict__ bias_out, int N, int K) {
+                      float* __restrict__ bias_out, int N, int K,
+                      __nv_bfloat16* __restrict__ Wq_lo = nullptr /* fp32x3 mode: low halves, included in colsum */) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
   float s = 0.f, bb = 0.f;
   for (int k = lane; k < K; k += 32) {
     const float w = W[static_cast<long>(n) * K + k];
-    const __nv_bfloat16 wq = __float2bfloat16_rn(w * gamma[k]);
+    const float wg = w * gamma[k];
+    const __nv_bfloat16 wq = __float2bfloat16_rn(wg);
     Wq[static_cast<long>(n) * K + k] = wq;
     s += __bfloat162float(wq);
+    if (Wq_lo != nullptr) {
+      const __nv_bfloat16 wl = __float2bfloat16_rn(wg - __bfloat162float(wq));
+      Wq_lo[static_cast<long>(n) * K + k] = wl;
+      s += __bfloat162float(wl);
+    }
     bb = fmaf(beta[k], w, bb);
   }
   s = warp_sum(s), bb = warp_sum(bb);
@@ -259,6 +290,18 @@ f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out
   } else {
     for (long k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k]);
   }
+}
+
+// fp32 -> split bf16 (hi = bf16(x), lo = bf16(x - hi)): operands of the fp32x3 precision mode.
+__global__ void __launch_bounds__(256)
+f32_to_bf16_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                         long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = in[i];
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -38,6 +38,7 @@ class _Config(C.Structure):
         ("num_classes", C.c_int),
         ("max_batch", C.c_int),
         ("device", C.c_int),
+        ("precision", C.c_int),
     ]
 
 
@@ -87,6 +88,8 @@ SIGNATURES = {
     "vitb200_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_gemm_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P]),
     "vitb200_op_fold_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "vitb200_op_split_bf16": (_I, [_P, _P, _P, C.c_size_t, _P]),
+    "vitb200_op_gemm_split": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "vitb200_op_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "vitb200_op_attention_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
@@ -164,12 +167,15 @@ CONFIGS: Dict[str, VitConfig] = {
 class VitEngine:
     """One engine = one model replica on one GPU.  Thread-safe (the C side serialises calls)."""
 
-    def __init__(self, cfg: VitConfig, device: int = 0, max_batch: int = 1):
+    def __init__(self, cfg: VitConfig, device: int = 0, max_batch: int = 1, precision: str = "bf16"):
+        """precision: "bf16" (bf16 operands, fp32 accumulation) or "fp32x3" (split-bf16 operands: hi*hi + lo*hi +
+        hi*lo, <= 1e-3 of the fp32 reference, ~3x the tensor work; head dim 64 models)."""
         self.lib = load_library()
         self.cfg = cfg
         self.device = device
+        self.precision = precision
         c = _Config(cfg.image_size, cfg.patch_size, cfg.num_layers, cfg.num_heads, cfg.hidden_dim, cfg.mlp_dim,
-                    cfg.num_classes, max_batch, device)
+                    cfg.num_classes, max_batch, device, {"bf16": 0, "fp32x3": 1}[precision])
         h = C.c_void_p()
         check(self.lib.vitb200_create(C.byref(c), C.byref(h)))
         self._h = h
@@ -409,6 +415,30 @@ def op_gemm_ln(xb: torch.Tensor, stats: torch.Tensor, wq: torch.Tensor, colsum: 
     check(lib.vitb200_op_gemm_ex(xb.data_ptr(), wq.data_ptr(), bias.data_ptr(), None, out.data_ptr(), M, N, K, int(gelu), 0,
                                  None, None, stats.data_ptr(), colsum.data_ptr(), eps, None))
     return out
+
+
+def op_split_bf16(x: torch.Tensor):
+    """(hi, lo) bf16 tensors with hi + lo ~= x to ~2^-17 relative."""
+    lib = load_library()
+    x = x.contiguous()
+    hi = torch.empty_like(x, dtype=torch.bfloat16)
+    lo = torch.empty_like(x, dtype=torch.bfloat16)
+    check(lib.vitb200_op_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), None))
+    return hi, lo
+
+
+def op_gemm_split(a: torch.Tensor, w: torch.Tensor, bias=None, resid=None, gelu=False, out_f32=True):
+    """epilogue(a @ w.T) for fp32 a [M,K], w [N,K] through split-bf16 operands (the fp32x3 precision mode)."""
+    lib = load_library()
+    M, K = a.shape
+    N = w.shape[0]
+    ah, al = op_split_bf16(a)
+    wh, wl = op_split_bf16(w)
+    out = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    out_lo = None if out_f32 else torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    check(lib.vitb200_op_gemm_split(ah.data_ptr(), al.data_ptr(), wh.data_ptr(), wl.data_ptr(), _ptr(bias), _ptr(resid),
+                                    out.data_ptr(), _ptr(out_lo), M, N, K, int(gelu), int(out_f32), None))
+    return out if out_f32 else out.float() + out_lo.float()
 
 
 def op_attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, want_avg=True, want_cls=True, want_heads=False,

@@ -81,6 +81,35 @@ def test_gemm(E, M, N, K, bias, resid, gelu, out_f32):
     assert _rel(got, ref) < (F32_EPS if out_f32 else BF16_EPS)
 
 
+@pytest.mark.parametrize("M,N,K,resid,gelu,out_f32", [(788, 768, 768, True, False, True), (788, 2304, 768, False, False, False),
+                                                       (788, 3072, 768, False, True, False), (300, 768, 3072, True, False, True),
+                                                       (7, 1000, 768, False, False, True), (591, 1152, 384, False, False, False)])
+def test_gemm_split_bf16_operands(E, M, N, K, resid, gelu, out_f32):
+    """fp32x3 precision mode: fp32 operands as hi + lo bf16, product = hi*hi + lo*hi + hi*lo in three K passes, fp32
+    accumulation in TMEM.  Against an fp64 matmul: 5e-5 of the output range (a plain bf16 GEMM sits at 2e-3); the
+    non-fp32 output is itself a hi + lo pair."""
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device="cuda") * 0.5
+    w = torch.randn(N, K, device="cuda") * 0.05
+    b = torch.randn(N, device="cuda")
+    r = torch.randn(M, N, device="cuda") if resid else None
+    got = E.op_gemm_split(a, w, b, r, gelu, out_f32)
+    ref = a.double() @ w.double().t() + b.double()
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    if resid:
+        ref = ref + r.double()
+    assert got.shape == (M, N) and torch.isfinite(got).all()
+    assert ((got.double() - ref).abs().max() / ref.abs().max()).item() < 5e-5
+
+
+def test_split_bf16_is_a_17_bit_representation(E):
+    x = torch.randn(1 << 16, device="cuda") * torch.logspace(-3, 3, 1 << 16, device="cuda")
+    hi, lo = E.op_split_bf16(x)
+    assert torch.equal(hi, x.bfloat16())
+    assert ((hi.float() + lo.float() - x).abs() / x.abs().clamp_min(1e-30)).max().item() < 2.0 ** -16
+
+
 def test_gemm_full_size_linearity(E):
     """Size-independent property at the bench shape (M = 256 * 197): GEMM(a1 + a2) == GEMM(a1) + GEMM(a2) when
     the sum a1 + a2 is exact in bf16, and every row depends only on its own input row."""

@@ -111,6 +111,27 @@ def gemm_cluster():
 
 
 @case
+def gemm_split():
+    """fp32x3 GEMM (split-bf16 operands) against an fp64 reference."""
+    import torch
+    from interactive_vit_b200 import engine as E
+    for (M, N, K, gelu, f32, resid) in ((788, 768, 768, False, True, True), (788, 2304, 768, False, False, False),
+                                        (788, 3072, 768, True, False, False), (300, 768, 3072, False, True, True)):
+        torch.manual_seed(M + N)
+        a = torch.randn(M, K, device="cuda") * 0.5
+        w = torch.randn(N, K, device="cuda") * 0.05
+        b = torch.randn(N, device="cuda")
+        r = torch.randn(M, N, device="cuda") if resid else None
+        got = E.op_gemm_split(a, w, b, r, gelu, f32)
+        ref = a.double() @ w.double().t() + b.double()
+        if gelu:
+            ref = torch.nn.functional.gelu(ref)
+        if resid:
+            ref = ref + r.double()
+        _err(f"gemm_split M={M} N={N} K={K} gelu={gelu} f32={f32} resid={resid}", got.double(), ref)
+
+
+@case
 def gemm_ln_perf():
     """Plain bias epilogue vs the folded-LayerNorm consumer epilogue, and plain residual vs the producer epilogue."""
     import torch
@@ -287,6 +308,30 @@ def _forward_case(name, batch, init):
     # stage path
     eng.stage_embed(x)
     _err("stage embed", eng.get_tokens(batch), ref["embed"])
+
+
+@case
+def forward_precise():
+    """fp32x3 precision mode (split-bf16 operands) against the fp32 CPU oracle: north_star asks <= 1e-3."""
+    import torch
+    from interactive_vit_b200 import engine as E
+    from oracle import vit_oracle as O
+    for (name, batch, init) in (("vit_small_test", 3, "stress"), ("vit_577_test", 2, "stress"), ("vit_b_16", 2, "default"),
+                                ("vit_b_16", 1, "stress")):
+        ocfg = O.ORACLE_CONFIGS[name]
+        model = O.build_vit(ocfg, seed=0, init=init)
+        x = O.synthetic_images(batch, ocfg.image_size)
+        ref = O.forward_with_maps(model, x)
+        cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                          ocfg.num_classes)
+        eng = E.VitEngine(cfg, 0, batch, precision="fp32x3")
+        eng.load_state_dict(model.state_dict())
+        got = eng.forward_host(x, E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT | E.EMIT_HEADS | E.EMIT_HIDDEN)
+        print(f"  forward_precise {name} batch={batch} init={init}")
+        for k in ("logits", "avg_maps", "cls_maps", "rollout", "heads", "hidden"):
+            _err(k, got[k], ref[k])
+        print("    top1 equal:", bool((got["logits"].argmax(-1) == ref["logits"].argmax(-1)).all()), flush=True)
+        eng.close()
 
 
 @case
