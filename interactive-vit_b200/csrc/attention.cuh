@@ -66,7 +66,8 @@ struct AttnParams {
 // CTA 0's softmax warp 4 / lane 0 and the MMA warp write clock64() stamps per head to a global buffer.
 #ifdef VITB200_ATTN_TRACE
 __device__ long long g_attn_trace[64 * 32];
-#define ATTN_TS(slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 1)) g_attn_trace[(h) * 32 + (slot)] = clock64(); } while (0)
+#define ATTN_TS(slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 1)) g_attn_trace[(h) * 32 + (slot)] = clock64(); \
+    else if (blockIdx.x == 0 && lane == 0 && warp == 9 && (slot) >= 4 && (slot) < 16) g_attn_trace[(h) * 32 + 16 + (slot)] = clock64(); } while (0)
 #else
 #define ATTN_TS(slot) do { } while (0)
 #endif
@@ -310,16 +311,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     const bool row_ok = qrow < p.N;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int ngran = KP >> 3;                  // 8-key granules in a row
-    const int gbase = ngran / kColGroups, grem = ngran - gbase * kColGroups;
-    const int nmy = gbase + (cg < grem ? 1 : 0);               // granules of this thread
-    const int g0 = cg * gbase + (cg < grem ? cg : grem);       // first granule
+    // Granules are dealt round-robin: this thread owns g = 4 c + cg, c = 0 .. nmy-1.  Then g % 8 = cg | 4 (c & 1),
+    // g / 8 = c / 2, g / 4 = c, g % 4 = cg: every TMEM column and every swizzled smem address below is one of two
+    // per-thread bases plus a compile-time offset (contiguous ranges needed ~13 address instructions per granule).
+    const int nmy = ngran > cg ? (ngran - cg + kColGroups - 1) / kColGroups : 0;   // granules of this thread
     const float inv_h = 1.0f / static_cast<float>(p.H);
-    const bool has_pad = (g0 + nmy) * 8 > p.N;                 // warp-uniform: this column group owns padded keys
+    const bool has_pad = nmy > 0 && (kColGroups * (nmy - 1) + cg) * 8 + 8 > p.N;   // warp-uniform: owns padded keys
+    const int valid_last = p.N - (kColGroups * (nmy - 1) + cg) * 8;   // valid keys in this thread's last granule (< 8 iff has_pad)
     const bool want_cls = p.cls_map != nullptr && qt == 0 && quarter == 0;
     const uint32_t p_row = ptx::smem_u32(smem_p) + r * 128;
     const int sw = r & 7;
-    const uint32_t t_s = lane_base + kTmemS + g0 * 8;
-    const uint32_t t_avg = lane_base + kTmemAvg + g0 * 8;
+    const uint32_t sw4 = static_cast<uint32_t>(sw) << 4;
+    const uint32_t p_even = p_row + ((static_cast<uint32_t>(cg) << 4) ^ sw4);        // chunk cg     of K-block c / 2
+    const uint32_t p_odd = p_row + ((static_cast<uint32_t>(cg | 4) << 4) ^ sw4);     // chunk cg + 4 of K-block c / 2
+    const uint32_t t_s = lane_base + kTmemS + cg * 8;      // granule c: + 32 c columns
+    const uint32_t t_avg = lane_base + kTmemAvg + cg * 8;
     const uint32_t t_o = lane_base + kTmemO + cg * 16;  // this thread's 16 of the 64 context columns
 
     // Context columns of head hh: O is final (P was normalised before the MMA) -> bf16 -> smem quarter tile (32 rows x
@@ -365,8 +371,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       ATTN_TS(1);
       ptx::tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < kMaxGran; ++c)
-        if (c < nmy) ptx::tmem_ld_x8(t_s + c * 8, s[c]);
+      for (int c = 0; c < kMaxGran; ++c) {
+        if (c < nmy) {
+          ptx::tmem_ld_x8(t_s + c * 32, s[c]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[c][j] = 0u;   // never used as a score; scaled and packed (not stored) below
+        }
+      }
       ptx::tmem_ld_wait();
       ATTN_TS(2);
       ptx::tc_fence_before();
@@ -375,23 +387,31 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 
       ATTN_TS(3);
 
-      // ---- padded keys (>= N) count as -inf.  Only the last column group can own any (KP - N < 16): warp-uniform
+      // ---- padded keys (>= N) count as -inf.  KP - N < 16, so they sit in the last two granules of the row, each of
+      //      which is the LAST granule of its owner: one granule per thread to patch, and only in warps that own one
       if (has_pad) {
+        auto patch = [&](uint32_t (&row)[8]) {
 #pragma unroll
-        for (int c = 0; c < kMaxGran; ++c) {
-          const int key0 = (g0 + c) * 8;
-          if (c < nmy && key0 + 8 > p.N) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (key0 + j >= p.N) s[c][j] = 0xff800000u;  // -inf: exp2 gives 0, max ignores it
-          }
+          for (int j = 0; j < 8; ++j)
+            if (j >= valid_last) row[j] = 0xff800000u;  // -inf: exp2 gives 0, max ignores it
+        };
+        static_assert(kMaxGran == 7, "one case per possible granule count");
+        switch (nmy) {   // warp-uniform; compile-time row indices keep s[][] in registers
+          case 7: patch(s[6]); break;
+          case 6: patch(s[5]); break;
+          case 5: patch(s[4]); break;
+          case 4: patch(s[3]); break;
+          case 3: patch(s[2]); break;
+          case 2: patch(s[1]); break;
+          default: patch(s[0]); break;
         }
       }
 
       // ---- e = exp2((s - m_t) * c) with the maximum m_t of this thread's OWN columns: no exchange is needed before
       //      the exponentials.  Softmax is invariant to the shift, the four threads of a row reconcile afterwards:
       //      p = e * f_t,  f_t = exp2((m_t - M) c) / sum_u(sum_u exp2((m_u - M) c)),  M = max_u m_u.
-      float mx = -INFINITY;
+      float mx;
+      mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
         if (c < nmy) {
@@ -440,31 +460,37 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         inv = ptx::ex2_approx(mxs - M) * ptx::rcp_approx(tot);
         if (mx == -INFINITY) inv = 0.f;
       }
+      ATTN_TS(9);
 
       // ---- the P tile is about to be overwritten: the previous head's P V and Pbar MMAs (issued a whole softmax
       //      pass ago) must have retired
       if (h > 0) {
         ptx::mbar_wait(p_free, (h - 1) & 1);
+        ATTN_TS(10);
         // context of the previous head (its P V retired long ago): TMEM -> smem now, so that the fence below covers it
-        // and P V of THIS head finds the O columns free as soon as the P tile is handed over
+        // and P V of THIS head finds the O columns free as soon as the P tile is handed over.  (Reading O at the top of
+        // the head together with S, to hide the TMEM latency, measured 203 us against 190 us: 8 more live registers.)
         o_stage(h - 1);
       }
+      ATTN_TS(11);
 
       // ---- p = e / sum -> bf16 P tile (swizzled K-major A operand of P V and of the head-average MMAs); fp32 copies
       //      of row 0 / of every row for the CLS / per-head maps
+      //      The multiplies and packs run for all kMaxGran granules (a thread with fewer granules scales zeros) and only
+      //      the store is predicated: per-granule branches cost more issue slots than the arithmetic they skip.
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
-        if (c < nmy) {
-          const int g = g0 + c;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) s[c][j] = __float_as_uint(__uint_as_float(s[c][j]) * inv);
-          // keys [8 g, 8 g + 8): K-block g / 8, 16-byte chunk g % 8 of this row
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p_row + (g >> 3) * kPBlockBytes + (((g & 7) ^ sw) << 4)),
-                       "r"(pack_bf16x2_u(s[c][0], s[c][1])), "r"(pack_bf16x2_u(s[c][2], s[c][3])),
-                       "r"(pack_bf16x2_u(s[c][4], s[c][5])), "r"(pack_bf16x2_u(s[c][6], s[c][7]))
-                       : "memory");
-        }
+        for (int j = 0; j < 8; ++j) s[c][j] = __float_as_uint(__uint_as_float(s[c][j]) * inv);
+        // keys [8 g, 8 g + 8), g = 4 c + cg: K-block c / 2, 16-byte chunk (cg | 4 (c & 1)) ^ (row % 8) of this row
+        const uint32_t dst = ((c & 1) ? p_odd : p_even) + (c >> 1) * kPBlockBytes;
+        const uint32_t w0 = pack_bf16x2_u(s[c][0], s[c][1]), w1 = pack_bf16x2_u(s[c][2], s[c][3]);
+        const uint32_t w2 = pack_bf16x2_u(s[c][4], s[c][5]), w3 = pack_bf16x2_u(s[c][6], s[c][7]);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(dst), "r"(w0),
+                     "r"(w1), "r"(w2), "r"(w3), "r"(static_cast<uint32_t>(c < nmy))
+                     : "memory");
       }
+      ATTN_TS(12);
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
@@ -472,14 +498,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 
       // ---- context of the previous head: staged above, ordered by the same fence as the P tile
       if (h > 0) o_store(h - 1);
+      ATTN_TS(13);
 
       if (want_cls && lane == 0) {
         // query row 0 lives in lane 0 of the quarter-0 warp of every column group
         if (h > 0) ptx::mbar_wait(cls_free, (h - 1) & 1);
+        ATTN_TS(14);
 #pragma unroll
         for (int c = 0; c < kMaxGran; ++c) {
           if (c < nmy) {
-            float4* dst = reinterpret_cast<float4*>(cls_stage + (g0 + c) * 8);
+            float4* dst = reinterpret_cast<float4*>(cls_stage + (kColGroups * c + cg) * 8);
             dst[0] = make_float4(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]), __uint_as_float(s[c][2]),
                                  __uint_as_float(s[c][3]));
             dst[1] = make_float4(__uint_as_float(s[c][4]), __uint_as_float(s[c][5]), __uint_as_float(s[c][6]),
@@ -494,7 +522,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 #pragma unroll
           for (int c = 0; c < kMaxGran; ++c) {
             if (c < nmy) {
-              float4* dst = reinterpret_cast<float4*>(hp + (g0 + c) * 8);
+              float4* dst = reinterpret_cast<float4*>(hp + (kColGroups * c + cg) * 8);
               dst[0] = make_float4(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]), __uint_as_float(s[c][2]),
                                    __uint_as_float(s[c][3]));
               dst[1] = make_float4(__uint_as_float(s[c][4]), __uint_as_float(s[c][5]), __uint_as_float(s[c][6]),
@@ -522,15 +550,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       uint32_t a[kMaxGran][8];
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c)
-        if (c < nmy) ptx::tmem_ld_x8(t_avg + c * 8, a[c]);
+        if (c < nmy) ptx::tmem_ld_x8(t_avg + c * 32, a[c]);
       ptx::tmem_ld_wait();
       const uint32_t slab0 = ptx::smem_u32(smem) + r * 128;
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
         if (c < nmy) {
-          const int g = g0 + c;
-          const uint32_t dst = slab0 + (g >> 2) * (BM * 128);
-          const int ch = 2 * (g & 3);
+          // granule g = 4 c + cg: 32-column slab c, 16-byte chunks 2 cg and 2 cg + 1 of this row
+          const uint32_t dst = slab0 + c * (BM * 128);
+          const int ch = 2 * cg;
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((ch ^ sw) << 4)),
                        "f"(__uint_as_float(a[c][0]) * inv_h), "f"(__uint_as_float(a[c][1]) * inv_h),
                        "f"(__uint_as_float(a[c][2]) * inv_h), "f"(__uint_as_float(a[c][3]) * inv_h)

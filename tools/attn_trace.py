@@ -19,12 +19,15 @@ for maps in ((True, True), (False, False)):
     lib.vitb200_debug_attn_trace.argtypes = [C.c_void_p, C.c_int]
     assert lib.vitb200_debug_attn_trace(buf, 64 * 32) == 0
     t = [[buf[h * 32 + k] for k in range(32)] for h in range(H)]
-    names = {1: "s_full passed", 2: "S ld done", 4: "mask+max done", 5: "exp done", 6: "bar passed",
-             7: "P stored+arrive", 8: "O epi+maps done"}
+    names = {1: "s_full passed", 2: "S ld done", 4: "mask+max done", 5: "exp done", 6: "bar passed", 9: "inv computed",
+             10: "p_free passed", 11: "O staged (h-1)", 12: "P stored", 7: "fence+arrive", 13: "O store issued", 14: "cls_free passed",
+             8: "cls staged / end"}
     print(f"maps={maps}: softmax warp 4 lane 0, cycles since loop top of the head (mean over heads 2..{H - 2})")
-    for k in (1, 2, 4, 5, 6, 7, 8):
+    for k in (1, 2, 4, 5, 6, 9, 10, 11, 12, 7, 13, 14, 8):
         d = [t[h][k] - t[h][0] for h in range(2, H - 1)]
-        print(f"   {names[k]:16s} {sum(d) / len(d):8.0f}")
+        # warp 9 (quarter 1, column group 1): its stamps 4..15 live in slots 20..31, same time base (warp 4's loop top)
+        d9 = [t[h][16 + k] - t[h][0] for h in range(2, H - 1)] if 4 <= k < 16 else None
+        print(f"   {names[k]:16s} {sum(d) / len(d):8.0f}" + (f"   warp 9: {sum(d9) / len(d9):8.0f}" if d9 else ""))
     per_head = [t[h + 1][0] - t[h][0] for h in range(2, H - 2)]
     print(f"   head period    {sum(per_head) / len(per_head):8.0f}")
     print("  MMA thread: p_full wait %.0f, o_free wait %.0f, issue PV(+avg) %.0f, period %.0f" % (
