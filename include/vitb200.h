@@ -131,6 +131,11 @@ int vitb200_stage_transform(vitb200_engine* e, const float* images_host, int bat
                             float* out_host);
 int vitb200_stage_embed_resident(vitb200_engine* e, int batch);
 int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags);        /* TV:110-119 */
+/* The two halves of an EncoderBlock as separate nodes (`<model>:layer.<i>.attn`, `<model>:layer.<i>.mlp`; SURVEY.md
+ * section 8f-4, finer-grained graphs): attn = x + out_proj(MHA(LN1 x)) with the maps `flags` ask for (TV:112-116),
+ * mlp = x + MLP(LN2 x) (TV:118-119).  stage_attn_block followed by stage_mlp_block is stage_layer, bit for bit. */
+int vitb200_stage_attn_block(vitb200_engine* e, int layer, int batch, uint32_t flags);
+int vitb200_stage_mlp_block(vitb200_engine* e, int layer, int batch);
 int vitb200_stage_head(vitb200_engine* e, int batch, float* logits_host);                /* TV:157,302-304 */
 int vitb200_stage_rollout(vitb200_engine* e, int batch, float* rollout_host);            /* needs avg maps of all layers */
 int vitb200_set_tokens(vitb200_engine* e, const float* tokens_host, int batch);          /* [B, N, d] */

@@ -558,7 +558,8 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
   return VITB200_OK;
 }
 
-static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream_t st) {
+// First half of an EncoderBlock (vision_transformer.py:112-116): x <- x + out_proj(MHA(LN1 x)), maps as requested.
+static int run_attn_block(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream_t st) {
   const vitb200_config& c = e->cfg;
   const LayerWeights& w = e->layers[l];
   const int M = B * e->N, d = c.hidden_dim;
@@ -594,6 +595,20 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
     ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots, ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
     VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st, e->ctx_lo.p, w.w_o_lo));
   }
+  e->launches += 4;
+  return VITB200_OK;
+}
+
+// Second half (vision_transformer.py:118-119): x <- x + fc2(GELU(fc1(LN2 x))).
+static int run_mlp_block(vitb200_engine* e, int l, int B, cudaStream_t st) {
+  const vitb200_config& c = e->cfg;
+  const LayerWeights& w = e->layers[l];
+  const int M = B * e->N, d = c.hidden_dim;
+  float* x = (float*)e->x.p;
+  __nv_bfloat16* xb = (__nv_bfloat16*)e->xb.p;
+  float2* stats = (float2*)e->ln_stats.p;
+  float2* affine = (float2*)e->ln_affine.p;
+  const int slots = d / 32;
   prof_mark(e, "ln_row_stats", st);
   row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
   CU_TRY(cudaGetLastError());
@@ -611,10 +626,17 @@ static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream
     ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots, ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
     VT_TRY(launch_gemm(e->mlp.p, c.mlp_dim, w.w_fc2, M, d, c.mlp_dim, ep, false, true, st, e->mlp_lo.p, w.w_fc2_lo));
   }
-  e->launches += 7;
+  e->launches += 3;
+  return VITB200_OK;
+}
+
+static int run_layer(vitb200_engine* e, int l, int B, uint32_t flags, cudaStream_t st) {
+  VT_TRY(run_attn_block(e, l, B, flags, st));
+  VT_TRY(run_mlp_block(e, l, B, st));
   if (flags & VITB200_EMIT_HIDDEN) {
-    float* hid = (float*)e->hidden.p + (size_t)l * e->cap_batch * e->N * d;
-    CU_TRY(cudaMemcpyAsync(hid, x, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, st));
+    const size_t n = (size_t)B * e->N * e->cfg.hidden_dim;
+    float* hid = (float*)e->hidden.p + (size_t)l * e->cap_batch * e->N * e->cfg.hidden_dim;
+    CU_TRY(cudaMemcpyAsync(hid, e->x.p, n * 4, cudaMemcpyDeviceToDevice, st));
   }
   return VITB200_OK;
 }
@@ -1150,6 +1172,22 @@ int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags)
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)
   VT_TRY(run_layer(e, layer, batch, flags, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_stage_attn_block(vitb200_engine* e, int layer, int batch, uint32_t flags) {
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  STAGE_PROLOGUE(batch, flags)
+  VT_TRY(run_attn_block(e, layer, batch, flags, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_stage_mlp_block(vitb200_engine* e, int layer, int batch) {
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  STAGE_PROLOGUE(batch, 0)
+  VT_TRY(run_mlp_block(e, layer, batch, st));
   CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }

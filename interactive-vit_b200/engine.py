@@ -76,6 +76,8 @@ SIGNATURES = {
     "vitb200_stage_transform": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "vitb200_stage_embed_resident": (_I, [_P, _I]),
     "vitb200_stage_layer": (_I, [_P, _I, _I, _U32]),
+    "vitb200_stage_attn_block": (_I, [_P, _I, _I, _U32]),
+    "vitb200_stage_mlp_block": (_I, [_P, _I, _I]),
     "vitb200_stage_head": (_I, [_P, _I, _P]),
     "vitb200_stage_rollout": (_I, [_P, _I, _P]),
     "vitb200_set_tokens": (_I, [_P, _P, _I]),
@@ -302,6 +304,14 @@ class VitEngine:
 
     def stage_layer(self, layer: int, batch: int, flags: int) -> None:
         check(self.lib.vitb200_stage_layer(self._h, layer, batch, flags))
+
+    def stage_attn_block(self, layer: int, batch: int, flags: int = EMIT_AVG | EMIT_CLS) -> None:
+        """First half of an EncoderBlock on the resident token stream: x <- x + out_proj(MHA(LN1 x)), maps per `flags`."""
+        check(self.lib.vitb200_stage_attn_block(self._h, layer, batch, flags))
+
+    def stage_mlp_block(self, layer: int, batch: int) -> None:
+        """Second half: x <- x + MLP(LN2 x)."""
+        check(self.lib.vitb200_stage_mlp_block(self._h, layer, batch))
 
     def stage_head(self, batch: int) -> torch.Tensor:
         out = torch.empty(batch, self.cfg.num_classes, dtype=torch.float32)

@@ -52,6 +52,7 @@ class Edge:
         self.input = src
         self.output = tgt
         self.tensor: Optional[torch.Tensor] = None
+        self.taps: List["Edge"] = []   # further consumers of the same producer channel (Graph(fan_out=True) only)
 
 
 class Node:
@@ -82,14 +83,17 @@ class Node:
             if edge is None:
                 edge = self.outputs[ch] = Edge(Port(self, ch, "out"), None)
             edge.tensor = t
+            for tap in edge.taps:
+                tap.tensor = t
 
     def label(self) -> str:
         return self.name + "?" + urlencode(self.params)
 
 
 class Graph:
-    def __init__(self) -> None:
+    def __init__(self, fan_out: bool = False) -> None:
         self.nodes: List[Node] = []
+        self.fan_out = fan_out
 
     def add_node(self, name: str, params: Dict[str, str]) -> Node:
         node = Node(name, params, len(self.nodes))
@@ -98,7 +102,11 @@ class Graph:
 
     def connect(self, a: Node, a_ch: str, b: Node, b_ch: str) -> Edge:
         edge = Edge(Port(a, a_ch, "out"), Port(b, b_ch, "in"))
-        a.outputs[a_ch] = edge
+        first = a.outputs.get(a_ch) if self.fan_out else None
+        if first is not None:
+            first.taps.append(edge)      # extension: a second consumer taps the first consumer's edge
+        else:
+            a.outputs[a_ch] = edge       # reference behaviour: the newest consumer replaces the record
         b.inputs[b_ch] = edge
         return edge
 

@@ -56,8 +56,8 @@ def _decode_block(buf: memoryview, pos: int, index: int):
 
 
 class Request:
-    def __init__(self) -> None:
-        self.graph = Graph()
+    def __init__(self, fan_out: bool = False) -> None:
+        self.graph = Graph(fan_out=fan_out)   # fan_out: see graph.py (opt-in extension, off = reference behaviour)
 
     def decode(self, b: bytes) -> None:
         buf = memoryview(b)

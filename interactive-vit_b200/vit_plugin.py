@@ -10,6 +10,9 @@ Nodes (``<name>`` is the model name, e.g. ``vit_b_16``):
     <name>:embed      ins [o]            outs [o]              [3,S,S] or [B,3,S,S] -> tokens [N,d] / [B,N,d]
     <name>:layer.<i>  ins [o]            outs [o, attn, cls]   tokens -> tokens, head-averaged map [N,N],
                                           (+ heads if params["heads"] == "1")   per-head CLS maps [H,g,g], [H,N,N]
+    <name>:layer.<i>.attn  ins [o]       outs [o, attn, cls]   first half of the block: x + out_proj(MHA(LN1 x)) and its maps
+    <name>:layer.<i>.mlp   ins [o]       outs [o]              second half: x + MLP(LN2 x)   (finer-grained graphs, SURVEY 8f-4;
+                                                               registered, but not part of the default graph file)
     <name>:head       ins [o]            outs [o]              tokens -> logits [classes]
     <name>:rollout    ins [a0..a{L-1}]   outs [o]              head-averaged maps -> rollout map [g,g]
 
@@ -102,14 +105,23 @@ def make_vit_model_class(ModelBase, PinoutCls):
             if sub in ("embed", "head", "rollout", "transform"):
                 return sub
             if sub.startswith("layer."):
-                i = int(sub[len("layer."):])
-                if 0 <= i < self.cfg.num_layers:
-                    return "layer"
+                idx, _, half = sub[len("layer."):].partition(".")
+                if idx.isdigit() and 0 <= int(idx) < self.cfg.num_layers and half in ("", "attn", "mlp"):
+                    return {"": "layer", "attn": "attn_block", "mlp": "mlp_block"}[half]
             raise KeyError(node_name)
+
+        def _layer_index(self, node_name: str) -> int:
+            return int(node_name.removeprefix(self.prefix())[len("layer."):].partition(".")[0])
+
+        def fine_node_names(self) -> List[str]:
+            """Half-block nodes (`layer.<i>.attn`, `layer.<i>.mlp`): registered next to the block-granular ones."""
+            return [self.prefix() + f"layer.{i}.{half}" for i in range(self.cfg.num_layers) for half in ("attn", "mlp")]
 
         def io(self, node_name: str, params: Optional[Dict[str, str]] = None) -> Dict:
             kind = self._kind(node_name)
-            if kind == "layer":
+            if kind == "mlp_block":
+                return {"ins": ["o"], "outs": ["o"]}
+            if kind in ("layer", "attn_block"):
                 outs = ["o", "attn", "cls"]
                 if params is not None and str(params.get("heads", "0")) == "1":
                     outs.append("heads")
@@ -124,6 +136,8 @@ def make_vit_model_class(ModelBase, PinoutCls):
             what = {
                 "embed": f"patch {c.patch_size}x{c.patch_size} embedding + class token + position ({c.tokens} tokens x {c.hidden_dim})",
                 "layer": f"EncoderBlock: {c.num_heads}-head attention + MLP {c.mlp_dim} (outs: o, attn, cls)",
+                "attn_block": f"x + {c.num_heads}-head attention(LayerNorm x) (outs: o, attn, cls)",
+                "mlp_block": f"x + MLP {c.mlp_dim}(LayerNorm x)",
                 "head": f"LayerNorm + Linear -> {c.num_classes} logits",
                 "rollout": f"attention rollout over {c.num_layers} layers -> {c.image_size // c.patch_size}x{c.image_size // c.patch_size}",
                 "transform": f"resize (antialiased bilinear) + centre crop {c.image_size} + ImageNet normalisation",
@@ -178,6 +192,8 @@ def make_vit_model_class(ModelBase, PinoutCls):
             if x is self._tokens_out and batch == self._tokens_batch:
                 return batch  # still resident from the previous node of this request
             self.engine.set_tokens(self._host(x).reshape(batch, c.tokens, c.hidden_dim))
+            # the engine now holds x, not what it handed out last (a fanned-out graph may come back to an older tensor)
+            self._tokens_out, self._tokens_batch = x, batch
             return batch
 
         def _emit_tokens(self, batch: int, batched: bool) -> torch.Tensor:
@@ -215,14 +231,24 @@ def make_vit_model_class(ModelBase, PinoutCls):
                         self.engine.stage_embed(self._host(x).reshape(-1, 3, c.image_size, c.image_size))
                     self._images_out = None
                     out.set("o", self._emit_tokens(nimg, batched))
-                elif kind == "layer":
-                    i = int(node_name.removeprefix(self.prefix())[len("layer."):])
+                elif kind == "mlp_block":
+                    i = self._layer_index(node_name)
+                    x = self._need(pinin, "o")
+                    batched = x.dim() == 3
+                    batch = self._bind_tokens(x)
+                    self.engine.stage_mlp_block(i, batch)
+                    out.set("o", self._emit_tokens(batch, batched))
+                elif kind in ("layer", "attn_block"):
+                    i = self._layer_index(node_name)
                     x = self._need(pinin, "o")
                     batched = x.dim() == 3
                     batch = self._bind_tokens(x)
                     want_heads = params is not None and str(params.get("heads", "0")) == "1"
                     flags = E.EMIT_AVG | E.EMIT_CLS | (E.EMIT_HEADS if want_heads else 0)
-                    self.engine.stage_layer(i, batch, flags)
+                    if kind == "layer":
+                        self.engine.stage_layer(i, batch, flags)
+                    else:
+                        self.engine.stage_attn_block(i, batch, flags)
                     out.set("o", self._emit_tokens(batch, batched))
                     amap = self.engine.get_avg_map(i, batch)
                     cls = self.engine.get_cls_map(i, batch)[:, :, 1:].reshape(batch, c.num_heads, g, g)
@@ -256,7 +282,7 @@ def make_vit_model_class(ModelBase, PinoutCls):
         #      main/context.py:119-129, so the per-node params variant is wired through our own node class)
         def register(self, ctx) -> None:
             super().register(ctx)  # graph json + one ModelNode per name
-            for node_name in self.list_node_names():
+            for node_name in self.list_node_names() + self.fine_node_names():
                 ctx.register(_ParamNode(self, node_name))
 
     class _ParamNode:

@@ -30,8 +30,13 @@ def make_oracle_model_class(ModelBase, PinoutCls):
         def list_node_names(self) -> List[str]:
             return self.node_names
 
+        def fine_node_names(self) -> List[str]:
+            return [self.prefix() + f"layer.{i}.{half}" for i in range(self.cfg.num_layers) for half in ("attn", "mlp")]
+
         def io(self, node_name: str, params=None) -> Dict:
             sub = node_name.removeprefix(self.prefix())
+            if sub.startswith("layer.") and sub.endswith(".mlp"):
+                return {"ins": ["o"], "outs": ["o"]}
             if sub.startswith("layer."):
                 return {"ins": ["o"], "outs": ["o", "attn", "cls"]}
             if sub == "rollout":
@@ -53,12 +58,21 @@ def make_oracle_model_class(ModelBase, PinoutCls):
                     batched = x.dim() == 4
                     t = O.embed(self.model, x if batched else x[None])
                     out.set("o", t if batched else t[0])
-                elif sub.startswith("layer."):
-                    i = int(sub[len("layer."):])
+                elif sub.startswith("layer.") and sub.endswith(".mlp"):
+                    i = int(sub[len("layer."):-len(".mlp")])
                     x = pinin.get("o")
                     assert x is not None
                     batched = x.dim() == 3
-                    t, p = O.encoder_layer(self.model, i, x if batched else x[None])
+                    t = O.encoder_mlp_half(self.model, i, x if batched else x[None])
+                    out.set("o", t if batched else t[0])
+                elif sub.startswith("layer."):
+                    half = sub.endswith(".attn")
+                    i = int(sub[len("layer."):-len(".attn")] if half else sub[len("layer."):])
+                    x = pinin.get("o")
+                    assert x is not None
+                    batched = x.dim() == 3
+                    fn = O.encoder_attn_half if half else O.encoder_layer
+                    t, p = fn(self.model, i, x if batched else x[None])
                     avg = p.mean(dim=1)
                     cls = p[:, :, 0, 1:].reshape(p.shape[0], c.num_heads, g, g).contiguous()
                     out.set("o", t if batched else t[0])

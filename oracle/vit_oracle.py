@@ -162,6 +162,23 @@ def encoder_layer(model: VisionTransformer, i: int, x: torch.Tensor):
 
 
 @torch.no_grad()
+def encoder_attn_half(model: VisionTransformer, i: int, x: torch.Tensor):
+    """First half of EncoderBlock.forward (vision_transformer.py:112-116): x + dropout(MHA(ln_1 x)), weights kept.
+    Returns (tokens [B,N,d], per-head probabilities [B,H,N,N])."""
+    blk = model.encoder.layers[i]
+    h = blk.ln_1(x)
+    a, p = blk.self_attention(h, h, h, need_weights=True, average_attn_weights=False)
+    return blk.dropout(a) + x, p
+
+
+@torch.no_grad()
+def encoder_mlp_half(model: VisionTransformer, i: int, x: torch.Tensor) -> torch.Tensor:
+    """Second half (vision_transformer.py:118-119): x + mlp(ln_2 x)."""
+    blk = model.encoder.layers[i]
+    return x + blk.mlp(blk.ln_2(x))
+
+
+@torch.no_grad()
 def head(model: VisionTransformer, x: torch.Tensor) -> torch.Tensor:
     """Final LayerNorm (vision_transformer.py:157), class token (302), classifier (304).  [B,N,d] -> [B,classes]."""
     return model.heads(model.encoder.ln(x)[:, 0])

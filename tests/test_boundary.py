@@ -76,6 +76,45 @@ def test_fanout_failure_mode_is_preserved(kats):
             b.get_pinin()
 
 
+def test_fan_out_extension_feeds_every_consumer():
+    """with Graph(fan_out=True) one output channel reaches all its consumers (the default
+    keeps the reference's overwrite, test above), the response still lists the channel once, and the visit order
+    is the same worklist."""
+    g = G.Graph(fan_out=True)
+    a, b, c, d = (g.add_node(n, {}) for n in "abcd")
+    g.connect(a, "o", b, "o")
+    g.connect(a, "o", c, "o")
+    g.connect(a, "o", d, "x")
+    assert a.outputs["o"].output.node is b and [t.output.node for t in a.outputs["o"].taps] == [c, d]
+    pin = G.Pinout()
+    t = torch.arange(3.0)
+    pin.set("o", t)
+    a.set_pinout(pin)
+    assert b.get_pinin().get("o") is t and c.get_pinin().get("o") is t and d.get_pinin().get("x") is t
+    assert list(a.get_pinout().pinout) == ["o"]
+    order = [n.name for n in g.order()]
+    assert order[0] == "a" and sorted(order[1:]) == ["b", "c", "d"]
+
+    # through the wire: a "logit lens" request (the head applied to the embedding AND to the last layer) decodes into
+    # a graph whose embed output has two consumers
+    from interactive_vit_b200 import message as M
+
+    nodes = [{"endpoint": "m:embed", "params": {}}, {"endpoint": "m:layer.0", "params": {}},
+             {"endpoint": "m:head", "params": {}}, {"endpoint": "m:head", "params": {}}]
+    edges = [{"tensor": 0, "out_port": {"node": 0, "channel": "o"}},
+             {"in_port": {"node": 0, "channel": "o"}, "out_port": {"node": 1, "channel": "o"}},
+             {"in_port": {"node": 1, "channel": "o"}, "out_port": {"node": 2, "channel": "o"}},
+             {"in_port": {"node": 0, "channel": "o"}, "out_port": {"node": 3, "channel": "o"}}]
+    blob = M.encode_request(nodes, edges, [torch.zeros(3, 8, 8)])
+    req = M.Request(fan_out=True)
+    req.decode(blob)
+    n = req.graph.nodes
+    assert n[0].outputs["o"].output.node is n[1] and n[0].outputs["o"].taps[0].output.node is n[3]
+    ref_like = M.Request()
+    ref_like.decode(blob)
+    assert ref_like.graph.nodes[0].outputs["o"].output.node is ref_like.graph.nodes[3]   # reference: last consumer wins
+
+
 def test_model_wrapper_matches_reference(kats, tmp_path):
     toy = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.ReLU(), torch.nn.Sequential(torch.nn.Linear(4, 2), torch.nn.Tanh()))
     m = C.Model(toy, "toy")
@@ -255,6 +294,12 @@ def test_vit_plugin_catalogue_without_gpu():
         assert plug.io(n) == oracle.io(n)
         assert n in plug.contents(n)
         assert "/" not in n                                  # node names are URL path segments (main/urls.py:12-13)
+    assert plug.fine_node_names() == oracle.fine_node_names() and len(plug.fine_node_names()) == 2 * ocfg.num_layers
+    for n in plug.fine_node_names():                         # half-block nodes: registered, not in the default graph
+        assert plug.io(n) == oracle.io(n) and n in plug.contents(n) and "/" not in n
+    assert plug.io("vit_tiny_test:layer.1.mlp") == {"ins": ["o"], "outs": ["o"]}
+    with pytest.raises(KeyError):
+        plug.io("vit_tiny_test:layer.1.qkv")
     assert plug.io("vit_tiny_test:layer.0", {"heads": "1"})["outs"] == ["o", "attn", "cls", "heads"]
     with pytest.raises(KeyError):
         plug.io("vit_tiny_test:layer.7")
@@ -278,7 +323,8 @@ def test_vit_plugin_catalogue_without_gpu():
         try:
             ctx = C.Context()
             plug.register(ctx)
-            assert sorted(ctx.nodes) == sorted(plug.list_node_names())
+            assert sorted(ctx.nodes) == sorted(plug.list_node_names() + plug.fine_node_names())
+            assert ctx.get_node("vit_tiny_test:layer.1.attn").io({})["outs"] == ["o", "attn", "cls"]
             assert json.load(open(os.path.join(d, "static", "graphs", "vit_tiny_test.json"))) == g
             assert ctx.get_node("vit_tiny_test:layer.1").io({"heads": "1"})["outs"][-1] == "heads"
         finally:

@@ -298,6 +298,72 @@ def test_plugin_through_scheduler_and_wire_codec(E, golden_dir):
     plug.engine.close()
 
 
+def test_half_block_nodes_and_fanned_out_graph(E):
+    """SURVEY.md section 8f-4.  (1) `layer.<i>.attn` + `layer.<i>.mlp` through the C ABI equal `layer.<i>` bit for bit
+    and match the oracle's halves.  (2) A finer-grained request with server-side fan-out (Graph(fan_out=True)): the
+    half-block chain, plus a "logit lens" head tapping the output of every block, through Request.decode ->
+    Context.compute -> Response.encode, against the oracle plugin on the same request."""
+    from interactive_vit_b200 import context as C, graph as G, message as M, vit_plugin as P
+    from oracle import oracle_plugin, vit_oracle as O
+
+    name = "vit_small_test"
+    ocfg = O.ORACLE_CONFIGS[name]
+    module = O.build_vit(ocfg, seed=0, init="stress")
+    x = O.synthetic_images(2, ocfg.image_size)
+    eng = _engine_for(E, ocfg, module, 2)
+    whole = eng.forward_host(x, ALL)
+    eng.stage_embed(x)
+    t_ref = O.embed(module, x)
+    for i in range(ocfg.num_layers):
+        eng.stage_attn_block(i, 2, E.EMIT_AVG | E.EMIT_CLS)
+        a_ref, p_ref = O.encoder_attn_half(module, i, t_ref)
+        assert _rel(eng.get_tokens(2), a_ref) < TOL
+        assert torch.equal(eng.get_avg_map(i, 2), whole["avg_maps"][i])
+        assert torch.equal(eng.get_cls_map(i, 2), whole["cls_maps"][i])
+        eng.stage_mlp_block(i, 2)
+        assert torch.equal(eng.get_tokens(2), whole["hidden"][i])
+        t_ref = O.encoder_mlp_half(module, i, a_ref)
+    assert torch.equal(eng.stage_head(2), whole["logits"])
+
+    L = ocfg.num_layers
+    nodes = [{"endpoint": f"{name}:embed", "params": {}}]
+    for i in range(L):
+        nodes += [{"endpoint": f"{name}:layer.{i}.attn", "params": {}}, {"endpoint": f"{name}:layer.{i}.mlp", "params": {}}]
+    lens0 = len(nodes)
+    nodes += [{"endpoint": f"{name}:head", "params": {}} for _ in range(L)]          # logit lens after every block
+    rollout_idx = len(nodes)
+    nodes.append({"endpoint": f"{name}:rollout", "params": {}})
+    edges = [{"tensor": 0, "out_port": {"node": 0, "channel": "o"}}]
+    for i in range(1, 2 * L + 1):
+        edges.append({"in_port": {"node": i - 1, "channel": "o"}, "out_port": {"node": i, "channel": "o"}})
+    for i in range(L):
+        edges.append({"in_port": {"node": 2 + 2 * i, "channel": "o"}, "out_port": {"node": lens0 + i, "channel": "o"}})
+        edges.append({"in_port": {"node": 1 + 2 * i, "channel": "attn"}, "out_port": {"node": rollout_idx, "channel": f"a{i}"}})
+    blob = M.encode_request(nodes, edges, [x[0]])
+
+    def serve(plug):
+        ctx = C.Context()
+        for n in plug.list_node_names() + plug.fine_node_names():
+            C.ModelNode(plug, n).register(ctx)
+        req = M.Request(fan_out=True)
+        req.decode(blob)
+        ctx.compute(req.graph)
+        return M.decode_response(M.Response(req.graph).encode())
+
+    plug = P.VitB200Model(name, eng.cfg, module, 0, 2, engine=eng)
+    got = serve(plug)
+    want = serve(oracle_plugin.make_oracle_model_class(C.Model, G.Pinout)(name, ocfg, module))
+    assert {k: sorted(v) for k, v in got.items()} == {k: sorted(v) for k, v in want.items()}
+    for node in want:
+        for ch in want[node]:
+            assert got[node][ch].shape == want[node][ch].shape, (node, ch)
+            assert _rel(got[node][ch], want[node][ch]) < TOL, (node, ch, _rel(got[node][ch], want[node][ch]))
+    for i in range(L):   # every lens head saw ITS block's tokens, not the stream's latest
+        assert got[lens0 + i]["o"].argmax() == want[lens0 + i]["o"].argmax()
+    assert torch.equal(got[lens0 + L - 1]["o"], whole["logits"][0])
+    eng.close()
+
+
 def test_bench_size_properties(E):
     """ViT-B/16, batch 256 (BASELINE config 2) — properties that need no oracle at this size: every image's result
     is bit-identical to running that image alone (rows never mix), softmax rows sum to one, rollout rows sum to
