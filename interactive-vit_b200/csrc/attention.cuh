@@ -539,7 +539,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     o_stage(nh - 1);
     ptx::fence_proxy_async_smem();
     o_store(nh - 1);
-    ptx::tma_store_wait<0>();
 
     // head-averaged map rows -> HBM, once per (image, query tile): Pbar holds the SUM over heads.  The tile goes
     // through shared memory (the Q/K/V stages are dead by now) as 32-column slabs of 128 rows x 128 B in the 128-B
@@ -578,10 +577,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
           else ptx::tma_store_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, b);
         }
         ptx::tma_store_commit();
-        ptx::tma_store_wait<0>();
       }
       __syncwarp();
     }
+    // shared memory must outlive the bulk stores' READS only (the writes land on their own; kernel completion makes
+    // them visible): threads without an outstanding bulk group fall through
+    ptx::tma_store_wait_read<0>();
   }
 
   ptx::tc_fence_before();
