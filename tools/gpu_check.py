@@ -259,7 +259,7 @@ def attention_perf():
     from interactive_vit_b200 import engine as E
     B, N, H = 256, 197, 12
     qkv = torch.randn(B * N, 3 * H * 64, device="cuda").bfloat16()
-    for flags in ((True, True, False), (False, False, False)):
+    for flags in ((True, True, False), (True, False, False), (False, True, False), (False, False, False)):
         for _ in range(3):
             E.op_attention(qkv, B, N, H, *flags)
         torch.cuda.synchronize()
