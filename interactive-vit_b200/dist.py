@@ -64,3 +64,97 @@ def gather_results(local: Dict[str, torch.Tensor], total: int, batch_dims: Dict[
 
 
 RESULT_BATCH_DIMS = {"logits": 0, "rollout": 0, "avg_maps": 1, "cls_maps": 1, "heads": 1, "hidden": 1}
+
+
+class PackedGather:
+    """One fixed-size gather per step, overlapped with the next step's forward.
+
+    Every rank packs its results image-major into ONE staging row block ``[cap, F]`` (F = floats per image over all
+    results), a single ``dist.gather`` moves it into rank 0's preallocated ``[world, cap, F]`` buffer, and rank 0 reads
+    the results as views of that buffer — no per-result collectives, no allocation and no concatenation inside the
+    step.  Two staging / receive sets alternate, and on CUDA the collective is issued from a side stream behind an
+    event, so the gather of step i runs under the forward of step i + 1; ``submit`` only makes the compute stream wait
+    for the gather that used the same set two steps earlier.
+
+    spec: ``{name: (per-image shape, batch_dim of the local tensor)}``, e.g. ``{"logits": ((1000,), 0),
+    "cls_maps": ((12, 12, 197), 1)}`` for a local ``[L, b, H, N]`` tensor.  Results come back image-major:
+    ``result(name)`` is ``[total, *per-image shape]`` (for cls_maps: ``[total, L, H, N]``).
+    """
+
+    def __init__(self, spec: Dict[str, Tuple[Tuple[int, ...], int]], total: int, device, group=None,
+                 dtype: torch.dtype = torch.float32):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.total = total
+        self.counts = [shard_range(total, self.world, r)[1] for r in range(self.world)]
+        self.cap = max(self.counts) if self.counts else 0
+        self.spec, self.offsets, off = dict(spec), {}, 0
+        for name in sorted(spec):
+            n = 1
+            for s in spec[name][0]:
+                n *= s
+            self.offsets[name] = (off, n)
+            off += n
+        self.width = off
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.staging = [torch.zeros(self.cap, self.width, dtype=dtype, device=self.device) for _ in range(2)]
+        self.recv = ([torch.empty(self.world, self.cap, self.width, dtype=dtype, device=self.device) for _ in range(2)]
+                     if self.rank == 0 else [None, None])
+        self.work = [None, None]
+        self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.step = 0
+        self.last = -1
+
+    def submit(self, local: Dict[str, torch.Tensor]) -> int:
+        """Pack `local` (on the current stream) and start its gather; returns the set index to pass to `result`."""
+        s = self.step & 1
+        self.step += 1
+        if self.work[s] is not None:
+            self.work[s].wait()          # CUDA: the current stream waits for the collective that last used this set
+            self.work[s] = None
+        stage = self.staging[s]
+        mine = self.counts[self.rank]
+        for name, (off, n) in self.offsets.items():
+            shape, bdim = self.spec[name]
+            x = local[name].movedim(bdim, 0)
+            if x.shape[0] != mine or tuple(x.shape[1:]) != tuple(shape):
+                raise ValueError(f"{name}: rank {self.rank} holds {tuple(local[name].shape)}, expected {mine} images of {shape}")
+            stage[:mine, off:off + n].view((mine,) + tuple(shape)).copy_(x)
+        if self.world == 1:
+            self.last = s
+            return s
+        bufs = list(self.recv[s].unbind(0)) if self.rank == 0 else None
+        if self.cuda:
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
+                self.work[s] = dist.gather(stage, bufs, dst=0, group=self.group, async_op=True)
+        else:
+            dist.gather(stage, bufs, dst=0, group=self.group)
+        self.last = s
+        return s
+
+    def finish(self) -> None:
+        """Make the current stream (CUDA) wait for every gather still in flight."""
+        for s in (0, 1):
+            if self.work[s] is not None:
+                self.work[s].wait()
+                self.work[s] = None
+
+    def result(self, name: str, s: Optional[int] = None) -> Optional[torch.Tensor]:
+        """Rank 0: `[total, *per-image shape]` of set `s` (default: the last submitted), after `finish()` (or after
+        the set's own wait); image order is rank order because shards are contiguous.  Other ranks: None."""
+        if self.rank != 0:
+            return None
+        s = self.last if s is None else s
+        off, n = self.offsets[name]
+        shape = tuple(self.spec[name][0])
+        if self.world == 1:
+            return self.staging[s][: self.total, off:off + n].reshape((self.total,) + shape)
+        rows = self.recv[s][:, :, off:off + n]
+        if all(c == self.cap for c in self.counts):
+            return rows.reshape((self.total,) + shape)
+        return torch.cat([rows[r, : self.counts[r]] for r in range(self.world)], dim=0).reshape((self.total,) + shape)

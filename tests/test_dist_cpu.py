@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from interactive_vit_b200.dist import RESULT_BATCH_DIMS, gather_results, shard_range
+from interactive_vit_b200.dist import RESULT_BATCH_DIMS, PackedGather, gather_results, shard_range
 
 
 def test_shard_range_partitions_every_image_exactly_once():
@@ -46,7 +46,24 @@ def _worker(rank, world, port, total, q):
             "cls_maps": idx[None, :, None, None].expand(L, count, H, N).clone(),
         }
         out = gather_results(local, total, RESULT_BATCH_DIMS)
+        # the pipelined packed gather (what bench.py uses): two steps in flight, image-major results, same values
+        pg = PackedGather({"logits": ((C,), 0), "cls_maps": ((L, H, N), 1), "rollout": ((N - 1,), 0)}, total, "cpu")
+        packed_ok = True
+        for step in range(3):
+            shifted = {k: v + step for k, v in local.items()}
+            s_idx = pg.submit(shifted)
+            pg.finish()
+            if rank == 0:
+                want = torch.arange(total, dtype=torch.float32) + step
+                packed_ok = packed_ok and pg.result("logits", s_idx).shape == (total, C)
+                packed_ok = packed_ok and torch.equal(pg.result("logits")[:, 0], want)
+                packed_ok = packed_ok and pg.result("cls_maps").shape == (total, L, H, N)
+                packed_ok = packed_ok and torch.equal(pg.result("cls_maps")[:, 1, 2, 4], want)
+                packed_ok = packed_ok and torch.equal(pg.result("rollout")[:, 0], want)
+            else:
+                assert pg.result("logits") is None
         if rank == 0:
+            assert packed_ok
             ok = out["logits"].shape == (total, C) and torch.equal(out["logits"][:, 0], torch.arange(total, dtype=torch.float32))
             ok = ok and out["avg_maps"].shape == (L, total, N, N)
             ok = ok and torch.equal(out["avg_maps"][1, :, 0, 0], torch.arange(total, dtype=torch.float32) + 1000)
