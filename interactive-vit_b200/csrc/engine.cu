@@ -263,15 +263,6 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
   VT_TRY(make_tmap_bf16(&maps[1], w, N, K, K, mode == 4 ? 64 : BN / pair, gemm_cfg::BK));
   maps[2] = maps[0], maps[3] = maps[1];
   GemmShape sh{M, N, K};
-  {
-    static int pf = -1;
-    if (pf < 0) {
-      const char* v = getenv("VITB200_GEMM_A_PREFETCH");
-      pf = v ? atoi(v) : 0;
-    }
-    // only worth it when A streams from HBM: more A bytes than L2 keeps next to everything else
-    if ((size_t)M * K * 2 > (size_t)96 << 20) sh.a_prefetch = pf;
-  }
   if (a_lo != nullptr) {
     VT_TRY(make_tmap_bf16(&maps[2], a_lo, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
     VT_TRY(make_tmap_bf16(&maps[3], w_lo, N, K, K, mode == 4 ? 64 : BN / pair, gemm_cfg::BK));

@@ -37,7 +37,6 @@
 //                   MEMBAR + ERRBAR and waited for every global store in flight (65% -> 82.7% tensor-pipe activity).
 #pragma once
 #include <cuda.h>
-#include <type_traits>
 #include "ptx.cuh"
 
 namespace vitb200 {
@@ -85,10 +84,6 @@ struct GemmShape {
   // matrices), and the product as A_hi W_hi + A_lo W_hi + A_hi W_lo -- the main loop runs three K passes over the
   // (hi, hi), (lo, hi), (hi, lo) operand pairs into the same fp32 accumulator (relative error ~2^-17 per product).
   int split = 1;
-  // > 0: the TMA producer prefetches the A boxes this many k-blocks ahead into L2 (across tile boundaries).  For A
-  // operands that stream from HBM (fc2: 310 MB) the MMA warp otherwise spends ~a fifth of its time waiting for the
-  // smem ring, whose 5-6 stages cover L2 latency but not HBM latency under load.
-  int a_prefetch = 0;
 };
 
 namespace gemm_cfg {
@@ -276,22 +271,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const CUtensorMap* ta = pass == 1 ? &tmap_a_lo : &tmap_a;
       const CUtensorMap* tw = pass == 2 ? &tmap_w_lo : &tmap_w;
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (kPairs == 1 && shape.a_prefetch > 0 && shape.split == 1) {
-          // k-block kb + distance of this tile, or the first blocks of this CTA's next tile
-          int pk = kb + shape.a_prefetch, prow = a_row;
-          bool ok = true;
-          if (pk >= num_kb) {
-            pk -= num_kb;
-            const int nu = unit + num_slots;
-            ok = nu < num_units && pk < num_kb;
-            if (ok) {
-              int m2, n2;
-              work.decode(nu, kPairs, pair_id, m2, n2);
-              prow = m2 * kTileM + static_cast<int>(cta_rank) * BM;
-            }
-          }
-          if (ok && ptx::elect_one()) ptx::tma_prefetch_2d(&tmap_a, pk * BK, prow);
-        }
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::kStageBytes;
         uint8_t* sb = sa + C::kStageBytesA;
@@ -447,7 +426,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       const int row_base = m_blk * kTileM + static_cast<int>(cta_rank) * BM + quarter * 32;
-      const bool tile_full = m_blk * kTileM + static_cast<int>(cta_rank) * BM + BM <= shape.M && (n_blk + 1) * BN <= shape.N;
       // folded LayerNorm: scale a = rstd and offset c = -rstd * mean of this thread's 8 rows (trow + 4 i), staged by warp 3
       float ln_a[8], ln_c[8];
       if (kLnIn) {
@@ -498,17 +476,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           continue;
         }
-        // Two instantiations of the chunk body: tiles that lie completely inside the output (every tile of the bench
-        // shapes) skip the per-row / per-column bounds predicates, which otherwise cost a branch pair per 4 outputs.
-        auto chunk_body = [&](auto full_tag) {
-        constexpr bool kFull = decltype(full_tag)::value;
         // registers (thread = row, 32 columns) -> slab
         float* srow = slab + lane * kSlabStride;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         __syncwarp();
         const int col = col0 + 4 * tcol;
-        const bool col_ok = kFull || col < shape.N;
+        const bool col_ok = col < shape.N;
         const float4 bias4 = bias_c[c], csum4 = csum_c[c];
         // transposed pass: 8 rows (trow + 4 i) x 4 columns per thread.  With a residual all 8 rows form one batch so
         // that 8 independent 16-byte loads per thread are in flight (the out_proj / fc2 epilogues are bound by
@@ -527,7 +501,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int i = 0; i < kRowBatch; ++i) {
             const int row = row_base + trow + 4 * (i0 + i);
             v[i] = *reinterpret_cast<const float4*>(sl + 4 * (i0 + i) * kSlabStride);
-            ok[i] = kFull || (row < shape.M && col_ok);
+            ok[i] = row < shape.M && col_ok;
             long out_row = row, resid_row = row;
             if (kRemap) {
               const int g = row / ep.group_rows;
@@ -623,7 +597,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float f2 = (b0 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? c2[0] : c2[1], 1);
             // this lane now owns row index tcol of the batch (bit 2 chose rows 4..7, bit 1 rows +2, bit 0 rows +1)
             const int row = row_base + trow + 4 * tcol;
-            if (kFull || row < shape.M) {
+            if (row < shape.M) {
               long out_row = row;
               if (kRemap) {
                 const int g = row / ep.group_rows;
@@ -633,9 +607,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
         }
-        };  // chunk_body
-        if (tile_full) chunk_body(std::true_type{});
-        else chunk_body(std::false_type{});
         __syncwarp();  // slab is rewritten by the next chunk
       }
     }

@@ -286,13 +286,6 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
-// L2 prefetch of one box of a tiled tensor map (no smem, no barrier): warms L2 ahead of the smem ring for operands that
-// stream from HBM.
-__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
 // Same, multicast: the box lands at the same smem offset in every CTA of `cta_mask` (cluster ranks) and each
 // destination's bytes are counted on the mbarrier at this offset in the leader of the DESTINATION's pair.
 __device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
