@@ -169,6 +169,38 @@ def make_vit_model_class(ModelBase, PinoutCls):
             edges.append({"in_port": {"node": head_idx, "channel": "o"}, "out_port": {"node": cat_idx, "channel": "o"}})
             return {"nodes": nodes, "edges": edges}
 
+        def generate_fine_graph_json(self) -> Dict:
+            """The half-block variant of the graph file: transform -> embed -> layer.0.attn ->
+            layer.0.mlp -> ... -> head -> category, layer.i.attn `attn` -> rollout.  Same file format; every output
+            channel still has one server-side consumer, so it loads in the unpatched reference too."""
+            L = self.cfg.num_layers
+            names = ([self.prefix() + "transform", self.prefix() + "embed"] + self.fine_node_names()
+                     + [self.prefix() + "head", self.prefix() + "rollout"])
+            w = int(math.sqrt(len(names) + 1))
+            nodes = [{"instance": {"kind": "net_node", "endpoint": n, "params": {}},
+                      "pos": {"x": (i % w) * 200, "y": int(i / w) * 200}} for i, n in enumerate(names)]
+            head_idx, rollout_idx = 2 + 2 * L, 3 + 2 * L
+            edges = [{"in_port": {"node": i - 1, "channel": "o"}, "out_port": {"node": i, "channel": "o"}}
+                     for i in range(1, head_idx + 1)]
+            edges += [{"in_port": {"node": 2 + 2 * i, "channel": "attn"}, "out_port": {"node": rollout_idx, "channel": f"a{i}"}}
+                      for i in range(L)]
+            cat_idx = len(nodes)
+            nodes.append({"instance": {"kind": "category", "cats": imagenet_categories(self.cfg.num_classes)},
+                          "pos": {"x": (cat_idx % w) * 200, "y": int(cat_idx / w) * 200}})
+            edges.append({"in_port": {"node": head_idx, "channel": "o"}, "out_port": {"node": cat_idx, "channel": "o"}})
+            return {"nodes": nodes, "edges": edges}
+
+        def _graphs_dir(self) -> str:
+            """static/graphs under the host's base directory: Django's settings.BASE_DIR when the class is bound to the
+            reference's main.context.Model (main/context.py:99), this package's base dir otherwise."""
+            if ModelBase.__module__.startswith("main."):
+                from django.conf import settings
+
+                return os.path.join(str(settings.BASE_DIR), "static/graphs")
+            from .context import get_base_dir
+
+            return os.path.join(get_base_dir(), "static/graphs")
+
         # ---- compute -----------------------------------------------------------------------------
         @staticmethod
         def _need(pinin, ch: str) -> torch.Tensor:
@@ -284,6 +316,17 @@ def make_vit_model_class(ModelBase, PinoutCls):
             super().register(ctx)  # graph json + one ModelNode per name
             for node_name in self.list_node_names() + self.fine_node_names():
                 ctx.register(_ParamNode(self, node_name))
+            try:  # the half-block graph next to the default one; same policy as the reference: log, keep going
+                path = os.path.join(self._graphs_dir(), self.name + "_fine.json")
+                if not os.path.exists(path):
+                    import json
+
+                    with open(path, "w") as f:
+                        f.write(json.dumps(self.generate_fine_graph_json()))
+            except Exception as e:
+                import logging
+
+                logging.getLogger(__name__).error("could not generate the fine-grained graph: %s", e)
 
     class _ParamNode:
         """Same surface as ModelNode (get_name / compute / contents / io / register) but passes ``params`` on."""

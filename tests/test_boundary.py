@@ -327,5 +327,13 @@ def test_vit_plugin_catalogue_without_gpu():
             assert ctx.get_node("vit_tiny_test:layer.1.attn").io({})["outs"] == ["o", "attn", "cls"]
             assert json.load(open(os.path.join(d, "static", "graphs", "vit_tiny_test.json"))) == g
             assert ctx.get_node("vit_tiny_test:layer.1").io({"heads": "1"})["outs"][-1] == "heads"
+            # the half-block graph file: a chain with one consumer per channel, every endpoint registered
+            fine = json.load(open(os.path.join(d, "static", "graphs", "vit_tiny_test_fine.json")))
+            assert fine == plug.generate_fine_graph_json()
+            ends = [n["instance"].get("endpoint") for n in fine["nodes"][:-1]]
+            assert ends[:4] == ["vit_tiny_test:transform", "vit_tiny_test:embed", "vit_tiny_test:layer.0.attn", "vit_tiny_test:layer.0.mlp"]
+            assert all(e in ctx.nodes for e in ends)
+            fo = [(e["in_port"]["node"], e["in_port"]["channel"]) for e in fine["edges"]]
+            assert len(fo) == len(set(fo)) and (2 + 2 * L, "o") in fo
         finally:
             C.set_base_dir(None)
