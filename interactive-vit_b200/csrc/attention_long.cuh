@@ -53,6 +53,10 @@ constexpr int kSmemCtx = 6 * kTileBytes + 2 * 2 * BM * 4 + 256;
 // fp32x3 mode (head dim 64 only): every 32 KB operand slot holds [hi box | lo box]; one more 32 KB tile for P_lo
 constexpr int kSmemCtxSplit = 7 * kTileBytes + 2 * 2 * BM * 4 + 256;
 constexpr int kSmemMaps = 4 * kTileBytes + 256;
+// compact context kernel (head dim 64, bf16 mode): one 16 KB box per operand, ONE V stage, one S buffer -> 96 KB of
+// smem and 192 TMEM columns, so that TWO CTAs share an SM and one CTA's exponential pass runs under the other's
+// loads, maxima and epilogue (the per-CTA chain is serial: ~22k cycles of which the SM's pipes are busy a third)
+constexpr int kSmemCtxCompact = 4 * kBoxBytes + 2 * kBoxBytes + 2 * 2 * BM * 4 + 256;   // Q + 2 K + V, P (32 KB)
 }  // namespace attn_long_cfg
 
 __device__ __forceinline__ uint32_t pack_bf16x2_f(float a, float b) {
@@ -94,20 +98,25 @@ __device__ __forceinline__ void issue_qk_long_split(uint32_t tmem_s, uint32_t sq
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool kSplit>
-__global__ void __launch_bounds__(attn_long_cfg::kThreads, 1)
+template <bool kSplit, bool kCompact = false>
+__global__ void __launch_bounds__(attn_long_cfg::kThreads, kCompact ? 2 : 1)
 attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 64 x 128 over qkv viewed as [B][N][3d]
                           const __grid_constant__ CUtensorMap tmap_qkv_lo,  // kSplit: the low halves, same geometry
                           AttnLongParams p) {
   using namespace attn_long_cfg;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  static_assert(!(kSplit && kCompact), "the compact layout is for plain bf16 operands");
+  constexpr int kOp = kCompact ? kBoxBytes : kTileBytes;   // bytes of one operand tile slot
+  constexpr int kVStages = kCompact ? 1 : 2;
+  constexpr int kSBufs = kCompact ? 1 : 2;                 // S buffers in TMEM
+  constexpr uint32_t kTmemOc = kCompact ? 128 : kTmemO;    // O columns behind the S buffer(s)
   uint8_t* s_q = smem;
-  uint8_t* s_k = smem + kTileBytes;          // 2 stages
-  uint8_t* s_v = smem + 3 * kTileBytes;      // 2 stages
-  uint8_t* s_p = smem + 5 * kTileBytes;      // 2 K-blocks of 64 keys: [128 rows x 128 B] each
-  uint8_t* s_p_lo = smem + 6 * kTileBytes;   // kSplit only
-  float* red = reinterpret_cast<float*>(smem + (kSplit ? 7 : 6) * kTileBytes);  // [2 kinds][2 halves][128 rows]
+  uint8_t* s_k = smem + kOp;                       // 2 stages
+  uint8_t* s_v = smem + 3 * kOp;                   // kVStages stages
+  uint8_t* s_p = smem + (3 + kVStages) * kOp;      // 2 K-blocks of 64 keys: [128 rows x 128 B] each
+  uint8_t* s_p_lo = s_p + kTileBytes;              // kSplit only
+  float* red = reinterpret_cast<float*>(s_p + (kSplit ? 2 : 1) * kTileBytes);  // [2 kinds][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * 2 * BM);
   uint64_t* q_full = bars;          // Q landed
   uint64_t* k_full = bars + 1;      // [2]
@@ -127,7 +136,7 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
   const int b = blockIdx.x / (p.H * p.q_tiles);
   const int nb = p.k_blocks;
   const int D = p.D;
-  const bool two_box = !kSplit && D > 64;
+  const bool two_box = !kSplit && !kCompact && D > 64;
   const uint32_t tile_tx = (kSplit || two_box) ? kTileBytes : kBoxBytes;
 
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_qkv);
@@ -141,7 +150,7 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
     ptx::mbar_init(p_full, 8), ptx::mbar_init(p_free, 1), ptx::mbar_init(o_full, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
+  if (warp == 2) ptx::tmem_alloc<kCompact ? 256 : 512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -163,12 +172,13 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
       for (int blk = 0; blk < nb; ++blk, ++it) {
         const int st = it & 1;
         ptx::mbar_wait(&k_empty[st], ((it >> 1) & 1) ^ 1);
-        if (ptx::elect_one()) load_tile(s_k + st * kTileBytes, &k_full[st], p.d + h * D, blk * BK);
+        if (ptx::elect_one()) load_tile(s_k + st * kOp, &k_full[st], p.d + h * D, blk * BK);
         __syncwarp();
         if (pass == 1) {
-          const int vs = blk & 1;
-          ptx::mbar_wait(&v_empty[vs], ((blk >> 1) & 1) ^ 1);
-          if (ptx::elect_one()) load_tile(s_v + vs * kTileBytes, &v_full[vs], 2 * p.d + h * D, blk * BK);
+          const int vs = kVStages == 2 ? (blk & 1) : 0;
+          const uint32_t vph = kVStages == 2 ? ((blk >> 1) & 1) : (blk & 1);
+          ptx::mbar_wait(&v_empty[vs], vph ^ 1);
+          if (ptx::elect_one()) load_tile(s_v + vs * kOp, &v_full[vs], 2 * p.d + h * D, blk * BK);
           __syncwarp();
         }
       }
@@ -178,15 +188,20 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
     const uint32_t sq = ptx::smem_u32(s_q);
     ptx::mbar_wait(q_full, 0);
     auto issue_qk = [&](int it) {  // it: running S / K use index over both passes
-      const int st = it & 1;
+      const int st = it & 1;                        // K stage
+      const int sb = kSBufs == 2 ? st : 0;          // S buffer
       ptx::mbar_wait(&k_full[st], (it >> 1) & 1);
-      if (it >= 2) ptx::mbar_wait(&s_free[st], ((it - 2) >> 1) & 1);
+      if (kSBufs == 2) {
+        if (it >= 2) ptx::mbar_wait(&s_free[sb], ((it - 2) >> 1) & 1);
+      } else {
+        if (it >= 1) ptx::mbar_wait(&s_free[0], (it - 1) & 1);   // the single buffer: the previous block has been read
+      }
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        if (kSplit) issue_qk_long_split(tmem_base + kTmemS + st * BK, sq, ptx::smem_u32(s_k + st * kTileBytes));
-        else issue_qk_long(tmem_base + kTmemS + st * BK, sq, ptx::smem_u32(s_k + st * kTileBytes), D);
+        if (kSplit) issue_qk_long_split(tmem_base + kTmemS + sb * BK, sq, ptx::smem_u32(s_k + st * kOp));
+        else issue_qk_long(tmem_base + kTmemS + sb * BK, sq, ptx::smem_u32(s_k + st * kOp), D);
         ptx::umma_commit(&k_empty[st]);
-        ptx::umma_commit(&s_full[st]);
+        ptx::umma_commit(&s_full[sb]);
       }
       __syncwarp();
     };
@@ -198,12 +213,12 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
     const uint32_t idesc_pv1 = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(two_box ? D - 64 : 16), 0, 1);
     for (int blk = 0; blk < nb; ++blk) {
       if (blk + 1 < nb) issue_qk(nb + blk + 1);
-      const int vs = blk & 1;
-      ptx::mbar_wait(&v_full[vs], (blk >> 1) & 1);
+      const int vs = kVStages == 2 ? (blk & 1) : 0;
+      ptx::mbar_wait(&v_full[vs], kVStages == 2 ? ((blk >> 1) & 1) : (blk & 1));
       ptx::mbar_wait(p_full, blk & 1);
       ptx::tc_fence_after();
       const uint64_t dp0 = ptx::make_smem_desc_sw128(ptx::smem_u32(s_p), 16, 1024);
-      const uint64_t dv0 = ptx::make_smem_desc_sw128(ptx::smem_u32(s_v + vs * kTileBytes), 1024, 1024);
+      const uint64_t dv0 = ptx::make_smem_desc_sw128(ptx::smem_u32(s_v + vs * kOp), 1024, 1024);
       if (ptx::elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < BK / 16; ++ks) {
@@ -211,13 +226,13 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
           const uint64_t dp = dp0 + static_cast<uint64_t>((ks >> 2) * (kBoxBytes >> 4) + 2 * (ks & 3));
           const uint64_t dv = dv0 + static_cast<uint64_t>(ks * (2048 >> 4));
           const uint32_t acc = (blk | ks) != 0 ? 1u : 0u;
-          ptx::umma_bf16_ss(tmem_base + kTmemO, dp, dv, idesc_pv0, acc);
+          ptx::umma_bf16_ss(tmem_base + kTmemOc, dp, dv, idesc_pv0, acc);
           if (kSplit) {
             // + P_lo V_hi + P_hi V_lo (the P_lo tile sits one 32 KB slot after P_hi, V_lo one box after V_hi)
-            ptx::umma_bf16_ss(tmem_base + kTmemO, dp + (kTileBytes >> 4), dv, idesc_pv0, 1u);
-            ptx::umma_bf16_ss(tmem_base + kTmemO, dp, dv + (kBoxBytes >> 4), idesc_pv0, 1u);
+            ptx::umma_bf16_ss(tmem_base + kTmemOc, dp + (kTileBytes >> 4), dv, idesc_pv0, 1u);
+            ptx::umma_bf16_ss(tmem_base + kTmemOc, dp, dv + (kBoxBytes >> 4), idesc_pv0, 1u);
           } else if (two_box) {
-            ptx::umma_bf16_ss(tmem_base + kTmemO + 64, dp, dv + (kBoxBytes >> 4), idesc_pv1, acc);
+            ptx::umma_bf16_ss(tmem_base + kTmemOc + 64, dp, dv + (kBoxBytes >> 4), idesc_pv1, acc);
           }
         }
         ptx::umma_commit(&v_empty[vs]);
@@ -241,8 +256,8 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
 
     uint32_t s[4][16];
     auto load_s = [&](int it) {
-      const int st = it & 1;
-      ptx::mbar_wait(&s_full[st], (it >> 1) & 1);
+      const int st = kSBufs == 2 ? (it & 1) : 0;
+      ptx::mbar_wait(&s_full[st], kSBufs == 2 ? ((it >> 1) & 1) : (it & 1));
       ptx::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 4; ++c) ptx::tmem_ld_x16(lane_base + kTmemS + st * BK + half * 64 + c * 16, s[c]);
@@ -328,7 +343,7 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
     __nv_bfloat16* op = p.ctx + (static_cast<size_t>(b) * p.N + qrow) * p.d + h * D + half * cols;
     for (int c0 = 0; c0 < cols; c0 += 8) {
       uint32_t o[8];
-      ptx::tmem_ld_x8(lane_base + kTmemO + half * cols + c0, o);
+      ptx::tmem_ld_x8(lane_base + kTmemOc + half * cols + c0, o);
       ptx::tmem_ld_wait();
       if (row_ok) {
         uint4 v;
@@ -354,7 +369,7 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<512>(tmem_base);
+    ptx::tmem_dealloc<kCompact ? 256 : 512>(tmem_base);
   }
 }
 

@@ -317,6 +317,7 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
   if (!configured) {
     CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtx));
     CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtxSplit));
+    CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtxCompact));
     CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
     CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
     CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
@@ -328,7 +329,14 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
   p.q_tiles = (N + BM - 1) / BM, p.k_blocks = (N + BK - 1) / BK;
   p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
   p.ctx = ctx, p.ctx_lo = ctx_lo, p.stats = stats, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
+  // head dim 64 in bf16 mode: the compact instantiation, two CTAs per SM (VITB200_ATTN_LONG_COMPACT=0 keeps one)
+  static int compact_mode = -1;
+  if (compact_mode < 0) {
+    const char* v = getenv("VITB200_ATTN_LONG_COMPACT");
+    compact_mode = (v && v[0] == '0') ? 0 : 1;
+  }
   if (split) attention_long_ctx_kernel<true><<<B * p.q_tiles * H, kThreads, kSmemCtxSplit, st>>>(tqkv, tqkv_lo, p);
+  else if (D == 64 && compact_mode) attention_long_ctx_kernel<false, true><<<B * p.q_tiles * H, kThreads, kSmemCtxCompact, st>>>(tqkv, tqkv_lo, p);
   else attention_long_ctx_kernel<false><<<B * p.q_tiles * H, kThreads, kSmemCtx, st>>>(tqkv, tqkv_lo, p);
   CU_TRY(cudaGetLastError());
   if (avg || cls || heads) {
