@@ -56,6 +56,9 @@ constexpr int kSmemMaps = 4 * kTileBytes + 256;
 // compact context kernel (head dim 64, bf16 mode): one 16 KB box per operand, ONE V stage, one S buffer -> 96 KB of
 // smem and 192 TMEM columns, so that TWO CTAs share an SM and one CTA's exponential pass runs under the other's
 // loads, maxima and epilogue (the per-CTA chain is serial: ~22k cycles of which the SM's pipes are busy a third)
+// compact map kernel (head dim 64, bf16 mode): 64-key blocks -> 32 accumulators per thread, 2 x (16 + 8) KB of smem and
+// 128 TMEM columns: two CTAs per SM here too
+constexpr int kSmemMapsCompact = 2 * kBoxBytes + 2 * (kBoxBytes / 2) + 256;
 constexpr int kSmemCtxCompact = 4 * kBoxBytes + 2 * kBoxBytes + 2 * 2 * BM * 4 + 256;   // Q + 2 K + V, P (32 KB)
 }  // namespace attn_long_cfg
 
@@ -65,9 +68,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2_f(float a, float b) {
 }
 
 // S[128 x 128] (+)= Q[128 x D] K[128 x D]^T from two-box operand tiles: K = 64 from box 0, D - 64 from box 1.
-__device__ __forceinline__ void issue_qk_long(uint32_t tmem_s, uint32_t sq, uint32_t sk, int D) {
+__device__ __forceinline__ void issue_qk_long(uint32_t tmem_s, uint32_t sq, uint32_t sk, int D, int keys = attn_long_cfg::BK) {
   using namespace attn_long_cfg;
-  const uint32_t idesc = ptx::make_idesc_bf16(BM, BK, 0, 0);
+  const uint32_t idesc = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(keys), 0, 0);
   const uint64_t dq = ptx::make_smem_desc_sw128(sq, 16, 1024);
   const uint64_t dk = ptx::make_smem_desc_sw128(sk, 16, 1024);
   const int ksteps = D >> 4;
@@ -374,16 +377,24 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool kHeads, bool kSplit>
-__global__ void __launch_bounds__(attn_long_cfg::kThreads, 1)
+// kCompact (head dim 64, plain bf16): key blocks of 64 (p.k_blocks counts THOSE), K tiles through `tmap_qkv_lo`, which
+// the host then builds as a 64-row box map of the same tensor.
+template <bool kHeads, bool kSplit, bool kCompact = false>
+__global__ void __launch_bounds__(attn_long_cfg::kThreads, kCompact ? 2 : 1)
 attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_qkv_lo,
                            AttnLongParams p) {
   using namespace attn_long_cfg;
+  static_assert(!(kSplit && kCompact), "the compact layout is for plain bf16 operands");
+  constexpr int kKeys = kCompact ? 64 : BK;                    // keys per block
+  constexpr int kQb = kCompact ? kBoxBytes : kTileBytes;       // bytes of a Q stage
+  constexpr int kKb = kCompact ? kBoxBytes / 2 : kTileBytes;   // bytes of a K stage
+  constexpr int kPer = kKeys / 2;                              // keys per thread (two threads per row)
+  constexpr int kC = kPer / 16;                                // 16-column TMEM loads per thread
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* s_q = smem;                     // 2 stages over heads
-  uint8_t* s_k = smem + 2 * kTileBytes;    // 2 stages over heads
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * kTileBytes);
+  uint8_t* s_k = smem + 2 * kQb;           // 2 stages over heads
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQb + 2 * kKb);
   uint64_t* full = bars;         // [2] Q_h and K_h landed
   uint64_t* empty = bars + 2;    // [2]
   uint64_t* s_full = bars + 4;   // [2]
@@ -395,8 +406,8 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
   const int qt = (blockIdx.x / p.k_blocks) % p.q_tiles;
   const int b = blockIdx.x / (p.k_blocks * p.q_tiles);
   const int D = p.D;
-  const bool two_box = !kSplit && D > 64;
-  const uint32_t stage_tx = 2 * ((kSplit || two_box) ? kTileBytes : kBoxBytes);
+  const bool two_box = !kSplit && !kCompact && D > 64;
+  const uint32_t stage_tx = kCompact ? (kQb + kKb) : 2 * ((kSplit || two_box) ? kTileBytes : kBoxBytes);
 
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_qkv);
   if (warp == 1 && lane == 0) {
@@ -406,7 +417,7 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 2) ptx::tmem_alloc<256>(tmem_slot);
+  if (warp == 2) ptx::tmem_alloc<kCompact ? 128 : 256>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -417,11 +428,12 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       const int st = h & 1;
       ptx::mbar_wait(&empty[st], ((h >> 1) & 1) ^ 1);
       if (ptx::elect_one()) {
-        uint8_t* q = s_q + st * kTileBytes;
-        uint8_t* k = s_k + st * kTileBytes;
+        uint8_t* q = s_q + st * kQb;
+        uint8_t* k = s_k + st * kKb;
         ptx::mbar_arrive_expect_tx(&full[st], stage_tx);
         ptx::tma_load_3d(q, &tmap_qkv, &full[st], h * D, qt * BM, b);
-        ptx::tma_load_3d(k, &tmap_qkv, &full[st], p.d + h * D, kb * BK, b);
+        if (kCompact) ptx::tma_load_3d(k, &tmap_qkv_lo, &full[st], p.d + h * D, kb * kKeys, b);   // 64-row box map
+        else ptx::tma_load_3d(k, &tmap_qkv, &full[st], p.d + h * D, kb * BK, b);
         if (kSplit) {
           ptx::tma_load_3d(q + kBoxBytes, &tmap_qkv_lo, &full[st], h * D, qt * BM, b);
           ptx::tma_load_3d(k + kBoxBytes, &tmap_qkv_lo, &full[st], p.d + h * D, kb * BK, b);
@@ -440,7 +452,7 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         if (kSplit) issue_qk_long_split(tmem_base + st * BK, ptx::smem_u32(s_q + st * kTileBytes), ptx::smem_u32(s_k + st * kTileBytes));
-        else issue_qk_long(tmem_base + st * BK, ptx::smem_u32(s_q + st * kTileBytes), ptx::smem_u32(s_k + st * kTileBytes), D);
+        else issue_qk_long(tmem_base + st * kKeys, ptx::smem_u32(s_q + st * kQb), ptx::smem_u32(s_k + st * kKb), D, kKeys);
         ptx::umma_commit(&empty[st]);
         ptx::umma_commit(&s_full[st]);
       }
@@ -452,22 +464,27 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
     const int qrow = qt * BM + r;
     const bool row_ok = qrow < p.N;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int key0 = kb * BK + half * 64;
+    const int key0 = kb * kKeys + half * kPer;
     const bool want_avg = p.avg_map != nullptr;
-    float acc[4][16];
+    const bool tail = key0 + kPer > p.N;   // this thread's keys include padding (warp-uniform)
+    float acc[kC][16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < kC; ++c)
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[c][j] = 0.f;
+    // row statistics of the next head are fetched one head ahead (a dependent ~1 us global load per head otherwise
+    // sits in front of every exponential pass)
+    float2 ms_next = make_float2(0.f, 0.f);
+    if (row_ok) ms_next = p.stats[(static_cast<size_t>(b) * p.H) * p.N + qrow];
     for (int h = 0; h < p.H; ++h) {
       const int st = h & 1;
-      float2 ms = make_float2(0.f, 0.f);
-      if (row_ok) ms = p.stats[(static_cast<size_t>(b) * p.H + h) * p.N + qrow];
+      const float2 ms = ms_next;
+      if (row_ok && h + 1 < p.H) ms_next = p.stats[(static_cast<size_t>(b) * p.H + h + 1) * p.N + qrow];
       ptx::mbar_wait(&s_full[st], (h >> 1) & 1);
       ptx::tc_fence_after();
-      uint32_t s[4][16];
+      uint32_t s[kC][16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) ptx::tmem_ld_x16(lane_base + st * BK + half * 64 + c * 16, s[c]);
+      for (int c = 0; c < kC; ++c) ptx::tmem_ld_x16(lane_base + st * kKeys + half * kPer + c * 16, s[c]);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
@@ -476,8 +493,19 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       if (kHeads && p.head_map != nullptr && row_ok)
         hp = p.head_map + ((static_cast<size_t>(b) * p.H + h) * p.N + qrow) * p.ldmap + key0;
       float* cp = (p.cls_map != nullptr && qrow == 0) ? p.cls_map + (static_cast<size_t>(b) * p.H + h) * p.N : nullptr;
+      // Common case -- every key of the block is real, no per-head output from this thread: three instructions per
+      // probability (scale-and-shift, exp2, accumulate).  The general path below costs ~15 (bounds predicates, the
+      // separate product for the per-head outputs), which made this kernel issue-bound.
+      if (!tail && hp == nullptr && cp == nullptr) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kC; ++c)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            acc[c][j] = fmaf(ptx::ex2_approx(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -ms.x)), ms.y, acc[c][j]);
+        continue;
+      }
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
         float pr[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -502,7 +530,7 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
       const float inv_h = 1.0f / static_cast<float>(p.H);
       float* ap = p.avg_map + (static_cast<size_t>(b) * p.N + qrow) * p.ldmap + key0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < kC; ++c)
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
           if (key0 + c * 16 + j < p.ldmap)
@@ -515,7 +543,7 @@ attention_long_maps_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const _
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<256>(tmem_base);
+    ptx::tmem_dealloc<kCompact ? 128 : 256>(tmem_base);
   }
 }
 

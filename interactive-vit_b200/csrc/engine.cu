@@ -318,6 +318,8 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
     CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtx));
     CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtxSplit));
     CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtxCompact));
+    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMapsCompact));
+    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMapsCompact));
     CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
     CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
     CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
@@ -344,6 +346,15 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
     if (split) {
       if (heads) attention_long_maps_kernel<true, true><<<grid, kThreads, kSmemMaps, st>>>(tqkv, tqkv_lo, p);
       else attention_long_maps_kernel<false, true><<<grid, kThreads, kSmemMaps, st>>>(tqkv, tqkv_lo, p);
+    } else if (D == 64 && compact_mode) {
+      // 64-key blocks, two CTAs per SM; the second map argument carries the 64-row K box
+      CUtensorMap tk64;
+      VT_TRY(make_tmap_bf16_3d(&tk64, qkv, B, N, 3 * d, 3 * d, 64, 64));
+      AttnLongParams pc = p;
+      pc.k_blocks = (N + 63) / 64;
+      const int gridc = B * pc.q_tiles * pc.k_blocks;
+      if (heads) attention_long_maps_kernel<true, false, true><<<gridc, kThreads, kSmemMapsCompact, st>>>(tqkv, tk64, pc);
+      else attention_long_maps_kernel<false, false, true><<<gridc, kThreads, kSmemMapsCompact, st>>>(tqkv, tk64, pc);
     } else {
       if (heads) attention_long_maps_kernel<true, false><<<grid, kThreads, kSmemMaps, st>>>(tqkv, tqkv_lo, p);
       else attention_long_maps_kernel<false, false><<<grid, kThreads, kSmemMaps, st>>>(tqkv, tqkv_lo, p);
