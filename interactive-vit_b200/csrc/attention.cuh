@@ -102,7 +102,9 @@ static_assert(kSmemBytes <= 227 * 1024, "attention: shared memory budget");
 
 // kHeads: also write the full per-head probabilities (opt-in; a separate instantiation keeps that code out of
 // the instruction stream of the common variant).
-template <bool kHeads>
+// kFull: KP == 208 (197 tokens, the production shape): every thread owns granules 0..5 and column groups 0 and 1 a
+// seventh, so the per-granule guards fold at compile time instead of costing a branch pair per granule and phase.
+template <bool kHeads, bool kFull = false>
 __global__ void __launch_bounds__(attn_cfg::kThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 over qkv [B*N, 3d]
                  const __grid_constant__ CUtensorMap tmap_kv,  // box 64 x (KP/2) over the same tensor
@@ -315,6 +317,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     // g / 8 = c / 2, g / 4 = c, g % 4 = cg: every TMEM column and every swizzled smem address below is one of two
     // per-thread bases plus a compile-time offset (contiguous ranges needed ~13 address instructions per granule).
     const int nmy = ngran > cg ? (ngran - cg + kColGroups - 1) / kColGroups : 0;   // granules of this thread
+#define OWNS(c) (kFull ? ((c) < kMaxGran - 1 || cg < 2) : ((c) < nmy))
     const float inv_h = 1.0f / static_cast<float>(p.H);
     const bool has_pad = nmy > 0 && (kColGroups * (nmy - 1) + cg) * 8 + 8 > p.N;   // warp-uniform: owns padded keys
     const int valid_last = p.N - (kColGroups * (nmy - 1) + cg) * 8;   // valid keys in this thread's last granule (< 8 iff has_pad)
@@ -372,7 +375,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       ptx::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
-        if (c < nmy) {
+        if OWNS(c) {
           ptx::tmem_ld_x8(t_s + c * 32, s[c]);
         } else {
 #pragma unroll
@@ -414,7 +417,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
-        if (c < nmy) {
+        if OWNS(c) {
 #pragma unroll
           for (int j = 0; j < 8; j += 2) mx = ptx::fmax3(mx, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
         }
@@ -425,7 +428,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
-        if (c < nmy) {
+        if OWNS(c) {
 #pragma unroll
           for (int j = 0; j < 8; j += 4) {
             const float v0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -mxs));
@@ -487,7 +490,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         const uint32_t w0 = pack_bf16x2_u(s[c][0], s[c][1]), w1 = pack_bf16x2_u(s[c][2], s[c][3]);
         const uint32_t w2 = pack_bf16x2_u(s[c][4], s[c][5]), w3 = pack_bf16x2_u(s[c][6], s[c][7]);
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(dst), "r"(w0),
-                     "r"(w1), "r"(w2), "r"(w3), "r"(static_cast<uint32_t>(c < nmy))
+                     "r"(w1), "r"(w2), "r"(w3), "r"(static_cast<uint32_t>OWNS(c))
                      : "memory");
       }
       ATTN_TS(12);
@@ -506,7 +509,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         ATTN_TS(14);
 #pragma unroll
         for (int c = 0; c < kMaxGran; ++c) {
-          if (c < nmy) {
+          if OWNS(c) {
             float4* dst = reinterpret_cast<float4*>(cls_stage + (kColGroups * c + cg) * 8);
             dst[0] = make_float4(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]), __uint_as_float(s[c][2]),
                                  __uint_as_float(s[c][3]));
@@ -521,7 +524,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
           float* hp = p.head_map + ((static_cast<size_t>(b) * p.H + h0 + h) * p.N + qrow) * p.ldmap;
 #pragma unroll
           for (int c = 0; c < kMaxGran; ++c) {
-            if (c < nmy) {
+            if OWNS(c) {
               float4* dst = reinterpret_cast<float4*>(hp + (kColGroups * c + cg) * 8);
               dst[0] = make_float4(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]), __uint_as_float(s[c][2]),
                                    __uint_as_float(s[c][3]));
@@ -549,12 +552,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       uint32_t a[kMaxGran][8];
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c)
-        if (c < nmy) ptx::tmem_ld_x8(t_avg + c * 32, a[c]);
+        if OWNS(c) ptx::tmem_ld_x8(t_avg + c * 32, a[c]);
       ptx::tmem_ld_wait();
       const uint32_t slab0 = ptx::smem_u32(smem) + r * 128;
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
-        if (c < nmy) {
+        if OWNS(c) {
           // granule g = 4 c + cg: 32-column slab c, 16-byte chunks 2 cg and 2 cg + 1 of this row
           const uint32_t dst = slab0 + c * (BM * 128);
           const int ch = 2 * cg;
@@ -591,6 +594,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
   }
+#undef OWNS
 }
 
 }  // namespace vitb200

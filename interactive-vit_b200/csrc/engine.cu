@@ -388,6 +388,7 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   if (!configured) {
     CU_TRY(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     CU_TRY(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CU_TRY(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
   AttnParams p;
@@ -412,7 +413,13 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
     const int b0 = p.full_items / p.q_tiles;
     CU_TRY(cudaMemsetAsync(avg + (size_t)b0 * N * pitch, 0, (size_t)(B - b0) * N * pitch * sizeof(float), st));
   }
+  static int full_mode = -1;   // VITB200_ATTN_FULL=0: generic granule guards also at KP = 208
+  if (full_mode < 0) {
+    const char* v = getenv("VITB200_ATTN_FULL");
+    full_mode = (v && v[0] == '0') ? 0 : 1;
+  }
   if (heads) attention_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
+  else if (KP == KP_MAX && full_mode) attention_kernel<false, true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   else attention_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   CU_TRY(cudaGetLastError());
   return VITB200_OK;
