@@ -259,10 +259,40 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     # N > 1: one packed gather of logits + CLS maps + rollout per step to rank 0, issued from a side stream so that it
     # runs under the next step's forward (dist.PackedGather); the timed region ends only when the last one has landed
     spec = {"logits": ((cfg.num_classes,), 0), "cls_maps": ((L, H, N), 1), "rollout": ((N - 1,), 0)}
-    gatherer = D.PackedGather(spec, total, torch.device("cuda", local_rank)) if world > 1 else None
+    # Device-resident arm, N > 1: `--gather push` (default "auto" tries it first) removes the collective altogether -- the
+    # producing kernels store logits / CLS maps / rollout straight into rank 0's receive set over NVLink peer memory
+    # (dist.PeerPush, vitb200_bind_outputs), one device-side barrier per step on a side stream.
+    gatherer, pusher, gather_how = None, None, "none"
+    if world > 1:
+        if args.gather in ("auto", "push"):
+            ok = torch.ones(1, device="cuda")
+            try:
+                pusher = D.PeerPush(eng, total, torch.device("cuda", local_rank))
+            except Exception as ex:
+                print(f"[bench] rank {rank}: peer-memory push unavailable ({type(ex).__name__}: {str(ex)[:200]})",
+                      file=sys.stderr, flush=True)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                if args.gather == "push":
+                    raise RuntimeError("--gather push: symmetric-memory rendezvous failed on at least one rank")
+                pusher = None
+        if pusher is not None:
+            gather_how = ("logits + CLS maps + rollout to rank 0 with NO collective: the producing kernels store into "
+                          "rank 0's receive set over NVLink peer memory (symmetric memory), one device-side barrier per "
+                          "step on a side stream, three sets in rotation")
+        else:
+            gatherer = D.PackedGather(spec, total, torch.device("cuda", local_rank))
+            gather_how = ("logits + CLS maps + rollout to rank 0: one packed NCCL gather per step on a side stream, "
+                          "overlapping the next forward")
     e2e_gatherer = D.PackedGather(spec, total, torch.device("cuda", local_rank)) if world > 1 else None
 
     def step():
+        if pusher is not None:
+            pusher.begin()
+            eng.forward_device(images, flags, stream.cuda_stream)
+            pusher.end()
+            return
         eng.forward_device(images, flags, stream.cuda_stream)
         if gatherer is not None:
             gatherer.submit({"logits": eng.device_output(0, (B, cfg.num_classes)),
@@ -286,10 +316,34 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 step()
             if gatherer is not None:
                 gatherer.finish()
+            if pusher is not None:
+                pusher.finish()
             ev1.record(stream)
             barrier()
         ms = ev0.elapsed_time(ev1) / args.steps
         launches = eng.launch_count() - launches0
+        if pusher is not None:
+            # the pushed results on rank 0 against this rank's own forward into the engine's buffers (rank 0's slice is
+            # the same input, so it must match bit for bit) -- outside the timed region
+            push_check = None
+            if rank == 0:
+                got = {k: pusher.result(k).clone() for k in ("logits", "cls_maps", "rollout")}
+            pusher.close()
+            dist.barrier()
+            if rank == 0:
+                eng.forward_device(images, flags, stream.cuda_stream)
+                torch.cuda.synchronize()
+                own = {"logits": eng.device_output(0, (B, cfg.num_classes)),
+                       "cls_maps": eng.device_output(E.EMIT_CLS, (L, B, H, N)),
+                       "rollout": eng.device_output(E.EMIT_ROLLOUT, (B, N - 1))}
+                push_check = bool(torch.equal(got["logits"][:B], own["logits"]) and
+                                  torch.equal(got["cls_maps"][:, :B], own["cls_maps"]) and
+                                  torch.equal(got["rollout"][:B], own["rollout"]) and
+                                  all(bool(torch.isfinite(v).all()) and float(v[B:].abs().sum()) > 0 for v in
+                                      (got["logits"], got["rollout"])))
+                if not push_check:
+                    raise RuntimeError("peer-memory push: rank 0's receive set does not match its own forward")
+            gather_how += "; rank 0's slice verified bit-identical after the run"
 
         # ---- per-kernel times inside real forwards (CUDA events in front of every launch on the launch stream; the
         # figures are event-to-event, so each includes the gap to the next launch), and the dominant kernel's roofline.
@@ -395,7 +449,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                    f"maps + rollout for all {L} layers; random-init weights", "global_batch": total,
                        "l2": f"inputs larger than L2 ({B * 3 * cfg.image_size ** 2 * 4 >> 20} MiB images, "
                              f"{B * N * cfg.hidden_dim * 4 >> 20} MiB token stream per step)",
-                       "parallelism": f"dp{world}", "gather": "logits + CLS maps + rollout to rank 0: one packed NCCL gather per step on a side stream, overlapping the next forward" if world > 1 else "none"},
+                       "parallelism": f"dp{world}", "gather": gather_how},
             "clocks": clocks.summary(),
             "e2e": {"value": total / e2e_ms * 1e3, "unit": "img/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2 * 4,
@@ -426,6 +480,8 @@ def main():
     ap.add_argument("--model", default="vit_b_16")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="auto", choices=["auto", "push", "nccl"],
+                    help="N > 1 result exchange of the device-resident arm: peer-memory push (no collective) or packed NCCL gather")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -92,6 +92,19 @@ int vitb200_forward_host(vitb200_engine* e, const float* images_host, int batch,
                          const vitb200_host_outputs* out);
 int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, void* stream);
 
+/* Multi-GPU result exchange without a collective (the reference is single-process, so this
+ * replaces nothing there).  Routes the small results of vitb200_forward_device into caller-owned device memory --
+ * typically this rank's slice of rank 0's receive buffer, mapped into this process over NVLink (CUDA peer / symmetric
+ * memory): the kernels that PRODUCE the results (head GEMM epilogue -> logits, the attention kernel's CLS-row writer,
+ * the rollout kernel) store there directly, so the "gather" has no pack kernel, no staging copy and no NCCL call;
+ * the caller only signals completion (dist.PeerPush).
+ *   logits_dev : [batch, classes] rows (16-byte aligned), or NULL = engine buffer
+ *   cls_dev    : layer l, image b, head h at cls_dev + l * cls_layer_stride + (b * heads + h) * tokens  (floats), or NULL
+ *   rollout_dev: [batch, tokens - 1] rows, or NULL
+ * All NULL restores the engine's own buffers.  Only vitb200_forward_device honours the binding; the host, pipelined and
+ * node-granular entry points keep using the engine's buffers. */
+int vitb200_bind_outputs(vitb200_engine* e, float* logits_dev, float* cls_dev, long cls_layer_stride, float* rollout_dev);
+
 /* Pipelined variant of vitb200_forward_host for request streams: returns once the work is enqueued.  Up to two
  * requests are in flight; the host-to-device copy of request i+1 and the device-to-host copies of request i-1
  * overlap the forward of request i (separate copy streams, double-buffered device inputs, per-request staging of

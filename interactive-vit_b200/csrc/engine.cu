@@ -473,6 +473,14 @@ struct vitb200_engine {
   Buffer images, patches, x, xb, ln_stats, ln_affine, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
   Buffer patches_lo, xb_lo, qkv_lo, ctx_lo, mlp_lo, cls_ln_lo;  // fp32x3 mode: low halves of the bf16 operands
 
+  // vitb200_bind_outputs: caller-owned destinations of the small results (typically slices of rank 0's receive
+  // buffer mapped over NVLink).  Honoured by vitb200_forward_device only (`use_bound` is set for its duration).
+  float* bound_logits = nullptr;
+  float* bound_cls = nullptr;
+  float* bound_rollout = nullptr;
+  long bound_cls_layer_stride = 0;
+  bool use_bound = false;
+
   // vitb200_submit_host / vitb200_wait: two requests in flight.  H2D of request i+1 (copy_in stream) and D2H of
   // request i-1 (copy_out stream, from per-slot staging copies of the small outputs) overlap the forward of request i.
   struct Slot {
@@ -607,6 +615,7 @@ static int run_attn_block(vitb200_engine* e, int l, int B, uint32_t flags, cudaS
   const bool want_avg = (flags & (VITB200_EMIT_AVG | VITB200_EMIT_ROLLOUT)) != 0;
   float* avg = want_avg ? (float*)e->avg.p + (size_t)l * e->cap_batch * e->N * e->pitch : nullptr;
   float* cls = (flags & VITB200_EMIT_CLS) ? (float*)e->cls.p + (size_t)l * e->cap_batch * c.num_heads * e->N : nullptr;
+  if (cls && e->use_bound && e->bound_cls) cls = e->bound_cls + (size_t)l * e->bound_cls_layer_stride;
   float* hm = (flags & VITB200_EMIT_HEADS)
                   ? (float*)e->heads.p + (size_t)l * e->cap_batch * c.num_heads * e->N * e->pitch
                   : nullptr;
@@ -674,7 +683,7 @@ static int run_head(vitb200_engine* e, int B, cudaStream_t st) {
   VT_TRY(launch_layernorm((const float*)e->x.p, (long)e->N * d, e->lnf_g, e->lnf_b, (__nv_bfloat16*)e->cls_ln.p, B, d,
                           1e-6f, st, (__nv_bfloat16*)e->cls_ln_lo.p));
   GemmEpilogue ep;
-  ep.bias = e->b_head, ep.out = e->logits.p, ep.ldo = c.num_classes;
+  ep.bias = e->b_head, ep.out = (e->use_bound && e->bound_logits) ? (void*)e->bound_logits : e->logits.p, ep.ldo = c.num_classes;
   prof_mark(e, "gemm_head", st);
   VT_TRY(launch_gemm(e->cls_ln.p, d, e->w_head, B, c.num_classes, d, ep, false, true, st, e->cls_ln_lo.p, e->w_head_lo));
   e->launches += 2;
@@ -701,7 +710,7 @@ static int launch_rollout(const float* maps, long layer_stride, int L, int B, in
 static int run_rollout(vitb200_engine* e, int B, cudaStream_t st) {
   prof_mark(e, "rollout", st);
   VT_TRY(launch_rollout((const float*)e->avg.p, (long)e->cap_batch * e->N * e->pitch, e->cfg.num_layers, B, e->N, e->pitch,
-                        (float*)e->rollout.p, st));
+                        (e->use_bound && e->bound_rollout) ? e->bound_rollout : (float*)e->rollout.p, st));
   e->launches += 1;
   return VITB200_OK;
 }
@@ -942,7 +951,24 @@ int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch
   std::lock_guard<std::mutex> lock(e->mu);
   CU_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-  return forward_device_locked(e, images_dev, batch, flags, st);
+  e->use_bound = true;
+  const int rc = forward_device_locked(e, images_dev, batch, flags, st);
+  e->use_bound = false;
+  return rc;
+}
+
+int vitb200_bind_outputs(vitb200_engine* e, float* logits_dev, float* cls_dev, long cls_layer_stride, float* rollout_dev) {
+  if (!e) return fail(VITB200_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (cls_dev && cls_layer_stride < (long)e->cfg.num_heads * e->N)
+    return fail(VITB200_ERR_INVALID, "bind_outputs: CLS layer stride %ld is smaller than one image (%ld floats)",
+                cls_layer_stride, (long)e->cfg.num_heads * e->N);
+  // the head GEMM stores float4; the CLS-row writer and the rollout kernel store single floats
+  if (((uintptr_t)logits_dev & 15u) || (((uintptr_t)cls_dev | (uintptr_t)rollout_dev) & 3u))
+    return fail(VITB200_ERR_INVALID, "bind_outputs: logits must be 16-byte aligned, CLS maps and rollout 4-byte aligned");
+  e->bound_logits = logits_dev, e->bound_cls = cls_dev, e->bound_rollout = rollout_dev;
+  e->bound_cls_layer_stride = cls_dev ? cls_layer_stride : 0;
+  return VITB200_OK;
 }
 
 int vitb200_profile_forward(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, char* report,

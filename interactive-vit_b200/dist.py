@@ -158,3 +158,128 @@ class PackedGather:
         if all(c == self.cap for c in self.counts):
             return rows.reshape((self.total,) + shape)
         return torch.cat([rows[r, : self.counts[r]] for r in range(self.world)], dim=0).reshape((self.total,) + shape)
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class PushLayout:
+    """Where every rank's results live inside ONE receive set on rank 0 (offsets in floats).
+
+    A set holds the gathered tensors in their final, image-ordered layouts, so rank 0 reads them as plain views:
+    ``logits [total, classes]``, ``cls_maps [L, total, H, N]``, ``rollout [total, N - 1]``.  Rank r owns the images
+    ``shard_range(total, world, r)`` of each; for the CLS maps that is a strided region (one slab per layer), which is
+    why the engine takes a layer stride (``vitb200_bind_outputs``).  Regions start on 16-byte boundaries."""
+
+    def __init__(self, total: int, world: int, classes: int, layers: int, heads: int, tokens: int):
+        self.total, self.world = total, world
+        self.classes, self.layers, self.heads, self.tokens = classes, layers, heads, tokens
+        self.starts = [shard_range(total, world, r)[0] for r in range(world)]
+        self.counts = [shard_range(total, world, r)[1] for r in range(world)]
+        self.logits_off = 0
+        self.cls_off = _round_up(total * classes, 4)
+        self.cls_layer_stride = total * heads * tokens
+        self.rollout_off = self.cls_off + _round_up(layers * self.cls_layer_stride, 4)
+        self.set_floats = _round_up(self.rollout_off + total * (tokens - 1), 4)
+
+    def rank_offsets(self, rank: int) -> Dict[str, int]:
+        """Float offsets (inside a set) of the first image of `rank` in each result."""
+        s = self.starts[rank]
+        return {"logits": self.logits_off + s * self.classes,
+                "cls_maps": self.cls_off + s * self.heads * self.tokens,
+                "rollout": self.rollout_off + s * (self.tokens - 1)}
+
+    def views(self, set_buf: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Rank 0: the three gathered results as views of one set (a flat float tensor of `set_floats`)."""
+        t, L, H, N = self.total, self.layers, self.heads, self.tokens
+        return {"logits": set_buf[self.logits_off:self.logits_off + t * self.classes].view(t, self.classes),
+                "cls_maps": set_buf[self.cls_off:self.cls_off + L * self.cls_layer_stride].view(L, t, H, N),
+                "rollout": set_buf[self.rollout_off:self.rollout_off + t * (N - 1)].view(t, N - 1)}
+
+
+class PeerPush:
+    """The result exchange of the data-parallel forward without a collective: every rank's PRODUCING kernels (head GEMM
+    epilogue, the attention kernel's CLS-row writer, the rollout kernel) store their results straight into rank 0's
+    receive set over NVLink / NVSwitch peer memory (`VitEngine.bind_outputs` on addresses of a symmetric-memory
+    allocation), already in the final image-ordered layout.  There is no pack kernel, no staging copy, no NCCL call
+    and nothing to concatenate; what remains of the "gather" is one device-side barrier per step, issued from a side
+    stream so that it never sits between two forwards.
+
+    Protocol (per rank, stream-ordered): ``begin()`` binds set ``i % sets`` and makes the current stream wait for the
+    barrier of step ``i - sets + 1``; the forward writes; ``end()`` issues barrier ``i`` on the side stream behind the
+    forward.  On rank 0 a set is complete after ``wait(s)``; reads of it enqueued on the submitting stream before the
+    next ``end()`` are ordered before any rank writes that set again (their barrier waits for rank 0's, which waits
+    for those reads).  With three sets a rank may run up to two forwards ahead of the slowest one.
+
+    Needs CUDA peer access between the ranks' GPUs (one box) and `torch.distributed._symmetric_memory`; raises if
+    the rendezvous fails — callers that want a fallback transport use `PackedGather` (NCCL)."""
+
+    def __init__(self, eng, total: int, device, group=None, sets: int = 3):
+        import torch.distributed._symmetric_memory as symm
+
+        self.eng = eng
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        cfg = eng.cfg
+        self.layout = PushLayout(total, self.world, cfg.num_classes, cfg.num_layers, cfg.num_heads, cfg.tokens)
+        self.sets = sets
+        self.device = torch.device(device)
+        self.buf = symm.empty(sets * self.layout.set_floats, dtype=torch.float32, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.root_ptr = int(self.hdl.buffer_ptrs[0])   # rank 0's buffer as mapped into THIS process
+        self.side = torch.cuda.Stream(device=self.device)
+        self.closed = [None] * sets     # event behind the barrier that completed set s
+        self.step = 0
+        self.last = -1
+
+    def begin(self) -> int:
+        """Bind this step's receive set as the engine's output destination; returns the set index."""
+        i, s = self.step, self.step % self.sets
+        if i >= self.sets - 1:
+            prev = self.closed[(i - self.sets + 1) % self.sets]
+            if prev is not None:
+                torch.cuda.current_stream(self.device).wait_event(prev)
+        off = self.layout.rank_offsets(self.rank)
+        base = self.root_ptr + 4 * s * self.layout.set_floats
+        self.eng.bind_outputs(base + 4 * off["logits"], base + 4 * off["cls_maps"], self.layout.cls_layer_stride,
+                              base + 4 * off["rollout"])
+        return s
+
+    def end(self) -> int:
+        """Behind the forward: signal that this rank's part of the set is written (device-side barrier, side stream)."""
+        s = self.step % self.sets
+        self.step += 1
+        written = torch.cuda.Event()
+        written.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(written)
+            self.hdl.barrier(channel=0)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self.closed[s] = done
+        self.last = s
+        return s
+
+    def wait(self, s: Optional[int] = None) -> None:
+        """Make the current stream wait until set `s` (default: the last one) is complete on rank 0."""
+        s = self.last if s is None else s
+        if self.closed[s] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.closed[s])
+
+    def finish(self) -> None:
+        for s in range(self.sets):
+            self.wait(s)
+
+    def result(self, name: str, s: Optional[int] = None) -> Optional[torch.Tensor]:
+        """Rank 0: view of the gathered result in set `s` (valid after `wait(s)`); other ranks: None."""
+        if self.rank != 0:
+            return None
+        s = self.last if s is None else s
+        n = self.layout.set_floats
+        return self.layout.views(self.buf[s * n:(s + 1) * n])[name]
+
+    def close(self) -> None:
+        self.finish()
+        self.eng.bind_outputs()

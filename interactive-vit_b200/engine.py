@@ -66,6 +66,7 @@ SIGNATURES = {
     "vitb200_weights_ready": (_I, [_P]),
     "vitb200_forward_host": (_I, [_P, _P, _I, _U32, C.POINTER(_HostOutputs)]),
     "vitb200_forward_device": (_I, [_P, _P, _I, _U32, _P]),
+    "vitb200_bind_outputs": (_I, [_P, _P, _P, _L, _P]),
     "vitb200_submit_host": (_I, [_P, _P, _I, _U32, C.POINTER(_HostOutputs), C.POINTER(C.c_uint64)]),
     "vitb200_wait": (_I, [_P, C.c_uint64]),
     "vitb200_staged_output": (_I, [_P, C.c_uint64, _U32, C.POINTER(_P)]),
@@ -261,6 +262,13 @@ class VitEngine:
         """images: CUDA fp32 [B,3,S,S] on this engine's device; enqueues on `stream` (raw cudaStream_t)."""
         assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
         check(self.lib.vitb200_forward_device(self._h, images.data_ptr(), images.shape[0], flags, stream))
+
+    def bind_outputs(self, logits: Optional[int] = None, cls_maps: Optional[int] = None, cls_layer_stride: int = 0,
+                     rollout: Optional[int] = None) -> None:
+        """Raw device addresses (possibly peer-mapped: another GPU's memory over NVLink) that forward_device's producing
+        kernels store logits / CLS maps / rollout into; all None restores the engine's own buffers.  See
+        include/vitb200.h (vitb200_bind_outputs) for the layouts and dist.PeerPush for the multi-GPU use."""
+        check(self.lib.vitb200_bind_outputs(self._h, logits, cls_maps, cls_layer_stride, rollout))
 
     def profile_forward(self, images: torch.Tensor, flags: int = 0) -> Dict[str, tuple]:
         """One forward with a CUDA event in front of every launch: {kernel: (launches, total_ms)} plus "total"."""

@@ -88,3 +88,29 @@ def test_gather_results_gloo(world, total):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_push_layout_regions_are_disjoint_aligned_and_in_image_order():
+    """dist.PushLayout: every rank's slice of every result lies inside its region of the receive set, slices of
+    different ranks do not overlap, regions start on 16-byte boundaries, and the views rank 0 reads are the final
+    image-ordered tensors (rank order = image order because shards are contiguous)."""
+    from interactive_vit_b200.dist import PushLayout
+
+    for total, world in ((8, 2), (7, 3), (512, 8), (3, 4)):
+        C, L, H, N = 1000, 3, 6, 197
+        lay = PushLayout(total, world, C, L, H, N)
+        assert lay.cls_off % 4 == 0 and lay.rollout_off % 4 == 0 and lay.set_floats % 4 == 0
+        owner = torch.full((lay.set_floats,), -1, dtype=torch.int32)
+        for r in range(world):
+            off, cnt = lay.rank_offsets(r), lay.counts[r]
+            spans = [(off["logits"], cnt * C), (off["rollout"], cnt * (N - 1))]
+            spans += [(off["cls_maps"] + l * lay.cls_layer_stride, cnt * H * N) for l in range(L)]
+            for a, n in spans:
+                assert a >= 0 and a + n <= lay.set_floats
+                assert (owner[a:a + n] == -1).all(), "two ranks (or two results) share floats of the set"
+                owner[a:a + n] = r
+        v = lay.views(owner)
+        assert v["logits"].shape == (total, C) and v["cls_maps"].shape == (L, total, H, N) and v["rollout"].shape == (total, N - 1)
+        for r in range(world):
+            s, c = lay.starts[r], lay.counts[r]
+            assert (v["logits"][s:s + c] == r).all() and (v["cls_maps"][:, s:s + c] == r).all() and (v["rollout"][s:s + c] == r).all()

@@ -399,3 +399,122 @@ def test_bench_size_properties(E):
     again = eng.forward_host(x, flags)
     assert torch.equal(again["avg_maps"], big["avg_maps"]) and torch.equal(again["rollout"], big["rollout"])
     eng.close()
+
+
+def test_bound_outputs_land_in_the_callers_layout_bit_identically(E):
+    """vitb200_bind_outputs: the head GEMM, the CLS-row writer and the rollout kernel store straight into a
+    caller-owned buffer laid out for MORE images than this engine holds (rank 0's receive set in the multi-GPU case:
+    dist.PushLayout).  The bound results equal the engine's own buffers bit for bit, nothing outside this "rank"'s
+    slice is touched, and unbinding restores the default destinations."""
+    from interactive_vit_b200.dist import PushLayout
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_small_test"]
+    model = O.build_vit(ocfg, seed=0, init="stress")
+    B, world, rank = 2, 3, 1
+    total = B * world
+    eng = _engine_for(E, ocfg, model, B)
+    cfg = eng.cfg
+    L, H, N, C = cfg.num_layers, cfg.num_heads, cfg.tokens, cfg.num_classes
+    x = O.synthetic_images(B, ocfg.image_size).cuda()
+    flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
+    eng.forward_device(x, flags)
+    eng.synchronize()
+    own = {"logits": eng.device_output(0, (B, C)).clone(), "cls_maps": eng.device_output(E.EMIT_CLS, (L, B, H, N)).clone(),
+           "rollout": eng.device_output(E.EMIT_ROLLOUT, (B, N - 1)).clone()}
+    lay = PushLayout(total, world, C, L, H, N)
+    SENT = -12345.0
+    recv = torch.full((lay.set_floats,), SENT, device="cuda")
+    off = lay.rank_offsets(rank)
+    base = recv.data_ptr()
+    eng.bind_outputs(base + 4 * off["logits"], base + 4 * off["cls_maps"], lay.cls_layer_stride, base + 4 * off["rollout"])
+    eng.device_output(0, (B, C)).fill_(SENT)     # the engine's own buffers must stay untouched while bound
+    eng.forward_device(x, flags)
+    eng.synchronize()
+    assert (eng.device_output(0, (B, C)) == SENT).all()
+    v = lay.views(recv)
+    s = lay.starts[rank]
+    for k, bd in (("logits", 0), ("cls_maps", 1), ("rollout", 0)):
+        mine = v[k].narrow(bd, s, B)
+        assert torch.equal(mine, own[k]), k
+        rest = torch.cat([v[k].narrow(bd, 0, s).flatten(), v[k].narrow(bd, s + B, total - s - B).flatten()])
+        assert (rest == SENT).all(), f"{k}: wrote outside this rank's images"
+    eng.bind_outputs()
+    eng.forward_device(x, flags)
+    eng.synchronize()
+    assert torch.equal(eng.device_output(0, (B, C)), own["logits"])
+    with pytest.raises(E.EngineError):
+        eng.bind_outputs(base + 4, None, 0, None)      # logits must be 16-byte aligned
+    with pytest.raises(E.EngineError):
+        eng.bind_outputs(None, base, 1, None)          # layer stride smaller than one image
+    eng.close()
+
+
+def _peer_push_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import interactive_vit_b200.engine as E
+    from interactive_vit_b200.dist import PeerPush
+    from oracle import vit_oracle as O
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ocfg = O.ORACLE_CONFIGS["vit_small_test"]
+        model = O.build_vit(ocfg, seed=0, init="stress")
+        B = 2
+        cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim,
+                          ocfg.mlp_dim, ocfg.num_classes)
+        eng = E.VitEngine(cfg, rank, B)
+        eng.load_state_dict(model.state_dict())
+        allx = O.synthetic_images(B * world, ocfg.image_size)
+        x = allx[rank * B:(rank + 1) * B].cuda()
+        flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
+        push = PeerPush(eng, B * world, torch.device("cuda", rank))
+        for _ in range(5):      # more steps than sets: exercises the rotation and the write-after-read ordering
+            push.begin()
+            eng.forward_device(x, flags, torch.cuda.current_stream().cuda_stream)
+            s = push.end()
+        push.wait(s)
+        torch.cuda.synchronize()
+        if rank == 0:
+            got = {k: push.result(k, s).cpu() for k in ("logits", "cls_maps", "rollout")}
+        push.close()
+        dist.barrier()
+        if rank == 0:
+            ref = E.VitEngine(cfg, 0, B * world)
+            ref.load_state_dict(model.state_dict())
+            want = ref.forward_host(allx, E.EMIT_CLS | E.EMIT_ROLLOUT)
+            # logits and CLS rows are batch-invariant bit for bit; the rollout inherits the head average, whose last fp32
+            # bit depends on whether the attention kernel split an image's heads over two CTAs (test_bench_size_properties)
+            q.put({k: bool(torch.equal(got[k], want[k])) if k != "rollout" else
+                   bool((got[k] - want[k]).abs().max() < 1e-6) for k in got})
+            ref.close()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with peer access")
+def test_peer_push_two_ranks_matches_one_engine_on_the_whole_batch(E):
+    """dist.PeerPush on two GPUs: both ranks' kernels store into rank 0's receive set over NVLink; what rank 0 reads
+    equals one engine running the whole batch (logits and CLS maps bit for bit: the forward is batch-invariant per
+    image; rollout within 1e-6)."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_push_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res == {"logits": True, "cls_maps": True, "rollout": True}, res
