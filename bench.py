@@ -218,7 +218,8 @@ def plugin_request_latency(model_name, cfg, eng, P, n=20):
     return {"ms_per_request": times[len(times) // 2], "img_per_s": 1e3 / times[len(times) // 2], "requests": n,
             "response_bytes": len(resp),
             "path": "wire request -> Request.decode -> Context.compute (embed, layer.0.., head, rollout nodes on the GPU) -> "
-                    "Response.encode; every node output returned as CPU fp32 like the reference's"}
+                    "Response.encode; every node output returned as CPU fp32 like the reference's (pinned, deferred: one wait for "
+                    "the device per request, single-copy encode)"}
 
 
 # ------------------------------------------------------------------------------------------ our arm

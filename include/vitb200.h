@@ -134,6 +134,13 @@ int vitb200_synchronize(vitb200_engine* e);
  * rollout), i.e. one per Model.compute call of the reference (main/context.py:79-88).  The token stream
  * [B, N, d] fp32 lives in the engine between calls; set/get move it across the boundary when a node's input
  * did not come from (or its output must leave) the engine. */
+/* Deferred mode for the node-granular calls below (one request = ~15 node calls on one stream): with on != 0 the calls
+ * that take no host INPUT (stage_embed_resident / stage_layer / stage_attn_block / stage_mlp_block / stage_head /
+ * stage_rollout / get_*) enqueue their kernels and device-to-host copies and return WITHOUT synchronising; the host
+ * outputs (which should be pinned, and must stay allocated) are valid after vitb200_synchronize.  Calls with a host
+ * input (stage_embed, stage_transform, set_*) still wait, so the caller's source buffer is free on return.  The plugin
+ * (vit_plugin.py) hands such outputs out as tensors that synchronise on first access. */
+int vitb200_set_deferred(vitb200_engine* e, int on);
 int vitb200_stage_embed(vitb200_engine* e, const float* images_host, int batch);         /* TV:268-287,295-296 + pos add TV:155 */
 /* `<model>:transform` node: torchvision's ImageClassification preset (transforms/_presets.py:58-65; the reference's
  * VggModel runs weights.transforms() on the CPU, static/models/vgg16.py:40-42): antialiased bilinear resize of the
@@ -157,6 +164,7 @@ int vitb200_set_avg_map(vitb200_engine* e, int layer, const float* map_host, int
 int vitb200_get_avg_map(vitb200_engine* e, int layer, float* map_host, int batch);
 int vitb200_get_cls_map(vitb200_engine* e, int layer, float* map_host, int batch);       /* [B, H, N] */
 int vitb200_get_head_map(vitb200_engine* e, int layer, float* map_host, int batch);      /* [B, H, N, N] */
+int vitb200_get_cls_grid(vitb200_engine* e, int layer, float* map_host, int batch);      /* [B, H, N-1]: CLS rows without the class column (the UI's [H, g, g] view) */
 
 /* Counters for the harness: kernels launched by this engine since creation. */
 uint64_t vitb200_launch_count(vitb200_engine* e);

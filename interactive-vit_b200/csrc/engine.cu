@@ -481,6 +481,10 @@ struct vitb200_engine {
   long bound_cls_layer_stride = 0;
   bool use_bound = false;
 
+  // vitb200_set_deferred: node-granular calls that have no host INPUT return without synchronising; their host
+  // outputs are valid after vitb200_synchronize (one wait per request instead of four per node)
+  bool deferred = false;
+
   // vitb200_submit_host / vitb200_wait: two requests in flight.  H2D of request i+1 (copy_in stream) and D2H of
   // request i-1 (copy_out stream, from per-slot staging copies of the small outputs) overlap the forward of request i.
   struct Slot {
@@ -1185,6 +1189,13 @@ uint64_t vitb200_launch_count(vitb200_engine* e) { return e ? e->launches : 0; }
   VT_TRY(ensure_workspace(e, (B) > e->cap_batch ? (B) : e->cap_batch, (FLAGS) | e->cap_flags)); \
   cudaStream_t st = e->stream;
 
+int vitb200_set_deferred(vitb200_engine* e, int on) {
+  if (!e) return fail(VITB200_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->deferred = on != 0;
+  return VITB200_OK;
+}
+
 int vitb200_stage_embed(vitb200_engine* e, const float* images_host, int batch) {
   if (!images_host) return fail(VITB200_ERR_INVALID, "null images");
   STAGE_PROLOGUE(batch, 0)
@@ -1216,7 +1227,7 @@ int vitb200_stage_transform(vitb200_engine* e, const float* images_host, int bat
 int vitb200_stage_embed_resident(vitb200_engine* e, int batch) {
   STAGE_PROLOGUE(batch, 0)
   VT_TRY(run_embed(e, (const float*)e->images.p, batch, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1224,7 +1235,7 @@ int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags)
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)
   VT_TRY(run_layer(e, layer, batch, flags, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1232,7 +1243,7 @@ int vitb200_stage_attn_block(vitb200_engine* e, int layer, int batch, uint32_t f
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)
   VT_TRY(run_attn_block(e, layer, batch, flags, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1240,7 +1251,7 @@ int vitb200_stage_mlp_block(vitb200_engine* e, int layer, int batch) {
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, 0)
   VT_TRY(run_mlp_block(e, layer, batch, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1249,7 +1260,7 @@ int vitb200_stage_head(vitb200_engine* e, int batch, float* logits_host) {
   VT_TRY(run_head(e, batch, st));
   if (logits_host)
     CU_TRY(cudaMemcpyAsync(logits_host, e->logits.p, (size_t)batch * e->cfg.num_classes * 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1258,7 +1269,7 @@ int vitb200_stage_rollout(vitb200_engine* e, int batch, float* rollout_host) {
   VT_TRY(run_rollout(e, batch, st));
   if (rollout_host)
     CU_TRY(cudaMemcpyAsync(rollout_host, e->rollout.p, (size_t)batch * (e->N - 1) * 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1280,7 +1291,7 @@ int vitb200_get_tokens(vitb200_engine* e, float* tokens_host, int batch) {
   if (!tokens_host) return fail(VITB200_ERR_INVALID, "null tokens");
   STAGE_PROLOGUE(batch, 0)
   CU_TRY(cudaMemcpyAsync(tokens_host, e->x.p, (size_t)batch * e->N * e->cfg.hidden_dim * 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1301,7 +1312,7 @@ int vitb200_get_avg_map(vitb200_engine* e, int layer, float* map_host, int batch
   STAGE_PROLOGUE(batch, VITB200_EMIT_AVG)
   const float* src = (const float*)e->avg.p + (size_t)layer * e->cap_batch * e->N * e->pitch;
   VT_TRY(copy_rows_to_host(map_host, src, (size_t)batch * e->N, e->N, e->pitch, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1311,7 +1322,18 @@ int vitb200_get_cls_map(vitb200_engine* e, int layer, float* map_host, int batch
   STAGE_PROLOGUE(batch, VITB200_EMIT_CLS)
   const float* src = (const float*)e->cls.p + (size_t)layer * e->cap_batch * e->cfg.num_heads * e->N;
   CU_TRY(cudaMemcpyAsync(map_host, src, (size_t)batch * e->cfg.num_heads * e->N * 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
+int vitb200_get_cls_grid(vitb200_engine* e, int layer, float* map_host, int batch) {
+  if (!map_host) return fail(VITB200_ERR_INVALID, "null map");
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  STAGE_PROLOGUE(batch, VITB200_EMIT_CLS)
+  // the class token's attention to the PATCH tokens only: column 0 (class -> class) is dropped by the strided copy
+  const float* src = (const float*)e->cls.p + (size_t)layer * e->cap_batch * e->cfg.num_heads * e->N + 1;
+  VT_TRY(copy_rows_to_host(map_host, src, (size_t)batch * e->cfg.num_heads, e->N - 1, e->N, st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
@@ -1321,7 +1343,7 @@ int vitb200_get_head_map(vitb200_engine* e, int layer, float* map_host, int batc
   STAGE_PROLOGUE(batch, VITB200_EMIT_HEADS)
   const float* src = (const float*)e->heads.p + (size_t)layer * e->cap_batch * e->cfg.num_heads * e->N * e->pitch;
   VT_TRY(copy_rows_to_host(map_host, src, (size_t)batch * e->cfg.num_heads * e->N, e->N, e->pitch, st));
-  CU_TRY(cudaStreamSynchronize(st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 

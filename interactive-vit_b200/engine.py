@@ -73,6 +73,7 @@ SIGNATURES = {
     "vitb200_profile_forward": (_I, [_P, _P, _I, _U32, C.c_char_p, C.c_size_t]),
     "vitb200_device_output": (_I, [_P, _U32, C.POINTER(_P), C.POINTER(_I)]),
     "vitb200_synchronize": (_I, [_P]),
+    "vitb200_set_deferred": (_I, [_P, _I]),
     "vitb200_stage_embed": (_I, [_P, _P, _I]),
     "vitb200_stage_transform": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "vitb200_stage_embed_resident": (_I, [_P, _I]),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "vitb200_get_avg_map": (_I, [_P, _I, _P, _I]),
     "vitb200_get_cls_map": (_I, [_P, _I, _P, _I]),
     "vitb200_get_head_map": (_I, [_P, _I, _P, _I]),
+    "vitb200_get_cls_grid": (_I, [_P, _I, _P, _I]),
     "vitb200_launch_count": (C.c_uint64, [_P]),
     "vitb200_op_gemm": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_gemm_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P]),
@@ -167,6 +169,47 @@ CONFIGS: Dict[str, VitConfig] = {
 }
 
 
+def _pending_args(args):
+    for a in args:
+        if isinstance(a, PendingTensor):
+            yield a
+        elif isinstance(a, (list, tuple)):
+            yield from _pending_args(a)
+
+
+class PendingTensor(torch.Tensor):
+    """CPU fp32 tensor over pinned host memory whose contents are still being written by a device-to-host copy queued
+    on the engine's stream (deferred mode, `VitEngine.set_deferred`).  It IS a `torch.Tensor` for the reference's
+    graph code (`Edge.tensor`, main/graph.py:53; shipped by `t.numpy().tobytes()`, main/message.py:111-121): the first
+    operation that can see the data -- `numpy()`, `data_ptr()`, any torch function -- waits for the engine's stream
+    once (one wait per request instead of four per node); metadata (`shape`, `dim()`, `dtype`, `device` ...) does not.
+    Results of operations are plain tensors."""
+
+    _NO_WAIT = None
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if cls._NO_WAIT is None:
+            T = torch.Tensor
+            cls._NO_WAIT = {T.dim, T.size, T.numel, T.stride, T.is_contiguous, T.element_size, T.shape.__get__,
+                            T.ndim.__get__, T.dtype.__get__, T.device.__get__, T.is_cuda.__get__, T.layout.__get__,
+                            T.requires_grad.__get__, T.is_pinned, T.__len__}
+        if func not in cls._NO_WAIT:
+            for a in _pending_args(args):
+                a.wait()
+            for a in _pending_args(tuple(kwargs.values())):
+                a.wait()
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*args, **kwargs)
+
+    def wait(self) -> None:
+        eng = getattr(self, "_engine", None)
+        if eng is not None:
+            eng._drain(self._seq)
+            self._engine = None
+
+
 class VitEngine:
     """One engine = one model replica on one GPU.  Thread-safe (the C side serialises calls)."""
 
@@ -182,6 +225,12 @@ class VitEngine:
         h = C.c_void_p()
         check(self.lib.vitb200_create(C.byref(c), C.byref(h)))
         self._h = h
+        # deferred mode (set_deferred): host outputs handed out as PendingTensor; `_issued` counts them, `_drained` is the
+        # highest count known to have landed, `_inflight` keeps their pinned storage allocated until then
+        self._deferred = False
+        self._issued = 0
+        self._drained = 0
+        self._inflight = []
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -290,6 +339,45 @@ class VitEngine:
     def synchronize(self) -> None:
         check(self.lib.vitb200_synchronize(self._h))
 
+    # ---- deferred host outputs -----------------------------------------------------------------------
+    def set_deferred(self, on: bool) -> None:
+        """Node-granular calls without a host input stop synchronising; their results come back as PendingTensor
+        (pinned, valid on first access).  See vitb200_set_deferred in include/vitb200.h."""
+        if not on and self._deferred:
+            self._drain(self._issued)
+        check(self.lib.vitb200_set_deferred(self._h, 1 if on else 0))
+        self._deferred = bool(on)
+
+    def _host_out(self, *shape) -> torch.Tensor:
+        if not self._deferred:
+            return torch.empty(*shape, dtype=torch.float32)
+        return torch.empty(*shape, dtype=torch.float32, pin_memory=True)
+
+    def _issue(self, out: torch.Tensor, shape=None) -> torch.Tensor:
+        """Called right AFTER the copy into `out` was enqueued: a count read before a synchronize therefore only
+        covers copies that the synchronize waits for.  `shape`: the view to hand out (taken here, on the plain
+        tensor, because a view of a PendingTensor would have to wait)."""
+        if shape is not None:
+            out = out.view(shape)
+        if not self._deferred:
+            return out
+        if len(self._inflight) >= 1024:      # nobody looked at the results: do not pile up pinned buffers
+            self._drain(self._issued)
+        t = out.as_subclass(PendingTensor)
+        self._issued += 1
+        t._seq, t._engine = self._issued, self
+        self._inflight.append((t._seq, out))
+        return t
+
+    def _drain(self, seq: int) -> None:
+        if seq <= self._drained:
+            return
+        mark = self._issued
+        self.synchronize()
+        if mark > self._drained:
+            self._drained = mark
+        self._inflight = [(s_, t) for s_, t in self._inflight if s_ > self._drained]
+
     def launch_count(self) -> int:
         return int(self.lib.vitb200_launch_count(self._h))
 
@@ -321,45 +409,51 @@ class VitEngine:
         """Second half: x <- x + MLP(LN2 x)."""
         check(self.lib.vitb200_stage_mlp_block(self._h, layer, batch))
 
-    def stage_head(self, batch: int) -> torch.Tensor:
-        out = torch.empty(batch, self.cfg.num_classes, dtype=torch.float32)
+    def stage_head(self, batch: int, shape=None) -> torch.Tensor:
+        out = self._host_out(batch, self.cfg.num_classes)
         check(self.lib.vitb200_stage_head(self._h, batch, out.data_ptr()))
-        return out
+        return self._issue(out, shape)
 
-    def stage_rollout(self, batch: int) -> torch.Tensor:
-        out = torch.empty(batch, self.cfg.tokens - 1, dtype=torch.float32)
+    def stage_rollout(self, batch: int, shape=None) -> torch.Tensor:
+        out = self._host_out(batch, self.cfg.tokens - 1)
         check(self.lib.vitb200_stage_rollout(self._h, batch, out.data_ptr()))
-        return out
+        return self._issue(out, shape)
 
     def set_tokens(self, tokens: torch.Tensor) -> None:
         assert tokens.device.type == "cpu" and tokens.dtype == torch.float32 and tokens.is_contiguous()
         check(self.lib.vitb200_set_tokens(self._h, tokens.data_ptr(), tokens.shape[0]))
 
-    def get_tokens(self, batch: int) -> torch.Tensor:
-        out = torch.empty(batch, self.cfg.tokens, self.cfg.hidden_dim, dtype=torch.float32)
+    def get_tokens(self, batch: int, shape=None) -> torch.Tensor:
+        out = self._host_out(batch, self.cfg.tokens, self.cfg.hidden_dim)
         check(self.lib.vitb200_get_tokens(self._h, out.data_ptr(), batch))
-        return out
+        return self._issue(out, shape)
 
     def set_avg_map(self, layer: int, amap: torch.Tensor) -> None:
         assert amap.device.type == "cpu" and amap.dtype == torch.float32 and amap.is_contiguous()
         check(self.lib.vitb200_set_avg_map(self._h, layer, amap.data_ptr(), amap.shape[0]))
 
-    def get_avg_map(self, layer: int, batch: int) -> torch.Tensor:
+    def get_avg_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         N = self.cfg.tokens
-        out = torch.empty(batch, N, N, dtype=torch.float32)
+        out = self._host_out(batch, N, N)
         check(self.lib.vitb200_get_avg_map(self._h, layer, out.data_ptr(), batch))
-        return out
+        return self._issue(out, shape)
 
-    def get_cls_map(self, layer: int, batch: int) -> torch.Tensor:
-        out = torch.empty(batch, self.cfg.num_heads, self.cfg.tokens, dtype=torch.float32)
+    def get_cls_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
+        out = self._host_out(batch, self.cfg.num_heads, self.cfg.tokens)
         check(self.lib.vitb200_get_cls_map(self._h, layer, out.data_ptr(), batch))
-        return out
+        return self._issue(out, shape)
 
-    def get_head_map(self, layer: int, batch: int) -> torch.Tensor:
+    def get_cls_grid(self, layer: int, batch: int, shape=None) -> torch.Tensor:
+        """[B, H, N-1]: the class token's attention to the patch tokens per head (class column dropped by the copy)."""
+        out = self._host_out(batch, self.cfg.num_heads, self.cfg.tokens - 1)
+        check(self.lib.vitb200_get_cls_grid(self._h, layer, out.data_ptr(), batch))
+        return self._issue(out, shape)
+
+    def get_head_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         N = self.cfg.tokens
-        out = torch.empty(batch, self.cfg.num_heads, N, N, dtype=torch.float32)
+        out = self._host_out(batch, self.cfg.num_heads, N, N)
         check(self.lib.vitb200_get_head_map(self._h, layer, out.data_ptr(), batch))
-        return out
+        return self._issue(out, shape)
 
 
 def _device_view(ptr: int, shape, device: int) -> torch.Tensor:

@@ -111,7 +111,9 @@ class Response:
         for t in tensors:
             if t.device.type != "cpu" or t.dtype != torch.float32:
                 t = t.detach().to(device="cpu", dtype=torch.float32)
-            payload = t.detach().contiguous().numpy().tobytes()
+            # the tensor's own memory as a bytes-like object: join() below is then the only copy of the payload (the
+            # reference's t.numpy().tobytes() + array('f') + BytesIO path copies it four times, message.py:111-121)
+            payload = memoryview(t.detach().contiguous().numpy().reshape(-1)).cast("B")
             dims = list(t.shape)
             parts.append(struct.pack(f"<II{len(dims)}I", 8 + 4 * len(dims) + len(payload), len(dims), *dims))
             parts.append(payload)

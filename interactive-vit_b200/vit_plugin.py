@@ -88,6 +88,10 @@ def make_vit_model_class(ModelBase, PinoutCls):
             self.cfg = cfg
             self.engine = engine if engine is not None else E.VitEngine(cfg, device, max_batch)
             self.engine.load_state_dict(module.state_dict())
+            # Deferred host outputs (default on; VITB200_DEFERRED=0 restores a wait per call): node outputs are pinned CPU
+            # fp32 tensors that wait for the engine's stream on first access (engine.PendingTensor), so a request costs
+            # one wait -- when Response.encode reads the first tensor -- instead of four per node.
+            self.engine.set_deferred(os.environ.get("VITB200_DEFERRED", "1") != "0")
             self._lock = threading.Lock()
             self._tokens_out: Optional[torch.Tensor] = None   # last token tensor handed out (device-resident copy valid)
             self._tokens_batch = 0
@@ -218,19 +222,19 @@ def make_vit_model_class(ModelBase, PinoutCls):
         def _bind_tokens(self, x: torch.Tensor) -> int:
             """Make the engine's token stream equal to `x` ([N,d] or [B,N,d]); returns the batch size."""
             c = self.cfg
+            if x is self._tokens_out:
+                return self._tokens_batch  # still resident from the previous node of this request
             if x.dim() not in (2, 3) or tuple(x.shape[-2:]) != (c.tokens, c.hidden_dim):
                 raise Exception(f"expected tokens of shape [{c.tokens}, {c.hidden_dim}] (optionally batched), got {list(x.shape)}")
             batch = 1 if x.dim() == 2 else x.shape[0]
-            if x is self._tokens_out and batch == self._tokens_batch:
-                return batch  # still resident from the previous node of this request
             self.engine.set_tokens(self._host(x).reshape(batch, c.tokens, c.hidden_dim))
             # the engine now holds x, not what it handed out last (a fanned-out graph may come back to an older tensor)
             self._tokens_out, self._tokens_batch = x, batch
             return batch
 
         def _emit_tokens(self, batch: int, batched: bool) -> torch.Tensor:
-            t = self.engine.get_tokens(batch)
-            t = t if batched else t[0]
+            c = self.cfg
+            t = self.engine.get_tokens(batch, (batch, c.tokens, c.hidden_dim) if batched else (c.tokens, c.hidden_dim))
             self._tokens_out, self._tokens_batch = t, batch
             return t
 
@@ -282,21 +286,18 @@ def make_vit_model_class(ModelBase, PinoutCls):
                     else:
                         self.engine.stage_attn_block(i, batch, flags)
                     out.set("o", self._emit_tokens(batch, batched))
-                    amap = self.engine.get_avg_map(i, batch)
-                    cls = self.engine.get_cls_map(i, batch)[:, :, 1:].reshape(batch, c.num_heads, g, g)
-                    amap = amap if batched else amap[0]
+                    lead = (batch,) if batched else ()
+                    amap = self.engine.get_avg_map(i, batch, lead + (c.tokens, c.tokens))
                     self._maps_out[i] = amap
                     out.set("attn", amap)
-                    out.set("cls", cls if batched else cls[0])
+                    out.set("cls", self.engine.get_cls_grid(i, batch, lead + (c.num_heads, g, g)))
                     if want_heads:
-                        hm = self.engine.get_head_map(i, batch)
-                        out.set("heads", hm if batched else hm[0])
+                        out.set("heads", self.engine.get_head_map(i, batch, lead + (c.num_heads, c.tokens, c.tokens)))
                 elif kind == "head":
                     x = self._need(pinin, "o")
                     batched = x.dim() == 3
                     batch = self._bind_tokens(x)
-                    logits = self.engine.stage_head(batch)
-                    out.set("o", logits if batched else logits[0])
+                    out.set("o", self.engine.stage_head(batch, (batch, c.num_classes) if batched else (c.num_classes,)))
                 else:  # rollout
                     maps = [self._need(pinin, f"a{i}") for i in range(c.num_layers)]
                     batched = maps[0].dim() == 3
@@ -306,8 +307,7 @@ def make_vit_model_class(ModelBase, PinoutCls):
                             raise Exception(f"a{i}: expected a [{c.tokens}, {c.tokens}] map, got {list(m.shape)}")
                         if m is not self._maps_out.get(i):
                             self.engine.set_avg_map(i, self._host(m).reshape(batch, c.tokens, c.tokens))
-                    r = self.engine.stage_rollout(batch).reshape(batch, g, g)
-                    out.set("o", r if batched else r[0])
+                    out.set("o", self.engine.stage_rollout(batch, (batch, g, g) if batched else (g, g)))
             return out
 
         # ---- registration: ModelNode forwards (params are dropped by the reference's ModelNode,

@@ -284,6 +284,9 @@ def test_vit_plugin_catalogue_without_gpu():
         def load_state_dict(self, sd):
             self.keys = sorted(sd)
 
+        def set_deferred(self, on):
+            self.deferred = on
+
     ocfg = O.ORACLE_CONFIGS["vit_tiny_test"]
     cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
                       ocfg.num_classes)

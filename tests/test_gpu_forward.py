@@ -518,3 +518,72 @@ def test_peer_push_two_ranks_matches_one_engine_on_the_whole_batch(E):
         p.join(60)
         assert p.exitcode == 0
     assert res == {"logits": True, "cls_maps": True, "rollout": True}, res
+
+
+def test_deferred_node_outputs_wait_on_first_access_and_equal_the_synchronous_path(E, golden_dir, monkeypatch):
+    """Deferred host outputs (vitb200_set_deferred, engine.PendingTensor; the plugin's default): the same wire request
+    gives byte-identical response bytes with a wait per call (VITB200_DEFERRED=0) and with one wait per request;
+    node outputs are torch.Tensors whose metadata is readable without waiting, whose first data access drains the
+    stream once for every output of the request, and which also work when only an inner node's output is read
+    (a graph without head / rollout) and through the UNMODIFIED codec idiom t.numpy().tobytes()."""
+    from interactive_vit_b200 import context as C, message as M, vit_plugin as P
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_tiny_test"]
+    module = O.build_vit(ocfg, seed=0, init="stress")
+    cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                      ocfg.num_classes)
+    body = open(os.path.join(golden_dir, "wire_tiny.request.bin"), "rb").read()
+
+    def respond(plug):
+        ctx = C.Context()
+        for name in plug.list_node_names():
+            C.ModelNode(plug, name).register(ctx)
+        req = M.Request()
+        req.decode(body)
+        ctx.compute(req.graph)
+        return req, M.Response(req.graph).encode()
+
+    monkeypatch.setenv("VITB200_DEFERRED", "0")
+    sync_plug = P.VitB200Model("vit_tiny_test", cfg, module, 0, 1)
+    _, want = respond(sync_plug)
+    monkeypatch.setenv("VITB200_DEFERRED", "1")
+    plug = P.VitB200Model("vit_tiny_test", cfg, module, 0, 1)
+    eng = plug.engine
+    for _ in range(3):       # repeated requests recycle pinned buffers
+        req, got = respond(plug)
+        assert got == want
+    assert eng._drained == eng._issued and not eng._inflight
+
+    # one request by hand: nothing waits until the data is touched
+    from interactive_vit_b200.graph import Pinout
+
+    img = O.synthetic_images(1, ocfg.image_size)[0]
+    pin = Pinout()
+    pin.set("o", img)
+    tok = plug.compute("vit_tiny_test:embed", pin).get("o")
+    pin = Pinout()
+    pin.set("o", tok)
+    out = plug.compute("vit_tiny_test:layer.0", pin)
+    h, a, c = out.get("o"), out.get("attn"), out.get("cls")
+    g = cfg.image_size // cfg.patch_size
+    for t in (tok, h, a, c):
+        assert isinstance(t, torch.Tensor) and isinstance(t, E.PendingTensor)
+    before = eng._drained
+    assert tuple(h.shape) == (cfg.tokens, cfg.hidden_dim) and a.dim() == 2 and tuple(c.shape) == (cfg.num_heads, g, g)
+    assert h.dtype == torch.float32 and h.device.type == "cpu" and h.is_contiguous()
+    assert eng._drained == before, "metadata access must not wait for the device"
+    raw = a.numpy().tobytes()                      # the reference's Response.encode idiom (main/message.py:115)
+    assert eng._drained == eng._issued, "first data access drains every pending output of the request"
+    assert len(raw) == cfg.tokens * cfg.tokens * 4
+    assert (a.sum(-1) - 1).abs().max() < 4e-3 and torch.isfinite(h).all()
+    assert type(h + 1) is torch.Tensor            # results of operations are plain tensors
+    # the same nodes with a wait per call give the same numbers
+    pin = Pinout()
+    pin.set("o", img)
+    tok2 = sync_plug.compute("vit_tiny_test:embed", pin).get("o")
+    pin = Pinout()
+    pin.set("o", tok2)
+    out2 = sync_plug.compute("vit_tiny_test:layer.0", pin)
+    assert type(tok2) is torch.Tensor
+    assert torch.equal(tok, tok2) and torch.equal(h, out2.get("o")) and torch.equal(a, out2.get("attn")) and torch.equal(c, out2.get("cls"))
