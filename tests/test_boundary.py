@@ -340,3 +340,56 @@ def test_vit_plugin_catalogue_without_gpu():
             assert len(fo) == len(set(fo)) and (2 + 2 * L, "o") in fo
         finally:
             C.set_base_dir(None)
+
+
+def test_pending_tensor_waits_on_first_data_access_only():
+    """engine.PendingTensor (deferred node outputs) without a GPU: it is a torch.Tensor for the reference's graph
+    code; metadata never waits; numpy() / data_ptr() / any torch function / the reference codec idiom wait exactly
+    once through the engine's drain; results of operations are plain tensors; nested arguments are found."""
+    import numpy as np
+
+    import interactive_vit_b200.engine as E
+
+    class FakeEngine:
+        def __init__(self):
+            self.drains = []
+
+        def _drain(self, seq):
+            self.drains.append(seq)
+
+    def pending(eng, seq, *shape):
+        t = torch.arange(float(np.prod(shape))).reshape(*shape).as_subclass(E.PendingTensor)
+        t._seq, t._engine = seq, eng
+        return t
+
+    eng = FakeEngine()
+    t = pending(eng, 7, 2, 3)
+    assert isinstance(t, torch.Tensor)
+    assert tuple(t.shape) == (2, 3) and t.dim() == 2 and t.ndim == 2 and t.numel() == 6 and len(t) == 2
+    assert t.dtype == torch.float32 and t.device.type == "cpu" and t.is_contiguous() and t.size(1) == 3
+    assert eng.drains == [], "metadata must not wait"
+    raw = t.numpy().tobytes()                       # main/message.py:115
+    assert eng.drains == [7] and len(raw) == 24
+    assert type(t + 1) is torch.Tensor and type(t[0]) is torch.Tensor and type(t.detach()) is torch.Tensor
+    assert eng.drains == [7], "a tensor waits once"
+    for touch in (lambda x: x.data_ptr(), lambda x: np.asarray(x), lambda x: x.sum().item(), lambda x: x.reshape(3, 2),
+                  lambda x: x.to(torch.float64), lambda x: torch.equal(x, x), lambda x: x.tolist(), lambda x: x.clone()):
+        e2 = FakeEngine()
+        touch(pending(e2, 1, 2, 3))
+        assert e2.drains == [1], touch
+    e3 = FakeEngine()
+    a, b = pending(e3, 1, 2, 3), pending(e3, 2, 2, 3)
+    out = torch.cat([a, b])                         # tensors inside a list argument
+    assert sorted(e3.drains) == [1, 2] and type(out) is torch.Tensor and out.shape == (4, 3)
+    e4 = FakeEngine()
+    torch.add(torch.zeros(2, 3), other=pending(e4, 5, 2, 3))   # keyword argument
+    assert e4.drains == [5]
+    # through this package's encoder and the byte-compatible decoder
+    from interactive_vit_b200 import message as M
+
+    e5 = FakeEngine()
+    r = M.Response.__new__(M.Response)
+    r.outputs = {}
+    r.set_output(0, "o", pending(e5, 9, 2, 3))
+    back = M.decode_response(r.encode())
+    assert e5.drains == [9] and torch.equal(back[0]["o"], torch.arange(6.0).reshape(2, 3))
