@@ -216,8 +216,6 @@ class PeerPush:
     the rendezvous fails — callers that want a fallback transport use `PackedGather` (NCCL)."""
 
     def __init__(self, eng, total: int, device, group=None, sets: int = 3):
-        import torch.distributed._symmetric_memory as symm
-
         self.eng = eng
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -226,7 +224,22 @@ class PeerPush:
         self.layout = PushLayout(total, self.world, cfg.num_classes, cfg.num_layers, cfg.num_heads, cfg.tokens)
         self.sets = sets
         self.device = torch.device(device)
-        self.buf = symm.empty(sets * self.layout.set_floats, dtype=torch.float32, device=self.device)
+        self.buf = self.hdl = None
+        # Two phases, so that a rank whose LOCAL allocation fails never leaves the others waiting in the rendezvous:
+        # (1) allocate, (2) agree (MIN over ranks), (3) rendezvous -- a collective whose failures are symmetric.
+        err: Optional[Exception] = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            self.buf = symm.empty(sets * self.layout.set_floats, dtype=torch.float32, device=self.device)
+        except Exception as ex:      # reported below, on every rank
+            err = ex
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() == 0:
+            self.buf = None
+            raise RuntimeError(f"PeerPush: symmetric-memory allocation failed on at least one rank"
+                               f"{'' if err is None else f' (here: {type(err).__name__}: {err})'}")
         self.hdl = symm.rendezvous(self.buf, self.group)
         self.root_ptr = int(self.hdl.buffer_ptrs[0])   # rank 0's buffer as mapped into THIS process
         self.side = torch.cuda.Stream(device=self.device)
