@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -226,11 +227,14 @@ class VitEngine:
         check(self.lib.vitb200_create(C.byref(c), C.byref(h)))
         self._h = h
         # deferred mode (set_deferred): host outputs handed out as PendingTensor; `_issued` counts them, `_drained` is the
-        # highest count known to have landed, `_inflight` keeps their pinned storage allocated until then
+        # highest count known to have landed, `_keep` holds their pinned storage allocated until then
         self._deferred = False
         self._issued = 0
         self._drained = 0
-        self._inflight = []
+        self._keep = []
+        self._slab: Optional[torch.Tensor] = None    # current request's pinned slab (uint8) and its fill level
+        self._slab_off = 0
+        self._book = threading.Lock()    # guards the three fields above (requests may be encoded on other threads)
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -348,10 +352,41 @@ class VitEngine:
         check(self.lib.vitb200_set_deferred(self._h, 1 if on else 0))
         self._deferred = bool(on)
 
+    def _request_bytes(self, batch: int) -> int:
+        """Pinned bytes the outputs of one default-graph request need (embed + L layers with maps + head + rollout)."""
+        c = self.cfg
+        floats = ((c.num_layers + 1) * c.tokens * c.hidden_dim + c.num_layers * (c.tokens * c.tokens + c.num_heads * (c.tokens - 1))
+                  + c.num_classes + c.tokens - 1)
+        return batch * floats * 4 + 256 * (3 * c.num_layers + 4)
+
+    def prewarm_host_outputs(self, batch: int = 1, requests: int = 16) -> None:
+        """Fill torch's pinned-memory cache with `requests` request slabs.  The reference's request graphs are reference
+        cycles (Node <-> Edge, main/graph.py:6-53), so the tensors of a finished request are only released by the cyclic
+        collector some requests later; without this every request until the first collections pays a cudaHostAlloc
+        (milliseconds)."""
+        held = [torch.empty(self._request_bytes(batch), dtype=torch.uint8, pin_memory=True) for _ in range(requests)]
+        del held
+
+    def begin_request(self) -> None:
+        """Deferred mode: the next host output starts a fresh pinned slab (called by the plugin at a request's first
+        node).  Outputs are bump-allocated views of ONE pinned allocation per request -- a region is never handed out
+        twice, so earlier responses stay valid, and the slab returns to torch's cache when its last view dies."""
+        self._slab = None
+
     def _host_out(self, *shape) -> torch.Tensor:
         if not self._deferred:
             return torch.empty(*shape, dtype=torch.float32)
-        return torch.empty(*shape, dtype=torch.float32, pin_memory=True)
+        n = 1
+        for d_ in shape:
+            n *= d_
+        need = (n * 4 + 255) // 256 * 256
+        if self._slab is None or self._slab_off + need > self._slab.numel():
+            size = max(self._request_bytes(shape[0]), need)
+            self._slab = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+            self._slab_off = 0
+        v = self._slab[self._slab_off:self._slab_off + n * 4].view(torch.float32).view(*shape)
+        self._slab_off += need
+        return v
 
     def _issue(self, out: torch.Tensor, shape=None) -> torch.Tensor:
         """Called right AFTER the copy into `out` was enqueued: a count read before a synchronize therefore only
@@ -361,22 +396,25 @@ class VitEngine:
             out = out.view(shape)
         if not self._deferred:
             return out
-        if len(self._inflight) >= 1024:      # nobody looked at the results: do not pile up pinned buffers
+        if len(self._keep) >= 1024:      # nobody looked at the results: do not pile up pinned buffers
             self._drain(self._issued)
         t = out.as_subclass(PendingTensor)
-        self._issued += 1
-        t._seq, t._engine = self._issued, self
-        self._inflight.append((t._seq, out))
+        with self._book:
+            self._issued += 1
+            t._seq, t._engine = self._issued, self
+            self._keep.append((t._seq, out))
         return t
 
     def _drain(self, seq: int) -> None:
-        if seq <= self._drained:
-            return
-        mark = self._issued
+        with self._book:
+            if seq <= self._drained:
+                return
+            mark = self._issued      # every copy counted here was enqueued before the wait below starts
         self.synchronize()
-        if mark > self._drained:
-            self._drained = mark
-        self._inflight = [(s_, t) for s_, t in self._inflight if s_ > self._drained]
+        with self._book:
+            if mark > self._drained:
+                self._drained = mark
+            self._keep = [(s_, t) for s_, t in self._keep if s_ > self._drained]
 
     def launch_count(self) -> int:
         return int(self.lib.vitb200_launch_count(self._h))

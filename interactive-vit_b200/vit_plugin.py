@@ -91,7 +91,10 @@ def make_vit_model_class(ModelBase, PinoutCls):
             # Deferred host outputs (default on; VITB200_DEFERRED=0 restores a wait per call): node outputs are pinned CPU
             # fp32 tensors that wait for the engine's stream on first access (engine.PendingTensor), so a request costs
             # one wait -- when Response.encode reads the first tensor -- instead of four per node.
-            self.engine.set_deferred(os.environ.get("VITB200_DEFERRED", "1") != "0")
+            deferred = os.environ.get("VITB200_DEFERRED", "1") != "0"
+            self.engine.set_deferred(deferred)
+            if deferred and hasattr(self.engine, "prewarm_host_outputs"):
+                self.engine.prewarm_host_outputs(1, int(os.environ.get("VITB200_PREWARM_REQUESTS", "16")))
             self._lock = threading.Lock()
             self._tokens_out: Optional[torch.Tensor] = None   # last token tensor handed out (device-resident copy valid)
             self._tokens_batch = 0
@@ -244,6 +247,8 @@ def make_vit_model_class(ModelBase, PinoutCls):
             g = c.image_size // c.patch_size
             out = PinoutCls()
             with self._lock:
+                if kind in ("transform", "embed") and hasattr(self.engine, "begin_request"):
+                    self.engine.begin_request()     # a request's first node: its outputs get a pinned slab of their own
                 if kind == "transform":
                     x = self._need(pinin, "o")
                     if x.dim() not in (3, 4) or x.shape[-3] != 3:

@@ -553,7 +553,7 @@ def test_deferred_node_outputs_wait_on_first_access_and_equal_the_synchronous_pa
     for _ in range(3):       # repeated requests recycle pinned buffers
         req, got = respond(plug)
         assert got == want
-    assert eng._drained == eng._issued and not eng._inflight
+    assert eng._drained == eng._issued and not eng._keep
 
     # one request by hand: nothing waits until the data is touched
     from interactive_vit_b200.graph import Pinout

@@ -30,13 +30,19 @@ for name, node in ctx.nodes.items():
         return f
     node.compute = wrap(node.compute)
 N = 30
-for it in range(N + 3):
-    if it == 3:
-        acc = {k: 0.0 for k in acc}; per_node = {}
+WARM = 12     # past the first cyclic-GC passes: finished requests' pinned blocks are back in torch's cache
+totals = []
+for it in range(N + WARM):
+    if it == WARM:
+        acc = {k: 0.0 for k in acc}; per_node = {}; totals = []
     t0 = time.perf_counter(); req = M.Request(); req.decode(body)
     t1 = time.perf_counter(); ctx.compute(req.graph)
     t2 = time.perf_counter(); out = M.Response(req.graph).encode()
     t3 = time.perf_counter()
     acc["decode"] += t1 - t0; acc["compute"] += t2 - t1; acc["encode"] += t3 - t2
+    totals.append((t3 - t0) * 1e3)
 print({k: round(v / N * 1e3, 3) for k, v in acc.items()}, "ms per request;", len(out), "response bytes")
 print({k: round(v / N * 1e3, 3) for k, v in per_node.items()}, "ms per request by node kind")
+totals.sort()
+print("request total ms: median %.3f  min %.3f  max %.3f  (deferred=%s)" % (totals[len(totals) // 2], totals[0], totals[-1],
+                                                                              os.environ.get("VITB200_DEFERRED", "1")))
