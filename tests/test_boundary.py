@@ -393,3 +393,42 @@ def test_pending_tensor_waits_on_first_data_access_only():
     r.set_output(0, "o", pending(e5, 9, 2, 3))
     back = M.decode_response(r.encode())
     assert e5.drains == [9] and torch.equal(back[0]["o"], torch.arange(6.0).reshape(2, 3))
+
+
+def test_pending_tensor_through_the_unmodified_reference_graph_and_encoder():
+    """The reference's OWN code (main/graph.py Node/Pinout/Edge plumbing, main/message.py Response.encode, imported
+    unmodified from /root/reference) handles PendingTensors: they pass through set_pinout / get_pinin by reference
+    without waiting, and Response.encode's t.numpy().tobytes() (message.py:115) waits once and ships the right bytes."""
+    from oracle import refhost
+
+    if not refhost.available():
+        pytest.skip("/root/reference is only present in the build container")
+    import interactive_vit_b200.engine as E
+    from interactive_vit_b200 import message as M
+
+    rgraph, _, rmessage, _ = refhost.load()
+
+    class FakeEngine:
+        def __init__(self):
+            self.drains = []
+
+        def _drain(self, seq):
+            self.drains.append(seq)
+
+    eng = FakeEngine()
+    vals = torch.arange(12.0).reshape(3, 4)
+    t = vals.clone().as_subclass(E.PendingTensor)
+    t._seq, t._engine = 3, eng
+    g = rgraph.Graph()
+    a = g.add_node("producer", {})
+    b = g.add_node("consumer", {})
+    g.connect(a, "o", b, "o")
+    out = rgraph.Pinout()
+    out.set("o", t)
+    a.set_pinout(out)                       # graph.py:22-29
+    got = b.get_pinin().get("o")            # graph.py:15-20
+    assert got is t and eng.drains == [], "moving the tensor between nodes must neither copy nor wait"
+    wire = rmessage.Response(g).encode()    # message.py:75-121, unmodified
+    assert eng.drains == [3]
+    back = M.decode_response(wire)
+    assert torch.equal(back[a.index]["o"], vals)
