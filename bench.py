@@ -152,6 +152,14 @@ class ReferencePath:
         return done, time.perf_counter() - t0
 
 
+def _workload(model: str, batch: int) -> str:
+    import interactive_vit_b200.engine as E
+
+    cfg = E.CONFIGS[model]
+    return (f"{model} {cfg.image_size}px batch {batch} per GPU, forward + head-averaged maps + per-head CLS maps + rollout "
+            f"for all {cfg.num_layers} layers; random-init weights")
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -173,7 +181,11 @@ def run_reference(args, rank: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": args.gpus, "steps": len(steps),
         "warmup": args.warmup, "ms_per_step": secs / len(steps) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} 224px forward + attention maps, 1 unbatched image per request on CPU"},
+        # the same workload as the product arm's line (its `config.workload`); each reference step is a bounded sample of
+        # it, run the only way the reference's path runs: one unbatched image per request on the host cores
+        "config": {"workload": _workload(args.model, args.batch), "global_batch": args.batch * max(1, args.gpus),
+                   "parallelism": "cpu", "reference_sample": f"{per_step} unbatched single-image requests per step through the "
+                   "reference path (wire decode -> scheduler -> torchvision CPU fp32 plugin with attention maps -> wire encode)"},
         "cpu_baseline": {"value": value, "unit": "img/s", "cores": ref.cores, "kind": "port", "sample": sample,
                          "batched": ref.batched()},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -446,8 +458,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{args.model} {cfg.image_size}px batch {B} per GPU, forward + head-averaged maps + per-head CLS "
-                                   f"maps + rollout for all {L} layers; random-init weights", "global_batch": total,
+            "config": {"workload": _workload(args.model, B), "global_batch": total,
                        "l2": f"inputs larger than L2 ({B * 3 * cfg.image_size ** 2 * 4 >> 20} MiB images, "
                              f"{B * N * cfg.hidden_dim * 4 >> 20} MiB token stream per step)",
                        "parallelism": f"dp{world}", "gather": gather_how},
