@@ -405,7 +405,9 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
     split_mode = (v && v[0] == '0') ? 0 : 1;
   }
   p.full_items = items;
-  if (split_mode && H >= 2 && items > sms && rem > 0 && 2 * rem <= sms) p.full_items = items - rem;
+  // (also when the whole launch is such a round: up to sms / 2 items -- small batches, the single-image request path --
+  // run on twice the SMs.  Two-way only: a + b is commutative, so the reduce-add stays bit-reproducible.)
+  if (split_mode && H >= 2 && rem > 0 && 2 * rem <= sms) p.full_items = items - rem;
   const int grid = p.full_items + 2 * (items - p.full_items);
   if (avg && p.full_items < items) {
     // the split CTAs reduce-add their halves of the head average: zero the images they touch first (a full CTA of
