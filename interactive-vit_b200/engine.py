@@ -238,6 +238,11 @@ class VitEngine:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
+            if getattr(self, "_deferred", False):
+                try:       # outstanding PendingTensors become plain, valid CPU tensors before the engine goes away
+                    self._drain(self._issued)
+                except Exception:
+                    pass
             self.lib.vitb200_destroy(self._h)
             self._h = None
 
@@ -407,7 +412,7 @@ class VitEngine:
 
     def _drain(self, seq: int) -> None:
         with self._book:
-            if seq <= self._drained:
+            if seq <= self._drained or not self._h:      # a closed engine drained everything in close()
                 return
             mark = self._issued      # every copy counted here was enqueued before the wait below starts
         self.synchronize()
