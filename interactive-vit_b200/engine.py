@@ -369,7 +369,10 @@ class VitEngine:
         cycles (Node <-> Edge, main/graph.py:6-53), so the tensors of a finished request are only released by the cyclic
         collector some requests later; without this every request until the first collections pays a cudaHostAlloc
         (milliseconds)."""
-        held = [torch.empty(self._request_bytes(batch), dtype=torch.uint8, pin_memory=True) for _ in range(requests)]
+        slab = self._request_bytes(batch)
+        rounded = 1 << (slab - 1).bit_length()          # torch's pinned cache rounds block sizes up to a power of two
+        requests = max(2, min(requests, (512 << 20) // rounded))   # at most 512 MiB of pinned memory for the warm-up
+        held = [torch.empty(slab, dtype=torch.uint8, pin_memory=True) for _ in range(requests)]
         del held
 
     def begin_request(self) -> None:
