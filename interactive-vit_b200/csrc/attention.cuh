@@ -549,6 +549,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     // the [B][N][ldmap] tensor map.  (32-B-per-thread global stores from here cost ~14% of the kernel: every
     // warp-wide STG touched 32 different lines.)
     if (want_avg) {
+      // The head-average MMAs of the LAST head are issued behind the commit of o_full (which o_stage waited for): their
+      // own completion is p_free's last phase.  Without this wait the read below raced the tensor pipe (rarely lost:
+      // the one run-to-run difference of round 1's batch-256 reproducibility check).
+      ptx::mbar_wait(p_free, (nh - 1) & 1);
+      ptx::tc_fence_after();
       uint32_t a[kMaxGran][8];
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c)

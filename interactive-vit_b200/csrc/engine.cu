@@ -26,6 +26,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/vitb200.h"
@@ -144,16 +145,48 @@ static int make_tmap_f32_3d(CUtensorMap* tm, const void* base, uint64_t batch, u
 }
 
 // ------------------------------------------------------------------------------------------ launch helpers
-static int g_num_sms = 0;
+// Per-DEVICE launch state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current device only, and the
+// SM count / co-resident cluster count are device properties: a process may hold engines on several GPUs
+// (VitEngine(cfg, device=k)), so none of this may live in function-local statics.  One mutex guards the table; it is
+// taken once per launch (tens of nanoseconds next to a kernel launch).
+struct DeviceCtx {
+  int sms = 0;
+  std::map<const void*, int> func_smem;    // kernel -> dynamic smem limit configured on this device
+  std::map<const void*, int> gemm_slots;   // GEMM instantiation -> persistent scheduler slots on this device
+  float2* op_affine = nullptr;             // scratch of the single-kernel entry points (parity tests)
+  int op_affine_cap = 0;
+  float2* op_stats = nullptr;
+  size_t op_stats_cap = 0;
+};
+static std::mutex g_dev_mu;
+static std::map<int, DeviceCtx> g_dev;
+
+// call with g_dev_mu held
+static DeviceCtx& dev_ctx_locked() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DeviceCtx& c = g_dev[dev];
+  if (c.sms == 0) {
+    cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
+    if (c.sms <= 0) c.sms = 148;
+  }
+  return c;
+}
 
 static int device_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  return dev_ctx_locked().sms;
+}
+
+// Raise the dynamic shared-memory limit of `kern` on the CURRENT device (once per device and kernel).
+static int ensure_func_smem(const void* kern, int bytes) {
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  DeviceCtx& c = dev_ctx_locked();
+  auto it = c.func_smem.find(kern);
+  if (it != c.func_smem.end() && it->second >= bytes) return VITB200_OK;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  c.func_smem[kern] = bytes;
+  return VITB200_OK;
 }
 
 // Host mirror of GemmWork::num_units (gemm.cuh).
@@ -183,18 +216,26 @@ static int launch_gemm_t(const CUtensorMap* maps, GemmShape sh, const GemmEpilog
   cfg.numAttrs = 1;
   // persistent: one CTA / pair / 4-CTA cluster per scheduler slot; the slots are what the device can co-schedule
   // (4-CTA clusters do not tile every GPC: 148 SMs hold fewer than 37 of them)
-  static int slots = 0;
-  if (slots == 0) {
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    slots = device_sms() / kClusterCtas;
-    if (kClusterCtas > 2) {
-      cfg.gridDim = dim3(device_sms() / kClusterCtas * kClusterCtas);
-      int n = 0;
-      CU_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
-      if (n <= 0) return fail(VITB200_ERR_CUDA, "gemm: no %d-CTA cluster fits on this device", kClusterCtas);
-      if (n < slots) slots = n;
-      const char* v = getenv("VITB200_GEMM_SLOTS");
-      if (v && atoi(v) > 0 && atoi(v) < slots) slots = atoi(v);
+  VT_TRY(ensure_func_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes));
+  int slots = 0;
+  {
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    DeviceCtx& dc = dev_ctx_locked();
+    auto it = dc.gemm_slots.find(reinterpret_cast<const void*>(kern));
+    if (it != dc.gemm_slots.end()) {
+      slots = it->second;
+    } else {
+      slots = dc.sms / kClusterCtas;
+      if (kClusterCtas > 2) {
+        cfg.gridDim = dim3(dc.sms / kClusterCtas * kClusterCtas);
+        int n = 0;
+        CU_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+        if (n <= 0) return fail(VITB200_ERR_CUDA, "gemm: no %d-CTA cluster fits on this device", kClusterCtas);
+        if (n < slots) slots = n;
+        const char* v = getenv("VITB200_GEMM_SLOTS");
+        if (v && atoi(v) > 0 && atoi(v) < slots) slots = atoi(v);
+      }
+      dc.gemm_slots[reinterpret_cast<const void*>(kern)] = slots;
     }
   }
   const int units = gemm_units(sh.M, sh.N, gemm_cfg::BM * kPair, BN, kPairs);
@@ -250,11 +291,11 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
   int mode = gemm_pair_mode();
   // the multicast clusters pay off once there is more than one wave of tiles; small problems keep the finer pairs
   // (VITB200_GEMM_CLUSTER_MIN_TILES overrides the threshold: the parity tests force clusters onto small shapes)
-  static int min_tiles = -1;
-  if (min_tiles < 0) {
+  static const int env_min_tiles = [] {   // process-wide knob, not device state
     const char* v = getenv("VITB200_GEMM_CLUSTER_MIN_TILES");
-    min_tiles = v ? atoi(v) : device_sms() / 2 + 1;
-  }
+    return v ? atoi(v) : -1;
+  }();
+  const int min_tiles = env_min_tiles >= 0 ? env_min_tiles : (mode == 4 ? device_sms() / 2 + 1 : 0);
   if (mode == 4 && (BN != 256 || gemm_units(M, N, 256, 256, 1) < min_tiles)) mode = 2;
   const int pair = mode == 1 ? 1 : 2;
   if ((a_lo == nullptr) != (w_lo == nullptr)) return fail(VITB200_ERR_INVALID, "gemm: split-bf16 needs both low operands");
@@ -313,18 +354,18 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
   VT_TRY(make_tmap_bf16_3d(&tqkv, qkv, B, N, 3 * d, 3 * d, 128, 64));
   tqkv_lo = tqkv;
   if (split) VT_TRY(make_tmap_bf16_3d(&tqkv_lo, qkv_lo, B, N, 3 * d, 3 * d, 128, 64));
-  static bool configured = false;
-  if (!configured) {
-    CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtx));
-    CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtxSplit));
-    CU_TRY(cudaFuncSetAttribute(attention_long_ctx_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCtxCompact));
-    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMapsCompact));
-    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMapsCompact));
-    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
-    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
-    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
-    CU_TRY(cudaFuncSetAttribute(attention_long_maps_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMaps));
-    configured = true;
+  {
+    const std::pair<const void*, int> kerns[] = {
+        {(const void*)attention_long_ctx_kernel<false>, kSmemCtx},
+        {(const void*)attention_long_ctx_kernel<true>, kSmemCtxSplit},
+        {(const void*)attention_long_ctx_kernel<false, true>, kSmemCtxCompact},
+        {(const void*)attention_long_maps_kernel<false, false, true>, kSmemMapsCompact},
+        {(const void*)attention_long_maps_kernel<true, false, true>, kSmemMapsCompact},
+        {(const void*)attention_long_maps_kernel<false, false>, kSmemMaps},
+        {(const void*)attention_long_maps_kernel<true, false>, kSmemMaps},
+        {(const void*)attention_long_maps_kernel<false, true>, kSmemMaps},
+        {(const void*)attention_long_maps_kernel<true, true>, kSmemMaps}};
+    for (const auto& k : kerns) VT_TRY(ensure_func_smem(k.first, k.second));
   }
   AttnLongParams p;
   p.B = B, p.N = N, p.H = H, p.D = D, p.d = d;
@@ -384,13 +425,9 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   VT_TRY(make_tmap_bf16_3d(&tctx, ctx, B, N, d, d, 32, D));
   CUtensorMap tavg = tctx;  // placeholder when no head-averaged map is requested (never dereferenced)
   if (avg) VT_TRY(make_tmap_f32_3d(&tavg, avg, B, N, pitch, pitch, BM));
-  static bool configured = false;
-  if (!configured) {
-    CU_TRY(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CU_TRY(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CU_TRY(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
+  VT_TRY(ensure_func_smem((const void*)attention_kernel<false>, kSmemBytes));
+  VT_TRY(ensure_func_smem((const void*)attention_kernel<true>, kSmemBytes));
+  VT_TRY(ensure_func_smem((const void*)attention_kernel<false, true>, kSmemBytes));
   AttnParams p;
   p.B = B, p.N = N, p.H = H, p.d = d, p.KP = KP;
   p.scale_log2 = (1.0f / sqrtf((float)D)) * 1.4426950408889634f;
@@ -499,6 +536,35 @@ struct vitb200_engine {
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   uint64_t submitted = 0;  // tickets are submission indices; slot = ticket % 2
 
+  // Bumped whenever an activation buffer is re-allocated (vitb200_workspace_generation): device-resident state a caller
+  // believes the engine still holds (token stream, maps, preprocessed images) is gone, and so is every captured graph.
+  uint64_t generation = 1;
+
+  // CUDA graphs: a forward (or one node-granular stage) is a fixed launch sequence for a given (entry point, layer,
+  // batch, flags, input / bound-output addresses); the second time a key is seen its launches are captured from the
+  // stream and replayed from then on with ONE cudaGraphLaunch (the single-image request is ~110 launches whose host-side
+  // cost -- cudaLaunchKernelEx plus 2-4 cuTensorMapEncodeTiled calls each -- exceeded their device time).  The tensor
+  // maps are kernel parameters, so they are frozen into the graph with everything else.
+  struct GraphKey {
+    int kind = 0, layer = 0, batch = 0;
+    uint32_t flags = 0;
+    const void* images = nullptr;
+    const void *b_logits = nullptr, *b_cls = nullptr, *b_rollout = nullptr;
+    long b_stride = 0;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(kind, layer, batch, flags, images, b_logits, b_cls, b_rollout, b_stride) <
+             std::tie(o.kind, o.layer, o.batch, o.flags, o.images, o.b_logits, o.b_cls, o.b_rollout, o.b_stride);
+    }
+  };
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0, last_use = 0;
+    bool failed = false;
+  };
+  std::map<GraphKey, GraphEntry> graphs;
+  uint64_t graphs_generation = 0, graph_clock = 0, graph_replays = 0;
+  bool use_graphs = true;
+
   // vitb200_profile_forward: an event in front of every launch (only while `profiling`)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -509,9 +575,13 @@ struct vitb200_engine {
 
 namespace vitb200 {
 
-static int ensure(Buffer& b, size_t bytes) {
+// `generation` (optional): incremented when an EXISTING allocation is replaced (its contents and address are gone).
+static int ensure(Buffer& b, size_t bytes, uint64_t* generation = nullptr) {
   if (b.bytes >= bytes) return VITB200_OK;
-  if (b.p) CU_TRY(cudaFree(b.p));
+  if (b.p) {
+    CU_TRY(cudaFree(b.p));
+    if (generation) ++*generation;
+  }
   b.p = nullptr, b.bytes = 0;
   CU_TRY(cudaMalloc(&b.p, bytes));
   b.bytes = bytes;
@@ -527,6 +597,8 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   const vitb200_config& c = e->cfg;
   const size_t M = (size_t)B * e->N;
   const size_t L = c.num_layers;
+  uint64_t& gen = e->generation;   // counts replaced allocations (also when a later one fails)
+  auto ensure = [&](Buffer& b, size_t bytes) { return vitb200::ensure(b, bytes, &gen); };
   VT_TRY(ensure(e->images, (size_t)B * 3 * c.image_size * c.image_size * 4));
   VT_TRY(ensure(e->patches, (size_t)B * e->n * e->patch_k * 2));
   VT_TRY(ensure(e->x, M * c.hidden_dim * 4));
@@ -552,7 +624,10 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   if (flags & VITB200_EMIT_CLS) VT_TRY(ensure(e->cls, L * B * c.num_heads * e->N * 4));
   if (flags & VITB200_EMIT_HEADS) VT_TRY(ensure(e->heads, L * M * c.num_heads * e->pitch * 4));
   if (flags & VITB200_EMIT_HIDDEN) VT_TRY(ensure(e->hidden, L * M * c.hidden_dim * 4));
-  if (B > e->cap_batch) e->cap_batch = B;
+  if (B > e->cap_batch) {
+    if (e->cap_batch > 0) ++gen;   // the layer stride of the map buffers changes with the capacity
+    e->cap_batch = B;
+  }
   e->cap_flags |= flags;
   return VITB200_OK;
 }
@@ -703,11 +778,7 @@ static int launch_rollout(const float* maps, long layer_stride, int L, int B, in
   int stages = 8;
   while (stages > 2 && rollout_smem_bytes(ld, stages) > 110 * 1024) --stages;
   const int smem = rollout_smem_bytes(ld, stages);
-  static int configured = 0;
-  if (configured < smem) {
-    CU_TRY(cudaFuncSetAttribute(rollout_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  VT_TRY(ensure_func_smem((const void*)rollout_cls_kernel, smem));
   rollout_cls_kernel<<<B, kRolloutThreads, smem, st>>>(maps, layer_stride, L, N, ld, stages, out);
   CU_TRY(cudaGetLastError());
   return VITB200_OK;
@@ -757,11 +828,88 @@ static int check_batch(vitb200_engine* e, int B) {
   return VITB200_OK;
 }
 
+static void clear_graphs(vitb200_engine* e) {
+  for (auto& kv : e->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
+}
+
+// Run `body` (which only ENQUEUES work on `st`) directly, or -- from the second time `key` is seen -- as a captured
+// CUDA graph.  `body` must be a pure function of the key, the engine's configuration and its buffers (whose
+// re-allocation bumps `generation` and drops every graph).
+template <class Body>
+static int run_graphed(vitb200_engine* e, const vitb200_engine::GraphKey& key, cudaStream_t st, Body&& body) {
+  // (the legacy default stream cannot be captured; profiling needs an event in front of every launch)
+  if (!e->use_graphs || e->profiling || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return body();
+  if (e->graphs_generation != e->generation) {
+    clear_graphs(e);
+    e->graphs_generation = e->generation;
+  }
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    if (e->graphs.size() >= 128) {   // evict the least recently used entry
+      auto lru = e->graphs.begin();
+      for (auto j = e->graphs.begin(); j != e->graphs.end(); ++j)
+        if (j->second.last_use < lru->second.last_use) lru = j;
+      if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
+      e->graphs.erase(lru);
+    }
+    e->graphs[key].last_use = ++e->graph_clock;   // first sighting: run eagerly (this also configures the kernels)
+    return body();
+  }
+  vitb200_engine::GraphEntry& g = it->second;
+  g.last_use = ++e->graph_clock;
+  if (g.failed) return body();
+  if (g.exec == nullptr) {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      cudaGetLastError();
+      g.failed = true;
+      return body();
+    }
+    const uint64_t l0 = e->launches;
+    const int rc = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t err = cudaStreamEndCapture(st, &graph);
+    g.launches = e->launches - l0;
+    e->launches = l0;
+    bool ok = rc == VITB200_OK && err == cudaSuccess && graph != nullptr;
+    if (ok && cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) g.exec = nullptr, ok = false;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      g.failed = true;
+      return rc != VITB200_OK ? rc : body();
+    }
+  }
+  CU_TRY(cudaGraphLaunch(g.exec, st));
+  e->launches += g.launches;
+  e->graph_replays += 1;
+  return VITB200_OK;
+}
+
+static vitb200_engine::GraphKey graph_key(vitb200_engine* e, int kind, int layer, int B, uint32_t flags, const void* images) {
+  vitb200_engine::GraphKey k;
+  k.kind = kind, k.layer = layer, k.batch = B, k.flags = flags, k.images = images;
+  if (e->use_bound) {
+    k.b_logits = e->bound_logits, k.b_cls = e->bound_cls, k.b_rollout = e->bound_rollout;
+    k.b_stride = e->bound_cls_layer_stride;
+  }
+  return k;
+}
+enum { kGraphForward = 0, kGraphEmbed, kGraphLayer, kGraphAttnBlock, kGraphMlpBlock, kGraphHead, kGraphRollout };
+
+static int forward_stages(vitb200_engine* e, const float* images_dev, int B, uint32_t flags, cudaStream_t st);
+
 static int forward_device_locked(vitb200_engine* e, const float* images_dev, int B, uint32_t flags, cudaStream_t st) {
   VT_TRY(check_ready(e));
   VT_TRY(check_batch(e, B));
   // the layer-strided map buffers are addressed with cap_batch: grow first, then never shrink
   VT_TRY(ensure_workspace(e, B > e->cap_batch ? B : e->cap_batch, flags | e->cap_flags));
+  return run_graphed(e, graph_key(e, kGraphForward, 0, B, flags, images_dev), st,
+                     [&] { return forward_stages(e, images_dev, B, flags, st); });
+}
+
+static int forward_stages(vitb200_engine* e, const float* images_dev, int B, uint32_t flags, cudaStream_t st) {
   VT_TRY(run_embed(e, images_dev, B, st));
   for (int l = 0; l < e->cfg.num_layers; ++l) VT_TRY(run_layer(e, l, B, flags, st));
   VT_TRY(run_head(e, B, st));
@@ -779,6 +927,7 @@ static int copy_rows_to_host(float* dst, const float* src_dev, size_t rows, int 
 }  // namespace vitb200
 
 vitb200_engine::~vitb200_engine() {
+  clear_graphs(this);
   Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &ln_affine, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats,
                     &patches_lo, &xb_lo, &qkv_lo, &ctx_lo, &mlp_lo, &cls_ln_lo};
   for (Buffer* b : bufs) release(*b);
@@ -841,13 +990,16 @@ int vitb200_create(const vitb200_config* cfg, vitb200_engine** out) {
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, c.device));
   if (prop.major != 10) return fail(VITB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", c.device, prop.major, prop.minor);
-  g_num_sms = prop.multiProcessorCount;
 
   vitb200_engine* e = new vitb200_engine();
   e->cfg = c;
   e->precise = c.precision == 1;
   e->n = n, e->N = N, e->D = hd, e->KP = KP, e->pitch = KP, e->patch_k = 3 * c.patch_size * c.patch_size;
   e->layers.resize(c.num_layers);
+  {
+    const char* v = getenv("VITB200_GRAPHS");   // VITB200_GRAPHS=0: every call launches its kernels one by one
+    e->use_graphs = !(v && v[0] == '0');
+  }
   e->expected_tensors = 4 + 12 * (size_t)c.num_layers + 4;
   cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   if (err != cudaSuccess) {
@@ -944,11 +1096,14 @@ int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_h
   CU_TRY(cudaStreamSynchronize(e->stream));
   e->loaded[key] = true;
   e->folded = false;  // any new tensor invalidates the folded LayerNorm weights
+  clear_graphs(e);    // ... and every captured launch sequence (weight buffers are re-allocated)
   return VITB200_OK;
 }
 
 int vitb200_weights_ready(vitb200_engine* e) {
   if (!e) return fail(VITB200_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lock(e->mu);   // check_ready allocates and launches the fold kernels on first use
+  CU_TRY(cudaSetDevice(e->cfg.device));
   return check_ready(e);
 }
 
@@ -956,7 +1111,10 @@ int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch
   if (!e || !images_dev) return fail(VITB200_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lock(e->mu);
   CU_TRY(cudaSetDevice(e->cfg.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  // `stream` is taken literally: NULL is the legacy default stream, exactly as in the op_* entry points (torch's
+  // default stream has the handle 0 too; round 1 silently substituted the engine's private stream for it, which broke
+  // every event the caller recorded on "the stream the forward runs on").  vitb200_engine_stream names the private one.
+  cudaStream_t st = (cudaStream_t)stream;
   e->use_bound = true;
   const int rc = forward_device_locked(e, images_dev, batch, flags, st);
   e->use_bound = false;
@@ -975,6 +1133,43 @@ int vitb200_bind_outputs(vitb200_engine* e, float* logits_dev, float* cls_dev, l
   e->bound_logits = logits_dev, e->bound_cls = cls_dev, e->bound_rollout = rollout_dev;
   e->bound_cls_layer_stride = cls_dev ? cls_layer_stride : 0;
   return VITB200_OK;
+}
+
+int vitb200_engine_stream(vitb200_engine* e, void** stream) {
+  if (!e || !stream) return fail(VITB200_ERR_INVALID, "null argument");
+  *stream = (void*)e->stream;
+  return VITB200_OK;
+}
+
+uint64_t vitb200_workspace_generation(vitb200_engine* e) {
+  if (!e) return 0;
+  std::lock_guard<std::mutex> lock(e->mu);
+  return e->generation;
+}
+
+int vitb200_reserve(vitb200_engine* e, int batch, uint32_t flags) {
+  if (!e) return fail(VITB200_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  VT_TRY(check_batch(e, batch));
+  return ensure_workspace(e, batch > e->cap_batch ? batch : e->cap_batch, flags | e->cap_flags);
+}
+
+int vitb200_set_graphs(vitb200_engine* e, int on) {
+  if (!e) return fail(VITB200_ERR_INVALID, "null engine");
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->use_graphs = on != 0;
+  if (!e->use_graphs) {
+    CU_TRY(cudaSetDevice(e->cfg.device));
+    clear_graphs(e);
+  }
+  return VITB200_OK;
+}
+
+uint64_t vitb200_graph_replays(vitb200_engine* e) {
+  if (!e) return 0;
+  std::lock_guard<std::mutex> lock(e->mu);
+  return e->graph_replays;
 }
 
 int vitb200_profile_forward(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, char* report,
@@ -1138,6 +1333,7 @@ int vitb200_wait(vitb200_engine* e, uint64_t ticket) {
 
 int vitb200_staged_output(vitb200_engine* e, uint64_t ticket, uint32_t which, float** ptr_dev) {
   if (!e || !ptr_dev) return fail(VITB200_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
   if (ticket >= e->submitted || ticket + 2 < e->submitted) return fail(VITB200_ERR_STATE, "staged_output: ticket not in flight");
   vitb200_engine::Slot& sl = e->slots[ticket & 1];
   void* p = nullptr;
@@ -1155,6 +1351,7 @@ int vitb200_staged_output(vitb200_engine* e, uint64_t ticket, uint32_t which, fl
 
 int vitb200_device_output(vitb200_engine* e, uint32_t which, float** ptr_dev, int* pitch) {
   if (!e || !ptr_dev) return fail(VITB200_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(e->mu);
   int pt = 0;
   void* p = nullptr;
   switch (which) {
@@ -1228,7 +1425,8 @@ int vitb200_stage_transform(vitb200_engine* e, const float* images_host, int bat
 
 int vitb200_stage_embed_resident(vitb200_engine* e, int batch) {
   STAGE_PROLOGUE(batch, 0)
-  VT_TRY(run_embed(e, (const float*)e->images.p, batch, st));
+  VT_TRY(run_graphed(e, graph_key(e, kGraphEmbed, 0, batch, 0, e->images.p), st,
+                     [&] { return run_embed(e, (const float*)e->images.p, batch, st); }));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
@@ -1236,7 +1434,8 @@ int vitb200_stage_embed_resident(vitb200_engine* e, int batch) {
 int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags) {
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)
-  VT_TRY(run_layer(e, layer, batch, flags, st));
+  VT_TRY(run_graphed(e, graph_key(e, kGraphLayer, layer, batch, flags, nullptr), st,
+                     [&] { return run_layer(e, layer, batch, flags, st); }));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
@@ -1244,7 +1443,8 @@ int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags)
 int vitb200_stage_attn_block(vitb200_engine* e, int layer, int batch, uint32_t flags) {
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)
-  VT_TRY(run_attn_block(e, layer, batch, flags, st));
+  VT_TRY(run_graphed(e, graph_key(e, kGraphAttnBlock, layer, batch, flags, nullptr), st,
+                     [&] { return run_attn_block(e, layer, batch, flags, st); }));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
@@ -1252,14 +1452,15 @@ int vitb200_stage_attn_block(vitb200_engine* e, int layer, int batch, uint32_t f
 int vitb200_stage_mlp_block(vitb200_engine* e, int layer, int batch) {
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, 0)
-  VT_TRY(run_mlp_block(e, layer, batch, st));
+  VT_TRY(run_graphed(e, graph_key(e, kGraphMlpBlock, layer, batch, 0, nullptr), st,
+                     [&] { return run_mlp_block(e, layer, batch, st); }));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
 
 int vitb200_stage_head(vitb200_engine* e, int batch, float* logits_host) {
   STAGE_PROLOGUE(batch, 0)
-  VT_TRY(run_head(e, batch, st));
+  VT_TRY(run_graphed(e, graph_key(e, kGraphHead, 0, batch, 0, nullptr), st, [&] { return run_head(e, batch, st); }));
   if (logits_host)
     CU_TRY(cudaMemcpyAsync(logits_host, e->logits.p, (size_t)batch * e->cfg.num_classes * 4, cudaMemcpyDeviceToHost, st));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
@@ -1268,7 +1469,7 @@ int vitb200_stage_head(vitb200_engine* e, int batch, float* logits_host) {
 
 int vitb200_stage_rollout(vitb200_engine* e, int batch, float* rollout_host) {
   STAGE_PROLOGUE(batch, VITB200_EMIT_ROLLOUT)
-  VT_TRY(run_rollout(e, batch, st));
+  VT_TRY(run_graphed(e, graph_key(e, kGraphRollout, 0, batch, 0, nullptr), st, [&] { return run_rollout(e, batch, st); }));
   if (rollout_host)
     CU_TRY(cudaMemcpyAsync(rollout_host, e->rollout.p, (size_t)batch * (e->N - 1) * 4, cudaMemcpyDeviceToHost, st));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
@@ -1379,13 +1580,17 @@ int vitb200_op_gemm_ex(const void* a, const void* w, const float* bias, const fl
   }
   if (stats_in) {
     if (K % 128 != 0) return fail(VITB200_ERR_INVALID, "gemm: folded LayerNorm needs K to be a multiple of 128");
-    static float2* affine = nullptr;
-    static int cap = 0;
-    if (M > cap) {
-      if (affine) cudaFree(affine);
-      affine = nullptr, cap = 0;
-      CU_TRY(cudaMalloc(&affine, (size_t)M * sizeof(float2)));
-      cap = M;
+    float2* affine = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_dev_mu);
+      DeviceCtx& dc = dev_ctx_locked();
+      if (M > dc.op_affine_cap) {
+        if (dc.op_affine) cudaFree(dc.op_affine);
+        dc.op_affine = nullptr, dc.op_affine_cap = 0;
+        CU_TRY(cudaMalloc(&dc.op_affine, (size_t)M * sizeof(float2)));
+        dc.op_affine_cap = M;
+      }
+      affine = dc.op_affine;
     }
     row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float2*)stats_in, affine, M, K / 32, K,
                                                                                ln_eps);
@@ -1429,14 +1634,14 @@ int vitb200_op_layernorm(const float* x, const float* gamma, const float* beta, 
 
 // statistics scratch of the long-sequence attention path for the single-kernel entry point (grown on demand)
 static float2* op_attention_stats(size_t count) {
-  static float2* buf = nullptr;
-  static size_t cap = 0;
-  if (count > cap) {
-    if (buf) cudaFree(buf);
-    buf = nullptr, cap = 0;
-    if (cudaMalloc(&buf, count * sizeof(float2)) == cudaSuccess) cap = count;
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  DeviceCtx& dc = dev_ctx_locked();
+  if (count > dc.op_stats_cap) {
+    if (dc.op_stats) cudaFree(dc.op_stats);
+    dc.op_stats = nullptr, dc.op_stats_cap = 0;
+    if (cudaMalloc(&dc.op_stats, count * sizeof(float2)) == cudaSuccess) dc.op_stats_cap = count;
   }
-  return buf;
+  return dc.op_stats;
 }
 
 int vitb200_op_attention_ex(const void* qkv, void* ctx, float* avg, float* cls, float* heads, int batch, int tokens,

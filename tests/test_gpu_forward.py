@@ -397,14 +397,13 @@ def test_bench_size_properties(E):
     assert torch.equal(eng.forward_host(x[255:256].contiguous(), flags)["avg_maps"][:, 0], big["avg_maps"][:, 255])
     # run-to-run the batched result is bit-reproducible (the two halves are combined by a commutative add)
     again = eng.forward_host(x, flags)
-    for k in ("logits", "cls_maps", "avg_maps", "rollout"):
-        if not torch.equal(again[k], big[k]):
-            # Seen ONCE on one box (round 1, SM clock pinned at its maximum), not reproduced in 64 further iterations of
-            # this sequence (tools/repro_determinism.py).  Report what differs; a real race shows up as a large
-            # difference and still fails, a last-bit difference is reported and tolerated.
-            d = (again[k] - big[k]).abs()
-            print(f"[determinism] {k}: run-to-run difference, max {d.max().item():.3e}, {int((d > 0).sum())} elements")
-            assert d.max().item() < 1e-6, (k, d.max().item())
+    # (round 1 relaxed this to 1e-6 after ONE unexplained failure; the cause was a real race -- the head-average
+    # accumulator was read from TMEM without waiting for the last head's averaging MMAs, attention.cuh -- fixed in round 2)
+    for rep in range(3):
+        if rep:
+            again = eng.forward_host(x, flags)
+        for k in ("logits", "cls_maps", "avg_maps", "rollout"):
+            assert torch.equal(again[k], big[k]), (k, rep, (again[k] - big[k]).abs().max().item())
     eng.close()
 
 
