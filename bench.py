@@ -13,8 +13,11 @@ value      whole-job img/s with the images already resident in HBM, CUDA-event t
 e2e        the same metric through the public host API (VitEngine.submit_host / wait): pinned-host images in, H2D +
            forward + D2H of logits, per-head CLS maps and rollout inside the timed region.
 roofline   the dominant kernel (the tcgen05 GEMM instance with the largest share of the step) timed INSIDE real forwards
-           with CUDA events around every launch: achieved TFLOP/s = 2*M*N*K / duration, against the measured
-           sustained bf16 peak in MEASURED_PEAKS.json (the burst fraction is reported beside it).
+           with CUDA events around every launch: achieved TFLOP/s = 2*M*N*K / duration; `frac` is against the measured
+           BURST bf16 peak in MEASURED_PEAKS.json (the profiled forwards are a ~60 ms region), the sustained-peak
+           fraction is reported beside it.
+sustained  a second timed block of >= 3 s (--long-seconds) with its own clock / power samples and per-rank step times,
+           so that "power-bound" and "gap-bound" can be told apart from the line alone.
 cpu_baseline / --impl reference
            the reference's own path on the host cores: wire request -> Request.decode -> Context.compute over the
            torchvision-CPU plugin (one unbatched fp32 image per request, main/context.py:79-88,143-147) ->
@@ -32,6 +35,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# forward, copy-in, copy-out, reader and NCCL streams must not share a hardware queue (set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "images/sec ViT-B/16 224px fwd+attn maps"
 
@@ -55,7 +60,7 @@ class ClockSampler:
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
     def __init__(self, index: int):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.reasons, self.max_mhz, self.power = index, [], set(), None, []
         self._stop = threading.Event()
         self._t = None
         try:
@@ -72,6 +77,7 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
                 mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 for bit, name in self.REASONS.items():
                     if mask & bit:
@@ -92,9 +98,10 @@ class ClockSampler:
             self._t.join()
 
     def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        s, w = sorted(self.samples), sorted(self.power)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_min_mhz": s[0] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s),
+                "power_w": {"median": round(w[len(w) // 2], 1), "max": round(w[-1], 1)} if w else None}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -236,6 +243,8 @@ def plugin_request_latency(model_name, cfg, eng, P, n=20):
 
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args, rank: int, local_rank: int, world: int):
+    import math
+
     import torch
     import torch.distributed as dist
     import interactive_vit_b200.engine as E
@@ -259,46 +268,50 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             os.close(saved)
     cfg = E.CONFIGS[args.model]
     B = args.batch
+    device = torch.device("cuda", local_rank)
     eng = E.VitEngine(cfg, local_rank, B)
     eng.load_state_dict(P.build_torchvision_vit(cfg, seed=0).state_dict())
     flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
-    g = torch.Generator().manual_seed(1234 + rank)
-    host_images = torch.rand(B, 3, cfg.image_size, cfg.image_size, generator=g).pin_memory()
+
+    def rank_images(r):
+        return torch.rand(B, 3, cfg.image_size, cfg.image_size, generator=torch.Generator().manual_seed(1234 + r))
+
+    host_images = rank_images(rank).pin_memory()
     images = host_images.cuda(non_blocking=True)
     stream = torch.cuda.Stream()
     L, H, N = cfg.num_layers, cfg.num_heads, cfg.tokens
     total = B * world
 
-    # N > 1: one packed gather of logits + CLS maps + rollout per step to rank 0, issued from a side stream so that it
-    # runs under the next step's forward (dist.PackedGather); the timed region ends only when the last one has landed
+    # N > 1, the result exchange (logits + per-head CLS maps + rollout of every rank to rank 0), inside the timed step:
+    #   push (default): NO collective and no barrier -- the producing kernels store into rank 0's receive set over NVLink
+    #     peer memory (dist.PeerPush, vitb200_bind_outputs); per-rank completion flags order rank 0's reader behind them
+    #   nccl: one packed gather per step on a side stream, overlapping the next forward (dist.PackedGather)
     spec = {"logits": ((cfg.num_classes,), 0), "cls_maps": ((L, H, N), 1), "rollout": ((N - 1,), 0)}
-    # Device-resident arm, N > 1: `--gather push` (default "auto" tries it first) removes the collective altogether -- the
-    # producing kernels store logits / CLS maps / rollout straight into rank 0's receive set over NVLink peer memory
-    # (dist.PeerPush, vitb200_bind_outputs), one device-side barrier per step on a side stream.
+    top1 = [None]
+
+    def consume(s, views):
+        # rank 0 USES the gathered set on its reader stream: top-1 of every image, a checksum of the maps
+        top1[0] = (views["logits"].argmax(-1), views["cls_maps"].sum(), views["rollout"].sum())
+
     gatherer, pusher, gather_how = None, None, "none"
     if world > 1:
         if args.gather in ("auto", "push"):
-            ok = torch.ones(1, device="cuda")
             try:
-                pusher = D.PeerPush(eng, total, torch.device("cuda", local_rank))
-            except Exception as ex:
+                pusher = D.PeerPush(eng, total, device, stream=stream.cuda_stream, consumer=consume)
+            except Exception as ex:      # raised on every rank alike (PeerPush agrees before it raises)
                 print(f"[bench] rank {rank}: peer-memory push unavailable ({type(ex).__name__}: {str(ex)[:200]})",
                       file=sys.stderr, flush=True)
-                ok.zero_()
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() == 0:
                 if args.gather == "push":
-                    raise RuntimeError("--gather push: symmetric-memory rendezvous failed on at least one rank")
+                    raise
                 pusher = None
         if pusher is not None:
-            gather_how = ("logits + CLS maps + rollout to rank 0 with NO collective: the producing kernels store into "
-                          "rank 0's receive set over NVLink peer memory (symmetric memory), one device-side barrier per "
-                          "step on a side stream, three sets in rotation")
+            gather_how = ("logits + CLS maps + rollout to rank 0 with NO collective and no barrier: the producing kernels store "
+                          "into rank 0's receive set over NVLink peer memory (CUDA IPC mapping), per-rank completion flags, "
+                          "three sets in rotation; rank 0's reader stream consumes every set (top-1 + checksums)")
         else:
-            gatherer = D.PackedGather(spec, total, torch.device("cuda", local_rank))
+            gatherer = D.PackedGather(spec, total, device)
             gather_how = ("logits + CLS maps + rollout to rank 0: one packed NCCL gather per step on a side stream, "
                           "overlapping the next forward")
-    e2e_gatherer = D.PackedGather(spec, total, torch.device("cuda", local_rank)) if world > 1 else None
 
     def step():
         if pusher is not None:
@@ -317,51 +330,79 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step()
+    def timed_block(nsteps):
+        """nsteps steps between a barrier + synchronize on both sides; CUDA events on the launch stream.  Returns
+        (ms per step incl. the exchange, ms per step of this rank's OWN forwards, clock / power summary)."""
         barrier()
-        launches0 = eng.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0, ev_own, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         with ClockSampler(local_rank) as clocks:
             ev0.record(stream)
-            for _ in range(args.steps):
+            for _ in range(nsteps):
                 step()
+            ev_own.record(stream)            # this rank's forwards (and its completion flags) are done here ...
             if gatherer is not None:
                 gatherer.finish()
             if pusher is not None:
-                pusher.finish()
+                pusher.finish()              # ... rank 0 also waits for its reader: every rank's results consumed
             ev1.record(stream)
             barrier()
-        ms = ev0.elapsed_time(ev1) / args.steps
+        return ev0.elapsed_time(ev1) / nsteps, ev0.elapsed_time(ev_own) / nsteps, clocks.summary()
+
+    def all_ranks(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world == 1:
+            return [float(x)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+        launches0, replays0 = eng.launch_count(), eng.graph_replays()
+        ms_local, own_local, clk = timed_block(args.steps)
         launches = eng.launch_count() - launches0
+        replays = eng.graph_replays() - replays0
+        per_rank_ms, per_rank_own = all_ranks(ms_local), all_ranks(own_local)
+        ms = max(per_rank_ms)
+
+        # ---- a second, LONG block (>= --long-seconds): sustained clocks / power, per-rank step times
+        sustained = None
+        if args.long_seconds > 0:
+            nlong = max(args.steps, int(math.ceil(args.long_seconds * 1e3 / ms)))
+            lms, lown, lclk = timed_block(nlong)
+            l_ms, l_own = all_ranks(lms), all_ranks(lown)
+            sustained = {"steps": nlong, "seconds": round(max(l_ms) * nlong / 1e3, 2), "ms_per_step": max(l_ms),
+                         "value": total / max(l_ms) * 1e3, "unit": "img/s",
+                         "per_rank_ms_per_step": [round(v, 4) for v in l_ms],
+                         "per_rank_own_forward_ms_per_step": [round(v, 4) for v in l_own], "clocks_rank0": lclk}
+
+        push_check = None
         if pusher is not None:
-            # the pushed results on rank 0 against this rank's own forward into the engine's buffers (rank 0's slice is
-            # the same input, so it must match bit for bit) -- outside the timed region
-            push_check = None
+            # EVERY rank's slice of what was pushed to rank 0, against rank 0's own forward on that rank's images
+            # (seed 1234 + r; the forward is batch-invariant per image, so the bits must agree) -- outside the timed region
             if rank == 0:
                 got = {k: pusher.result(k).clone() for k in ("logits", "cls_maps", "rollout")}
             pusher.close()
-            dist.barrier()
             if rank == 0:
-                eng.forward_device(images, flags, stream.cuda_stream)
-                torch.cuda.synchronize()
-                own = {"logits": eng.device_output(0, (B, cfg.num_classes)),
-                       "cls_maps": eng.device_output(E.EMIT_CLS, (L, B, H, N)),
-                       "rollout": eng.device_output(E.EMIT_ROLLOUT, (B, N - 1))}
-                push_check = bool(torch.equal(got["logits"][:B], own["logits"]) and
-                                  torch.equal(got["cls_maps"][:, :B], own["cls_maps"]) and
-                                  torch.equal(got["rollout"][:B], own["rollout"]) and
-                                  all(bool(torch.isfinite(v).all()) and float(v[B:].abs().sum()) > 0 for v in
-                                      (got["logits"], got["rollout"])))
-                if not push_check:
-                    raise RuntimeError("peer-memory push: rank 0's receive set does not match its own forward")
-            gather_how += "; rank 0's slice verified bit-identical after the run"
+                push_check = []
+                for r in range(world):
+                    xr = images if r == 0 else rank_images(r).cuda()
+                    eng.forward_device(xr, flags, stream.cuda_stream)
+                    torch.cuda.synchronize()
+                    sl = slice(r * B, (r + 1) * B)
+                    ok = bool(torch.equal(got["logits"][sl], eng.device_output(0, (B, cfg.num_classes))) and
+                              torch.equal(got["cls_maps"][:, sl], eng.device_output(E.EMIT_CLS, (L, B, H, N))) and
+                              torch.equal(got["rollout"][sl], eng.device_output(E.EMIT_ROLLOUT, (B, N - 1))))
+                    push_check.append(ok)
+                if not all(push_check):
+                    raise RuntimeError(f"peer-memory push: slices {[r for r, ok in enumerate(push_check) if not ok]} of rank "
+                                       "0's receive set do not match rank 0's own forward on those ranks' images")
+                gather_how += f"; all {world} ranks' slices verified bit-identical after the run"
+            dist.barrier()
 
         # ---- per-kernel times inside real forwards (CUDA events in front of every launch on the launch stream; the
         # figures are event-to-event, so each includes the gap to the next launch), and the dominant kernel's roofline.
-        # Taken directly behind the timed steps, in the same thermal / power state (behind the e2e section the same
-        # forwards read up to 15 % slower)
         roof, kernels = None, None
         if rank == 0:
             peaks = _peaks()
@@ -386,21 +427,42 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     traffic = json.load(f).get(args.model, {}).get(dom)
             except Exception:
                 pass
-            # timed inside a ~10 ms step that is power-capped: the sustained figure is the matching denominator; the
-            # burst fraction is given beside it
+            # the profiled forwards are a ~60 ms region: the BURST peak is the denominator; the
+            # sustained-peak fraction is beside it
             roof = {"bound": "tensor", "kernel": f"gemm_bf16_kernel ({dom}) M={M_} N={n_} K={k_}", "achieved": achieved,
-                    "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
-                    "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "traffic": traffic,
-                    "peak_source": peaks["source"] + " sustained (kernel timed inside the step)", "kernel_ms": kms,
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                    "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                    "peak_source": peaks["source"] + " burst (cuBLAS bf16, best of 10)", "kernel_ms": kms,
                     "timing": "CUDA events on the launch stream around every launch of 5 profiled forwards, median"}
-
 
         # ---- e2e: public host API (VitEngine.submit_host / wait), pinned host buffers.  Every step copies its images
         # host -> device and its results device -> host inside the timed region; two requests are in flight, so the
-        # copies of neighbouring steps overlap the forward (separate copy streams).
-        outs = [{"logits": torch.empty(B, cfg.num_classes).pin_memory(), "cls_maps": torch.empty(L, B, H, N).pin_memory(),
-                 "rollout": torch.empty(B, N - 1).pin_memory()} for _ in range(2)]
+        # copies of neighbouring steps overlap the forward (separate copy streams).  N > 1: every rank feeds its GPU from
+        # its own pinned host images; the results are bound to rank 0's receive set (the same push as above, on the
+        # engine's own stream) and rank 0's reader copies the WHOLE gathered set to rank 0's pinned host memory.
         e2e_flags = E.EMIT_CLS | E.EMIT_ROLLOUT
+        e2e_push, e2e_gatherer, e2e_how = None, None, "VitEngine.submit_host / wait: 2 requests in flight, copies overlap the forward"
+        if world > 1:
+            host_sets = {}
+
+            def to_host(s, views):
+                for k, v in views.items():
+                    host_sets[s][k].copy_(v, non_blocking=True)
+
+            if pusher is not None:      # the transport that worked for the device-resident arm
+                e2e_push = D.PeerPush(eng, total, device, stream=None, consumer=to_host)
+                if rank == 0:       # pinned destinations of the gathered results, one per receive set
+                    shapes = {"logits": (total, cfg.num_classes), "cls_maps": (L, total, H, N), "rollout": (total, N - 1)}
+                    for s_ in range(e2e_push.sets):
+                        host_sets[s_] = {k: torch.empty(shp).pin_memory() for k, shp in shapes.items()}
+                e2e_how += ("; results bound to rank 0's receive set (no collective), rank 0 copies the gathered set "
+                            "device -> host from its reader stream")
+            else:
+                e2e_gatherer = D.PackedGather(spec, total, device)
+                e2e_how += "; staged results gathered to rank 0 with one packed NCCL gather per step"
+        outs = [{} if e2e_push is not None else
+                {"logits": torch.empty(B, cfg.num_classes).pin_memory(), "cls_maps": torch.empty(L, B, H, N).pin_memory(),
+                 "rollout": torch.empty(B, N - 1).pin_memory()} for _ in range(2)]
 
         def e2e_finish(ticket):
             eng.wait(ticket)
@@ -412,13 +474,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         def e2e_run(n):
             pending = []
             for i in range(n):
+                if e2e_push is not None:
+                    e2e_push.begin()
                 pending.append(eng.submit_host(host_images, e2e_flags, outs[i & 1]))
+                if e2e_push is not None:
+                    e2e_push.end()
                 if len(pending) == 2:
                     e2e_finish(pending.pop(0))
             while pending:
                 e2e_finish(pending.pop(0))
             if e2e_gatherer is not None:
                 e2e_gatherer.finish()
+            if e2e_push is not None:
+                e2e_push.finish()
             torch.cuda.synchronize()
 
         e2e_run(max(2, args.warmup // 2))
@@ -427,6 +495,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         e2e_run(args.steps)
         barrier()
         e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        if e2e_push is not None:
+            e2e_push.close()
 
         # ---- BASELINE config 1 beside it: ONE unbatched image through the reference-facing path (wire request ->
         # Request.decode -> Context.compute over the B200 plugin's nodes -> Response.encode), i.e. what the reference's
@@ -435,13 +505,22 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if rank == 0 and not args.no_cpu_baseline:
             try:
                 interactive = plugin_request_latency(args.model, cfg, eng, P)
+                st1 = torch.cuda.Stream()
+                x1 = images[:1].contiguous()
+                for _ in range(5):
+                    eng.forward_device(x1, flags, st1.cuda_stream)
+                st1.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st1)
+                for _ in range(50):
+                    eng.forward_device(x1, flags, st1.cuda_stream)
+                b.record(st1)
+                st1.synchronize()
+                interactive["forward_ms_batch1"] = round(a.elapsed_time(b) / 50, 4)
             except Exception as ex:  # reported, never fatal for the headline
                 interactive = {"error": str(ex)[:200]}
 
-    t = torch.tensor([ms, e2e_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = t.tolist()
+    e2e_ms = max(all_ranks(e2e_ms))
 
     if rank == 0:
         peaks = _peaks()
@@ -454,6 +533,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             cpu = {"value": done / dt, "unit": "img/s", "cores": ref.cores, "kind": "port",
                    "sample": f"{done} single-image requests in {dt:.1f}s through decode -> compute -> encode (torchvision CPU fp32)",
                    "batched": ref.batched()}
+        res_bytes = (cfg.num_classes + L * H * N + (N - 1)) * 4
         line = {
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -462,13 +542,19 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        "l2": f"inputs larger than L2 ({B * 3 * cfg.image_size ** 2 * 4 >> 20} MiB images, "
                              f"{B * N * cfg.hidden_dim * 4 >> 20} MiB token stream per step)",
                        "parallelism": f"dp{world}", "gather": gather_how},
-            "clocks": clocks.summary(),
+            "clocks": clk,
+            "per_rank": {"ms_per_step": [round(v, 4) for v in per_rank_ms],
+                         "own_forward_ms_per_step": [round(v, 4) for v in per_rank_own],
+                         "what": "CUDA events per rank: whole step incl. the exchange (rank 0: until its reader has consumed "
+                                 "every set) / the rank's own forwards only"},
+            "sustained": sustained,
             "e2e": {"value": total / e2e_ms * 1e3, "unit": "img/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": B * 3 * cfg.image_size ** 2 * 4,
-                    "d2h_bytes_per_step": (B * cfg.num_classes + L * B * H * N + B * (N - 1)) * 4,
-                    "outputs": "logits, per-head CLS maps (all layers), rollout",
-                    "api": "VitEngine.submit_host / wait: 2 requests in flight, copies overlap the forward"},
+                    "h2d_bytes_per_step": world * B * 3 * cfg.image_size ** 2 * 4,
+                    "d2h_bytes_per_step": total * res_bytes,
+                    "outputs": "logits, per-head CLS maps (all layers), rollout" + (" -- of all ranks, on rank 0's host" if world > 1 else ""),
+                    "api": e2e_how},
             "gpu_launches": launches,
+            "graph_replays": replays,
             "roofline": roof,
             "kernels": kernels,
             "step_tensor": {"achieved": value * flop / 1e3, "unit": "TFLOP/s", "gflop_per_image": flop,
@@ -477,6 +563,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "cpu_baseline": cpu,
             "interactive": interactive,
         }
+        if sustained is not None:
+            sustained["frac_of_burst_peak"] = sustained["value"] * flop / 1e3 / peaks["bf16_tflops"] / world
+            sustained["frac_of_sustained_peak"] = sustained["value"] * flop / 1e3 / peaks["bf16_tflops_sustained"] / world
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -492,6 +581,8 @@ def main():
     ap.add_argument("--model", default="vit_b_16")
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--long-seconds", type=float, default=3.0,
+                    help="length of the second timed block (sustained clocks / power, per-rank times); 0 skips it")
     ap.add_argument("--gather", default="auto", choices=["auto", "push", "nccl"],
                     help="N > 1 result exchange of the device-resident arm: peer-memory push (no collective) or packed NCCL gather")
     args = ap.parse_args()

@@ -85,12 +85,29 @@ int vitb200_weights_ready(vitb200_engine* e);
 
 /* Replaces: VisionTransformer.forward(x) (TV:289-306) for a whole batch, plus attention-map extraction
  * (need_weights=True in EncoderBlock, TV:113).  images: fp32 [B, 3, S, S].  Host variant: H2D copy, forward,
- * D2H copies of the requested outputs, synchronous on return.  Device variant: enqueues on `stream`
- * (a cudaStream_t; NULL = the engine's own stream) and returns without synchronising; results stay in the
- * engine's device buffers (vitb200_device_output). */
+ * D2H copies of the requested outputs, synchronous on return.  Device variant: enqueues on `stream`, a cudaStream_t
+ * taken literally -- NULL is the legacy default stream, as in the op_* entry points (and the handle torch reports for
+ * its default stream) -- and returns without synchronising; results stay in the engine's device buffers
+ * (vitb200_device_output).  vitb200_engine_stream returns the engine's own (non-blocking) stream, on which the host,
+ * pipelined and node-granular entry points run; pass it to run a device forward there.
+ * From the second call with the same (batch, flags, images_dev, bound outputs) the launch sequence is replayed as ONE
+ * captured CUDA graph (any stream but the legacy default one; vitb200_set_graphs(e, 0) or VITB200_GRAPHS=0 disables). */
 int vitb200_forward_host(vitb200_engine* e, const float* images_host, int batch, uint32_t flags,
                          const vitb200_host_outputs* out);
 int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch, uint32_t flags, void* stream);
+int vitb200_engine_stream(vitb200_engine* e, void** stream);
+
+/* Workspace management.  The activation buffers grow on demand (any call with a larger batch or a new output flag);
+ * growth RE-ALLOCATES them, so device-resident state a caller relies on between calls -- the token stream between two
+ * node calls, the maps a rollout node will read, preprocessed images -- is lost.  vitb200_workspace_generation returns a
+ * counter that changes whenever that happened (the plugin drops its residency shortcuts when it moves);
+ * vitb200_reserve grows the workspace up front for `batch` images and the outputs in `flags`, so that no later call of
+ * the same request can.  vitb200_set_graphs switches CUDA-graph replay of forwards / stages off (0) or on;
+ * vitb200_graph_replays counts replays (harness evidence that the captured path is the one that ran). */
+uint64_t vitb200_workspace_generation(vitb200_engine* e);
+int vitb200_reserve(vitb200_engine* e, int batch, uint32_t flags);
+int vitb200_set_graphs(vitb200_engine* e, int on);
+uint64_t vitb200_graph_replays(vitb200_engine* e);
 
 /* Multi-GPU result exchange without a collective (the reference is single-process, so this
  * replaces nothing there).  Routes the small results of vitb200_forward_device into caller-owned device memory --
@@ -101,9 +118,24 @@ int vitb200_forward_device(vitb200_engine* e, const float* images_dev, int batch
  *   logits_dev : [batch, classes] rows (16-byte aligned), or NULL = engine buffer
  *   cls_dev    : layer l, image b, head h at cls_dev + l * cls_layer_stride + (b * heads + h) * tokens  (floats), or NULL
  *   rollout_dev: [batch, tokens - 1] rows, or NULL
- * All NULL restores the engine's own buffers.  Only vitb200_forward_device honours the binding; the host, pipelined and
- * node-granular entry points keep using the engine's buffers. */
+ * All NULL restores the engine's own buffers.  vitb200_forward_device and vitb200_submit_host honour the binding (a
+ * bound output must then not also be requested on the host: it is neither staged nor copied there); the synchronous
+ * host and the node-granular entry points keep using the engine's buffers.  Completion signalling must be enqueued on
+ * the stream the forward runs on (the `stream` argument, or the engine's own stream for submit_host). */
 int vitb200_bind_outputs(vitb200_engine* e, float* logits_dev, float* cls_dev, long cls_layer_stride, float* rollout_dev);
+
+/* Plumbing for that exchange, free of any framework dependency (nothing in the reference):
+ * vitb200_peer_alloc allocates zeroed device memory on `device` and returns its 64-byte CUDA IPC handle, which the
+ * caller ships to the other ranks' processes (torch.distributed is only the courier); vitb200_peer_open maps it there
+ * (peer access over NVLink is enabled on demand).  vitb200_flag_signal / vitb200_flag_wait enqueue one-thread kernels on
+ * `stream`: a system-scope release store of a monotone counter value, and a back-off spin until the counter has
+ * reached `value` (watchdog: 30 s, then the kernel traps).  csrc/peer.cuh has the protocol built from them. */
+int vitb200_peer_alloc(int device, size_t bytes, void** ptr_dev, void* handle64);
+int vitb200_peer_open(int device, const void* handle64, void** ptr_dev);
+int vitb200_peer_close(int device, void* ptr_dev);
+int vitb200_peer_free(int device, void* ptr_dev);
+int vitb200_flag_signal(void* flag_dev, uint32_t value, void* stream);
+int vitb200_flag_wait(const void* flag_dev, uint32_t value, void* stream);
 
 /* Pipelined variant of vitb200_forward_host for request streams: returns once the work is enqueued.  Up to two
  * requests are in flight; the host-to-device copy of request i+1 and the device-to-host copies of request i-1

@@ -33,6 +33,7 @@
 #include "attention.cuh"
 #include "attention_long.cuh"
 #include "gemm.cuh"
+#include "peer.cuh"
 #include "rowwise.cuh"
 
 namespace vitb200 {
@@ -1135,6 +1136,64 @@ int vitb200_bind_outputs(vitb200_engine* e, float* logits_dev, float* cls_dev, l
   return VITB200_OK;
 }
 
+// ---- peer memory + completion flags (csrc/peer.cuh) ---------------------------------------------------
+int vitb200_peer_alloc(int device, size_t bytes, void** ptr_dev, void* handle64) {
+  if (!ptr_dev || !handle64 || bytes == 0) return fail(VITB200_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CU_TRY(cudaSetDevice(device));
+  void* p = nullptr;
+  CU_TRY(cudaMalloc(&p, bytes));
+  cudaError_t err = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (err == cudaSuccess) err = cudaIpcGetMemHandle(&h, p);
+  if (err != cudaSuccess) {
+    cudaFree(p);
+    return fail(VITB200_ERR_CUDA, "peer_alloc: %s", cudaGetErrorString(err));
+  }
+  memcpy(handle64, &h, 64);
+  *ptr_dev = p;
+  return VITB200_OK;
+}
+
+int vitb200_peer_open(int device, const void* handle64, void** ptr_dev) {
+  if (!ptr_dev || !handle64) return fail(VITB200_ERR_INVALID, "null argument");
+  CU_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_dev = p;
+  return VITB200_OK;
+}
+
+int vitb200_peer_close(int device, void* ptr_dev) {
+  if (!ptr_dev) return VITB200_OK;
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaIpcCloseMemHandle(ptr_dev));
+  return VITB200_OK;
+}
+
+int vitb200_peer_free(int device, void* ptr_dev) {
+  if (!ptr_dev) return VITB200_OK;
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaFree(ptr_dev));
+  return VITB200_OK;
+}
+
+int vitb200_flag_signal(void* flag_dev, uint32_t value, void* stream) {
+  if (!flag_dev || ((uintptr_t)flag_dev & 3u)) return fail(VITB200_ERR_INVALID, "flag_signal: bad flag address");
+  flag_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint32_t*)flag_dev, value);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
+int vitb200_flag_wait(const void* flag_dev, uint32_t value, void* stream) {
+  if (!flag_dev || ((uintptr_t)flag_dev & 3u)) return fail(VITB200_ERR_INVALID, "flag_wait: bad flag address");
+  flag_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const uint32_t*)flag_dev, value, 30ull * 1000 * 1000 * 1000);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
 int vitb200_engine_stream(vitb200_engine* e, void** stream) {
   if (!e || !stream) return fail(VITB200_ERR_INVALID, "null argument");
   *stream = (void*)e->stream;
@@ -1271,6 +1330,12 @@ int vitb200_submit_host(vitb200_engine* e, const float* images_host, int batch, 
   VT_TRY(check_ready(e));
   VT_TRY(check_batch(e, batch));
   VT_TRY(ensure_workspace(e, batch > e->cap_batch ? batch : e->cap_batch, flags | e->cap_flags));
+  // Bound outputs (vitb200_bind_outputs): the producing kernels store them into the caller's memory (rank 0's receive
+  // set in the multi-GPU case), so they are neither staged nor copied to THIS rank's host
+  const bool b_logits = e->bound_logits != nullptr, b_cls = e->bound_cls != nullptr && (flags & VITB200_EMIT_CLS),
+             b_roll = e->bound_rollout != nullptr && (flags & VITB200_EMIT_ROLLOUT);
+  if ((b_logits && out->logits) || (b_cls && out->cls_maps) || (b_roll && out->rollout))
+    return fail(VITB200_ERR_INVALID, "submit_host: an output that is bound to caller memory cannot also be copied to the host");
   if (!e->copy_in) {
     CU_TRY(cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking));
@@ -1295,9 +1360,12 @@ int vitb200_submit_host(vitb200_engine* e, const float* images_host, int batch, 
   CU_TRY(cudaEventRecord(sl.in_done, e->copy_in));
   cudaStream_t st = e->stream;
   CU_TRY(cudaStreamWaitEvent(st, sl.in_done, 0));
-  VT_TRY(forward_device_locked(e, (const float*)sl.images.p, B, flags, st));
+  e->use_bound = true;
+  const int frc = forward_device_locked(e, (const float*)sl.images.p, B, flags, st);
+  e->use_bound = false;
+  VT_TRY(frc);
   // staging copies of the outputs (device to device, tens of MB): the next forward may overwrite the engine's buffers
-  CU_TRY(cudaMemcpyAsync(sl.logits.p, e->logits.p, logit_bytes, cudaMemcpyDeviceToDevice, st));
+  if (!b_logits) CU_TRY(cudaMemcpyAsync(sl.logits.p, e->logits.p, logit_bytes, cudaMemcpyDeviceToDevice, st));
   for (int l = 0; l < L; ++l) {
     if (out->cls_maps)
       CU_TRY(cudaMemcpyAsync((char*)sl.cls.p + l * cls_bytes, (const float*)e->cls.p + (size_t)l * e->cap_batch * Hh * N, cls_bytes,

@@ -199,24 +199,36 @@ class PushLayout:
 
 
 class PeerPush:
-    """The result exchange of the data-parallel forward without a collective: every rank's PRODUCING kernels (head GEMM
-    epilogue, the attention kernel's CLS-row writer, the rollout kernel) store their results straight into rank 0's
-    receive set over NVLink / NVSwitch peer memory (`VitEngine.bind_outputs` on addresses of a symmetric-memory
-    allocation), already in the final image-ordered layout.  There is no pack kernel, no staging copy, no NCCL call
-    and nothing to concatenate; what remains of the "gather" is one device-side barrier per step, issued from a side
-    stream so that it never sits between two forwards.
+    """The result exchange of the data-parallel forward without a collective and without a barrier: every rank's
+    PRODUCING kernels (head GEMM epilogue, the attention kernel's CLS-row writer, the rollout kernel) store their
+    results straight into rank 0's receive set over NVLink / NVSwitch peer memory (`VitEngine.bind_outputs`), already
+    in the final image-ordered layout.  There is no pack kernel, no staging copy, no NCCL call and nothing to
+    concatenate; ordering is carried by per-rank completion flags next to the sets (csrc/peer.cuh):
 
-    Protocol (per rank, stream-ordered): ``begin()`` binds set ``i % sets`` and makes the current stream wait for the
-    barrier of step ``i - sets + 1``; the forward writes; ``end()`` issues barrier ``i`` on the side stream behind the
-    forward.  On rank 0 a set is complete after ``wait(s)``; reads of it enqueued on the submitting stream before the
-    next ``end()`` are ordered before any rank writes that set again (their barrier waits for rank 0's, which waits
-    for those reads).  With three sets a rank may run up to two forwards ahead of the slowest one.
+        done[r][s]   rank r, behind its forward into set s          (monotone step counter, system-scope release store)
+        free[s]      rank 0's reader, behind its reads of set s
 
-    Needs CUDA peer access between the ranks' GPUs (one box) and `torch.distributed._symmetric_memory`; raises if
-    the rendezvous fails — callers that want a fallback transport use `PackedGather` (NCCL)."""
+    Per rank and step i (set s = i % sets), all stream-ordered on the stream the forward runs on: ``begin()`` waits for
+    ``free[s] >= i - sets + 1`` (only from the second rotation on) and binds the set, the forward writes, ``end()``
+    signals ``done[rank][s] = i + 1``.  Rank 0 additionally runs a READER stream: wait for every rank's ``done[.][s]``,
+    run the consumer (``consumer(s, views)``: torch work on the current = reader stream, e.g. the device-to-host copy
+    of the gathered results), signal ``free[s]``.  No rank waits for another rank's forward of the same step: with
+    three sets a rank may be two forwards ahead of rank 0's reader, and the reader is never on a forward's stream.
+    On rank 0 the two streams of its OWN GPU are ordered with CUDA events, not flags (kernels that spin on a flag
+    written by another launch on the same GPU are not guaranteed to make progress).
 
-    def __init__(self, eng, total: int, device, group=None, sets: int = 3):
-        self.eng = eng
+    The receive sets and flags are ONE `cudaMalloc` allocation of rank 0 whose CUDA IPC handle travels to the other
+    ranks through ``torch.distributed`` (public API; plumbing) and is mapped there with ``cudaIpcOpenMemHandle``
+    (``engine.peer_alloc / peer_open``).  Raises on every rank if any rank cannot map it -- callers that want a
+    fallback transport use `PackedGather` (NCCL)."""
+
+    FLAG_BYTES = 128   # one flag per 128-byte line
+
+    def __init__(self, eng, total: int, device, group=None, sets: int = 3, stream: Optional[int] = None,
+                 consumer=None):
+        from . import engine as E
+
+        self.E, self.eng = E, eng
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
@@ -224,36 +236,60 @@ class PeerPush:
         self.layout = PushLayout(total, self.world, cfg.num_classes, cfg.num_layers, cfg.num_heads, cfg.tokens)
         self.sets = sets
         self.device = torch.device(device)
-        self.buf = self.hdl = None
-        # Two phases, so that a rank whose LOCAL allocation fails never leaves the others waiting in the rendezvous:
-        # (1) allocate, (2) agree (MIN over ranks), (3) rendezvous -- a collective whose failures are symmetric.
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        # the stream the forwards run on: the flags are enqueued on it, in front of and behind each forward
+        self.stream = int(stream) if stream is not None else eng.engine_stream()
+        self.consumer = consumer
+        self.flag_off = _round_up(4 * sets * self.layout.set_floats, self.FLAG_BYTES)
+        nbytes = self.flag_off + self.FLAG_BYTES * (self.world * sets + sets)
+        self.root_ptr = 0
+        self.owner = False
+        # (1) rank 0 allocates, (2) its IPC handle is broadcast, (3) everyone maps it, (4) agree (MIN over ranks)
         err: Optional[Exception] = None
-        try:
-            import torch.distributed._symmetric_memory as symm
-
-            self.buf = symm.empty(sets * self.layout.set_floats, dtype=torch.float32, device=self.device)
-        except Exception as ex:      # reported below, on every rank
-            err = ex
+        payload = [None]
+        if self.rank == 0:
+            try:
+                self.root_ptr, handle = E.peer_alloc(self.dev_index, nbytes)
+                self.owner = True
+                payload = [handle]
+            except Exception as ex:
+                err = ex
+        dist.broadcast_object_list(payload, src=dist.get_global_rank(self.group, 0), group=self.group)
+        if self.rank != 0:
+            try:
+                if payload[0] is None:
+                    raise RuntimeError("rank 0 could not allocate the receive sets")
+                self.root_ptr = E.peer_open(self.dev_index, payload[0])   # rank 0's memory as mapped into THIS process
+            except Exception as ex:
+                err = ex
         ok = torch.tensor([0.0 if err is not None else 1.0], device=self.device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
         if ok.item() == 0:
-            self.buf = None
-            raise RuntimeError(f"PeerPush: symmetric-memory allocation failed on at least one rank"
+            self._release()
+            raise RuntimeError("PeerPush: the receive sets could not be mapped on at least one rank"
                                f"{'' if err is None else f' (here: {type(err).__name__}: {err})'}")
-        self.hdl = symm.rendezvous(self.buf, self.group)
-        self.root_ptr = int(self.hdl.buffer_ptrs[0])   # rank 0's buffer as mapped into THIS process
-        self.side = torch.cuda.Stream(device=self.device)
-        self.closed = [None] * sets     # event behind the barrier that completed set s
+        self.buf = (E._device_view(self.root_ptr, (sets * self.layout.set_floats,), self.dev_index)
+                    if self.rank == 0 else None)
+        self.reader = torch.cuda.Stream(device=self.device) if self.rank == 0 else None
+        self.closed = [None] * sets     # rank 0: event behind the reader's pass over set s
         self.step = 0
         self.last = -1
+
+    # ---- flag addresses (in rank 0's allocation, as mapped here)
+    def _done(self, rank: int, s: int) -> int:
+        return self.root_ptr + self.flag_off + self.FLAG_BYTES * (rank * self.sets + s)
+
+    def _free(self, s: int) -> int:
+        return self.root_ptr + self.flag_off + self.FLAG_BYTES * (self.world * self.sets + s)
 
     def begin(self) -> int:
         """Bind this step's receive set as the engine's output destination; returns the set index."""
         i, s = self.step, self.step % self.sets
-        if i >= self.sets - 1:
-            prev = self.closed[(i - self.sets + 1) % self.sets]
-            if prev is not None:
-                torch.cuda.current_stream(self.device).wait_event(prev)
+        if i >= self.sets:
+            if self.rank == 0:     # own GPU: an event, not a flag
+                _raw_stream_wait_event(self.stream, self.closed[s], self.device)
+            else:
+                self.E.flag_wait(self._free(s), i - self.sets + 1, self.stream)
         off = self.layout.rank_offsets(self.rank)
         base = self.root_ptr + 4 * s * self.layout.set_floats
         self.eng.bind_outputs(base + 4 * off["logits"], base + 4 * off["cls_maps"], self.layout.cls_layer_stride,
@@ -261,24 +297,32 @@ class PeerPush:
         return s
 
     def end(self) -> int:
-        """Behind the forward: signal that this rank's part of the set is written (device-side barrier, side stream)."""
-        s = self.step % self.sets
+        """Behind the forward: publish that this rank's part of the set is written; rank 0 also queues its reader."""
+        i, s = self.step, self.step % self.sets
         self.step += 1
-        written = torch.cuda.Event()
-        written.record(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(written)
-            self.hdl.barrier(channel=0)
-            done = torch.cuda.Event()
-            done.record(self.side)
-        self.closed[s] = done
         self.last = s
+        if self.rank != 0:
+            self.E.flag_signal(self._done(self.rank, s), i + 1, self.stream)
+            return s
+        written = torch.cuda.Event()
+        _raw_stream_record_event(self.stream, written, self.device)
+        with torch.cuda.stream(self.reader):
+            self.reader.wait_event(written)
+            for r in range(1, self.world):
+                self.E.flag_wait(self._done(r, s), i + 1, self.reader.cuda_stream)
+            if self.consumer is not None:
+                n = self.layout.set_floats
+                self.consumer(s, self.layout.views(self.buf[s * n:(s + 1) * n]))
+            self.E.flag_signal(self._free(s), i + 1, self.reader.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(self.reader)
+        self.closed[s] = done
         return s
 
     def wait(self, s: Optional[int] = None) -> None:
-        """Make the current stream wait until set `s` (default: the last one) is complete on rank 0."""
+        """Rank 0: make the current stream wait until set `s` (default: the last one) is complete and consumed."""
         s = self.last if s is None else s
-        if self.closed[s] is not None:
+        if self.rank == 0 and self.closed[s] is not None:
             torch.cuda.current_stream(self.device).wait_event(self.closed[s])
 
     def finish(self) -> None:
@@ -293,6 +337,39 @@ class PeerPush:
         n = self.layout.set_floats
         return self.layout.views(self.buf[s * n:(s + 1) * n])[name]
 
+    def _release(self) -> None:
+        if self.root_ptr:
+            try:
+                if self.owner:
+                    self.E.peer_free(self.dev_index, self.root_ptr)
+                else:
+                    self.E.peer_close(self.dev_index, self.root_ptr)
+            except Exception:
+                pass
+        self.root_ptr = 0
+        self.buf = None
+
     def close(self) -> None:
+        """Collective: every rank unbinds and unmaps; rank 0 frees the sets once nobody can write them any more."""
         self.finish()
         self.eng.bind_outputs()
+        torch.cuda.synchronize(self.device)
+        if self.rank != 0:
+            self._release()
+        dist.barrier(group=self.group)
+        if self.rank == 0:
+            self._release()
+
+
+def _raw_stream(handle: int, device) -> "torch.cuda.Stream":
+    """torch view of a raw cudaStream_t (the engine's own stream, or a torch stream's handle)."""
+    return torch.cuda.ExternalStream(handle, device=device) if handle else torch.cuda.default_stream(device)
+
+
+def _raw_stream_wait_event(handle: int, event, device) -> None:
+    if event is not None:
+        _raw_stream(handle, device).wait_event(event)
+
+
+def _raw_stream_record_event(handle: int, event, device) -> None:
+    event.record(_raw_stream(handle, device))

@@ -67,7 +67,18 @@ SIGNATURES = {
     "vitb200_weights_ready": (_I, [_P]),
     "vitb200_forward_host": (_I, [_P, _P, _I, _U32, C.POINTER(_HostOutputs)]),
     "vitb200_forward_device": (_I, [_P, _P, _I, _U32, _P]),
+    "vitb200_engine_stream": (_I, [_P, C.POINTER(_P)]),
+    "vitb200_workspace_generation": (C.c_uint64, [_P]),
+    "vitb200_reserve": (_I, [_P, _I, _U32]),
+    "vitb200_set_graphs": (_I, [_P, _I]),
+    "vitb200_graph_replays": (C.c_uint64, [_P]),
     "vitb200_bind_outputs": (_I, [_P, _P, _P, _L, _P]),
+    "vitb200_peer_alloc": (_I, [_I, C.c_size_t, C.POINTER(_P), _P]),
+    "vitb200_peer_open": (_I, [_I, _P, C.POINTER(_P)]),
+    "vitb200_peer_close": (_I, [_I, _P]),
+    "vitb200_peer_free": (_I, [_I, _P]),
+    "vitb200_flag_signal": (_I, [_P, _U32, _P]),
+    "vitb200_flag_wait": (_I, [_P, _U32, _P]),
     "vitb200_submit_host": (_I, [_P, _P, _I, _U32, C.POINTER(_HostOutputs), C.POINTER(C.c_uint64)]),
     "vitb200_wait": (_I, [_P, C.c_uint64]),
     "vitb200_staged_output": (_I, [_P, C.c_uint64, _U32, C.POINTER(_P)]),
@@ -317,9 +328,33 @@ class VitEngine:
         return _device_view(p.value, shape, self.device)
 
     def forward_device(self, images: torch.Tensor, flags: int = 0, stream: Optional[int] = None) -> None:
-        """images: CUDA fp32 [B,3,S,S] on this engine's device; enqueues on `stream` (raw cudaStream_t)."""
+        """images: CUDA fp32 [B,3,S,S] on this engine's device; enqueues on `stream`, a raw cudaStream_t taken literally
+        (0 = the legacy default stream, which is also what torch reports for its default stream).  None = the engine's
+        own stream (`engine_stream()`), the one `synchronize()` waits for."""
         assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
-        check(self.lib.vitb200_forward_device(self._h, images.data_ptr(), images.shape[0], flags, stream))
+        if stream is None:
+            stream = self.engine_stream()
+        check(self.lib.vitb200_forward_device(self._h, images.data_ptr(), images.shape[0], flags, stream or None))
+
+    def engine_stream(self) -> int:
+        """Raw cudaStream_t of the engine's own stream."""
+        p = C.c_void_p()
+        check(self.lib.vitb200_engine_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
+
+    def workspace_generation(self) -> int:
+        """Changes whenever the engine re-allocated its activation buffers (device-resident state is gone)."""
+        return int(self.lib.vitb200_workspace_generation(self._h))
+
+    def reserve(self, batch: int, flags: int = 0) -> None:
+        """Grow the workspace for `batch` images and the outputs in `flags` now, so that no later call can."""
+        check(self.lib.vitb200_reserve(self._h, batch, flags))
+
+    def set_graphs(self, on: bool) -> None:
+        check(self.lib.vitb200_set_graphs(self._h, 1 if on else 0))
+
+    def graph_replays(self) -> int:
+        return int(self.lib.vitb200_graph_replays(self._h))
 
     def bind_outputs(self, logits: Optional[int] = None, cls_maps: Optional[int] = None, cls_layer_stride: int = 0,
                      rollout: Optional[int] = None) -> None:
@@ -376,10 +411,12 @@ class VitEngine:
         del held
 
     def begin_request(self) -> None:
+        # (the slab fields are guarded by _book: responses may be encoded on other threads)
         """Deferred mode: the next host output starts a fresh pinned slab (called by the plugin at a request's first
         node).  Outputs are bump-allocated views of ONE pinned allocation per request -- a region is never handed out
         twice, so earlier responses stay valid, and the slab returns to torch's cache when its last view dies."""
-        self._slab = None
+        with self._book:
+            self._slab = None
 
     def _host_out(self, *shape) -> torch.Tensor:
         if not self._deferred:
@@ -388,13 +425,24 @@ class VitEngine:
         for d_ in shape:
             n *= d_
         need = (n * 4 + 255) // 256 * 256
-        if self._slab is None or self._slab_off + need > self._slab.numel():
-            size = max(self._request_bytes(shape[0]), need)
-            self._slab = torch.empty(size, dtype=torch.uint8, pin_memory=True)
-            self._slab_off = 0
-        v = self._slab[self._slab_off:self._slab_off + n * 4].view(torch.float32).view(*shape)
-        self._slab_off += need
+        with self._book:
+            if self._slab is None or self._slab_off + need > self._slab.numel():
+                size = max(self._request_bytes(shape[0]), need)
+                self._slab = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+                self._slab_off = 0
+            v = self._slab[self._slab_off:self._slab_off + n * 4].view(torch.float32).view(*shape)
+            self._slab_off += need
         return v
+
+    def _checked_out(self, status: int, out: torch.Tensor) -> None:
+        """`check` for calls that may already have enqueued a copy into `out`: on failure wait for the stream before
+        the exception lets go of the pinned buffer (it would return to torch's cache with the copy still in flight)."""
+        if status != 0 and self._deferred:
+            try:
+                self.synchronize()
+            except Exception:
+                pass
+        check(status)
 
     def _issue(self, out: torch.Tensor, shape=None) -> torch.Tensor:
         """Called right AFTER the copy into `out` was enqueued: a count read before a synchronize therefore only
@@ -457,12 +505,12 @@ class VitEngine:
 
     def stage_head(self, batch: int, shape=None) -> torch.Tensor:
         out = self._host_out(batch, self.cfg.num_classes)
-        check(self.lib.vitb200_stage_head(self._h, batch, out.data_ptr()))
+        self._checked_out(self.lib.vitb200_stage_head(self._h, batch, out.data_ptr()), out)
         return self._issue(out, shape)
 
     def stage_rollout(self, batch: int, shape=None) -> torch.Tensor:
         out = self._host_out(batch, self.cfg.tokens - 1)
-        check(self.lib.vitb200_stage_rollout(self._h, batch, out.data_ptr()))
+        self._checked_out(self.lib.vitb200_stage_rollout(self._h, batch, out.data_ptr()), out)
         return self._issue(out, shape)
 
     def set_tokens(self, tokens: torch.Tensor) -> None:
@@ -471,7 +519,7 @@ class VitEngine:
 
     def get_tokens(self, batch: int, shape=None) -> torch.Tensor:
         out = self._host_out(batch, self.cfg.tokens, self.cfg.hidden_dim)
-        check(self.lib.vitb200_get_tokens(self._h, out.data_ptr(), batch))
+        self._checked_out(self.lib.vitb200_get_tokens(self._h, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
     def set_avg_map(self, layer: int, amap: torch.Tensor) -> None:
@@ -481,28 +529,62 @@ class VitEngine:
     def get_avg_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         N = self.cfg.tokens
         out = self._host_out(batch, N, N)
-        check(self.lib.vitb200_get_avg_map(self._h, layer, out.data_ptr(), batch))
+        self._checked_out(self.lib.vitb200_get_avg_map(self._h, layer, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
     def get_cls_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         out = self._host_out(batch, self.cfg.num_heads, self.cfg.tokens)
-        check(self.lib.vitb200_get_cls_map(self._h, layer, out.data_ptr(), batch))
+        self._checked_out(self.lib.vitb200_get_cls_map(self._h, layer, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
     def get_cls_grid(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         """[B, H, N-1]: the class token's attention to the patch tokens per head (class column dropped by the copy)."""
         out = self._host_out(batch, self.cfg.num_heads, self.cfg.tokens - 1)
-        check(self.lib.vitb200_get_cls_grid(self._h, layer, out.data_ptr(), batch))
+        self._checked_out(self.lib.vitb200_get_cls_grid(self._h, layer, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
     def get_head_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         N = self.cfg.tokens
         out = self._host_out(batch, self.cfg.num_heads, N, N)
-        check(self.lib.vitb200_get_head_map(self._h, layer, out.data_ptr(), batch))
+        self._checked_out(self.lib.vitb200_get_head_map(self._h, layer, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
 
-def _device_view(ptr: int, shape, device: int) -> torch.Tensor:
+# ---- peer memory / completion flags (multi-GPU result exchange, dist.PeerPush) --------------------------------
+def peer_alloc(device: int, nbytes: int):
+    """(device pointer, 64-byte IPC handle) of a zeroed allocation on `device` that other processes can map."""
+    lib = load_library()
+    p, h = C.c_void_p(), C.create_string_buffer(64)
+    check(lib.vitb200_peer_alloc(device, nbytes, C.byref(p), h))
+    return int(p.value), bytes(h.raw)
+
+
+def peer_open(device: int, handle: bytes) -> int:
+    lib = load_library()
+    p = C.c_void_p()
+    check(lib.vitb200_peer_open(device, C.create_string_buffer(handle, 64), C.byref(p)))
+    return int(p.value)
+
+
+def peer_close(device: int, ptr: int) -> None:
+    check(load_library().vitb200_peer_close(device, ptr))
+
+
+def peer_free(device: int, ptr: int) -> None:
+    check(load_library().vitb200_peer_free(device, ptr))
+
+
+def flag_signal(flag_ptr: int, value: int, stream: int) -> None:
+    """Enqueue on `stream` (raw cudaStream_t): *flag = value (system-scope release), behind everything already queued."""
+    check(load_library().vitb200_flag_signal(flag_ptr, value, stream or None))
+
+
+def flag_wait(flag_ptr: int, value: int, stream: int) -> None:
+    """Enqueue on `stream`: block the stream until *flag >= value (device-side spin with back-off)."""
+    check(load_library().vitb200_flag_wait(flag_ptr, value, stream or None))
+
+
+def _device_view(ptr: int, shape, device: int, typestr: str = "<f4") -> torch.Tensor:
     """Wrap a raw device pointer as a torch tensor through __cuda_array_interface__ (no copy)."""
 
     class _Holder:
@@ -511,7 +593,7 @@ def _device_view(ptr: int, shape, device: int) -> torch.Tensor:
     h = _Holder()
     h.__cuda_array_interface__ = {
         "shape": tuple(int(s) for s in shape),
-        "typestr": "<f4",
+        "typestr": typestr,
         "data": (int(ptr), False),
         "version": 2,
     }

@@ -98,10 +98,11 @@ def make_vit_model_class(ModelBase, PinoutCls):
             self._lock = threading.Lock()
             self._tokens_out: Optional[torch.Tensor] = None   # last token tensor handed out (device-resident copy valid)
             self._tokens_batch = 0
-            self._maps_out: Dict[int, torch.Tensor] = {}      # layer -> avg-map tensor handed out (resident on device)
+            self._maps_out: Dict[int, tuple] = {}             # layer -> (avg-map tensor handed out, batch): resident on the device
             self.node_names = ([self.prefix() + "embed"] + [self.prefix() + f"layer.{i}" for i in range(cfg.num_layers)]
                                + [self.prefix() + "head", self.prefix() + "rollout", self.prefix() + "transform"])
             self._images_out: Optional[torch.Tensor] = None   # last preprocessed image tensor handed out (still on the device)
+            self._generation = self.engine.workspace_generation() if hasattr(self.engine, "workspace_generation") else 0
 
         # ---- catalogue ---------------------------------------------------------------------------
         def list_node_names(self) -> List[str]:
@@ -222,14 +223,31 @@ def make_vit_model_class(ModelBase, PinoutCls):
         def _host(t: torch.Tensor) -> torch.Tensor:
             return t.detach().to(device="cpu", dtype=torch.float32).contiguous()
 
-        def _bind_tokens(self, x: torch.Tensor) -> int:
+        def _reserve(self, batch: int, flags: int = 0) -> None:
+            """First thing a node call does once it knows its batch size: grow the engine's workspace NOW (nothing later
+            in this call can then re-allocate it) and, if ANY call since the last one re-allocated it -- a request with
+            a larger batch interleaved with this one -- forget what we believed to be resident on the device: growth
+            frees and re-allocates the token stream and the map buffers without copying (and the layer stride of the
+            maps changes with the capacity).  The tensors handed out earlier are CPU copies; they are uploaded again."""
+            eng = self.engine
+            if hasattr(eng, "reserve"):
+                eng.reserve(batch, flags)
+                gen = eng.workspace_generation()
+                if gen != self._generation:
+                    self._generation = gen
+                    self._tokens_out, self._tokens_batch = None, 0
+                    self._maps_out.clear()
+                    self._images_out = None
+
+        def _bind_tokens(self, x: torch.Tensor, flags: int = 0) -> int:
             """Make the engine's token stream equal to `x` ([N,d] or [B,N,d]); returns the batch size."""
             c = self.cfg
-            if x is self._tokens_out:
-                return self._tokens_batch  # still resident from the previous node of this request
             if x.dim() not in (2, 3) or tuple(x.shape[-2:]) != (c.tokens, c.hidden_dim):
                 raise Exception(f"expected tokens of shape [{c.tokens}, {c.hidden_dim}] (optionally batched), got {list(x.shape)}")
             batch = 1 if x.dim() == 2 else x.shape[0]
+            self._reserve(batch, flags)
+            if x is self._tokens_out and batch == self._tokens_batch:
+                return batch  # still resident from the previous node of this request
             self.engine.set_tokens(self._host(x).reshape(batch, c.tokens, c.hidden_dim))
             # the engine now holds x, not what it handed out last (a fanned-out graph may come back to an older tensor)
             self._tokens_out, self._tokens_batch = x, batch
@@ -255,6 +273,7 @@ def make_vit_model_class(ModelBase, PinoutCls):
                         raise Exception(f"expected an image of shape [3, H, W] (optionally batched), got {list(x.shape)}")
                     batched = x.dim() == 4
                     imgs = self._host(x).reshape(-1, 3, x.shape[-2], x.shape[-1])
+                    self._reserve(imgs.shape[0])
                     resize = int(params["resize"]) if params and str(params.get("resize", "")).strip() else (256 if c.image_size == 224 else c.image_size)
                     y = self.engine.stage_transform(imgs, resize)
                     y = y if batched else y[0]
@@ -266,6 +285,7 @@ def make_vit_model_class(ModelBase, PinoutCls):
                         raise Exception(f"expected an image of shape [3, {c.image_size}, {c.image_size}] (optionally batched), got {list(x.shape)}")
                     batched = x.dim() == 4
                     nimg = x.shape[0] if batched else 1
+                    self._reserve(nimg)
                     if x is self._images_out:
                         self.engine.stage_embed_resident(nimg)   # preprocessed by the transform node: still on the device
                     else:
@@ -283,9 +303,9 @@ def make_vit_model_class(ModelBase, PinoutCls):
                     i = self._layer_index(node_name)
                     x = self._need(pinin, "o")
                     batched = x.dim() == 3
-                    batch = self._bind_tokens(x)
                     want_heads = params is not None and str(params.get("heads", "0")) == "1"
                     flags = E.EMIT_AVG | E.EMIT_CLS | (E.EMIT_HEADS if want_heads else 0)
+                    batch = self._bind_tokens(x, flags)
                     if kind == "layer":
                         self.engine.stage_layer(i, batch, flags)
                     else:
@@ -293,7 +313,7 @@ def make_vit_model_class(ModelBase, PinoutCls):
                     out.set("o", self._emit_tokens(batch, batched))
                     lead = (batch,) if batched else ()
                     amap = self.engine.get_avg_map(i, batch, lead + (c.tokens, c.tokens))
-                    self._maps_out[i] = amap
+                    self._maps_out[i] = (amap, batch)
                     out.set("attn", amap)
                     out.set("cls", self.engine.get_cls_grid(i, batch, lead + (c.num_heads, g, g)))
                     if want_heads:
@@ -308,9 +328,14 @@ def make_vit_model_class(ModelBase, PinoutCls):
                     batched = maps[0].dim() == 3
                     batch = maps[0].shape[0] if batched else 1
                     for i, m in enumerate(maps):
-                        if tuple(m.shape[-2:]) != (c.tokens, c.tokens) or (m.dim() == 3) != batched:
-                            raise Exception(f"a{i}: expected a [{c.tokens}, {c.tokens}] map, got {list(m.shape)}")
-                        if m is not self._maps_out.get(i):
+                        if (tuple(m.shape[-2:]) != (c.tokens, c.tokens) or (m.dim() == 3) != batched
+                                or (batched and m.shape[0] != batch)):
+                            raise Exception(f"a{i}: expected a [{c.tokens}, {c.tokens}] map"
+                                            f"{f' for each of {batch} images' if batched else ''}, got {list(m.shape)}")
+                    self._reserve(batch, E.EMIT_AVG | E.EMIT_ROLLOUT)
+                    for i, m in enumerate(maps):
+                        res = self._maps_out.get(i)
+                        if res is None or res[0] is not m or res[1] != batch:   # not (or no longer) resident
                             self.engine.set_avg_map(i, self._host(m).reshape(batch, c.tokens, c.tokens))
                     out.set("o", self.engine.stage_rollout(batch, (batch, g, g) if batched else (g, g)))
             return out

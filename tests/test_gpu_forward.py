@@ -468,34 +468,51 @@ def _peer_push_worker(rank, world, port, q):
     try:
         ocfg = O.ORACLE_CONFIGS["vit_small_test"]
         model = O.build_vit(ocfg, seed=0, init="stress")
-        B = 2
+        B, steps = 2, 7        # more steps than sets: exercises the rotation and the write-after-read ordering
         cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim,
                           ocfg.mlp_dim, ocfg.num_classes)
         eng = E.VitEngine(cfg, rank, B)
         eng.load_state_dict(model.state_dict())
-        allx = O.synthetic_images(B * world, ocfg.image_size)
-        x = allx[rank * B:(rank + 1) * B].cuda()
+        # DIFFERENT images every step: a set that is read half-written, or overwritten while it is read, shows up
+        allx = [O.synthetic_images(B * world, ocfg.image_size, seed=100 + i) for i in range(steps)]
         flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
-        push = PeerPush(eng, B * world, torch.device("cuda", rank))
-        for _ in range(5):      # more steps than sets: exercises the rotation and the write-after-read ordering
-            push.begin()
-            eng.forward_device(x, flags, torch.cuda.current_stream().cuda_stream)
-            s = push.end()
-        push.wait(s)
-        torch.cuda.synchronize()
+        verdict = {}
+        # once on a dedicated stream (graph replay from the second sighting of a set), once on torch's default stream
+        # (raw handle 0 = the legacy default stream: taken literally, never silently replaced by the engine's stream)
+        for how in ("side", "default"):
+            st = torch.cuda.Stream() if how == "side" else torch.cuda.default_stream()
+            seen = []
+
+            def consumer(s, views):      # runs on rank 0's reader stream, behind every rank's completion flag
+                seen.append({k: views[k].clone() for k in ("logits", "cls_maps", "rollout")})
+
+            push = PeerPush(eng, B * world, torch.device("cuda", rank), stream=st.cuda_stream, consumer=consumer)
+            with torch.cuda.stream(st):
+                for i in range(steps):
+                    x = allx[i][rank * B:(rank + 1) * B].cuda(non_blocking=False)
+                    push.begin()
+                    eng.forward_device(x, flags, st.cuda_stream)
+                    push.end()
+                push.finish()
+            torch.cuda.synchronize()
+            push.close()
+            if rank == 0:
+                ref = E.VitEngine(cfg, 0, B * world)
+                ref.load_state_dict(model.state_dict())
+                ok = {"logits": True, "cls_maps": True, "rollout": True}
+                assert len(seen) == steps
+                for i in range(steps):
+                    want = ref.forward_host(allx[i], E.EMIT_CLS | E.EMIT_ROLLOUT)
+                    # logits and CLS rows are batch-invariant bit for bit; the rollout inherits the head average, whose
+                    # last fp32 bit depends on whether the attention kernel split an image's heads over two CTAs
+                    for k in ok:
+                        got = seen[i][k].cpu()
+                        ok[k] = ok[k] and (bool(torch.equal(got, want[k])) if k != "rollout" else
+                                           bool((got - want[k]).abs().max() < 1e-6))
+                ref.close()
+                verdict[how] = ok
         if rank == 0:
-            got = {k: push.result(k, s).cpu() for k in ("logits", "cls_maps", "rollout")}
-        push.close()
-        dist.barrier()
-        if rank == 0:
-            ref = E.VitEngine(cfg, 0, B * world)
-            ref.load_state_dict(model.state_dict())
-            want = ref.forward_host(allx, E.EMIT_CLS | E.EMIT_ROLLOUT)
-            # logits and CLS rows are batch-invariant bit for bit; the rollout inherits the head average, whose last fp32
-            # bit depends on whether the attention kernel split an image's heads over two CTAs (test_bench_size_properties)
-            q.put({k: bool(torch.equal(got[k], want[k])) if k != "rollout" else
-                   bool((got[k] - want[k]).abs().max() < 1e-6) for k in got})
-            ref.close()
+            q.put(verdict)
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -503,9 +520,10 @@ def _peer_push_worker(rank, world, port, q):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with peer access")
 def test_peer_push_two_ranks_matches_one_engine_on_the_whole_batch(E):
-    """dist.PeerPush on two GPUs: both ranks' kernels store into rank 0's receive set over NVLink; what rank 0 reads
-    equals one engine running the whole batch (logits and CLS maps bit for bit: the forward is batch-invariant per
-    image; rollout within 1e-6)."""
+    """dist.PeerPush on two GPUs: both ranks' kernels store into rank 0's receive set over NVLink, ordered by per-rank
+    completion flags (no collective, no barrier).  What rank 0's reader sees at EVERY step -- different images each
+    step, more steps than sets -- equals one engine running the whole batch (logits and CLS maps bit for bit: the
+    forward is batch-invariant per image; rollout within 1e-6), on a side stream and on torch's default stream."""
     import socket
 
     import torch.multiprocessing as mp
@@ -523,7 +541,8 @@ def test_peer_push_two_ranks_matches_one_engine_on_the_whole_batch(E):
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    assert res == {"logits": True, "cls_maps": True, "rollout": True}, res
+    good = {"logits": True, "cls_maps": True, "rollout": True}
+    assert res == {"side": good, "default": good}, res
 
 
 def test_deferred_node_outputs_wait_on_first_access_and_equal_the_synchronous_path(E, golden_dir, monkeypatch):
@@ -593,3 +612,329 @@ def test_deferred_node_outputs_wait_on_first_access_and_equal_the_synchronous_pa
     out2 = sync_plug.compute("vit_tiny_test:layer.0", pin)
     assert type(tok2) is torch.Tensor
     assert torch.equal(tok, tok2) and torch.equal(h, out2.get("o")) and torch.equal(a, out2.get("attn")) and torch.equal(c, out2.get("cls"))
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+def _row_metrics(got, ref):
+    """Per-ROW error of attention maps (last dim = keys): the largest L1 distance between a row and the reference row
+    (rows sum to 1, so this is a total-variation bound), and the largest RELATIVE error over the entries that matter
+    (reference probability >= 1 / N, i.e. at least uniform) -- the global max|diff| / max|ref| can hide both."""
+    got, ref = got.float(), ref.float()
+    l1 = (got - ref).abs().sum(-1).max().item()
+    big = ref >= 1.0 / ref.shape[-1]
+    rel = ((got - ref).abs() / ref.clamp_min(1e-30))[big].max().item() if big.any() else 0.0
+    return l1, rel
+
+
+# bf16 tolerance of north_star (2e-2) applied per row: L1 distance of a probability row, and relative error of its
+# above-uniform entries (measured on the B200: ViT-B/16 avg maps L1 4e-3 / rel 1.6e-2 -- printed by the tests)
+ROW_L1_TOL = 2e-2
+ROW_REL_TOL = 5e-2
+
+
+@pytest.mark.parametrize("name,batch,init", [("vit_small_test", 2, "stress"), ("vit_b_16", 2, "default"),
+                                             ("vit_577_test", 2, "stress")])
+def test_attention_maps_per_row_metrics(E, name, batch, init):
+    """VERDICT r1 weak #3: per-row metrics next to the global one, for the head-averaged and per-head CLS maps."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS[name]
+    model = O.build_vit(ocfg, seed=0, init=init)
+    x = O.synthetic_images(batch, ocfg.image_size)
+    ref = O.forward_with_maps(model, x)
+    eng = _engine_for(E, ocfg, model, batch)
+    got = eng.forward_host(x, 1 | 2 | 4)
+    for k in ("avg_maps", "cls_maps"):
+        l1, rel = _row_metrics(got[k], ref[k])
+        print(f"[row-metrics] {name} {k}: max row L1 {l1:.3e}, max rel err over entries >= 1/N {rel:.3e}, "
+              f"global {_rel(got[k], ref[k]):.3e}")
+        assert l1 < ROW_L1_TOL and rel < ROW_REL_TOL, (k, l1, rel)
+    eng.close()
+
+
+def test_bench_batch_sample_against_oracle(E):
+    """BASELINE config 2 itself (ViT-B/16, batch 256) against the oracle: four images of the batch -- first, middle, the
+    last item that runs on one CTA per query tile, and one from the head-split tail -- compared with the CPU oracle run
+    on exactly those images (global and per-row metrics, top-1)."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_b_16"]
+    model = O.build_vit(ocfg, seed=0, init="default")
+    x = O.synthetic_images(256, ocfg.image_size)
+    eng = _engine_for(E, ocfg, model, 256)
+    got = eng.forward_host(x, 1 | 2 | 4)
+    pick = [0, 100, 221, 255]
+    ref = O.forward_with_maps(model, x[pick])
+    assert _rel(got["logits"][pick], ref["logits"]) < TOL
+    assert torch.equal(got["logits"][pick].argmax(-1), ref["logits"].argmax(-1))
+    assert _rel(got["rollout"][pick], ref["rollout"]) < TOL
+    for k in ("avg_maps", "cls_maps"):
+        g = got[k][:, pick]
+        assert _rel(g, ref[k]) < TOL, k
+        l1, rel = _row_metrics(g, ref[k])
+        print(f"[row-metrics] vit_b_16 batch 256 sample {k}: row L1 {l1:.3e}, rel {rel:.3e}")
+        assert l1 < ROW_L1_TOL and rel < ROW_REL_TOL, (k, l1, rel)
+    eng.close()
+
+
+def test_vit_h_full_depth(E):
+    """BASELINE config 5 at FULL depth (32 layers, 16 heads of 80, 577 tokens), one image, against the oracle."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_h_16_384"]
+    model = O.build_vit(ocfg, seed=0, init="default")
+    x = O.synthetic_images(1, ocfg.image_size)
+    ref = O.forward_with_maps(model, x)
+    eng = _engine_for(E, ocfg, model, 1)
+    got = eng.forward_host(x, 1 | 2 | 4)
+    for k in ("logits", "avg_maps", "cls_maps", "rollout"):
+        assert got[k].shape == ref[k].shape, k
+        assert _rel(got[k], ref[k]) < TOL, (k, _rel(got[k], ref[k]))
+    assert torch.equal(got["logits"].argmax(-1), ref["logits"].argmax(-1))
+    eng.close()
+
+
+def test_vit_l_batch_and_vit_s_sweep_sizes(E):
+    """ViT-L/16 at batch > 1 against the oracle; ViT-S/16 at the sweep's large batches (1024): three images of the
+    batch against the oracle, and bit-identical to running them alone (rows never mix at any batch size)."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_l_16"]
+    model = O.build_vit(ocfg, seed=0, init="default")
+    x = O.synthetic_images(3, ocfg.image_size)
+    ref = O.forward_with_maps(model, x)
+    eng = _engine_for(E, ocfg, model, 3)
+    got = eng.forward_host(x, 1 | 2 | 4)
+    for k in ("logits", "avg_maps", "cls_maps", "rollout"):
+        assert _rel(got[k], ref[k]) < TOL, (k, _rel(got[k], ref[k]))
+    assert torch.equal(got["logits"].argmax(-1), ref["logits"].argmax(-1))
+    eng.close()
+
+    ocfg = O.ORACLE_CONFIGS["vit_s_16"]
+    model = O.build_vit(ocfg, seed=0, init="default")
+    x = O.synthetic_images(1024, ocfg.image_size)
+    eng = _engine_for(E, ocfg, model, 1024)
+    flags = E.EMIT_CLS | E.EMIT_ROLLOUT
+    got = eng.forward_host(x, flags)
+    pick = [0, 511, 1023]
+    ref = O.forward_with_maps(model, x[pick])
+    assert _rel(got["logits"][pick], ref["logits"]) < TOL
+    assert torch.equal(got["logits"][pick].argmax(-1), ref["logits"].argmax(-1))
+    assert _rel(got["cls_maps"][:, pick], ref["cls_maps"]) < TOL
+    assert _rel(got["rollout"][pick], ref["rollout"]) < TOL
+    for i in pick:
+        one = eng.forward_host(x[i:i + 1].contiguous(), flags)
+        assert torch.equal(one["logits"][0], got["logits"][i])
+        assert torch.equal(one["cls_maps"][:, 0], got["cls_maps"][:, i])
+    eng.close()
+
+
+def _plugin_context(E, name, ocfg, module, max_batch=1):
+    import tempfile
+
+    from interactive_vit_b200 import context as C, vit_plugin as P
+
+    cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                      ocfg.num_classes)
+    plug = P.VitB200Model(name, cfg, module, 0, max_batch)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "static", "graphs"))
+        C.set_base_dir(d)
+        try:
+            ctx = C.Context()
+            plug.register(ctx)
+        finally:
+            C.set_base_dir(None)
+    return plug, ctx
+
+
+def _wire_request(ctx, name, num_layers, image):
+    from interactive_vit_b200 import message as M, vit_plugin as P
+
+    nodes, edges, tensors = P.vit_graph_request(name, num_layers, image)
+    req = M.Request()
+    req.decode(M.encode_request(nodes, edges, tensors))
+    ctx.compute(req.graph)
+    return M.decode_response(M.Response(req.graph).encode())
+
+
+def test_batched_wire_request_through_the_plugin(E):
+    """SURVEY §8f-4 / VERDICT r1 missing #2: a BATCHED request ([B,3,S,S] on the wire) through Request.decode ->
+    Context.compute (B200 plugin nodes) -> Response.encode.  Every node output carries the batch dimension, matches the
+    oracle per image, and equals what B single-image requests return (bit for bit where the forward is batch-invariant:
+    tokens, logits, CLS maps)."""
+    from oracle import vit_oracle as O
+
+    name = "vit_small_test"
+    ocfg = O.ORACLE_CONFIGS[name]
+    module = O.build_vit(ocfg, seed=0, init="stress")
+    plug, ctx = _plugin_context(E, name, ocfg, module)
+    B, L, N, H = 3, ocfg.num_layers, ocfg.tokens, ocfg.num_heads
+    g = ocfg.image_size // ocfg.patch_size
+    x = O.synthetic_images(B, ocfg.image_size)
+    got = _wire_request(ctx, name, L, x)
+    ref = O.forward_with_maps(module, x)
+    assert got[0]["o"].shape == (B, N, ocfg.hidden_dim) and _rel(got[0]["o"], ref["embed"]) < TOL
+    for i in range(L):
+        assert got[1 + i]["o"].shape == (B, N, ocfg.hidden_dim) and _rel(got[1 + i]["o"], ref["hidden"][i]) < TOL
+        assert got[1 + i]["attn"].shape == (B, N, N) and _rel(got[1 + i]["attn"], ref["avg_maps"][i]) < TOL
+        assert got[1 + i]["cls"].shape == (B, H, g, g)
+        assert _rel(got[1 + i]["cls"], ref["cls_maps"][i][:, :, 1:].reshape(B, H, g, g)) < TOL
+    assert got[1 + L]["o"].shape == (B, ocfg.num_classes) and _rel(got[1 + L]["o"], ref["logits"]) < TOL
+    assert torch.equal(got[1 + L]["o"].argmax(-1), ref["logits"].argmax(-1))
+    assert got[2 + L]["o"].shape == (B, g, g) and _rel(got[2 + L]["o"].reshape(B, -1), ref["rollout"]) < TOL
+    for b in range(B):
+        one = _wire_request(ctx, name, L, x[b])
+        assert torch.equal(one[1 + L]["o"], got[1 + L]["o"][b])
+        for i in range(L):
+            assert torch.equal(one[1 + i]["o"], got[1 + i]["o"][b])
+            assert torch.equal(one[1 + i]["cls"], got[1 + i]["cls"][b])
+            assert (one[1 + i]["attn"] - got[1 + i]["attn"][b]).abs().max() < 1e-6
+    plug.engine.close()
+
+
+def test_node_path_at_vit_b_size(E):
+    """The node path (Context.compute over embed / layer.i / head / rollout nodes) at ViT-B/16 size against the oracle."""
+    from oracle import vit_oracle as O
+
+    name = "vit_b_16"
+    ocfg = O.ORACLE_CONFIGS[name]
+    module = O.build_vit(ocfg, seed=0, init="default")
+    plug, ctx = _plugin_context(E, name, ocfg, module)
+    L = ocfg.num_layers
+    x = O.synthetic_images(1, ocfg.image_size)
+    got = _wire_request(ctx, name, L, x[0])
+    ref = O.forward_with_maps(module, x)
+    assert _rel(got[1 + L]["o"][None], ref["logits"]) < TOL
+    assert got[1 + L]["o"].argmax() == ref["logits"][0].argmax()
+    assert _rel(got[2 + L]["o"].reshape(1, -1), ref["rollout"]) < TOL
+    for i in range(L):
+        assert _rel(got[1 + i]["attn"][None], ref["avg_maps"][i]) < TOL, i
+    # the same request again: from its second sighting every stage is replayed as a captured graph -- same bytes
+    again = _wire_request(ctx, name, L, x[0])
+    third = _wire_request(ctx, name, L, x[0])
+    for node in got:
+        for ch in got[node]:
+            assert torch.equal(again[node][ch], got[node][ch]) and torch.equal(third[node][ch], got[node][ch]), (node, ch)
+    assert plug.engine.graph_replays() > 0
+    plug.engine.close()
+
+
+def test_interleaved_requests_with_a_growing_batch(E):
+    """ADVICE r1 (vit_plugin residency shortcuts): request A (one image) has finished its layers when request B's embed
+    arrives with a larger batch and makes the engine re-allocate its workspace.  A's rollout and head must not read the
+    re-allocated buffers: same results as an undisturbed request A."""
+    from interactive_vit_b200.graph import Pinout
+    from oracle import vit_oracle as O
+
+    name = "vit_small_test"
+    ocfg = O.ORACLE_CONFIGS[name]
+    module = O.build_vit(ocfg, seed=0, init="stress")
+    plug, ctx = _plugin_context(E, name, ocfg, module)
+    L = ocfg.num_layers
+    xa = O.synthetic_images(1, ocfg.image_size, seed=1)[0]
+    xb = O.synthetic_images(4, ocfg.image_size, seed=2)
+    want = _wire_request(ctx, name, L, xa)      # undisturbed
+
+    def call(node, **chans):
+        p = Pinout()
+        for k, v in chans.items():
+            p.set(k, v)
+        return plug.compute(f"{name}:{node}", p)
+
+    tok = call("embed", o=xa).get("o")
+    maps = []
+    for i in range(L):
+        out = call(f"layer.{i}", o=tok)
+        tok = out.get("o")
+        maps.append(out.get("attn"))
+    gen0 = plug.engine.workspace_generation()
+    tok_b = call("embed", o=xb).get("o")
+    assert plug.engine.workspace_generation() != gen0
+    roll = call("rollout", **{f"a{i}": m for i, m in enumerate(maps)}).get("o")
+    logits = call("head", o=tok).get("o")
+    assert torch.equal(logits, want[1 + L]["o"])
+    assert torch.equal(roll, want[2 + L]["o"])
+    out_b = call("layer.0", o=tok_b)            # request B goes on with ITS tokens (uploaded again: A's are resident)
+    ref_b = O.forward_with_maps(module, xb)
+    assert _rel(out_b.get("o"), ref_b["hidden"][0]) < TOL
+    plug.engine.close()
+
+
+def test_graph_replay_equals_eager_launches(E):
+    """CUDA-graph replay (from the second call with the same batch / flags / input address) is bit-identical to launching
+    the kernels one by one, for the whole forward and for the node-granular stages; a different batch or a re-allocated
+    workspace falls back to eager launches and re-captures."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_small_test"]
+    model = O.build_vit(ocfg, seed=0, init="stress")
+    eng = _engine_for(E, ocfg, model, 2)
+    L, H, N = ocfg.num_layers, ocfg.num_heads, ocfg.tokens
+    flags = E.EMIT_AVG | E.EMIT_CLS | E.EMIT_ROLLOUT
+    x = O.synthetic_images(2, ocfg.image_size).cuda()
+    y = O.synthetic_images(2, ocfg.image_size, seed=7).cuda()
+    st = torch.cuda.Stream()
+
+    def run(images):
+        eng.forward_device(images, flags, st.cuda_stream)
+        st.synchronize()
+        pitch = (N + 15) // 16 * 16
+        return {"logits": eng.device_output(0, (2, ocfg.num_classes)).clone(),
+                "cls": eng.device_output(E.EMIT_CLS, (L, 2, H, N)).clone(),
+                "avg": eng.device_output(E.EMIT_AVG, (L, 2, N, pitch))[..., :N].clone(),
+                "rollout": eng.device_output(E.EMIT_ROLLOUT, (2, N - 1)).clone()}
+
+    eng.set_graphs(False)
+    want_x, want_y = run(x), run(y)
+    eng.set_graphs(True)
+    r0 = eng.graph_replays()
+    n0 = eng.launch_count()
+    first = run(x)                      # first sighting: eager
+    per_forward = eng.launch_count() - n0
+    outs = [run(x) for _ in range(3)]   # captured at the second, replayed afterwards
+    assert eng.graph_replays() - r0 >= 3
+    assert eng.launch_count() - n0 == 4 * per_forward, "replays count the kernels they launch"
+    for o in [first] + outs:
+        for k in want_x:
+            assert torch.equal(o[k], want_x[k]), k
+    x.copy_(y)                          # same address, new contents: the graph reads the buffer, not a snapshot
+    got = run(x)
+    for k in want_y:
+        assert torch.equal(got[k], want_y[k]), k
+    # the default stream (raw handle 0) is never captured; results are the same
+    eng.forward_device(x, flags, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(eng.device_output(0, (2, ocfg.num_classes)), want_y["logits"])
+    # growing the workspace drops every graph (their buffers are gone); the next calls are eager, then captured again
+    big = O.synthetic_images(5, ocfg.image_size).cuda()
+    eng.forward_device(big, flags, st.cuda_stream)
+    st.synchronize()
+    for _ in range(3):
+        got = run(x)
+    for k in ("logits", "rollout"):
+        assert torch.equal(got[k], want_y[k]), k
+    eng.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_engines_on_two_devices_in_one_process(E):
+    """VERDICT r1 weak #11: launch state (dynamic shared-memory limits, SM counts, persistent-grid sizes) is kept per
+    DEVICE, so an engine on cuda:1 created after one on cuda:0 works, and both give the same bits."""
+    from oracle import vit_oracle as O
+
+    ocfg = O.ORACLE_CONFIGS["vit_small_test"]
+    model = O.build_vit(ocfg, seed=0, init="stress")
+    x = O.synthetic_images(2, ocfg.image_size)
+    cfg = E.VitConfig(ocfg.image_size, ocfg.patch_size, ocfg.num_layers, ocfg.num_heads, ocfg.hidden_dim, ocfg.mlp_dim,
+                      ocfg.num_classes)
+    engs = [E.VitEngine(cfg, dev, 2) for dev in (0, 1)]
+    outs = []
+    for eng in engs:
+        eng.load_state_dict(model.state_dict())
+    for _ in range(2):
+        outs = [eng.forward_host(x, 1 | 2 | 4) for eng in engs]      # alternating devices
+    for k in ("logits", "avg_maps", "cls_maps", "rollout"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    for eng in engs:
+        eng.close()
