@@ -206,8 +206,9 @@ uint64_t vitb200_launch_count(vitb200_engine* e);
 int vitb200_op_gemm(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, const float* resid_dev,
                     void* out_dev, int M, int N, int K, int gelu, int out_f32, void* stream);
 /* GEMM with the LayerNorm-folding epilogues (see the header comment of csrc/engine.cu).  Producer side (needs resid_dev):
- * xb_out_dev receives the bf16 copy of the fp32 result and stats_out_dev [M, N/32, 2] the per-32-column partial sums
- * (sum, sum of squares) of every row.  Consumer side: stats_in_dev [M, K/32, 2] + colsum_dev [N] turn the GEMM into
+ * xb_out_dev receives the bf16 copy of the fp32 result and stats_out_dev [M, N/w, 2] the partial sums (sum, sum of
+ * squares) of every row per group of w columns, w = 128 if N is a multiple of 256, else 64 (N a multiple of 128).
+ * Consumer side: stats_in_dev [M, K/w, 2] (same rule for K) + colsum_dev [N] turn the GEMM into
  * LayerNorm(x) W^T + b for weights prepared by vitb200_op_fold_ln.  Unused pointers are NULL. */
 int vitb200_op_gemm_ex(const void* a_bf16_dev, const void* w_bf16_dev, const float* bias_dev, const float* resid_dev,
                        void* out_dev, int M, int N, int K, int gelu, int out_f32, void* xb_out_dev, float* stats_out_dev,

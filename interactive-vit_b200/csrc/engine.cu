@@ -154,9 +154,7 @@ struct DeviceCtx {
   int sms = 0;
   std::map<const void*, int> func_smem;    // kernel -> dynamic smem limit configured on this device
   std::map<const void*, int> gemm_slots;   // GEMM instantiation -> persistent scheduler slots on this device
-  float2* op_affine = nullptr;             // scratch of the single-kernel entry points (parity tests)
-  int op_affine_cap = 0;
-  float2* op_stats = nullptr;
+  float2* op_stats = nullptr;              // scratch of the single-kernel attention entry point (parity tests)
   size_t op_stats_cap = 0;
 };
 static std::mutex g_dev_mu;
@@ -261,15 +259,19 @@ static int gemm_pair_mode() {
 template <int BN, int kPair, int kPairs>
 static int launch_gemm_bn(const CUtensorMap* maps, GemmShape sh, const GemmEpilogue& ep, bool gelu, bool out_f32,
                           cudaStream_t st) {
-  const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0, ln_in = ep.row_affine_in != nullptr;
+  const bool resid = ep.resid != nullptr, remap = ep.group_rows > 0, ln_in = ep.row_stats_in != nullptr;
   if (ln_in) {
     if (ep.colsum == nullptr || out_f32 || resid || remap)
       return fail(VITB200_ERR_INVALID, "gemm: folded-LayerNorm epilogue needs colsum and a bf16 output");
+    if (sh.K % 128 != 0 || ep.stats_in_slots != sh.K / ln_slot_width(sh.K))
+      return fail(VITB200_ERR_INVALID, "gemm: folded LayerNorm needs K a multiple of 128 and K / %d partial sums per row (K=%d, slots=%d)",
+                  ln_slot_width(sh.K), sh.K, ep.stats_in_slots);
     if (gelu) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false, true>(maps, sh, ep, st);
     return launch_gemm_t<BN, kPair, kPairs, false, false, false, false, true>(maps, sh, ep, st);
   }
-  if (ep.xb != nullptr && (!resid || ep.row_stats_out == nullptr || ep.stats_slots <= 0))
-    return fail(VITB200_ERR_INVALID, "gemm: the bf16 copy + row statistics are produced by residual epilogues only");
+  if (ep.xb != nullptr && (!resid || ep.row_stats_out == nullptr || sh.N % 128 != 0 || ep.stats_slots != sh.N / ln_slot_width(sh.N)))
+    return fail(VITB200_ERR_INVALID, "gemm: the bf16 copy + row statistics are produced by residual epilogues only, N a multiple "
+                                     "of 128, one slot per %d columns", ln_slot_width(sh.N));
   if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false>(maps, sh, ep, st);
   if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, false, false, false>(maps, sh, ep, st);
   if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, false, false>(maps, sh, ep, st);
@@ -510,7 +512,7 @@ struct vitb200_engine {
   // activations (sized for cap_batch images)
   int cap_batch = 0;
   uint32_t cap_flags = 0;
-  Buffer images, patches, x, xb, ln_stats, ln_affine, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
+  Buffer images, patches, x, xb, ln_stats, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
   Buffer patches_lo, xb_lo, qkv_lo, ctx_lo, mlp_lo, cls_ln_lo;  // fp32x3 mode: low halves of the bf16 operands
 
   // vitb200_bind_outputs: caller-owned destinations of the small results (typically slices of rank 0's receive
@@ -604,8 +606,7 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   VT_TRY(ensure(e->patches, (size_t)B * e->n * e->patch_k * 2));
   VT_TRY(ensure(e->x, M * c.hidden_dim * 4));
   VT_TRY(ensure(e->xb, M * c.hidden_dim * 2));
-  VT_TRY(ensure(e->ln_stats, M * (c.hidden_dim / 32) * sizeof(float2)));
-  VT_TRY(ensure(e->ln_affine, M * sizeof(float2)));
+  VT_TRY(ensure(e->ln_stats, M * (c.hidden_dim / ln_slot_width(c.hidden_dim)) * sizeof(float2)));
   VT_TRY(ensure(e->qkv, M * 3 * c.hidden_dim * 2));
   VT_TRY(ensure(e->ctx, M * c.hidden_dim * 2));
   if (e->precise || !attention_is_fused(e->N, e->D)) VT_TRY(ensure(e->attn_stats, M * c.num_heads * sizeof(float2)));
@@ -659,12 +660,12 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
   ep.group_rows = e->n, ep.out_group_stride = e->N, ep.out_row_offset = 1;
   ep.resid_broadcast = 1, ep.resid_row_offset = 1;
   ep.xb = (__nv_bfloat16*)e->xb.p, ep.ldxb = c.hidden_dim;
-  ep.row_stats_out = (float2*)e->ln_stats.p, ep.stats_slots = c.hidden_dim / 32;
+  ep.row_stats_out = (float2*)e->ln_stats.p, ep.stats_slots = c.hidden_dim / ln_slot_width(c.hidden_dim);
   ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
   prof_mark(e, "gemm_patch_embed", st);
   VT_TRY(launch_gemm(e->patches.p, e->patch_k, e->w_patch, B * e->n, c.hidden_dim, e->patch_k, ep, false, true, st,
                      e->patches_lo.p, e->w_patch_lo));
-  const long cthreads = (long)B * (c.hidden_dim / 32) * 32;
+  const long cthreads = (long)B * (c.hidden_dim / ln_slot_width(c.hidden_dim)) * 32;
   prof_mark(e, "cls_rows", st);
   cls_rows_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p,
                                                                       (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B,
@@ -682,16 +683,13 @@ static int run_attn_block(vitb200_engine* e, int l, int B, uint32_t flags, cudaS
   float* x = (float*)e->x.p;
   __nv_bfloat16* xb = (__nv_bfloat16*)e->xb.p;
   float2* stats = (float2*)e->ln_stats.p;
-  float2* affine = (float2*)e->ln_affine.p;
-  const int slots = d / 32;
-  prof_mark(e, "ln_row_stats", st);
-  row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
-  CU_TRY(cudaGetLastError());
+  const int slots = d / ln_slot_width(d);
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_qkv", st);
     ep.bias = w.bf_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
-    ep.row_affine_in = affine, ep.colsum = w.s_qkv, ep.out_lo = (__nv_bfloat16*)e->qkv_lo.p;
+    ep.row_stats_in = stats, ep.stats_in_slots = slots, ep.ln_eps = 1e-6f;
+    ep.colsum = w.s_qkv, ep.out_lo = (__nv_bfloat16*)e->qkv_lo.p;
     VT_TRY(launch_gemm(xb, d, w.w_qkv, M, 3 * d, d, ep, false, false, st, e->xb_lo.p, w.w_qkv_lo));
   }
   const bool want_avg = (flags & (VITB200_EMIT_AVG | VITB200_EMIT_ROLLOUT)) != 0;
@@ -712,7 +710,7 @@ static int run_attn_block(vitb200_engine* e, int l, int B, uint32_t flags, cudaS
     ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots, ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
     VT_TRY(launch_gemm(e->ctx.p, d, w.w_o, M, d, d, ep, false, true, st, e->ctx_lo.p, w.w_o_lo));
   }
-  e->launches += 4;
+  e->launches += 3;
   return VITB200_OK;
 }
 
@@ -724,16 +722,13 @@ static int run_mlp_block(vitb200_engine* e, int l, int B, cudaStream_t st) {
   float* x = (float*)e->x.p;
   __nv_bfloat16* xb = (__nv_bfloat16*)e->xb.p;
   float2* stats = (float2*)e->ln_stats.p;
-  float2* affine = (float2*)e->ln_affine.p;
-  const int slots = d / 32;
-  prof_mark(e, "ln_row_stats", st);
-  row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, st>>>(stats, affine, M, slots, d, 1e-6f);
-  CU_TRY(cudaGetLastError());
+  const int slots = d / ln_slot_width(d);
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_fc1_gelu", st);
     ep.bias = w.bf_fc1, ep.out = e->mlp.p, ep.ldo = c.mlp_dim;
-    ep.row_affine_in = affine, ep.colsum = w.s_fc1, ep.out_lo = (__nv_bfloat16*)e->mlp_lo.p;
+    ep.row_stats_in = stats, ep.stats_in_slots = slots, ep.ln_eps = 1e-6f;
+    ep.colsum = w.s_fc1, ep.out_lo = (__nv_bfloat16*)e->mlp_lo.p;
     VT_TRY(launch_gemm(xb, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st, e->xb_lo.p, w.w_fc1_lo));
   }
   {
@@ -743,7 +738,7 @@ static int run_mlp_block(vitb200_engine* e, int l, int B, cudaStream_t st) {
     ep.xb = xb, ep.ldxb = d, ep.row_stats_out = stats, ep.stats_slots = slots, ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
     VT_TRY(launch_gemm(e->mlp.p, c.mlp_dim, w.w_fc2, M, d, c.mlp_dim, ep, false, true, st, e->mlp_lo.p, w.w_fc2_lo));
   }
-  e->launches += 3;
+  e->launches += 2;
   return VITB200_OK;
 }
 
@@ -929,7 +924,7 @@ static int copy_rows_to_host(float* dst, const float* src_dev, size_t rows, int 
 
 vitb200_engine::~vitb200_engine() {
   clear_graphs(this);
-  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &ln_affine, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats,
+  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats,
                     &patches_lo, &xb_lo, &qkv_lo, &ctx_lo, &mlp_lo, &cls_ln_lo};
   for (Buffer* b : bufs) release(*b);
   auto fr = [](void* p) { if (p) cudaFree(p); };
@@ -1643,27 +1638,12 @@ int vitb200_op_gemm_ex(const void* a, const void* w, const float* bias, const fl
   GemmEpilogue ep;
   ep.bias = bias, ep.out = out, ep.ldo = N, ep.resid = resid, ep.ldr = N;
   if (xb_out) {
-    if (N % 32 != 0) return fail(VITB200_ERR_INVALID, "gemm: row statistics need N to be a multiple of 32");
-    ep.xb = (__nv_bfloat16*)xb_out, ep.ldxb = N, ep.row_stats_out = (float2*)stats_out, ep.stats_slots = N / 32;
+    if (N % 128 != 0) return fail(VITB200_ERR_INVALID, "gemm: row statistics need N to be a multiple of 128");
+    ep.xb = (__nv_bfloat16*)xb_out, ep.ldxb = N, ep.row_stats_out = (float2*)stats_out, ep.stats_slots = N / ln_slot_width(N);
   }
   if (stats_in) {
     if (K % 128 != 0) return fail(VITB200_ERR_INVALID, "gemm: folded LayerNorm needs K to be a multiple of 128");
-    float2* affine = nullptr;
-    {
-      std::lock_guard<std::mutex> lock(g_dev_mu);
-      DeviceCtx& dc = dev_ctx_locked();
-      if (M > dc.op_affine_cap) {
-        if (dc.op_affine) cudaFree(dc.op_affine);
-        dc.op_affine = nullptr, dc.op_affine_cap = 0;
-        CU_TRY(cudaMalloc(&dc.op_affine, (size_t)M * sizeof(float2)));
-        dc.op_affine_cap = M;
-      }
-      affine = dc.op_affine;
-    }
-    row_stats_finalize_kernel<<<(M * 4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float2*)stats_in, affine, M, K / 32, K,
-                                                                               ln_eps);
-    CU_TRY(cudaGetLastError());
-    ep.row_affine_in = affine, ep.colsum = colsum;
+    ep.row_stats_in = (const float2*)stats_in, ep.stats_in_slots = K / ln_slot_width(K), ep.ln_eps = ln_eps, ep.colsum = colsum;
   }
   return launch_gemm(a, K, w, M, N, K, ep, gelu != 0, out_f32 != 0, (cudaStream_t)stream);
 }

@@ -38,6 +38,7 @@
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
+#include "rowwise.cuh"
 
 namespace vitb200 {
 
@@ -59,13 +60,15 @@ struct GemmEpilogue {
   int resid_row_offset = 0;
   // LayerNorm folding (see engine.cu, "LayerNorm is folded into the GEMMs"):
   //  * producer side (kResid epilogues, optional): besides the fp32 result also write its bf16 copy `xb` (the A
-  //    operand of the next GEMM) and, per row and 32-column chunk, the partial sums (sum x, sum x^2) into
-  //    row_stats_out[out_row * stats_slots + col / 32] -- fixed slots, no atomics, so the statistics are
-  //    bit-reproducible.
-  //  * consumer side (kLnIn epilogues): out = rstd_m * (acc - mean_m * colsum[n]) + bias[n]; row_affine_in[m] =
-  //    (rstd_m, -rstd_m * mean_m) comes from row_stats_finalize_kernel (rowwise.cuh), which reduces the partial sums
-  //    in slot order; the weight operand holds gamma-scaled weights, `bias` the beta-folded bias,
-  //    colsum[n] = sum_k W'[n, k].
+  //    operand of the next GEMM) and, per row and COLUMN GROUP of one epilogue warp (ln_slot_width(N) = 128 or 64
+  //    columns), the partial sums (sum x, sum x^2) into row_stats_out[out_row * stats_slots + col / slot_width] --
+  //    fixed slots, no atomics, so the statistics are bit-reproducible.  (Round 1 wrote one slot per 32-column chunk:
+  //    4x the bytes, and the consumer needed several dependent L2 round trips per tile to reduce them.)
+  //  * consumer side (kLnIn epilogues): out = rstd_m * (acc - mean_m * colsum[n]) + bias[n].  (rstd_m, -rstd_m * mean_m)
+  //    is reduced from the producer's partial sums row_stats_in[m * stats_in_slots + s] BY THIS KERNEL (role 3, one tile
+  //    ahead of the epilogue, in a fixed slot order: bit-reproducible); round 1 ran a separate finalize kernel in front
+  //    of every consuming GEMM (24 launches of ~10 us per ViT-B forward).  The weight operand holds gamma-scaled
+  //    weights, `bias` the beta-folded bias, colsum[n] = sum_k W'[n, k].
   __nv_bfloat16* xb = nullptr;
   int ldxb = 0;
   // split-bf16 mode: low halves of the bf16 outputs (out for bf16 epilogues, xb for residual epilogues):
@@ -73,9 +76,11 @@ struct GemmEpilogue {
   __nv_bfloat16* out_lo = nullptr;
   __nv_bfloat16* xb_lo = nullptr;
   float2* row_stats_out = nullptr;
-  const float2* row_affine_in = nullptr;
+  const float2* row_stats_in = nullptr;
   const float* colsum = nullptr;
-  int stats_slots = 0;
+  int stats_slots = 0;      // producer side: slots per row of row_stats_out (= N / ln_slot_width(N))
+  int stats_in_slots = 0;   // consumer side: slots per row of row_stats_in (= K / ln_slot_width(K), even)
+  float ln_eps = 1e-6f;
 };
 
 struct GemmShape {
@@ -358,24 +363,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (kLnIn && warp == 3) {
     // ------------------------------------------------------------ LayerNorm row statistics (folded-LN GEMMs)
-    // Runs one tile ahead of the epilogue: fetches (rstd, -rstd * mean) of the tile's 128 rows (this CTA's) from the
-    // array row_stats_finalize_kernel wrote and stages them in smem, so that the epilogue never waits for an L2
-    // round trip (exposed, that latency cost ~2,000 cycles per tile).
+    // Runs one tile ahead of the epilogue: reduces the partial sums (sum x, sum x^2 per 32-column chunk, written by the
+    // GEMM that produced the rows) of the tile's 128 rows (this CTA's) to (rstd, -rstd * mean) and stages them in smem,
+    // so that the epilogue never waits for an L2 round trip (exposed, that latency cost ~2,000 cycles per tile).
+    // Four lanes per row: lane q of a row's quad sums the float4 pairs of slots q, q + 4, ... in ascending order, then
+    // two xor-shuffles -- the order is fixed, so the statistics are bit-reproducible (and identical to what round 1's
+    // separate row_stats_finalize kernel produced).  With one slot per 128 (64) columns a ViT-B row has 6 slots = 3
+    // float4: lanes q < 3 of a row's quad load one each, so a tile costs one L2 round trip of 16 independent loads per
+    // lane (2.4 MB per forward pass over the statistics, L2-resident behind the producing GEMM).
     int local = 0;
+    const int q = lane & 3, rq = lane >> 2;
+    const int n4 = ep.stats_in_slots >> 1;   // float4 = two slots
+    const float inv_w = 1.0f / static_cast<float>(shape.K);
     for (int unit = slot; unit < num_units; unit += num_slots, ++local) {
       int m_blk, n_blk;
       work.decode(unit, kPairs, pair_id, m_blk, n_blk);
       const int buf = local & 1;
       ptx::mbar_wait(&ln_empty_bar[buf], ((local >> 1) & 1) ^ 1);
       const int row0 = m_blk * kTileM + static_cast<int>(cta_rank) * BM;
-      float2 v[BM / 32];
+      constexpr int kGroups = 16;            // all 16 row groups (of 8 rows) at once: ONE L2 round trip per tile and j
+#pragma unroll 1
+      for (int g0 = 0; g0 < BM / 8; g0 += kGroups) {
+        float s1[kGroups], s2[kGroups];
 #pragma unroll
-      for (int rr = 0; rr < BM / 32; ++rr) {   // all four loads in flight: one L2 round trip per tile
-        const int row = row0 + rr * 32 + lane;
-        v[rr] = row < shape.M ? ep.row_affine_in[row] : make_float2(0.f, 0.f);
+        for (int g = 0; g < kGroups; ++g) s1[g] = 0.f, s2[g] = 0.f;
+        for (int j = q; j < n4; j += 4) {
+          float4 v[kGroups];
+#pragma unroll
+          for (int g = 0; g < kGroups; ++g) {
+            const int row = row0 + (g0 + g) * 8 + rq;
+            v[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < shape.M)
+              v[g] = reinterpret_cast<const float4*>(ep.row_stats_in + static_cast<long>(row) * ep.stats_in_slots)[j];
+          }
+#pragma unroll
+          for (int g = 0; g < kGroups; ++g) s1[g] += v[g].x, s2[g] += v[g].y, s1[g] += v[g].z, s2[g] += v[g].w;
+        }
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          float a = s1[g], b = s2[g];
+          a += __shfl_xor_sync(0xffffffffu, a, 1), b += __shfl_xor_sync(0xffffffffu, b, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2), b += __shfl_xor_sync(0xffffffffu, b, 2);
+          if (q == 0) {
+            const float mean = a * inv_w;
+            const float rstd = rsqrtf(fmaxf(b * inv_w - mean * mean, 0.f) + ep.ln_eps);
+            ln_rows[buf * BM + (g0 + g) * 8 + rq] = make_float2(rstd, -rstd * mean);
+          }
+        }
       }
-#pragma unroll
-      for (int rr = 0; rr < BM / 32; ++rr) ln_rows[buf * BM + rr * 32 + lane] = v[rr];
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ln_full_bar[buf]);
     }
@@ -450,6 +485,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (kLnIn) csum_c[c] = *reinterpret_cast<const float4*>(ep.colsum + col);
         }
       }
+      // producer side of the LayerNorm folding: this lane's row (trow + 4 * tcol of the quarter) summed over the warp's chunks
+      float st1 = 0.f, st2 = 0.f;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr0 =
@@ -595,19 +632,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const bool b0 = (tcol & 1) != 0;
             const float f1 = (b0 ? c1[1] : c1[0]) + __shfl_xor_sync(0xffffffffu, b0 ? c1[0] : c1[1], 1);
             const float f2 = (b0 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? c2[0] : c2[1], 1);
-            // this lane now owns row index tcol of the batch (bit 2 chose rows 4..7, bit 1 rows +2, bit 0 rows +1)
-            const int row = row_base + trow + 4 * tcol;
-            if (row < shape.M) {
-              long out_row = row;
-              if (kRemap) {
-                const int g = row / ep.group_rows;
-                out_row = static_cast<long>(g) * ep.out_group_stride + ep.out_row_offset + (row - g * ep.group_rows);
-              }
-              ep.row_stats_out[out_row * ep.stats_slots + (col0 >> 5)] = make_float2(f1, f2);
-            }
+            // this lane now owns row index tcol of the batch (bit 2 chose rows 4..7, bit 1 rows +2, bit 0 rows +1):
+            // chunk sums are added in ascending chunk order
+            st1 += f1, st2 += f2;
           }
         }
         __syncwarp();  // slab is rewritten by the next chunk
+      }
+      if (kResid && ep.xb != nullptr) {
+        static_assert(!kResid || (kGroupCols == 64 || kGroupCols == 128), "one statistics slot per epilogue-warp column group");
+        const int row = row_base + trow + 4 * tcol;
+        const int gcol = n_blk * BN + col_grp * kGroupCols;
+        if (row < shape.M && gcol < shape.N) {
+          long out_row = row;
+          if (kRemap) {
+            const int g = row / ep.group_rows;
+            out_row = static_cast<long>(g) * ep.out_group_stride + ep.out_row_offset + (row - g * ep.group_rows);
+          }
+          ep.row_stats_out[out_row * ep.stats_slots + gcol / kGroupCols] = make_float2(st1, st2);
+        }
       }
     }
   }

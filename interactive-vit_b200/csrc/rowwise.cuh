@@ -11,6 +11,11 @@
 
 namespace vitb200 {
 
+// Width (in columns) of one LayerNorm partial-sum slot of a row of width d: the column group one epilogue warp of the
+// producing GEMM owns (gemm.cuh: BN = 256 -> 128 columns, BN = 128 -> 64 columns).  Everything that writes or reads
+// the partial sums (GEMM epilogues, cls_rows / rows_bf16_stats below, the consuming GEMM's role 3) agrees on it.
+__host__ __device__ constexpr int ln_slot_width(int d) { return (d % 256 == 0) ? 128 : 64; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -179,22 +184,25 @@ __global__ void __launch_bounds__(256)
 cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                 __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int B, int N, int d,
                 __nv_bfloat16* __restrict__ xb_lo = nullptr) {
-  const int slots = d >> 5;
+  const int sw = ln_slot_width(d), slots = d / sw;
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= static_cast<long>(B) * slots) return;
-  const int b = static_cast<int>(warp / slots), chunk = static_cast<int>(warp % slots);
-  const int col = chunk * 32 + lane;
-  const float v = cls[col] + pos[col];
+  const int b = static_cast<int>(warp / slots), slot = static_cast<int>(warp % slots);
   const long row = static_cast<long>(b) * N;
-  x[row * d + col] = v;
-  if (xb != nullptr) {
-    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-    xb[row * d + col] = hb;
-    if (xb_lo != nullptr) xb_lo[row * d + col] = __float2bfloat16_rn(v - __bfloat162float(hb));
-    const float p1 = warp_sum(v), p2 = warp_sum(v * v);
-    if (lane == 0) stats[row * slots + chunk] = make_float2(p1, p2);
+  float p1 = 0.f, p2 = 0.f;
+  for (int c = 0; c < sw; c += 32) {     // chunk sums in ascending order: fixed order, bit-reproducible
+    const int col = slot * sw + c + lane;
+    const float v = cls[col] + pos[col];
+    x[row * d + col] = v;
+    if (xb != nullptr) {
+      const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+      xb[row * d + col] = hb;
+      if (xb_lo != nullptr) xb_lo[row * d + col] = __float2bfloat16_rn(v - __bfloat162float(hb));
+      p1 += warp_sum(v), p2 += warp_sum(v * v);
+    }
   }
+  if (xb != nullptr && lane == 0) stats[row * slots + slot] = make_float2(p1, p2);
 }
 
 // bf16 copy + partial LayerNorm sums of arbitrary fp32 rows (token streams that enter through the boundary,
@@ -205,45 +213,18 @@ rows_bf16_stats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ 
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int slots = d >> 5;
-  for (int chunk = 0; chunk < slots; ++chunk) {
-    const float v = x[row * d + chunk * 32 + lane];
-    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-    xb[row * d + chunk * 32 + lane] = hb;
-    if (xb_lo != nullptr) xb_lo[row * d + chunk * 32 + lane] = __float2bfloat16_rn(v - __bfloat162float(hb));
-    const float p1 = warp_sum(v), p2 = warp_sum(v * v);
-    if (lane == 0) stats[row * slots + chunk] = make_float2(p1, p2);
-  }
-}
-
-// LayerNorm folding, statistics side: partial sums [rows][slots] (sum, sum of squares per 32-column chunk, written by
-// the GEMM epilogues that produce the row) -> (rstd, -rstd * mean) per row, summed in slot order (bit-reproducible).
-// Four lanes per row (each sums every fourth 16-byte pair of slots, then two xor-shuffles): a warp instruction reads
-// 8 rows x 64 contiguous bytes.  The order of the additions is fixed, so the result is bit-reproducible.  Runs once
-// per LayerNorm instead of once per consuming output tile.
-__global__ void __launch_bounds__(256)
-row_stats_finalize_kernel(const float2* __restrict__ partial, float2* __restrict__ affine, long rows, int slots, int width,
-                          float eps) {
-  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 2;
-  const int q = threadIdx.x & 3;
-  const bool row_ok = row < rows;
-  const int n4 = slots >> 1;  // float4 = two slots
-  float s1 = 0.f, s2 = 0.f;
-  if (row_ok) {
-    const float4* sp = reinterpret_cast<const float4*>(partial + row * slots);
-#pragma unroll 4
-    for (int j = q; j < n4; j += 4) {
-      const float4 v = sp[j];
-      s1 += v.x, s2 += v.y, s1 += v.z, s2 += v.w;
+  const int sw = ln_slot_width(d), slots = d / sw;
+  for (int slot = 0; slot < slots; ++slot) {
+    float p1 = 0.f, p2 = 0.f;
+    for (int c = 0; c < sw; c += 32) {
+      const int col = slot * sw + c + lane;
+      const float v = x[row * d + col];
+      const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+      xb[row * d + col] = hb;
+      if (xb_lo != nullptr) xb_lo[row * d + col] = __float2bfloat16_rn(v - __bfloat162float(hb));
+      p1 += warp_sum(v), p2 += warp_sum(v * v);
     }
-  }
-  s1 += __shfl_xor_sync(0xffffffffu, s1, 1), s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-  s1 += __shfl_xor_sync(0xffffffffu, s1, 2), s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-  if (row_ok && q == 0) {
-    const float inv_w = 1.0f / static_cast<float>(width);
-    const float mean = s1 * inv_w;
-    const float rstd = rsqrtf(fmaxf(s2 * inv_w - mean * mean, 0.f) + eps);
-    affine[row] = make_float2(rstd, -rstd * mean);
+    if (lane == 0) stats[row * slots + slot] = make_float2(p1, p2);
   }
 }
 

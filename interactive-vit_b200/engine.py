@@ -620,14 +620,20 @@ def op_layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: 
     return y
 
 
+def ln_slot_width(d: int) -> int:
+    """Columns per LayerNorm partial-sum slot of a row of width d (csrc/rowwise.cuh ln_slot_width)."""
+    return 128 if d % 256 == 0 else 64
+
+
 def op_gemm_residual_stats(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, resid: torch.Tensor):
-    """Residual GEMM with the LayerNorm-folding producer epilogue: (x fp32 [M,N], bf16 copy, partial sums [M,N/32,2])."""
+    """Residual GEMM with the LayerNorm-folding producer epilogue: (x fp32 [M,N], bf16 copy, partial sums
+    [M, N / ln_slot_width(N), 2])."""
     lib = load_library()
     M, K = a.shape
     N = w.shape[0]
     out = torch.empty(M, N, device=a.device)
     xb = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
-    stats = torch.zeros(M, N // 32, 2, device=a.device)
+    stats = torch.zeros(M, N // ln_slot_width(N), 2, device=a.device)
     check(lib.vitb200_op_gemm_ex(a.data_ptr(), w.data_ptr(), bias.data_ptr(), resid.data_ptr(), out.data_ptr(), M, N, K, 0, 1,
                                  xb.data_ptr(), stats.data_ptr(), None, None, 0.0, None))
     return out, xb, stats

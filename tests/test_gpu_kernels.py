@@ -140,7 +140,9 @@ def test_layernorm_folded_into_gemms(E, M, d, n_out, gelu):
     x_ref = a.float() @ w0.float().t() + b0 + resid
     assert _rel(x, x_ref) < F32_EPS
     assert torch.equal(xb, x.bfloat16())                                     # the copy is the rounded fp32 result
-    chunks = x.reshape(M, d // 32, 32)
+    sw = E.ln_slot_width(d)       # one slot per epilogue-warp column group (128 columns, 64 for widths not divisible by 256)
+    assert stats.shape == (M, d // sw, 2)
+    chunks = x.reshape(M, d // sw, sw)
     assert _rel(stats[..., 0], chunks.sum(-1)) < 1e-5 and _rel(stats[..., 1], (chunks * chunks).sum(-1)) < 1e-5
     # consumer
     gamma = 1.0 + 0.1 * torch.randn(d, device="cuda")
