@@ -36,6 +36,7 @@
 // tiles, thread-local maxima and the class rows on a spare warp brought it to ~5,400.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 
 namespace vitb200 {
@@ -43,6 +44,18 @@ namespace vitb200 {
 __device__ __forceinline__ uint32_t pack_bf16x2_u(uint32_t a_f32_bits, uint32_t b_f32_bits) {
   __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(a_f32_bits), __uint_as_float(b_f32_bits));
   return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// fp32 pair -> packed fp16x2 / packed fp16x2 multiply.  The probabilities are carried in FP16 (not bf16): they lie in
+// [0, 1], where fp16 has 10 mantissa bits against bf16's 7, and fp16 makes the normalisation a packed multiply.
+__device__ __forceinline__ uint32_t pack_f16x2_f(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t hmul2_u(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
 }
 
 struct AttnParams {
@@ -95,7 +108,7 @@ constexpr int kPBytes = kPBlocks * kPBlockBytes;   // 64 KB
 constexpr int kIdentBytes = 16 * 128;              // 16 x 16 bf16 identity in 128-B rows (B operand of the head-average MMAs)
 constexpr int kCtxStageBytes = BM * D * 2;         // 16 KB: bf16 context tile of one head, staged for the TMA store
 constexpr int kRedBytes = 2 * 2 * kColGroups * BM * 4;  // row max / row sum exchange: [head parity][2 kinds][4 groups][128 rows]
-constexpr int kClsStageBytes = KP_MAX * 4;         // normalised probabilities of query row 0 (one head)
+constexpr int kClsStageBytes = KP_MAX * 4 + 16;    // exponentials of query row 0 (one head) + the 4 column groups' factors
 constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kCtxStageBytes + kIdentBytes + kRedBytes + kClsStageBytes + 128;
 static_assert(kSmemBytes <= 227 * 1024, "attention: shared memory budget");
 }  // namespace attn_cfg
@@ -120,7 +133,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   uint8_t* smem_ctx = smem_p + kPBytes;      // 4 quarter tiles of 32 rows x 128 B, 128-B swizzle
   uint8_t* smem_id = smem_ctx + kCtxStageBytes;
   float* red = reinterpret_cast<float*>(smem_id + kIdentBytes);  // [kind][group][row]
-  float* cls_stage = red + 2 * 2 * kColGroups * BM;               // [KP_MAX] normalised probabilities of query row 0
+  float* cls_stage = red + 2 * 2 * kColGroups * BM;               // [KP_MAX] exp2 values of query row 0 (not yet normalised)
+  float* cls_factor = cls_stage + KP_MAX;                         // [4] per column group: exp2(m_t - M) / sum
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_id + kIdentBytes + kRedBytes + kClsStageBytes);
   uint64_t* full_bar = bars;        // [2] Q/K/V of a head landed
   uint64_t* empty_bar = bars + 2;   // [2] Q/K/V stage consumed by the MMAs
@@ -179,7 +193,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   }
   if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
   if (warp == 3) {
-    // 16 x 16 bf16 identity, K-major rows of 128 B in the 128-B swizzle: element (n, k) lives in 16-B chunk
+    // 16 x 16 fp16 identity (the operand format of P), K-major rows of 128 B in the 128-B swizzle: element (n, k) lives in 16-B chunk
     // (k / 8) ^ (n % 8) of row n.  Pbar[:, 16 ks + n] += sum_k P[:, 16 ks + k] * I[n, k] accumulates the normalised
     // probabilities over the heads on the tensor pipe (fp32 in TMEM) instead of a TMEM load/add/store pass per head
     // in the softmax threads.
@@ -188,7 +202,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       const int n = i >> 3, c = (i & 7) ^ (n & 7);  // this physical chunk holds k in [8 c, 8 c + 8)
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if ((n >> 3) == c) {
-        const uint32_t one = 0x3F80u << (16 * (n & 1));  // bf16 1.0 at position n % 8 of the chunk
+        const uint32_t one = 0x3C00u << (16 * (n & 1));  // fp16 1.0 at position n % 8 of the chunk
         const int w = (n & 7) >> 1;
         v.x = w == 0 ? one : 0u, v.y = w == 1 ? one : 0u, v.z = w == 2 ? one : 0u, v.w = w == 3 ? one : 0u;
       }
@@ -227,10 +241,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
     const uint32_t idesc_qk = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(KP), 0, 0);
-    const uint32_t idesc_pv = ptx::make_idesc_bf16(BM, D, 0, 1);  // B (= V) is MN-major
+    // P V and the head average run with FP16 operands: P is fp16, and the qkv GEMM writes the V third of its output in
+    // fp16 for this kernel (kind::f16 traps on mixed A / B formats: measured); QK^T stays bf16
+    const uint32_t idesc_pv = ptx::make_idesc_f16kind(BM, D, 0, 0, 0, 1);  // B (= V) is MN-major
     const uint32_t sp = ptx::smem_u32(smem_p);
     const int ksteps = KP >> 4;
-    const uint32_t idesc_avg = ptx::make_idesc_bf16(BM, 16, 0, 0);
+    const uint32_t idesc_avg = ptx::make_idesc_f16kind(BM, 16, 0, 0, 0, 0);
     // A: P K-block (ks / 4), +32 B per 16 keys inside the swizzle span (descriptor addresses are in 16-B units:
     // +2 per 16 keys, +1024 = 16 KB to the next K-block).
     const uint64_t dp0 = ptx::make_smem_desc_sw128(sp, 16, 1024);
@@ -299,7 +315,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       for (int h = 0; h < nh; ++h) {
         ptx::mbar_wait(cls_full, h & 1);
         float* cp = p.cls_map + (static_cast<size_t>(b) * p.H + h0 + h) * p.N;
-        for (int j = lane; j < p.N; j += 32) cp[j] = cls_stage[j];
+        // staged: e = exp2((s - m_t) c) of row 0 in fp32 (written by the owning lanes during their exponential pass,
+        // off their critical path) and the four column groups' factors f_t; p = e f_t is the same fp32 product the
+        // softmax threads used to form
+        for (int j = lane; j < p.N; j += 32) cp[j] = cls_stage[j] * cls_factor[(j >> 3) & (kColGroups - 1)];
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(cls_free);
       }
@@ -367,19 +386,57 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     };
 
     for (int h = 0; h < nh; ++h) {
-      // ---- this thread's part of the S row -> registers (single TMEM read), then release the S columns
+      // ---- this thread's part of the S row -> registers (single TMEM read), then release the S columns.  The read is
+      //      issued in two halves so that the maximum of the first granules is taken while the others are in flight.
       uint32_t s[kMaxGran][8];
       ATTN_TS(0);
+      // (row-0 warps: the class-token stage of the previous head must have been streamed out before the exponential
+      //  pass below overwrites it; warp 3 finished that long ago, this is the barrier's fast path)
+      if (want_cls && h > 0) ptx::mbar_wait(cls_free, (h - 1) & 1);
       ptx::mbar_wait(s_full, h & 1);
       ATTN_TS(1);
       ptx::tc_fence_after();
+      constexpr int kFirst = 4;   // granules of the first half
 #pragma unroll
-      for (int c = 0; c < kMaxGran; ++c) {
+      for (int c = 0; c < kFirst; ++c) {
         if OWNS(c) {
           ptx::tmem_ld_x8(t_s + c * 32, s[c]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) s[c][j] = 0u;   // never used as a score; scaled and packed (not stored) below
+          for (int j = 0; j < 8; ++j) s[c][j] = 0xff800000u;   // -inf: no score, exp2 gives 0
+        }
+      }
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int c = kFirst; c < kMaxGran; ++c) {
+        if OWNS(c) {
+          ptx::tmem_ld_x8(t_s + c * 32, s[c]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s[c][j] = 0xff800000u;
+        }
+      }
+      // ---- padded keys (>= N) count as -inf.  KP - N < 16, so they sit in the last two granules of the row, each of
+      //      which is the LAST granule of its owner: one granule per thread to patch, and only in warps that own one
+      auto patch = [&](uint32_t (&row)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j >= valid_last) row[j] = 0xff800000u;  // -inf: exp2 gives 0, max ignores it
+      };
+      float mx = -INFINITY;
+      if (has_pad && nmy <= kFirst) {   // warp-uniform; compile-time row indices keep s[][] in registers
+        switch (nmy) {
+          case 4: patch(s[3]); break;
+          case 3: patch(s[2]); break;
+          case 2: patch(s[1]); break;
+          default: patch(s[0]); break;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kFirst; ++c) {
+        if OWNS(c) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) mx = ptx::fmax3(mx, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
         }
       }
       ptx::tmem_ld_wait();
@@ -387,57 +444,56 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(s_free);
-
       ATTN_TS(3);
-
-      // ---- padded keys (>= N) count as -inf.  KP - N < 16, so they sit in the last two granules of the row, each of
-      //      which is the LAST granule of its owner: one granule per thread to patch, and only in warps that own one
-      if (has_pad) {
-        auto patch = [&](uint32_t (&row)[8]) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j >= valid_last) row[j] = 0xff800000u;  // -inf: exp2 gives 0, max ignores it
-        };
-        static_assert(kMaxGran == 7, "one case per possible granule count");
-        switch (nmy) {   // warp-uniform; compile-time row indices keep s[][] in registers
+      static_assert(kMaxGran == 7, "one case per possible granule count");
+      if (has_pad && nmy > kFirst) {
+        switch (nmy) {
           case 7: patch(s[6]); break;
           case 6: patch(s[5]); break;
-          case 5: patch(s[4]); break;
-          case 4: patch(s[3]); break;
-          case 3: patch(s[2]); break;
-          case 2: patch(s[1]); break;
-          default: patch(s[0]); break;
+          default: patch(s[4]); break;
+        }
+      }
+#pragma unroll
+      for (int c = kFirst; c < kMaxGran; ++c) {
+        if OWNS(c) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) mx = ptx::fmax3(mx, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
         }
       }
 
       // ---- e = exp2((s - m_t) * c) with the maximum m_t of this thread's OWN columns: no exchange is needed before
       //      the exponentials.  Softmax is invariant to the shift, the four threads of a row reconcile afterwards:
       //      p = e * f_t,  f_t = exp2((m_t - M) c) / sum_u(sum_u exp2((m_u - M) c)),  M = max_u m_u.
-      float mx;
-      mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < kMaxGran; ++c) {
-        if OWNS(c) {
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) mx = ptx::fmax3(mx, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
-        }
-      }
+      //      The exponentials are packed to fp16 pairs as they are produced (the MUFU bounds this pass, the conversions
+      //      ride along on the ALU); the fp32 values of query row 0 go to the class-token stage from the owning lanes.
       // a thread whose columns are all padding (tiny test shapes) must not produce -inf - -inf
       const float mxs = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
       ATTN_TS(4);
       float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+      uint32_t e16[kMaxGran][4];
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
-        if OWNS(c) {
+        if (!OWNS(c)) {   // (compile-time for all but the last granule when kFull)
+          e16[c][0] = e16[c][1] = e16[c][2] = e16[c][3] = 0u;
+          continue;
+        }
 #pragma unroll
-          for (int j = 0; j < 8; j += 4) {
-            const float v0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -mxs));
-            const float v1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 1]), p.scale_log2, -mxs));
-            const float v2 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 2]), p.scale_log2, -mxs));
-            const float v3 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 3]), p.scale_log2, -mxs));
-            ps0 += v0, ps1 += v1, ps2 += v2, ps3 += v3;
+        for (int j = 0; j < 8; j += 4) {
+          const float v0 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -mxs));
+          const float v1 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 1]), p.scale_log2, -mxs));
+          const float v2 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 2]), p.scale_log2, -mxs));
+          const float v3 = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j + 3]), p.scale_log2, -mxs));
+          ps0 += v0, ps1 += v1, ps2 += v2, ps3 += v3;
+          e16[c][j >> 1] = pack_f16x2_f(v0, v1), e16[c][(j >> 1) + 1] = pack_f16x2_f(v2, v3);
+          if (kHeads) {
             s[c][j] = __float_as_uint(v0), s[c][j + 1] = __float_as_uint(v1);
             s[c][j + 2] = __float_as_uint(v2), s[c][j + 3] = __float_as_uint(v3);
+          }
+          if (want_cls) {   // warp-uniform; only lane 0 (query row 0) stores
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %5, 0;\n\t@p st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(
+                             ptx::smem_u32(cls_stage + (kColGroups * c + cg) * 8 + j)),
+                         "f"(v0), "f"(v1), "f"(v2), "f"(v3), "r"(static_cast<uint32_t>(lane))
+                         : "memory");
           }
         }
       }
@@ -449,9 +505,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       red_max[cg * BM + r] = (mx == -INFINITY) ? -INFINITY : mxs;   // already in the exp2 domain
       red_sum[cg * BM + r] = (ps0 + ps1) + (ps2 + ps3);
       // the context tile of head h-2 has been read out of smem before anyone can restage it (after this barrier);
-      // only the issuing thread has a bulk group outstanding, for everyone else this returns immediately
+      // only the issuing thread has a bulk group outstanding, for everyone else this returns immediately.
+      // The exchange (and the context tile) concern the four warps of ONE lane quarter only -- they sit on one SM
+      // sub-partition -- so the barrier is per quarter: the quarters do not wait for each other here.
       ptx::tma_store_wait_read<0>();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(8 + quarter) : "memory");
       ATTN_TS(6);
       float inv;
       {
@@ -463,6 +521,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         inv = ptx::ex2_approx(mxs - M) * ptx::rcp_approx(tot);
         if (mx == -INFINITY) inv = 0.f;
       }
+      if (want_cls && lane == 0) {
+        cls_factor[cg] = inv;
+        ptx::mbar_arrive(cls_full);  // release: stage + factor are visible to warp 3 once the four owners have arrived
+      }
+      const uint32_t inv16 = pack_f16x2_f(inv, inv);
       ATTN_TS(9);
 
       // ---- the P tile is about to be overwritten: the previous head's P V and Pbar MMAs (issued a whole softmax
@@ -471,24 +534,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         ptx::mbar_wait(p_free, (h - 1) & 1);
         ATTN_TS(10);
         // context of the previous head (its P V retired long ago): TMEM -> smem now, so that the fence below covers it
-        // and P V of THIS head finds the O columns free as soon as the P tile is handed over.  (Reading O at the top of
-        // the head together with S, to hide the TMEM latency, measured 203 us against 190 us: 8 more live registers.)
+        // and P V of THIS head finds the O columns free as soon as the P tile is handed over.
         o_stage(h - 1);
       }
       ATTN_TS(11);
 
-      // ---- p = e / sum -> bf16 P tile (swizzled K-major A operand of P V and of the head-average MMAs); fp32 copies
-      //      of row 0 / of every row for the CLS / per-head maps
-      //      The multiplies and packs run for all kMaxGran granules (a thread with fewer granules scales zeros) and only
-      //      the store is predicated: per-granule branches cost more issue slots than the arithmetic they skip.
+      // ---- p = e * f_t as packed fp16 multiplies -> fp16 P tile (swizzled K-major A operand of P V and of the
+      //      head-average MMAs).  All kMaxGran granules are multiplied (a thread with fewer granules scales zeros) and
+      //      only the store is predicated: per-granule branches cost more issue slots than the arithmetic they skip.
 #pragma unroll
       for (int c = 0; c < kMaxGran; ++c) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s[c][j] = __float_as_uint(__uint_as_float(s[c][j]) * inv);
         // keys [8 g, 8 g + 8), g = 4 c + cg: K-block c / 2, 16-byte chunk (cg | 4 (c & 1)) ^ (row % 8) of this row
         const uint32_t dst = ((c & 1) ? p_odd : p_even) + (c >> 1) * kPBlockBytes;
-        const uint32_t w0 = pack_bf16x2_u(s[c][0], s[c][1]), w1 = pack_bf16x2_u(s[c][2], s[c][3]);
-        const uint32_t w2 = pack_bf16x2_u(s[c][4], s[c][5]), w3 = pack_bf16x2_u(s[c][6], s[c][7]);
+        const uint32_t w0 = hmul2_u(e16[c][0], inv16), w1 = hmul2_u(e16[c][1], inv16);
+        const uint32_t w2 = hmul2_u(e16[c][2], inv16), w3 = hmul2_u(e16[c][3], inv16);
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(dst), "r"(w0),
                      "r"(w1), "r"(w2), "r"(w3), "r"(static_cast<uint32_t>OWNS(c))
                      : "memory");
@@ -503,22 +562,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       if (h > 0) o_store(h - 1);
       ATTN_TS(13);
 
-      if (want_cls && lane == 0) {
-        // query row 0 lives in lane 0 of the quarter-0 warp of every column group
-        if (h > 0) ptx::mbar_wait(cls_free, (h - 1) & 1);
-        ATTN_TS(14);
-#pragma unroll
-        for (int c = 0; c < kMaxGran; ++c) {
-          if OWNS(c) {
-            float4* dst = reinterpret_cast<float4*>(cls_stage + (kColGroups * c + cg) * 8);
-            dst[0] = make_float4(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]), __uint_as_float(s[c][2]),
-                                 __uint_as_float(s[c][3]));
-            dst[1] = make_float4(__uint_as_float(s[c][4]), __uint_as_float(s[c][5]), __uint_as_float(s[c][6]),
-                                 __uint_as_float(s[c][7]));
-          }
-        }
-        ptx::mbar_arrive(cls_full);  // release: the staged values are visible to warp 3 once the phase completes
-      }
       if (kHeads) {
         if (p.head_map != nullptr && row_ok) {
           float* hp = p.head_map + ((static_cast<size_t>(b) * p.H + h0 + h) * p.N + qrow) * p.ldmap;
@@ -526,10 +569,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
           for (int c = 0; c < kMaxGran; ++c) {
             if OWNS(c) {
               float4* dst = reinterpret_cast<float4*>(hp + (kColGroups * c + cg) * 8);
-              dst[0] = make_float4(__uint_as_float(s[c][0]), __uint_as_float(s[c][1]), __uint_as_float(s[c][2]),
-                                   __uint_as_float(s[c][3]));
-              dst[1] = make_float4(__uint_as_float(s[c][4]), __uint_as_float(s[c][5]), __uint_as_float(s[c][6]),
-                                   __uint_as_float(s[c][7]));
+              dst[0] = make_float4(__uint_as_float(s[c][0]) * inv, __uint_as_float(s[c][1]) * inv,
+                                   __uint_as_float(s[c][2]) * inv, __uint_as_float(s[c][3]) * inv);
+              dst[1] = make_float4(__uint_as_float(s[c][4]) * inv, __uint_as_float(s[c][5]) * inv,
+                                   __uint_as_float(s[c][6]) * inv, __uint_as_float(s[c][7]) * inv);
             }
           }
         }

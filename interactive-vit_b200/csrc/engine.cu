@@ -155,6 +155,8 @@ struct DeviceCtx {
   std::map<const void*, int> func_smem;    // kernel -> dynamic smem limit configured on this device
   std::map<const void*, int> gemm_slots;   // GEMM instantiation -> persistent scheduler slots on this device
   float2* op_stats = nullptr;              // scratch of the single-kernel attention entry point (parity tests)
+  void* op_qkv = nullptr;                  // ... and its fp16-V copy of the input
+  size_t op_qkv_cap = 0;
   size_t op_stats_cap = 0;
 };
 static std::mutex g_dev_mu;
@@ -690,6 +692,8 @@ static int run_attn_block(vitb200_engine* e, int l, int B, uint32_t flags, cudaS
     ep.bias = w.bf_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
     ep.row_stats_in = stats, ep.stats_in_slots = slots, ep.ln_eps = 1e-6f;
     ep.colsum = w.s_qkv, ep.out_lo = (__nv_bfloat16*)e->qkv_lo.p;
+    // the fused attention kernel takes V in fp16 (its probabilities are fp16; see attention.cuh)
+    if (!e->precise && attention_is_fused(e->N, e->D)) ep.f16_from_col = 2 * d;
     VT_TRY(launch_gemm(xb, d, w.w_qkv, M, 3 * d, d, ep, false, false, st, e->xb_lo.p, w.w_qkv_lo));
   }
   const bool want_avg = (flags & (VITB200_EMIT_AVG | VITB200_EMIT_ROLLOUT)) != 0;
@@ -1693,12 +1697,35 @@ static float2* op_attention_stats(size_t count) {
 }
 
 int vitb200_op_attention_ex(const void* qkv, void* ctx, float* avg, float* cls, float* heads, int batch, int tokens,
-                            int nheads, int head_dim, int pitch, void* stream) {
+                            int nheads, int head_dim, int pitch, int v_is_f16, void* stream) {
   if (!qkv || !ctx) return fail(VITB200_ERR_INVALID, "null argument");
   float2* stats = nullptr;
-  if (!attention_is_fused(tokens, head_dim)) {
+  const bool fused = attention_is_fused(tokens, head_dim);
+  if (!fused) {
+    if (v_is_f16) return fail(VITB200_ERR_INVALID, "attention: the key-blocked path takes V in bf16");
     stats = op_attention_stats((size_t)batch * nheads * tokens);
     if (!stats) return fail(VITB200_ERR_CUDA, "attention: cannot allocate the statistics scratch");
+  } else if (!v_is_f16) {
+    // the fused kernel wants the V third in fp16 (the forward's qkv GEMM writes it that way): convert a scratch copy
+    const long rows = (long)batch * tokens;
+    const int d = nheads * head_dim;
+    const size_t bytes = (size_t)rows * 3 * d * 2;
+    uint16_t* tmp = nullptr;
+    {
+      std::lock_guard<std::mutex> lock(g_dev_mu);
+      DeviceCtx& dc = dev_ctx_locked();
+      if (bytes > dc.op_qkv_cap) {
+        if (dc.op_qkv) cudaFree(dc.op_qkv);
+        dc.op_qkv = nullptr, dc.op_qkv_cap = 0;
+        CU_TRY(cudaMalloc(&dc.op_qkv, bytes));
+        dc.op_qkv_cap = bytes;
+      }
+      tmp = (uint16_t*)dc.op_qkv;
+    }
+    const long vecs = rows * 3 * d / 8;
+    qkv_v_to_f16_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, tmp, rows, d);
+    CU_TRY(cudaGetLastError());
+    qkv = tmp;
   }
   return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, avg, cls, heads, batch, tokens, nheads, head_dim,
                           pitch, stats, (cudaStream_t)stream);
@@ -1706,7 +1733,7 @@ int vitb200_op_attention_ex(const void* qkv, void* ctx, float* avg, float* cls, 
 
 int vitb200_op_attention(const void* qkv, void* ctx, float* avg, float* cls, float* heads, int batch, int tokens,
                          int nheads, int pitch, void* stream) {
-  return vitb200_op_attention_ex(qkv, ctx, avg, cls, heads, batch, tokens, nheads, 64, pitch, stream);
+  return vitb200_op_attention_ex(qkv, ctx, avg, cls, heads, batch, tokens, nheads, 64, pitch, 0, stream);
 }
 
 // torchvision F.resize with a single int (shorter side -> resize, longer = int(resize * long / short)) followed by

@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace vitb200 {
@@ -358,6 +359,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major,
                                                        uint32_t b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
+         ((m >> 4) << 24);
+}
+
+// Same with the operand formats spelled out (0 = f16, 1 = bf16): A and B may differ (fp16 probabilities x bf16 values).
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(uint32_t m, uint32_t n, uint32_t a_fmt, uint32_t b_fmt,
+                                                          uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
          ((m >> 4) << 24);
 }
 

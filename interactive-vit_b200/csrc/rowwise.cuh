@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace vitb200 {
@@ -256,6 +257,25 @@ fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ gam
   }
   s = warp_sum(s), bb = warp_sum(bb);
   if (lane == 0) colsum[n] = s, bias_out[n] = bias[n] + bb;
+}
+
+// Copy of a packed bf16 qkv activation [rows, 3d] with the V third converted to FP16 (what the qkv GEMM writes directly
+// on the forward path; this kernel serves the single-kernel attention entry point, which takes bf16 inputs).
+__global__ void __launch_bounds__(256)
+qkv_v_to_f16_kernel(const __nv_bfloat16* __restrict__ in, uint16_t* __restrict__ out, long rows, int d) {
+  const long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;   // 8 elements = 16 bytes
+  if (i >= rows * 3 * d) return;
+  uint4 v = *reinterpret_cast<const uint4*>(in + i);
+  if (static_cast<int>(i % (3 * d)) >= 2 * d) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+      const __half2 h = __floats2half2_rn(__low2float(b), __high2float(b));
+      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + i) = v;
 }
 
 // fp32 -> bf16 (weights at load time; also activations arriving from the wire).

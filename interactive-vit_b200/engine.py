@@ -109,7 +109,7 @@ SIGNATURES = {
     "vitb200_op_gemm_split": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "vitb200_op_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "vitb200_op_attention_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "vitb200_op_attention_ex": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_preprocess": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "vitb200_op_patchify": (_I, [_P, _P, _I, _I, _I, _P]),
     "vitb200_op_rollout": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
@@ -697,7 +697,7 @@ def op_attention(qkv: torch.Tensor, batch: int, tokens: int, heads: int, want_av
     cls = torch.zeros(batch, heads, tokens, device=qkv.device) if want_cls else None
     hm = torch.zeros(batch, heads, tokens, pitch, device=qkv.device) if want_heads else None
     check(lib.vitb200_op_attention_ex(qkv.data_ptr(), ctx.data_ptr(), _ptr(avg), _ptr(cls), _ptr(hm), batch, tokens, heads,
-                                      head_dim, pitch, None))
+                                      head_dim, pitch, 0, None))
     return ctx, (avg[..., :tokens] if avg is not None else None), cls, (hm[..., :tokens] if hm is not None else None)
 
 
