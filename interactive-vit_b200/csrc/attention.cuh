@@ -109,7 +109,7 @@ constexpr int kIdentBytes = 16 * 128;              // 16 x 16 bf16 identity in 1
 constexpr int kCtxStageBytes = BM * D * 2;         // 16 KB: bf16 context tile of one head, staged for the TMA store
 constexpr int kRedBytes = 2 * 2 * kColGroups * BM * 4;  // row max / row sum exchange: [head parity][2 kinds][4 groups][128 rows]
 constexpr int kClsStageBytes = KP_MAX * 4 + 16;    // exponentials of query row 0 (one head) + the 4 column groups' factors
-constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kCtxStageBytes + kIdentBytes + kRedBytes + kClsStageBytes + 128;
+constexpr int kSmemBytes = 2 * kStageBytes + kPBytes + kCtxStageBytes + kIdentBytes + kRedBytes + kClsStageBytes + 144;   // 16 mbarriers + the TMEM slot
 static_assert(kSmemBytes <= 227 * 1024, "attention: shared memory budget");
 }  // namespace attn_cfg
 
@@ -136,17 +136,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   float* cls_stage = red + 2 * 2 * kColGroups * BM;               // [KP_MAX] exp2 values of query row 0 (not yet normalised)
   float* cls_factor = cls_stage + KP_MAX;                         // [4] per column group: exp2(m_t - M) / sum
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_id + kIdentBytes + kRedBytes + kClsStageBytes);
-  uint64_t* full_bar = bars;        // [2] Q/K/V of a head landed
-  uint64_t* empty_bar = bars + 2;   // [2] Q/K/V stage consumed by the MMAs
-  uint64_t* s_full = bars + 4;      // S = QK^T complete
-  uint64_t* s_free = bars + 5;      // S copied to registers by all softmax warps
-  uint64_t* p_full = bars + 6;      // bf16 P tile written to smem by all softmax warps
-  uint64_t* o_full = bars + 7;      // O = PV complete (also releases the Q/K/V stage)
-  uint64_t* o_free = bars + 8;      // O columns read by all softmax warps
-  uint64_t* p_free = bars + 9;      // Pbar += P complete as well: the P tile may be overwritten
-  uint64_t* cls_full = bars + 10;   // row 0 of the normalised probabilities staged in smem (4 column-group warps)
-  uint64_t* cls_free = bars + 11;   // ... and copied out by warp 3
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  // Q / K and V of a head travel separately: the Q and K tiles of a stage are dead as soon as S = Q K^T has been
+  // computed (early in the head), V only after P V -- with one barrier pair per stage (round 1) the loads of head h + 2
+  // could only start behind P V of head h and S of head h + 2 arrived ~430 cycles late at every loop top (traced).
+  uint64_t* qk_full = bars;         // [2] Q and K of a head landed
+  uint64_t* v_full = bars + 2;      // [2] V of a head landed
+  uint64_t* qk_empty = bars + 4;    // [2] Q / K consumed by QK^T
+  uint64_t* v_empty = bars + 6;     // [2] V consumed by P V
+  uint64_t* s_full = bars + 8;      // S = QK^T complete
+  uint64_t* s_free = bars + 9;      // S copied to registers by all softmax warps
+  uint64_t* p_full = bars + 10;     // fp16 P tile written to smem by all softmax warps
+  uint64_t* o_full = bars + 11;     // O = PV complete
+  uint64_t* o_free = bars + 12;     // O columns read by the four control warps (one per TMEM lane quarter)
+  uint64_t* p_free = bars + 13;     // Pbar += P complete as well: the P tile may be overwritten
+  uint64_t* cls_full = bars + 14;   // row 0 of the exponentials + factors staged in smem (4 column-group warps)
+  uint64_t* cls_free = bars + 15;   // ... and copied out by warp 3
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   // role index: control roles 0..3 live on the highest hardware warp ids (scheduler priority), softmax roles 4..19 on
   // the lowest; role % 4 == hardware warp % 4 (TMEM lane quarters)
@@ -166,7 +171,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   const int qt = item - b * p.q_tiles;
   const int KP = p.KP;
   const int half_rows = KP >> 1;
-  const uint32_t stage_tx = kQBytes + 2 * static_cast<uint32_t>(KP) * D * 2;
+  const uint32_t kv_tx = static_cast<uint32_t>(KP) * D * 2;
   const bool want_avg = p.avg_map != nullptr;
 
   if (warp == 0 && lane == 0) {
@@ -176,16 +181,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     ptx::prefetch_tmap(&tmap_avg);
   }
   if (warp == 1 && lane == 0) {
-    ptx::mbar_init(&full_bar[0], 1);
-    ptx::mbar_init(&full_bar[1], 1);
-    ptx::mbar_init(&empty_bar[0], 1);
-    ptx::mbar_init(&empty_bar[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&qk_full[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&qk_empty[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+    }
     ptx::mbar_init(s_full, 1);
     // one arrival per softmax WARP (lane 0 after __syncwarp): 512 lanes arriving on one smem word serialise
     ptx::mbar_init(s_free, kSoftmaxWarps);
     ptx::mbar_init(p_full, kSoftmaxWarps);
     ptx::mbar_init(o_full, 1);
-    ptx::mbar_init(o_free, kSoftmaxWarps);
+    ptx::mbar_init(o_free, kCtrlWarps);
     ptx::mbar_init(p_free, 1);
     ptx::mbar_init(cls_full, kColGroups);
     ptx::mbar_init(cls_free, 1);
@@ -219,27 +226,76 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 
   // Producer and MMA loops run on whole warps with one elected lane issuing, so that addresses and descriptors
   // stay in uniform registers (a single-lane loop pays an R2UR chain in front of every UTMALDG / UTCHMMA).
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    for (int h = 0; h < nh; ++h) {   // h: head index local to this CTA (absolute head h0 + h)
-      const int st = h & 1;
-      const uint32_t ph = (h >> 1) & 1;
-      ptx::mbar_wait(&empty_bar[st], ph ^ 1);
-      uint8_t* sq = smem + st * kStageBytes;
-      uint8_t* sk = sq + kQBytes;
-      uint8_t* sv = sk + kKVBytes;
-      if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(&full_bar[st], stage_tx);
-        ptx::tma_load_2d(sq, &tmap_q, &full_bar[st], (h0 + h) * D, row0 + qt * BM);
-        ptx::tma_load_2d(sk, &tmap_kv, &full_bar[st], p.d + (h0 + h) * D, row0);
-        ptx::tma_load_2d(sk + half_rows * 128, &tmap_kv, &full_bar[st], p.d + (h0 + h) * D, row0 + half_rows);
-        ptx::tma_load_2d(sv, &tmap_kv, &full_bar[st], 2 * p.d + (h0 + h) * D, row0);
-        ptx::tma_load_2d(sv + half_rows * 128, &tmap_kv, &full_bar[st], 2 * p.d + (h0 + h) * D, row0 + half_rows);
-      }
-      __syncwarp();
+  // Context epilogue, one control warp per TMEM lane quarter (role q reads lanes 32 q .. 32 q + 31): O of head hh is final
+  // (P was normalised before the MMA) -> bf16 -> this quarter's smem tile (32 rows x 128 B, 128-B swizzle) -> one TMA
+  // store.  The tensor map views ctx as [B][N][d], so rows of the last query tile that lie beyond the image are clipped.
+  // Round 1 did this inside the softmax warps (~670 cycles of their ~4,800-cycle head period, traced); the control
+  // warps are otherwise waiting.
+  auto o_epilogue = [&](int hh) {
+    const int quarter = warp;   // control roles 0..3 sit on hardware warps = role (mod 4)
+    uint8_t* ctx_tile = smem_ctx + quarter * (32 * 128);
+    const uint32_t ctx_dst = ptx::smem_u32(ctx_tile) + lane * 128;
+    ptx::mbar_wait(o_full, hh & 1);
+    ptx::tc_fence_after();
+    uint32_t o[2][32];
+    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kTmemO;
+    ptx::tmem_ld_x32(t_o, o[0]);
+    ptx::tmem_ld_x32(t_o + 32, o[1]);
+    ptx::tmem_ld_wait();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(o_free);
+    // the tile of the previous head has been read out by its TMA store (only the issuing lane has a bulk group)
+    ptx::tma_store_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {   // 16-byte chunk k = context columns 8 k .. 8 k + 7 of this row
+      const uint32_t* v = &o[k >> 2][(k & 3) * 8];
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ctx_dst + ((k ^ (lane & 7)) << 4)),
+                   "r"(pack_bf16x2_u(v[0], v[1])), "r"(pack_bf16x2_u(v[2], v[3])), "r"(pack_bf16x2_u(v[4], v[5])),
+                   "r"(pack_bf16x2_u(v[6], v[7]))
+                   : "memory");
     }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (ptx::elect_one()) {
+      ptx::tma_store_3d(&tmap_ctx, ctx_tile, (h0 + hh) * D, qt * BM + quarter * 32, b);
+      ptx::tma_store_commit();
+    }
+    __syncwarp();
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (+ context epilogue of lane quarter 0)
+    for (int h = 0; h < nh + 2; ++h) {   // h: head index local to this CTA (absolute head h0 + h)
+      if (h < nh) {
+        const int st = h & 1;
+        const uint32_t ph = (h >> 1) & 1;
+        uint8_t* sq = smem + st * kStageBytes;
+        uint8_t* sk = sq + kQBytes;
+        uint8_t* sv = sk + kKVBytes;
+        ptx::mbar_wait(&qk_empty[st], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&qk_full[st], kQBytes + kv_tx);
+          ptx::tma_load_2d(sq, &tmap_q, &qk_full[st], (h0 + h) * D, row0 + qt * BM);
+          ptx::tma_load_2d(sk, &tmap_kv, &qk_full[st], p.d + (h0 + h) * D, row0);
+          ptx::tma_load_2d(sk + half_rows * 128, &tmap_kv, &qk_full[st], p.d + (h0 + h) * D, row0 + half_rows);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&v_empty[st], ph ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&v_full[st], kv_tx);
+          ptx::tma_load_2d(sv, &tmap_kv, &v_full[st], 2 * p.d + (h0 + h) * D, row0);
+          ptx::tma_load_2d(sv + half_rows * 128, &tmap_kv, &v_full[st], 2 * p.d + (h0 + h) * D, row0 + half_rows);
+        }
+        __syncwarp();
+      }
+      // P V of head h - 2 has just released this V slot (or the loop is draining): its context is complete
+      if (h >= 2) o_epilogue(h - 2);
+    }
+    ptx::tma_store_wait_read<0>();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ UMMA issuer
+    // ------------------------------------------------------------ UMMA issuer (+ context epilogue of lane quarter 1)
     const uint32_t idesc_qk = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(KP), 0, 0);
     // P V and the head average run with FP16 operands: P is fp16, and the qkv GEMM writes the V third of its output in
     // fp16 for this kernel (kind::f16 traps on mixed A / B formats: measured); QK^T stays bf16
@@ -253,7 +309,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     const uint64_t did = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_id), 16, 1024);
     auto issue_qk = [&](int h) {
       const int st = h & 1;
-      ptx::mbar_wait(&full_bar[st], (h >> 1) & 1);
+      ptx::mbar_wait(&qk_full[st], (h >> 1) & 1);
       if (h > 0) ptx::mbar_wait(s_free, (h - 1) & 1);
       ptx::tc_fence_after();
       const uint32_t sq = ptx::smem_u32(smem + st * kStageBytes);
@@ -263,6 +319,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
           ptx::umma_bf16_ss(tmem_base + kTmemS, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&qk_empty[st]);   // Q / K of this stage may be reloaded (head h + 2)
         ptx::umma_commit(s_full);
       }
       __syncwarp();
@@ -272,6 +329,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       if (h + 1 < nh) issue_qk(h + 1);
       const int st = h & 1;
       ATTN_TS(16);
+      ptx::mbar_wait(&v_full[st], (h >> 1) & 1);
       ptx::mbar_wait(p_full, h & 1);
       ATTN_TS(17);
       if (h > 0) ptx::mbar_wait(o_free, (h - 1) & 1);
@@ -290,7 +348,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
                               ks != 0 ? 1u : 0u);
           }
         }
-        ptx::umma_commit(&empty_bar[st]);
+        ptx::umma_commit(&v_empty[st]);
         ptx::umma_commit(o_full);
         if (want_avg) {
           // Pbar[:, 16 ks + n] += sum_k P[:, 16 ks + k] * I[n, k]: one M = 128, N = 16, K = 16 instruction per 16 keys
@@ -306,13 +364,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       }
       __syncwarp();
       ATTN_TS(19);
+      o_epilogue(h);   // P V was issued ahead of the head-average MMAs: O completes while those are being issued
     }
+    ptx::tma_store_wait_read<0>();
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ context epilogue of lane quarter 2
+    for (int h = 0; h < nh; ++h) o_epilogue(h);
+    ptx::tma_store_wait_read<0>();
   } else if (warp == 3) {
-    // ------------------------------------------------------------ CLS-row writer
-    // Row 0 of the normalised probabilities (fp32) is staged in smem by the four warps that own it; this otherwise
-    // idle warp streams it to HBM with coalesced stores, off the softmax warps' critical path.
-    if (p.cls_map != nullptr && qt == 0) {
-      for (int h = 0; h < nh; ++h) {
+    // ------------------------------------------------------------ CLS-row writer (+ context epilogue of lane quarter 3)
+    // Row 0 of the probabilities (fp32) is staged in smem by the four warps that own it; this otherwise idle warp
+    // streams it to HBM with coalesced stores, off the softmax warps' critical path.
+    const bool do_cls = p.cls_map != nullptr && qt == 0;
+    for (int h = 0; h < nh; ++h) {
+      if (do_cls) {
         ptx::mbar_wait(cls_full, h & 1);
         float* cp = p.cls_map + (static_cast<size_t>(b) * p.H + h0 + h) * p.N;
         // staged: e = exp2((s - m_t) c) of row 0 in fp32 (written by the owning lanes during their exponential pass,
@@ -322,7 +387,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(cls_free);
       }
+      o_epilogue(h);
     }
+    ptx::tma_store_wait_read<0>();
   } else if (warp >= kCtrlWarps) {
     // ------------------------------------------------------------ softmax / epilogue
     const int cg = (warp - kCtrlWarps) >> 2;    // column group: which quarter of the key granules
@@ -348,42 +415,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
     const uint32_t p_odd = p_row + ((static_cast<uint32_t>(cg | 4) << 4) ^ sw4);     // chunk cg + 4 of K-block c / 2
     const uint32_t t_s = lane_base + kTmemS + cg * 8;      // granule c: + 32 c columns
     const uint32_t t_avg = lane_base + kTmemAvg + cg * 8;
-    const uint32_t t_o = lane_base + kTmemO + cg * 16;  // this thread's 16 of the 64 context columns
-
-    // Context columns of head hh: O is final (P was normalised before the MMA) -> bf16 -> smem quarter tile (32 rows x
-    // 128 B, 128-B swizzle) -> one TMA store per quarter.  Direct 32-B-per-thread global stores cost a warp-wide
-    // STG 32 L1 wavefronts (32 different lines); the LSU backlog showed up as ~800 stall samples per head.
-    // The tensor map views ctx as [B][N][d], so rows of the last query tile that lie beyond the image are clipped.
-    uint8_t* ctx_tile = smem_ctx + quarter * (32 * 128);
-    const uint32_t ctx_dst = ptx::smem_u32(ctx_tile) + lane * 128;
-    // stage: TMEM -> bf16 -> smem tile (generic-proxy writes: the caller issues ONE fence.proxy.async for these and for
-    // the P tile); store: the quarter's four warps meet, one thread issues the TMA store.
-    auto o_stage = [&](int hh) {
-      ptx::mbar_wait(o_full, hh & 1);
-      ptx::tc_fence_after();
-      uint32_t o[16];
-      ptx::tmem_ld_x16(t_o, o);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(o_free);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ctx_dst + (((2 * cg) ^ (lane & 7)) << 4)),
-                   "r"(pack_bf16x2_u(o[0], o[1])), "r"(pack_bf16x2_u(o[2], o[3])), "r"(pack_bf16x2_u(o[4], o[5])),
-                   "r"(pack_bf16x2_u(o[6], o[7]))
-                   : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ctx_dst + (((2 * cg + 1) ^ (lane & 7)) << 4)),
-                   "r"(pack_bf16x2_u(o[8], o[9])), "r"(pack_bf16x2_u(o[10], o[11])), "r"(pack_bf16x2_u(o[12], o[13])),
-                   "r"(pack_bf16x2_u(o[14], o[15]))
-                   : "memory");
-    };
-    auto o_store = [&](int hh) {
-      asm volatile("bar.sync %0, 128;" ::"r"(3 + quarter) : "memory");  // the four column-group warps of this quarter
-      if (cg == 0 && ptx::elect_one()) {
-        ptx::tma_store_3d(&tmap_ctx, ctx_tile, (h0 + hh) * D, qt * BM + quarter * 32, b);
-        ptx::tma_store_commit();
-      }
-      __syncwarp();
-    };
 
     for (int h = 0; h < nh; ++h) {
       // ---- this thread's part of the S row -> registers (single TMEM read), then release the S columns.  The read is
@@ -504,11 +535,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       float* red_sum = red_max + kColGroups * BM;
       red_max[cg * BM + r] = (mx == -INFINITY) ? -INFINITY : mxs;   // already in the exp2 domain
       red_sum[cg * BM + r] = (ps0 + ps1) + (ps2 + ps3);
-      // the context tile of head h-2 has been read out of smem before anyone can restage it (after this barrier);
-      // only the issuing thread has a bulk group outstanding, for everyone else this returns immediately.
-      // The exchange (and the context tile) concern the four warps of ONE lane quarter only -- they sit on one SM
-      // sub-partition -- so the barrier is per quarter: the quarters do not wait for each other here.
-      ptx::tma_store_wait_read<0>();
+      // The exchange concerns the four warps of ONE lane quarter only -- they sit on one SM sub-partition -- so the
+      // barrier is per quarter: the quarters do not wait for each other here.
       asm volatile("bar.sync %0, 128;" ::"r"(8 + quarter) : "memory");
       ATTN_TS(6);
       float inv;
@@ -530,14 +558,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
 
       // ---- the P tile is about to be overwritten: the previous head's P V and Pbar MMAs (issued a whole softmax
       //      pass ago) must have retired
-      if (h > 0) {
-        ptx::mbar_wait(p_free, (h - 1) & 1);
-        ATTN_TS(10);
-        // context of the previous head (its P V retired long ago): TMEM -> smem now, so that the fence below covers it
-        // and P V of THIS head finds the O columns free as soon as the P tile is handed over.
-        o_stage(h - 1);
-      }
-      ATTN_TS(11);
+      if (h > 0) ptx::mbar_wait(p_free, (h - 1) & 1);
+      ATTN_TS(10);
 
       // ---- p = e * f_t as packed fp16 multiplies -> fp16 P tile (swizzled K-major A operand of P V and of the
       //      head-average MMAs).  All kMaxGran granules are multiplied (a thread with fewer granules scales zeros) and
@@ -558,9 +580,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       if (lane == 0) ptx::mbar_arrive(p_full);
       ATTN_TS(7);
 
-      // ---- context of the previous head: staged above, ordered by the same fence as the P tile
-      if (h > 0) o_store(h - 1);
-      ATTN_TS(13);
 
       if (kHeads) {
         if (p.head_map != nullptr && row_ok) {
@@ -579,21 +598,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       }
       ATTN_TS(8);
     }
-    // (restaging needs the previous store's smem reads done; every warp passes through the issuer's wait via bar 3+q)
-    ptx::tma_store_wait_read<0>();
-    asm volatile("bar.sync %0, 128;" ::"r"(3 + quarter) : "memory");
-    o_stage(nh - 1);
-    ptx::fence_proxy_async_smem();
-    o_store(nh - 1);
-
     // head-averaged map rows -> HBM, once per (image, query tile): Pbar holds the SUM over heads.  The tile goes
     // through shared memory (the Q/K/V stages are dead by now) as 32-column slabs of 128 rows x 128 B in the 128-B
     // swizzle and leaves with one TMA store per slab; rows beyond the image and columns beyond ldmap are clipped by
     // the [B][N][ldmap] tensor map.  (32-B-per-thread global stores from here cost ~14% of the kernel: every
     // warp-wide STG touched 32 different lines.)
     if (want_avg) {
-      // The head-average MMAs of the LAST head are issued behind the commit of o_full (which o_stage waited for): their
-      // own completion is p_free's last phase.  Without this wait the read below raced the tensor pipe (rarely lost:
+      // The head-average MMAs of the LAST head are issued behind the commit of o_full: their own completion is p_free's
+      // last phase (which also says that P V of the last head no longer reads the stage area reused below).  Without this wait the read below raced the tensor pipe (rarely lost:
       // the one run-to-run difference of round 1's batch-256 reproducibility check).
       ptx::mbar_wait(p_free, (nh - 1) & 1);
       ptx::tc_fence_after();
