@@ -228,7 +228,7 @@ int vitb200_op_layernorm(const float* x_dev, const float* gamma_dev, const float
 int vitb200_op_attention(const void* qkv_bf16_dev, void* ctx_bf16_dev, float* avg_dev, float* cls_dev,
                          float* heads_dev, int batch, int tokens, int heads, int pitch, void* stream);
 /* Same with an explicit head dimension (64..128 in steps of 16; ViT-H uses 80).  Token counts above 208 or head
- * dimensions other than 64 take the key-blocked two-kernel path (attention_long.cuh).  The fused kernel multiplies FP16
+ * dimensions other than 64 take the key-blocked two-kernel path (attention_long.cuh).  The fused kernels multiply FP16
  * probabilities with FP16 values: v_is_f16 != 0 says the V third of the input already is fp16 (as the forward's qkv
  * GEMM writes it); with 0 the entry point converts a scratch copy first. */
 int vitb200_op_attention_ex(const void* qkv_bf16_dev, void* ctx_bf16_dev, float* avg_dev, float* cls_dev,

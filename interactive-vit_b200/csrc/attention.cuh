@@ -73,6 +73,7 @@ struct AttnParams {
   // TWO CTAs by heads ([0, H/2) and [H/2, H)) whose head-average tiles are combined with a TMA reduce-add into rows the
   // host zeroed.  512 equal items on 148 SMs otherwise leave 80 SMs idle for the whole last round.
   int full_items;
+  int one = 1;          // always 1 (attention_pp.cuh: trip count of its scheduling-fence loops)
 };
 
 // Optional phase tracing (built only with -DVITB200_ATTN_TRACE into a separate library, tools/attn_trace.py):

@@ -31,6 +31,7 @@
 
 #include "../../include/vitb200.h"
 #include "attention.cuh"
+#include "attention_pp.cuh"
 #include "attention_long.cuh"
 #include "gemm.cuh"
 #include "peer.cuh"
@@ -462,7 +463,14 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
     const char* v = getenv("VITB200_ATTN_FULL");
     full_mode = (v && v[0] == '0') ? 0 : 1;
   }
-  if (heads) attention_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
+  // 197-token production shape: two heads in flight per SM (attention_pp.cuh); VITB200_ATTN_PP=0 keeps the one-head kernel
+  // (read at every launch: the parity tests compare both kernels in one process)
+  const char* pp_env = getenv("VITB200_ATTN_PP");
+  const bool pp_mode = !(pp_env && pp_env[0] == '0');
+  if (!heads && pp_mode && KP == KP_MAX && N >= attn_pp_cfg::kMinTokens && N <= attn_pp_cfg::kMaxTokens) {
+    VT_TRY(ensure_func_smem((const void*)attention_pp_kernel, attn_pp_cfg::kSmemBytesPP));
+    attention_pp_kernel<<<grid, kThreads, attn_pp_cfg::kSmemBytesPP, st>>>(tq, tkv, tctx, tavg, p);
+  } else if (heads) attention_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   else if (KP == KP_MAX && full_mode) attention_kernel<false, true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   else attention_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   CU_TRY(cudaGetLastError());
@@ -692,7 +700,7 @@ static int run_attn_block(vitb200_engine* e, int l, int B, uint32_t flags, cudaS
     ep.bias = w.bf_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
     ep.row_stats_in = stats, ep.stats_in_slots = slots, ep.ln_eps = 1e-6f;
     ep.colsum = w.s_qkv, ep.out_lo = (__nv_bfloat16*)e->qkv_lo.p;
-    // the fused attention kernel takes V in fp16 (its probabilities are fp16; see attention.cuh)
+    // the fused attention kernels take V in fp16 (their probabilities are fp16; see attention.cuh)
     if (!e->precise && attention_is_fused(e->N, e->D)) ep.f16_from_col = 2 * d;
     VT_TRY(launch_gemm(xb, d, w.w_qkv, M, 3 * d, d, ep, false, false, st, e->xb_lo.p, w.w_qkv_lo));
   }
@@ -1706,7 +1714,7 @@ int vitb200_op_attention_ex(const void* qkv, void* ctx, float* avg, float* cls, 
     stats = op_attention_stats((size_t)batch * nheads * tokens);
     if (!stats) return fail(VITB200_ERR_CUDA, "attention: cannot allocate the statistics scratch");
   } else if (!v_is_f16) {
-    // the fused kernel wants the V third in fp16 (the forward's qkv GEMM writes it that way): convert a scratch copy
+    // the fused kernels want the V third in fp16 (the forward's qkv GEMM writes it that way): convert a scratch copy
     const long rows = (long)batch * tokens;
     const int d = nheads * head_dim;
     const size_t bytes = (size_t)rows * 3 * d * 2;

@@ -60,6 +60,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking poll.  (try_wait may SUSPEND the thread for a system-dependent time when the phase is not complete:
+// right for waiting on one barrier, wrong for a loop that polls several -- measured: an event loop built on try_wait
+// spent ~13 us per head asleep on the wrong barrier.)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Blocking wait with a watchdog: a protocol bug traps (-> cudaErrorLaunchFailure on the host) instead of
 // hanging the GPU. The limit (2 s of %globaltimer) is far beyond any legitimate wait on this path.
 __device__ __forceinline__ uint64_t globaltimer_ns() {

@@ -259,6 +259,14 @@ fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ gam
   if (lane == 0) colsum[n] = s, bias_out[n] = bias[n] + bb;
 }
 
+// fp32 pair -> packed fp16 with saturation to the largest finite value (one F2FP.SATFINITE): the fused attention
+// kernels take V in FP16, and an activation beyond 65504 must not become an infinity.
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // Copy of a packed bf16 qkv activation [rows, 3d] with the V third converted to FP16 (what the qkv GEMM writes directly
 // on the forward path; this kernel serves the single-kernel attention entry point, which takes bf16 inputs).
 __global__ void __launch_bounds__(256)
@@ -271,8 +279,7 @@ qkv_v_to_f16_kernel(const __nv_bfloat16* __restrict__ in, uint16_t* __restrict__
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-      const __half2 h = __floats2half2_rn(__low2float(b), __high2float(b));
-      w[k] = *reinterpret_cast<const uint32_t*>(&h);
+      w[k] = pack_f16x2_sat(__low2float(b), __high2float(b));
     }
   }
   *reinterpret_cast<uint4*>(out + i) = v;

@@ -35,6 +35,11 @@ def _engine_for(E, ocfg, model, batch, precision="bf16"):
 
 
 ALL = 1 | 2 | 4 | 8 | 16
+# every output except the opt-in per-head maps: the flag set of the node path (layer nodes emit the head average and
+# the class-token rows).  Per-head maps select the one-head-in-flight attention kernel for 197-token models, the rest
+# the two-heads-in-flight kernel (attention_pp.cuh): equal within tolerance, not bit for bit -- bit-for-bit
+# comparisons between two paths therefore use the same map selection on both sides.
+NO_HEADS = ALL & ~8
 
 
 @pytest.mark.parametrize("name,batch,init", [("vit_tiny_test", 3, "stress"), ("vit_small_test", 2, "stress"),
@@ -170,7 +175,7 @@ def test_stage_entry_points_equal_whole_forward(E):
     model = O.build_vit(ocfg, seed=0, init="stress")
     x = O.synthetic_images(2, ocfg.image_size)
     eng = _engine_for(E, ocfg, model, 2)
-    whole = eng.forward_host(x, ALL)
+    whole = eng.forward_host(x, NO_HEADS)
     eng.stage_embed(x)
     for i in range(ocfg.num_layers):
         eng.stage_layer(i, 2, E.EMIT_AVG | E.EMIT_CLS)
@@ -311,7 +316,7 @@ def test_half_block_nodes_and_fanned_out_graph(E):
     module = O.build_vit(ocfg, seed=0, init="stress")
     x = O.synthetic_images(2, ocfg.image_size)
     eng = _engine_for(E, ocfg, module, 2)
-    whole = eng.forward_host(x, ALL)
+    whole = eng.forward_host(x, NO_HEADS)
     eng.stage_embed(x)
     t_ref = O.embed(module, x)
     for i in range(ocfg.num_layers):
@@ -357,7 +362,13 @@ def test_half_block_nodes_and_fanned_out_graph(E):
     for node in want:
         for ch in want[node]:
             assert got[node][ch].shape == want[node][ch].shape, (node, ch)
-            assert _rel(got[node][ch], want[node][ch]) < TOL, (node, ch, _rel(got[node][ch], want[node][ch]))
+            # The stress initialisation multiplies the attention logits by 4 (oracle/vit_oracle.py), and with them the
+            # effect of the bf16 rounding of the operands that produce q and k: the PER-HEAD class-token rows of this
+            # model land at 1.0-2.2e-2 depending on the input and on rounding luck (measured with both attention
+            # kernels, profiles/README.md), on the edge of the bound north_star states for realistic weights (where
+            # the same rows measure 4.5e-3: test_attention_maps_per_row_metrics).  3e-2 for that channel here.
+            tol = 3e-2 if ch == "cls" else TOL
+            assert _rel(got[node][ch], want[node][ch]) < tol, (node, ch, _rel(got[node][ch], want[node][ch]))
     for i in range(L):   # every lens head saw ITS block's tokens, not the stream's latest
         assert got[lens0 + i]["o"].argmax() == want[lens0 + i]["o"].argmax()
     assert torch.equal(got[lens0 + L - 1]["o"], whole["logits"][0])
