@@ -534,6 +534,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // HBM latency x outstanding bytes); otherwise two batches of 4 keep the instruction footprint small.
         constexpr int kRowBatch = kResid ? 8 : 4;
         const float* sl = slab + trow * kSlabStride + 4 * tcol;
+        // Addresses: without a row remap the 8 rows of a thread are 4 * ld apart, so every pointer is one 64-bit base per
+        // chunk plus a 32-bit multiple of the row step (one IMAD.WIDE per access; forming row * ld + col in 64 bits per
+        // row cost ~17 integer instructions per 4 outputs -- 40 % of the GELU epilogue's instruction stream).
+        constexpr unsigned kOutEsz = kOutF32 ? 4u : 2u;
+        const long first_row = row_base + trow;
+        char* const out0 = reinterpret_cast<char*>(ep.out) + (first_row * ep.ldo + col) * kOutEsz;
+        const unsigned out_st = 4u * static_cast<unsigned>(ep.ldo) * kOutEsz;
+        const char* const res0 = reinterpret_cast<const char*>(ep.resid) + (first_row * ep.ldr + col) * 4;
+        const unsigned res_st = 16u * static_cast<unsigned>(ep.ldr);
+        char* const xb0 = reinterpret_cast<char*>(ep.xb) + (first_row * ep.ldxb + col) * 2;
+        const unsigned xb_st = 8u * static_cast<unsigned>(ep.ldxb);
         // (unrolled for the folded-LayerNorm epilogue: its per-row scale / offset arrays need static indices)
         constexpr int kBatchUnroll = kLnIn ? 8 / kRowBatch : 1;
 #pragma unroll kBatchUnroll
@@ -557,7 +568,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             orow[i] = out_row;
             if (kResid && !kPrefetch) {
               q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok[i]) q[i] = *reinterpret_cast<const float4*>(ep.resid + resid_row * ep.ldr + col);
+              if (ok[i])
+                q[i] = kRemap ? *reinterpret_cast<const float4*>(ep.resid + resid_row * ep.ldr + col)
+                              : *reinterpret_cast<const float4*>(res0 + static_cast<unsigned>(i0 + i) * res_st);
             }
           }
           if (kPrefetch) {
@@ -586,33 +599,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const __nv_bfloat162 h01 = __floats2bfloat162_rn(t.x, t.y), h23 = __floats2bfloat162_rn(t.z, t.w);
                 uint2 pk;
                 pk.x = *reinterpret_cast<const uint32_t*>(&h01), pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-                *reinterpret_cast<uint2*>(ep.xb + orow[i] * ep.ldxb + col) = pk;
+                char* const xbp = kRemap ? reinterpret_cast<char*>(ep.xb + orow[i] * ep.ldxb + col)
+                                         : xb0 + static_cast<unsigned>(i0 + i) * xb_st;
+                *reinterpret_cast<uint2*>(xbp) = pk;
                 if (ep.xb_lo != nullptr) {
                   uint2 pl;
                   pl.x = pack2_bf16(t.x - __low2float(h01), t.y - __high2float(h01));
                   pl.y = pack2_bf16(t.z - __low2float(h23), t.w - __high2float(h23));
-                  *reinterpret_cast<uint2*>(ep.xb_lo + orow[i] * ep.ldxb + col) = pl;
+                  *reinterpret_cast<uint2*>(reinterpret_cast<char*>(ep.xb_lo) + (xbp - reinterpret_cast<char*>(ep.xb))) = pl;
                 }
               }
             }
             if (ok[i]) {
+              char* const outp = kRemap ? reinterpret_cast<char*>(ep.out) + (orow[i] * ep.ldo + col) * kOutEsz
+                                        : out0 + static_cast<unsigned>(i0 + i) * out_st;
               if (kOutF32) {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + orow[i] * ep.ldo + col) = t;
+                *reinterpret_cast<float4*>(outp) = t;
               } else {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y);
                 __nv_bfloat162 hi = __floats2bfloat162_rn(t.z, t.w);
                 uint2 pk;
                 pk.x = *reinterpret_cast<uint32_t*>(&lo);
                 pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                if (col0 >= ep.f16_from_col) {   // warp-uniform
+                if (!kGelu && col0 >= ep.f16_from_col) {   // warp-uniform (the qkv GEMM's V third; never a GELU epilogue)
                   pk.x = pack_f16x2_sat(t.x, t.y), pk.y = pack_f16x2_sat(t.z, t.w);
                 }
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + orow[i] * ep.ldo + col) = pk;
+                *reinterpret_cast<uint2*>(outp) = pk;
                 if (ep.out_lo != nullptr) {  // split-bf16: the rounding residue as a second bf16 matrix
                   uint2 pl;
                   pl.x = pack2_bf16(t.x - __low2float(lo), t.y - __high2float(lo));
                   pl.y = pack2_bf16(t.z - __low2float(hi), t.w - __high2float(hi));
-                  *reinterpret_cast<uint2*>(ep.out_lo + orow[i] * ep.ldo + col) = pl;
+                  *reinterpret_cast<uint2*>(reinterpret_cast<char*>(ep.out_lo) + (outp - reinterpret_cast<char*>(ep.out))) = pl;
                 }
               }
             }
