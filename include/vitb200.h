@@ -53,7 +53,8 @@ typedef struct vitb200_config {
   int device;      /* CUDA device ordinal                                              */
   int precision;   /* 0: bf16 operands, fp32 accumulation (<= 2e-2 of the fp32 reference)
                       1: "fp32x3": every matmul operand is carried as hi + lo bf16 and multiplied as
-                         hi*hi + lo*hi + hi*lo with fp32 accumulation (<= 1e-3; head dim 64 only; ~3x tensor work) */
+                         hi*hi + lo*hi + hi*lo with fp32 accumulation (<= 1e-3; ~3x tensor work; attention at head dims other than 64
+                         runs in fp32 on the CUDA cores) */
 } vitb200_config;
 
 /* Host-side result pointers for vitb200_forward_host; any pointer may be NULL (output skipped). */

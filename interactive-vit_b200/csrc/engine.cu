@@ -33,6 +33,7 @@
 #include "attention.cuh"
 #include "attention_pp.cuh"
 #include "attention_long.cuh"
+#include "attention_precise.cuh"
 #include "gemm.cuh"
 #include "peer.cuh"
 #include "rowwise.cuh"
@@ -354,8 +355,20 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
   if (!stats) return fail(VITB200_ERR_INVALID, "attention: statistics buffer missing");
   const int d = H * D;
   const bool split = qkv_lo != nullptr;
-  if (split && (D != 64 || ctx_lo == nullptr))
-    return fail(VITB200_ERR_INVALID, "attention: the fp32x3 mode supports head dim 64 only (got %d)", D);
+  if (split && ctx_lo == nullptr) return fail(VITB200_ERR_INVALID, "attention: the fp32x3 mode needs the low half of the context");
+  if (split && D != 64) {
+    // fp32x3 mode at head dims other than 64 (ViT-H: 80): fp32 on the CUDA cores (attention_precise.cuh)
+    AttnLongParams p;
+    p.B = B, p.N = N, p.H = H, p.D = D, p.d = d, p.q_tiles = 0, p.k_blocks = 0, p.scale_log2 = 0.f;
+    p.ctx = ctx, p.ctx_lo = ctx_lo, p.stats = stats, p.avg_map = avg, p.head_map = heads, p.cls_map = cls, p.ldmap = pitch;
+    const size_t smem = attn_precise_cfg::smem_bytes(N, D);
+    if (smem > 227 * 1024) return fail(VITB200_ERR_INVALID, "attention (fp32x3, head dim %d): %d tokens need %zu bytes of shared memory", D, N, smem);
+    VT_TRY(ensure_func_smem((const void*)attention_precise_kernel, (int)smem));
+    const int grid = B * ((N + attn_precise_cfg::QT - 1) / attn_precise_cfg::QT);
+    attention_precise_kernel<<<grid, attn_precise_cfg::kThreads, smem, st>>>(qkv, qkv_lo, p);
+    CU_TRY(cudaGetLastError());
+    return VITB200_OK;
+  }
   CUtensorMap tqkv, tqkv_lo;
   VT_TRY(make_tmap_bf16_3d(&tqkv, qkv, B, N, 3 * d, 3 * d, 128, 64));
   tqkv_lo = tqkv;
@@ -989,7 +1002,6 @@ int vitb200_create(const vitb200_config* cfg, vitb200_engine** out) {
   if (N > kRolloutThreads * kRolloutMaxCols)
     return fail(VITB200_ERR_INVALID, "%d tokens per image exceed the engine's limit (%d)", N, kRolloutThreads * kRolloutMaxCols);
   if (c.precision != 0 && c.precision != 1) return fail(VITB200_ERR_INVALID, "precision must be 0 (bf16) or 1 (fp32x3), got %d", c.precision);
-  if (c.precision == 1 && hd != 64) return fail(VITB200_ERR_INVALID, "the fp32x3 precision mode supports head dim 64 only (got %d)", hd);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(VITB200_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");

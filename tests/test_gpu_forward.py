@@ -72,7 +72,10 @@ def test_forward_matches_oracle(E, name, batch, init):
 
 @pytest.mark.parametrize("name,batch,init", [("vit_tiny_test", 3, "stress"), ("vit_small_test", 3, "stress"),
                                              ("vit_s_16", 2, "stress"), ("vit_b_16", 2, "default"),
-                                             ("vit_b_16", 1, "stress"), ("vit_577_test", 2, "stress")])
+                                             ("vit_b_16", 1, "stress"), ("vit_577_test", 2, "stress"),
+                                             # head dim 80 (ViT-H's layer shape, 577 tokens): the split GEMMs with the
+                                             # fp32 attention kernel (attention_precise.cuh)
+                                             ("vit_h_test", 2, "stress")])
 def test_precise_mode_matches_oracle(E, name, batch, init):
     """north_star's second tolerance: <= 1e-3 in the fp32-accumulate mode.  Every matmul of the forward (patch
     embedding, the four linears of each layer, QK^T, PV, the classifier) runs on split-bf16 operands; LayerNorm
