@@ -40,11 +40,12 @@ using namespace attn_cfg;
 constexpr int kGran = 13;                                   // granules per thread (c2 == 1: 12)
 constexpr int kGranA = 8;                                   // ... of which block A (keys < 128); block B: 5 (4)
 constexpr int kGranB = kGran - kGranA;
+constexpr int kKeysA = 16 * kGranA;                         // block A of both column halves = keys [0, 128)
 constexpr int kMaxTokens = 200;                             // granule 25 must be pure padding
 constexpr int kMinTokens = 193;                             // KP = 208 and granule 24 holds a valid key
 constexpr int kClsStagePP = 2 * kMaxTokens * 2;             // [group][200] fp16 exponentials of query row 0
 constexpr int kClsFactorPP = 2 * 2 * 2 * 4;                 // [group][half][block] normalising factors
-constexpr int kNumBars = 22;
+constexpr int kNumBars = 24;
 constexpr int kSmemBytesPP = 2 * kStageBytes + kPBytes + kCtxStageBytes + kIdentBytes + kClsStagePP + kClsFactorPP +
                              kNumBars * 8 + 8;
 static_assert(kSmemBytesPP <= 227 * 1024, "attention (ping-pong): shared memory budget");
@@ -54,7 +55,13 @@ static_assert((kClsStagePP + kClsFactorPP) % 8 == 0, "mbarriers are 8-byte align
 // Phase tracing (tracing build only, tools/attn_trace_pp.py): CTA 0, lane 0 of one softmax warp per group (quarter 0,
 // column half 0) stamps row h of g_attn_trace for its own heads (slots 0..15), the MMA warp slots 16..23.
 #ifdef VITB200_ATTN_TRACE
-#define PP_TS(slot) do { if (blockIdx.x == 0 && lane == 0 && quarter == 0 && c2 == 0) g_attn_trace[(h) * 32 + (slot)] = clock64(); } while (0)
+#ifndef PP_TRACE_Q
+#define PP_TRACE_Q 0
+#endif
+#ifndef PP_TRACE_C2
+#define PP_TRACE_C2 0
+#endif
+#define PP_TS(slot) do { if (blockIdx.x == 0 && lane == 0 && quarter == PP_TRACE_Q && c2 == PP_TRACE_C2) g_attn_trace[(h) * 32 + (slot)] = clock64(); } while (0)
 #define PP_TS_MMA(hh, slot) do { if (blockIdx.x == 0 && lane == 0) g_attn_trace[(hh) * 32 + (slot)] = clock64(); } while (0)
 #else
 #define PP_TS(slot) do { } while (0)
@@ -104,8 +111,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
   uint64_t* v_empty = bars + 6;      // [stage] V consumed by P V
   // Everything a group waits on or signals has one barrier PER GROUP: a barrier shared by both groups would let a
   // group that runs ahead mistake the other group's phase (same parity two phases later) for its own.
-  uint64_t* s_full = bars + 8;       // [group] S = QK^T of one of the group's heads complete
-  uint64_t* s_free = bars + 10;      // [group] ... copied out of TMEM by the group's 8 warps
+  uint64_t* s_full = bars + 8;       // [half][group] S = QK^T of one of the group's heads complete: keys [0, 128) / [128, 208)
+  uint64_t* s_free = bars + 22;      // [group] S copied out of TMEM by the group's 8 warps
   uint64_t* p_full = bars + 12;      // [group] fp16 P tile of the group's head written
   uint64_t* p_free = bars + 14;      // [group] P V and Pbar += P of the group's head complete: P tile reusable
   uint64_t* o_full = bars + 16;      // O = P V complete
@@ -146,6 +153,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
       ptx::mbar_init(&qk_empty[i], 1);
       ptx::mbar_init(&v_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_full[2 + i], 1);
       ptx::mbar_init(&s_free[i], kSoftmaxWarps / 2);   // one arrival per warp of the group
       ptx::mbar_init(&p_full[i], kSoftmaxWarps / 2);
       ptx::mbar_init(&p_free[i], 1);
@@ -215,30 +223,37 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (+ context epilogue of lane quarter 0)
-    for (int h = 0; h < nh + 2; ++h) {
-      if (h < nh) {
-        const int st = h & 1;
-        const uint32_t ph = (h >> 1) & 1;
+    // Order of this warp's events in the steady state: the Q / K slot of head i frees when QK^T of head i - 2 completes
+    // (early in that head), the V slot of head i - 1 and O of head i - 3 when P V of head i - 3 completes (~3,000
+    // cycles later), then the Q / K slot of head i + 1, ...  The loop takes them in that order.  (Traced: with the
+    // one-head kernel's order -- Q / K and V of the SAME head back to back -- the Q / K loads of head i + 1 queued
+    // behind the V wait and landed ~1,500 cycles after the S buffer had been handed back: qkv comes from HBM.)
+    for (int i = 0; i < nh + 3; ++i) {
+      if (i < nh) {
+        const int st = i & 1;
         uint8_t* sq = smem + st * kStageBytes;
         uint8_t* sk = sq + kQBytes;
-        uint8_t* sv = sk + kKVBytes;
-        ptx::mbar_wait(&qk_empty[st], ph ^ 1);
+        ptx::mbar_wait(&qk_empty[st], ((i >> 1) & 1) ^ 1);
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&qk_full[st], kQBytes + kv_tx);
-          ptx::tma_load_2d(sq, &tmap_q, &qk_full[st], (h0 + h) * D, row0 + qt * BM);
-          ptx::tma_load_2d(sk, &tmap_kv, &qk_full[st], p.d + (h0 + h) * D, row0);
-          ptx::tma_load_2d(sk + half_rows * 128, &tmap_kv, &qk_full[st], p.d + (h0 + h) * D, row0 + half_rows);
-        }
-        __syncwarp();
-        ptx::mbar_wait(&v_empty[st], ph ^ 1);
-        if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&v_full[st], kv_tx);
-          ptx::tma_load_2d(sv, &tmap_kv, &v_full[st], 2 * p.d + (h0 + h) * D, row0);
-          ptx::tma_load_2d(sv + half_rows * 128, &tmap_kv, &v_full[st], 2 * p.d + (h0 + h) * D, row0 + half_rows);
+          ptx::tma_load_2d(sq, &tmap_q, &qk_full[st], (h0 + i) * D, row0 + qt * BM);
+          ptx::tma_load_2d(sk, &tmap_kv, &qk_full[st], p.d + (h0 + i) * D, row0);
+          ptx::tma_load_2d(sk + half_rows * 128, &tmap_kv, &qk_full[st], p.d + (h0 + i) * D, row0 + half_rows);
         }
         __syncwarp();
       }
-      if (h >= 2) o_epilogue(h - 2);   // P V of head h - 2 has just released this V slot (or the loop is draining)
+      if (i >= 1 && i <= nh) {
+        const int j = i - 1, st = j & 1;
+        uint8_t* sv = smem + st * kStageBytes + kQBytes + kKVBytes;
+        ptx::mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&v_full[st], kv_tx);
+          ptx::tma_load_2d(sv, &tmap_kv, &v_full[st], 2 * p.d + (h0 + j) * D, row0);
+          ptx::tma_load_2d(sv + half_rows * 128, &tmap_kv, &v_full[st], 2 * p.d + (h0 + j) * D, row0 + half_rows);
+        }
+        __syncwarp();
+      }
+      if (i >= 3) o_epilogue(i - 3);   // P V of head i - 3 has just released the V slot (or the loop is draining)
     }
     ptx::tma_store_wait_read<0>();
   } else if (warp == 1) {
@@ -293,50 +308,43 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
     // quarter 2).  QK(h) needs the operands and the S buffer (copied out by the group of head h - 1); the epilogue of
     // head h needs O(h).  Which comes first depends on how the groups are running, so this warp polls both (test_wait
     // does not suspend; a short sleep between polls leaves the issue slots to this sub-partition's softmax warps).
-    constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(KP), 0, 0);
-    int next_qk = 0, next_ep = 0;
-    uint32_t spins = 0;
-    uint64_t t_spin = 0;
-    while (next_ep < nh) {
-      bool did_work = false;
-      if (next_qk < nh) {
-        const int h = next_qk, st = h & 1;
-        bool ok = ptx::mbar_test_wait(&qk_full[st], (h >> 1) & 1);
-        if (ok && h > 0) ok = ptx::mbar_test_wait(&s_free[(h - 1) & 1], ((h - 1) >> 1) & 1);
-        if (__all_sync(0xffffffffu, ok)) {
-          ptx::tc_fence_after();
-          PP_TS_MMA(h, 16);
-          const uint32_t sq = ptx::smem_u32(smem + st * kStageBytes);
-          const uint64_t dq = ptx::make_smem_desc_sw128(sq, 16, 1024);
-          const uint64_t dk = ptx::make_smem_desc_sw128(sq + kQBytes, 16, 1024);
-          if (ptx::elect_one()) {
+    // S is PRODUCED in two halves with a barrier each -- keys [0, 128) = block A of every softmax thread first, then
+    // keys [128, 208) -- so that the group starts copying block A out while the second half is still being computed
+    // (the S buffer is handed back whole).  Order of this warp's events in the steady state (traced): QK(h + 1) ~1,300
+    // cycles after S(h) became ready, the epilogue of head h - 1 ~1,100 later, QK(h + 2) a head period after QK(h + 1):
+    // strictly alternating, so plain blocking waits in that order (no polling: the first version polled both events
+    // and took issue slots from this sub-partition's softmax warps).  Neither wait can deadlock the other: everything
+    // S(h)'s consumers and O(h - 1)'s producers need was issued earlier.
+    constexpr uint32_t idesc_qa = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(kKeysA), 0, 0);
+    constexpr uint32_t idesc_qb = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(KP - kKeysA), 0, 0);
+    auto issue_qk = [&](int h) {
+      const int st = h & 1;
+      ptx::mbar_wait(&qk_full[st], (h >> 1) & 1);
+      if (h > 0) ptx::mbar_wait(&s_free[(h - 1) & 1], ((h - 1) >> 1) & 1);
+      ptx::tc_fence_after();
+      PP_TS_MMA(h, 16);
+      const uint32_t sq = ptx::smem_u32(smem + st * kStageBytes);
+      const uint64_t dq = ptx::make_smem_desc_sw128(sq, 16, 1024);
+      const uint64_t dk = ptx::make_smem_desc_sw128(sq + kQBytes, 16, 1024);
+      if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < D / 16; ++k)
-              ptx::umma_bf16_ss(tmem_base + kTmemS, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-            ptx::umma_commit(&qk_empty[st]);   // Q / K of this stage may be reloaded (head h + 2)
-            ptx::umma_commit(&s_full[h & 1]);
-          }
-          __syncwarp();
-          ++next_qk;
-          did_work = true;
-        }
+        for (int k = 0; k < D / 16; ++k)
+          ptx::umma_bf16_ss(tmem_base + kTmemS, dq + 2 * k, dk + 2 * k, idesc_qa, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&s_full[h & 1]);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)   // K rows 128..207: + 128 rows x 128 B = 1024 descriptor units
+          ptx::umma_bf16_ss(tmem_base + kTmemS + kKeysA, dq + 2 * k, dk + (kKeysA * 128 >> 4) + 2 * k, idesc_qb, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&qk_empty[st]);   // Q / K of this stage may be reloaded (head h + 2)
+        ptx::umma_commit(&s_full[2 + (h & 1)]);
       }
-      if (!did_work && __all_sync(0xffffffffu, ptx::mbar_test_wait(o_full, next_ep & 1))) {
-        o_epilogue(next_ep);
-        ++next_ep;
-        did_work = true;
-      }
-      if (did_work) {
-        spins = 0, t_spin = 0;
-      } else {
-        __nanosleep(32);
-        if ((++spins & 0x3FFu) == 0) {   // watchdog (see ptx::mbar_wait): a protocol bug traps instead of hanging the GPU
-          const uint64_t now = ptx::globaltimer_ns();
-          if (t_spin == 0) t_spin = now;
-          else if (now - t_spin > 2000000000ull) __trap();
-        }
-      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    for (int h = 0; h < nh; ++h) {
+      if (h + 1 < nh) issue_qk(h + 1);
+      if (h >= 1) o_epilogue(h - 1);
     }
+    o_epilogue(nh - 1);
     ptx::tma_store_wait_read<0>();
   } else if (warp == 3) {
     // ------------------------------------------------------------ class-token row writer (+ context epilogue of quarter 3)
@@ -400,6 +408,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
         // every row of this warp lies beyond the image (second query tile): keep the protocol going, no arithmetic
         ptx::tc_fence_before();
         __syncwarp();
+        ptx::mbar_wait(&s_full[2 + g], ph);
         if (lane == 0) ptx::mbar_arrive(&s_free[g]);
         if (h > 0) ptx::mbar_wait(&p_free[g ^ 1], ((h - 1) >> 1) & 1);
         __syncwarp();
@@ -420,7 +429,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
       float mxA, mxB, mxsA = 0.f, mxsB = 0.f;
 #pragma unroll 1
       for (int once = 0; once < p.one; ++once) {
-        uint32_t sA[kGranA][8];
+        uint32_t sA[kGranA][8], sB[kGranB][8];
 #pragma unroll
         for (int c = 0; c < kGranA; ++c) ptx::tmem_ld_x8(t_s + c * 16, sA[c]);
         ptx::tmem_ld_wait();
@@ -437,20 +446,27 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
           }
         mxA = fmaxf(mxA, mxA2);
         mxsA = mxA * p.scale_log2;
+        constexpr int kEarly = kGranA - 2;   // block B's reads are issued once this many granules of A are packed
 #pragma unroll
-        for (int c = 0; c < kGranA; ++c)
+        for (int c = 0; c < kGranA; ++c) {
 #pragma unroll
           for (int k = 0; k < 8; k += 2)
             d16[c][k >> 1] = pack_f16x2_f(fmaf(__uint_as_float(sA[c][k]), p.scale_log2, -mxsA),
                                           fmaf(__uint_as_float(sA[c][k + 1]), p.scale_log2, -mxsA));
-      }
-      PP_TS(2);
-#pragma unroll 1
-      for (int once = 0; once < p.one; ++once) {
-        uint32_t sB[kGranB][8];
+          if (c == kEarly - 1) {
+            // Block B's TMEM reads go out HERE, under the rest of block A's conversion: their address carries a real
+            // (never taken) dependency on the last packed register, so ptxas can neither hoist them above the
+            // conversion (104 live registers) nor sink them to their first use.
+            ptx::mbar_wait(&s_full[2 + g], ph);   // second half of S (long complete by now)
+            ptx::tc_fence_after();
+            uint32_t bump;
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.eq.u32 q, %1, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(bump) : "r"(d16[c][3]));
 #pragma unroll
-        for (int c = 0; c < kGranB; ++c)
-          if (c < kGranB - 1 || own13) ptx::tmem_ld_x8(t_s + (kGranA + c) * 16, sB[c]);
+            for (int cb = 0; cb < kGranB; ++cb)
+              if (cb < kGranB - 1 || own13) ptx::tmem_ld_x8(t_s + bump + (kGranA + cb) * 16, sB[cb]);
+          }
+        }
+        PP_TS(2);
         ptx::tmem_ld_wait();
         // every read of S has landed in registers: the S columns go back to the QK^T issuer (next head)
         ptx::tc_fence_before();
@@ -510,25 +526,27 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
       // ---- the four blocks of a row (two per thread) reconcile: p = e f_b,
       //      f_b = exp2(m_b - M) / sum_u(sum_u exp2(m_u - M)), M = max_u m_u.  (Every block holds a valid key for
       //      193 <= N <= 200, so every m_b is finite.)
+      //      Each thread first folds its own two blocks into (M_t, tot_t) -- under the wait for its partner -- so that
+      //      one MUFU level (not two) follows the exchange.
+      const float Mt = fmaxf(mxsA, mxsB);
+      const float eA = ptx::ex2_approx(mxsA - Mt), eB = ptx::ex2_approx(mxsB - Mt);
+      const float tot_t = (psA0 + psA1) * eA + (psB0 + psB1) * eB;
       //      (first barrier: the partner has read the previous head's values -- the exchange buffer is single)
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(red_addr(c2)), "f"(mxsA), "f"(psA0 + psA1), "f"(mxsB),
-                   "f"(psB0 + psB1)
-                   : "memory");
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red_addr(c2)), "f"(Mt), "f"(tot_t) : "memory");
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
       PP_TS(5);
       float invA, invB;
       {
-        float4 a0, a1;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0.x), "=f"(a0.y), "=f"(a0.z), "=f"(a0.w) : "r"(red_addr(0)) : "memory");
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a1.x), "=f"(a1.y), "=f"(a1.z), "=f"(a1.w) : "r"(red_addr(1)) : "memory");
-        const float M = fmaxf(fmaxf(a0.x, a0.z), fmaxf(a1.x, a1.z));
+        float2 a0, a1;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a0.x), "=f"(a0.y) : "r"(red_addr(0)) : "memory");
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a1.x), "=f"(a1.y) : "r"(red_addr(1)) : "memory");
+        const float M = fmaxf(a0.x, a1.x);
         // the same expression in both threads of the row: the factors of a row's blocks share one denominator
-        const float tot = (a0.y * ptx::ex2_approx(a0.x - M) + a0.w * ptx::ex2_approx(a0.z - M)) +
-                          (a1.y * ptx::ex2_approx(a1.x - M) + a1.w * ptx::ex2_approx(a1.z - M));
-        const float rt = ptx::rcp_approx(tot);
-        invA = ptx::ex2_approx(mxsA - M) * rt;
-        invB = ptx::ex2_approx(mxsB - M) * rt;
+        const float tot = a0.y * ptx::ex2_approx(a0.x - M) + a1.y * ptx::ex2_approx(a1.x - M);
+        const float gr = ptx::ex2_approx(Mt - M) * ptx::rcp_approx(tot);
+        invA = eA * gr;
+        invB = eB * gr;
       }
       if (want_cls && lane == 0) {
         cls_factor[(g * 2 + c2) * 2 + 0] = invA;
