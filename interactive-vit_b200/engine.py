@@ -212,7 +212,10 @@ class PendingTensor(torch.Tensor):
                 a.wait()
             for a in _pending_args(tuple(kwargs.values())):
                 a.wait()
-        with torch._C.DisableTorchFunctionSubclass():
+        # the idiom of PyTorch's "Extending torch" notes for a subclass that returns plain tensors (torch >= 2.0; the
+        # reference pins 2.9.1); older builds only have the broader DisableTorchFunction
+        guard = getattr(torch._C, "DisableTorchFunctionSubclass", None) or torch._C.DisableTorchFunction
+        with guard():
             return func(*args, **kwargs)
 
     def wait(self) -> None:
@@ -227,7 +230,8 @@ class VitEngine:
 
     def __init__(self, cfg: VitConfig, device: int = 0, max_batch: int = 1, precision: str = "bf16"):
         """precision: "bf16" (bf16 operands, fp32 accumulation) or "fp32x3" (split-bf16 operands: hi*hi + lo*hi +
-        hi*lo, <= 1e-3 of the fp32 reference, ~3x the tensor work; head dim 64 models)."""
+        hi*lo, <= 1e-3 of the fp32 reference, ~3x the tensor work; attention of head dims other than 64 in fp32 on the
+        CUDA cores)."""
         self.lib = load_library()
         self.cfg = cfg
         self.device = device
