@@ -250,6 +250,7 @@ class VitEngine:
         self._slab: Optional[torch.Tensor] = None    # current request's pinned slab (uint8) and its fill level
         self._slab_off = 0
         self._book = threading.Lock()    # guards the three fields above (requests may be encoded on other threads)
+        self._wire_pending: Dict[int, tuple] = {}    # data_ptr -> (slab, offset) between _host_out and _issue
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -401,7 +402,7 @@ class VitEngine:
         c = self.cfg
         floats = ((c.num_layers + 1) * c.tokens * c.hidden_dim + c.num_layers * (c.tokens * c.tokens + c.num_heads * (c.tokens - 1))
                   + c.num_classes + c.tokens - 1)
-        return batch * floats * 4 + 256 * (3 * c.num_layers + 4)
+        return batch * floats * 4 + 256 * (3 * c.num_layers + 4) + self.PREFIX_GAP
 
     def prewarm_host_outputs(self, batch: int = 1, requests: int = 16) -> None:
         """Fill torch's pinned-memory cache with `requests` request slabs.  The reference's request graphs are reference
@@ -422,20 +423,31 @@ class VitEngine:
         with self._book:
             self._slab = None
 
-    def _host_out(self, *shape) -> torch.Tensor:
+    # Wire-ready layout of the request slab (deferred mode): the slab is laid out as the RESPONSE the host mirror will
+    # encode (message.py: 16-byte header, JSON index, then per tensor an 8 + 4 * ndim byte block header followed by the
+    # fp32 payload), so that `Response.encode` writes the small headers into the gaps and returns a view of the slab --
+    # the 9.8 MB of a ViT-B/16 request are then copied once (device -> pinned host), not twice.  `_host_out` leaves the
+    # gap of the block header in front of every payload and `PREFIX_GAP` bytes in front of the first one.
+    PREFIX_GAP = 16384
+
+    def _host_out(self, *shape, final=None) -> torch.Tensor:
+        """A host buffer for an output of `shape`; `final` is the shape of the view that will be handed out (it fixes
+        the size of the wire block header reserved in front of the payload)."""
         if not self._deferred:
             return torch.empty(*shape, dtype=torch.float32)
         n = 1
         for d_ in shape:
             n *= d_
-        need = (n * 4 + 255) // 256 * 256
+        hdr = 8 + 4 * len(tuple(final) if final is not None else shape)
         with self._book:
-            if self._slab is None or self._slab_off + need > self._slab.numel():
-                size = max(self._request_bytes(shape[0]), need)
+            if self._slab is None or self._slab_off + hdr + n * 4 > self._slab.numel():
+                size = max(self._request_bytes(shape[0]), self.PREFIX_GAP + hdr + n * 4)
                 self._slab = torch.empty(size, dtype=torch.uint8, pin_memory=True)
-                self._slab_off = 0
-            v = self._slab[self._slab_off:self._slab_off + n * 4].view(torch.float32).view(*shape)
-            self._slab_off += need
+                self._slab_off = self.PREFIX_GAP
+            off = self._slab_off + hdr
+            v = self._slab[off:off + n * 4].view(torch.float32).view(*shape)
+            self._slab_off = off + n * 4
+            self._wire_pending[v.data_ptr()] = (self._slab, off)
         return v
 
     def _checked_out(self, status: int, out: torch.Tensor) -> None:
@@ -463,6 +475,7 @@ class VitEngine:
             self._issued += 1
             t._seq, t._engine = self._issued, self
             self._keep.append((t._seq, out))
+            t._wire = self._wire_pending.pop(out.data_ptr(), None)   # (slab, payload offset): message.Response.encode
         return t
 
     def _drain(self, seq: int) -> None:
@@ -508,12 +521,12 @@ class VitEngine:
         check(self.lib.vitb200_stage_mlp_block(self._h, layer, batch))
 
     def stage_head(self, batch: int, shape=None) -> torch.Tensor:
-        out = self._host_out(batch, self.cfg.num_classes)
+        out = self._host_out(batch, self.cfg.num_classes, final=shape)
         self._checked_out(self.lib.vitb200_stage_head(self._h, batch, out.data_ptr()), out)
         return self._issue(out, shape)
 
     def stage_rollout(self, batch: int, shape=None) -> torch.Tensor:
-        out = self._host_out(batch, self.cfg.tokens - 1)
+        out = self._host_out(batch, self.cfg.tokens - 1, final=shape)
         self._checked_out(self.lib.vitb200_stage_rollout(self._h, batch, out.data_ptr()), out)
         return self._issue(out, shape)
 
@@ -522,7 +535,7 @@ class VitEngine:
         check(self.lib.vitb200_set_tokens(self._h, tokens.data_ptr(), tokens.shape[0]))
 
     def get_tokens(self, batch: int, shape=None) -> torch.Tensor:
-        out = self._host_out(batch, self.cfg.tokens, self.cfg.hidden_dim)
+        out = self._host_out(batch, self.cfg.tokens, self.cfg.hidden_dim, final=shape)
         self._checked_out(self.lib.vitb200_get_tokens(self._h, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
@@ -532,24 +545,24 @@ class VitEngine:
 
     def get_avg_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         N = self.cfg.tokens
-        out = self._host_out(batch, N, N)
+        out = self._host_out(batch, N, N, final=shape)
         self._checked_out(self.lib.vitb200_get_avg_map(self._h, layer, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
     def get_cls_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
-        out = self._host_out(batch, self.cfg.num_heads, self.cfg.tokens)
+        out = self._host_out(batch, self.cfg.num_heads, self.cfg.tokens, final=shape)
         self._checked_out(self.lib.vitb200_get_cls_map(self._h, layer, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
     def get_cls_grid(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         """[B, H, N-1]: the class token's attention to the patch tokens per head (class column dropped by the copy)."""
-        out = self._host_out(batch, self.cfg.num_heads, self.cfg.tokens - 1)
+        out = self._host_out(batch, self.cfg.num_heads, self.cfg.tokens - 1, final=shape)
         self._checked_out(self.lib.vitb200_get_cls_grid(self._h, layer, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 
     def get_head_map(self, layer: int, batch: int, shape=None) -> torch.Tensor:
         N = self.cfg.tokens
-        out = self._host_out(batch, self.cfg.num_heads, N, N)
+        out = self._host_out(batch, self.cfg.num_heads, N, N, final=shape)
         self._checked_out(self.lib.vitb200_get_head_map(self._h, layer, out.data_ptr(), batch), out)
         return self._issue(out, shape)
 

@@ -99,20 +99,27 @@ class Response:
     def set_output(self, node: int, channel: str, t: torch.Tensor) -> None:
         self.outputs.setdefault(node, {})[channel] = t
 
-    def encode(self) -> bytes:
+    def encode(self):
+        """The response message (message.py:76-87's layout).  Returns a bytes-like object: `bytes`, or -- when every
+        output is an engine output of ONE request whose pinned slab was laid out wire-ready (engine.VitEngine._host_out)
+        -- a memoryview of that slab with the headers written into the gaps: no copy of the payload at all (the
+        reference's t.numpy().tobytes() + array('f') + BytesIO path copies it four times, message.py:111-121)."""
         index = []
         tensors: List[torch.Tensor] = []
         for node, chans in self.outputs.items():
             for channel, t in chans.items():
                 index.append({"node": node, "channel": channel})
                 tensors.append(t)
+        in_place = self._encode_in_place(index, tensors)
+        if in_place is not None:
+            return in_place
         json_utf8 = json.dumps(index).encode()
-        parts = [b"", json_utf8, b"\0" * (align_next(16 + len(json_utf8), 4) - 16 - len(json_utf8))]
+        pad = align_next(16 + len(json_utf8), 4) - 16 - len(json_utf8)
+        parts = [b"", json_utf8, b"\0" * pad]
         for t in tensors:
             if t.device.type != "cpu" or t.dtype != torch.float32:
                 t = t.detach().to(device="cpu", dtype=torch.float32)
-            # the tensor's own memory as a bytes-like object: join() below is then the only copy of the payload (the
-            # reference's t.numpy().tobytes() + array('f') + BytesIO path copies it four times, message.py:111-121)
+            # the tensor's own memory as a bytes-like object: join() below is then the only copy of the payload
             payload = memoryview(t.detach().contiguous().numpy().reshape(-1)).cast("B")
             dims = list(t.shape)
             parts.append(struct.pack(f"<II{len(dims)}I", 8 + 4 * len(dims) + len(payload), len(dims), *dims))
@@ -120,6 +127,46 @@ class Response:
         total = 16 + sum(len(p) for p in parts)
         parts[0] = _HEADER.pack(total, RESPONSE_MAGIC, len(tensors), len(json_utf8))
         return b"".join(parts)
+
+    @staticmethod
+    def _encode_in_place(index: List[Dict], tensors: List[torch.Tensor]):
+        """Zero-copy path: the tensors are the consecutive wire blocks of one pinned request slab (each carries
+        `_wire = (slab, payload offset)` from the engine).  The blocks are listed in SLAB order -- the order the nodes
+        ran in, which the scheduler's visit order can make differ from the node order (graph.py) -- and the JSON index
+        names them in that order: a decoder goes by the index (net_node.js:235-297).  None if anything differs."""
+        if not tensors:
+            return None
+        items = []
+        for ent, t in zip(index, tensors):
+            w = getattr(t, "_wire", None)
+            if w is None or t.dtype != torch.float32 or t.device.type != "cpu" or not t.is_contiguous():
+                return None
+            items.append((w[1], ent, t, w[0]))
+        items.sort(key=lambda it: it[0])
+        json_utf8 = json.dumps([it[1] for it in items]).encode()
+        pad = align_next(16 + len(json_utf8), 4) - 16 - len(json_utf8)
+        prefix = 16 + len(json_utf8) + pad
+        slab = items[0][3]
+        start = items[0][0] - (8 + 4 * items[0][2].dim()) - prefix
+        if start < 0:
+            return None
+        expect = start + prefix
+        for off, _, t, s in items:
+            if s is not slab or off - (8 + 4 * t.dim()) != expect:
+                return None
+            expect = off + t.numel() * 4
+        last = items[-1][2]
+        if hasattr(last, "wait"):
+            last.wait()          # stream order: every earlier copy of the request has landed as well
+        buf = memoryview(slab.numpy())          # the pinned slab itself (uint8)
+        _HEADER.pack_into(buf, start, expect - start, RESPONSE_MAGIC, len(items), len(json_utf8))
+        buf[start + 16:start + 16 + len(json_utf8)] = json_utf8
+        if pad:
+            buf[start + 16 + len(json_utf8):start + prefix] = b"\0" * pad
+        for off, _, t, _s in items:
+            dims = list(t.shape)
+            struct.pack_into(f"<II{len(dims)}I", buf, off - 8 - 4 * len(dims), 8 + 4 * len(dims) + t.numel() * 4, len(dims), *dims)
+        return buf[start:expect]
 
 
 # ---- the browser side of the protocol (net_node.js:56-175, 235-297), used by tests and the CPU baseline ----

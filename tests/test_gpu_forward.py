@@ -277,7 +277,19 @@ def test_plugin_through_scheduler_and_wire_codec(E, golden_dir):
     req = M.Request()
     req.decode(open(os.path.join(golden_dir, "wire_tiny.request.bin"), "rb").read())
     ctx.compute(req.graph)
-    got = M.decode_response(M.Response(req.graph).encode())
+    resp = M.Response(req.graph)
+    enc = resp.encode()
+    # deferred outputs of one request are laid out wire-ready in ONE pinned slab: the response is a view of it (no copy
+    # of the payload) that decodes to the same tensors as the copying encoder's bytes (blocks in the order the nodes ran)
+    assert isinstance(enc, memoryview) and enc.nbytes == len(enc)
+    plain = M.Response.__new__(M.Response)
+    plain.outputs = {n: {ch: t.clone() for ch, t in chans.items()} for n, chans in resp.outputs.items()}
+    joined = plain.encode()
+    assert isinstance(joined, bytes) and len(joined) == len(enc)
+    a, b = M.decode_response(enc), M.decode_response(joined)
+    assert all(torch.equal(a[n][ch], b[n][ch]) for n in b for ch in b[n]) and {n: sorted(v) for n, v in a.items()} == {n: sorted(v) for n, v in b.items()}
+    assert bytes(resp.encode()) == bytes(enc)                  # encoding twice rewrites the same headers
+    got = M.decode_response(enc)
     want = M.decode_response(open(os.path.join(golden_dir, "wire_tiny.response.bin"), "rb").read())
     assert {k: sorted(v) for k, v in got.items()} == {k: sorted(v) for k, v in want.items()}
     for node in want:
@@ -561,7 +573,9 @@ def test_peer_push_two_ranks_matches_one_engine_on_the_whole_batch(E):
 
 def test_deferred_node_outputs_wait_on_first_access_and_equal_the_synchronous_path(E, golden_dir, monkeypatch):
     """Deferred host outputs (vitb200_set_deferred, engine.PendingTensor; the plugin's default): the same wire request
-    gives byte-identical response bytes with a wait per call (VITB200_DEFERRED=0) and with one wait per request;
+    gives the same response -- every tensor bit-identical, the same length; the zero-copy encoder lists the blocks in
+    the order the nodes ran, the JSON index says which is which -- with a wait per call (VITB200_DEFERRED=0) and with
+    one wait per request;
     node outputs are torch.Tensors whose metadata is readable without waiting, whose first data access drains the
     stream once for every output of the request, and which also work when only an inner node's output is read
     (a graph without head / rollout) and through the UNMODIFIED codec idiom t.numpy().tobytes()."""
@@ -589,9 +603,12 @@ def test_deferred_node_outputs_wait_on_first_access_and_equal_the_synchronous_pa
     monkeypatch.setenv("VITB200_DEFERRED", "1")
     plug = P.VitB200Model("vit_tiny_test", cfg, module, 0, 1)
     eng = plug.engine
+    want_t = M.decode_response(want)
     for _ in range(3):       # repeated requests recycle pinned buffers
         req, got = respond(plug)
-        assert got == want
+        got_t = M.decode_response(got)
+        assert len(got) == len(want) and {n: sorted(v) for n, v in got_t.items()} == {n: sorted(v) for n, v in want_t.items()}
+        assert all(torch.equal(got_t[n][ch], want_t[n][ch]) for n in want_t for ch in want_t[n])
     assert eng._drained == eng._issued and not eng._keep
 
     # one request by hand: nothing waits until the data is touched
