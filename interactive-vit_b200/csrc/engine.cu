@@ -304,20 +304,32 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
   }();
   const int min_tiles = env_min_tiles >= 0 ? env_min_tiles : (mode == 4 ? device_sms() / 2 + 1 : 0);
   if (mode == 4 && (BN != 256 || gemm_units(M, N, 256, 256, 1) < min_tiles)) mode = 2;
-  const int pair = mode == 1 ? 1 : 2;
+  int pair = mode == 1 ? 1 : 2;
+  int bn = BN;
+  // Small problems (the single-image request: M = 197 -> one 256-row tile per 256 columns, 3..12 CTA pairs on 148 SMs)
+  // are latency-bound by ONE tile's main loop: single-CTA 128 x 128 tiles put 4x the SMs on the same work (fc2, K = 3072:
+  // 48 k-blocks of a quarter of the MMA time each).  Same k order per output element: results are bit-identical.
+  static const int small_mode = [] {
+    const char* v = getenv("VITB200_GEMM_SMALL");
+    return (v && v[0] == '0') ? 0 : 1;
+  }();
+  // (Not for the GEMMs that PRODUCE LayerNorm partial sums: their slot width is tied to the tile's column groups --
+  //  128 columns for widths that are multiples of 256 -- and a 128-wide tile has 64-column groups.)
+  if (small_mode && mode == 2 && N % 128 == 0 && ep.row_stats_out == nullptr && gemm_units(M, N, 256, BN, 1) * 4 <= device_sms())
+    pair = 1, bn = 128;
   if ((a_lo == nullptr) != (w_lo == nullptr)) return fail(VITB200_ERR_INVALID, "gemm: split-bf16 needs both low operands");
   CUtensorMap maps[4];  // A, W, A_lo, W_lo (the low maps alias the high ones when the operands are plain bf16)
   VT_TRY(make_tmap_bf16(&maps[0], a, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
-  VT_TRY(make_tmap_bf16(&maps[1], w, N, K, K, mode == 4 ? 64 : BN / pair, gemm_cfg::BK));
+  VT_TRY(make_tmap_bf16(&maps[1], w, N, K, K, mode == 4 ? 64 : bn / pair, gemm_cfg::BK));
   maps[2] = maps[0], maps[3] = maps[1];
   GemmShape sh{M, N, K};
   if (a_lo != nullptr) {
     VT_TRY(make_tmap_bf16(&maps[2], a_lo, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
-    VT_TRY(make_tmap_bf16(&maps[3], w_lo, N, K, K, mode == 4 ? 64 : BN / pair, gemm_cfg::BK));
+    VT_TRY(make_tmap_bf16(&maps[3], w_lo, N, K, K, mode == 4 ? 64 : bn / pair, gemm_cfg::BK));
     sh.split = 3;
   }
   if (mode == 4) return launch_gemm_bn<256, 2, 2>(maps, sh, ep, gelu, out_f32, st);
-  if (BN == 256) {
+  if (bn == 256) {
     return pair == 2 ? launch_gemm_bn<256, 2, 1>(maps, sh, ep, gelu, out_f32, st)
                      : launch_gemm_bn<256, 1, 1>(maps, sh, ep, gelu, out_f32, st);
   }
