@@ -267,15 +267,16 @@ static int launch_gemm_bn(const CUtensorMap* maps, GemmShape sh, const GemmEpilo
   if (ln_in) {
     if (ep.colsum == nullptr || out_f32 || resid || remap)
       return fail(VITB200_ERR_INVALID, "gemm: folded-LayerNorm epilogue needs colsum and a bf16 output");
-    if (sh.K % 128 != 0 || ep.stats_in_slots != sh.K / ln_slot_width(sh.K))
-      return fail(VITB200_ERR_INVALID, "gemm: folded LayerNorm needs K a multiple of 128 and K / %d partial sums per row (K=%d, slots=%d)",
-                  ln_slot_width(sh.K), sh.K, ep.stats_in_slots);
+    if (sh.K % 128 != 0 || (ep.stats_in_slots != sh.K / 64 && ep.stats_in_slots != sh.K / 128))
+      return fail(VITB200_ERR_INVALID, "gemm: folded LayerNorm needs K a multiple of 128 and K / 64 or K / 128 partial sums per row (K=%d, slots=%d)",
+                  sh.K, ep.stats_in_slots);
     if (gelu) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false, true>(maps, sh, ep, st);
     return launch_gemm_t<BN, kPair, kPairs, false, false, false, false, true>(maps, sh, ep, st);
   }
-  if (ep.xb != nullptr && (!resid || ep.row_stats_out == nullptr || sh.N % 128 != 0 || ep.stats_slots != sh.N / ln_slot_width(sh.N)))
+  // (one statistics slot per epilogue-warp column group: BN / 2 columns)
+  if (ep.xb != nullptr && (!resid || ep.row_stats_out == nullptr || sh.N % 128 != 0 || ep.stats_slots != sh.N / (BN / 2)))
     return fail(VITB200_ERR_INVALID, "gemm: the bf16 copy + row statistics are produced by residual epilogues only, N a multiple "
-                                     "of 128, one slot per %d columns", ln_slot_width(sh.N));
+                                     "of 128, one slot per %d columns (got %d slots for N = %d)", BN / 2, ep.stats_slots, sh.N);
   if (gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, true, false, false, false>(maps, sh, ep, st);
   if (!gelu && !out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, false, false, false>(maps, sh, ep, st);
   if (!gelu && out_f32 && !resid && !remap) return launch_gemm_t<BN, kPair, kPairs, false, true, false, false>(maps, sh, ep, st);
@@ -287,6 +288,21 @@ static int launch_gemm_bn(const CUtensorMap* maps, GemmShape sh, const GemmEpilo
   if (!gelu && out_f32 && resid && remap) return launch_gemm_t<BN, kPair, kPairs, false, true, true, true>(maps, sh, ep, st);
   return fail(VITB200_ERR_INVALID, "gemm: epilogue combination not instantiated (gelu=%d f32=%d resid=%d remap=%d)", gelu,
               out_f32, resid, remap);
+}
+
+// Small problem: at most a quarter of the SMs would get a 256 x 256 (or 256 x 128) pair tile.
+static bool gemm_small(int M, int N) { return gemm_units(M, N, 256, (N % 256 == 0) ? 256 : 128, 1) * 4 <= device_sms(); }
+
+// Columns per LayerNorm statistics slot for a forward over M token rows of width d: 128 for widths that are multiples of
+// 256 -- unless the problem is small, where the producing GEMMs (patch embedding, out_proj, fc2: N = d) run 128-wide
+// single-CTA tiles, whose epilogue-warp column groups are 64 wide.
+static int stats_width(int M, int d) {
+  static const int small_mode = [] {
+    const char* v = getenv("VITB200_GEMM_SMALL");
+    return (v && v[0] == '0') ? 0 : 1;
+  }();
+  if (d % 256 != 0) return 64;
+  return (small_mode && gemm_pair_mode() == 2 && gemm_small(M, d)) ? 64 : 128;
 }
 
 // out = epilogue(A[M,K] * W[N,K]^T): picks the tile width and the epilogue instantiation.
@@ -313,9 +329,10 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
     const char* v = getenv("VITB200_GEMM_SMALL");
     return (v && v[0] == '0') ? 0 : 1;
   }();
-  // (Not for the GEMMs that PRODUCE LayerNorm partial sums: their slot width is tied to the tile's column groups --
-  //  128 columns for widths that are multiples of 256 -- and a 128-wide tile has 64-column groups.)
-  if (small_mode && mode == 2 && N % 128 == 0 && ep.row_stats_out == nullptr && gemm_units(M, N, 256, BN, 1) * 4 <= device_sms())
+  // GEMMs that PRODUCE LayerNorm partial sums write one slot per epilogue-warp column group (tile width / 2), so their
+  // tile width follows the slot width the engine chose for this batch size (stats_width): 64 -> 128-wide tiles.
+  if (ep.row_stats_out != nullptr && ep.stats_slots > 0 && mode != 4) bn = (N / ep.stats_slots == 64) ? 128 : 256;
+  if (small_mode && mode == 2 && N % 128 == 0 && (ep.row_stats_out == nullptr || bn == 128) && gemm_small(M, N))
     pair = 1, bn = 128;
   if ((a_lo == nullptr) != (w_lo == nullptr)) return fail(VITB200_ERR_INVALID, "gemm: split-bf16 needs both low operands");
   CUtensorMap maps[4];  // A, W, A_lo, W_lo (the low maps alias the high ones when the operands are plain bf16)
@@ -641,7 +658,7 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   VT_TRY(ensure(e->patches, (size_t)B * e->n * e->patch_k * 2));
   VT_TRY(ensure(e->x, M * c.hidden_dim * 4));
   VT_TRY(ensure(e->xb, M * c.hidden_dim * 2));
-  VT_TRY(ensure(e->ln_stats, M * (c.hidden_dim / ln_slot_width(c.hidden_dim)) * sizeof(float2)));
+  VT_TRY(ensure(e->ln_stats, M * (c.hidden_dim / 64) * sizeof(float2)));   // sized for the narrow slots (stats_width)
   VT_TRY(ensure(e->qkv, M * 3 * c.hidden_dim * 2));
   VT_TRY(ensure(e->ctx, M * c.hidden_dim * 2));
   if (e->precise || !attention_is_fused(e->N, e->D)) VT_TRY(ensure(e->attn_stats, M * c.num_heads * sizeof(float2)));
@@ -695,16 +712,17 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
   ep.group_rows = e->n, ep.out_group_stride = e->N, ep.out_row_offset = 1;
   ep.resid_broadcast = 1, ep.resid_row_offset = 1;
   ep.xb = (__nv_bfloat16*)e->xb.p, ep.ldxb = c.hidden_dim;
-  ep.row_stats_out = (float2*)e->ln_stats.p, ep.stats_slots = c.hidden_dim / ln_slot_width(c.hidden_dim);
+  const int sw = stats_width(B * e->N, c.hidden_dim);
+  ep.row_stats_out = (float2*)e->ln_stats.p, ep.stats_slots = c.hidden_dim / sw;
   ep.xb_lo = (__nv_bfloat16*)e->xb_lo.p;
   prof_mark(e, "gemm_patch_embed", st);
   VT_TRY(launch_gemm(e->patches.p, e->patch_k, e->w_patch, B * e->n, c.hidden_dim, e->patch_k, ep, false, true, st,
                      e->patches_lo.p, e->w_patch_lo));
-  const long cthreads = (long)B * (c.hidden_dim / ln_slot_width(c.hidden_dim)) * 32;
+  const long cthreads = (long)B * (c.hidden_dim / sw) * 32;
   prof_mark(e, "cls_rows", st);
   cls_rows_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p,
                                                                       (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B,
-                                                                      e->N, c.hidden_dim, (__nv_bfloat16*)e->xb_lo.p);
+                                                                      e->N, c.hidden_dim, sw, (__nv_bfloat16*)e->xb_lo.p);
   CU_TRY(cudaGetLastError());
   e->launches += 3;
   return VITB200_OK;
@@ -718,12 +736,13 @@ static int run_attn_block(vitb200_engine* e, int l, int B, uint32_t flags, cudaS
   float* x = (float*)e->x.p;
   __nv_bfloat16* xb = (__nv_bfloat16*)e->xb.p;
   float2* stats = (float2*)e->ln_stats.p;
-  const int slots = d / ln_slot_width(d);
+  const int slots = d / stats_width(M, d);
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_qkv", st);
     ep.bias = w.bf_qkv, ep.out = e->qkv.p, ep.ldo = 3 * d;
     ep.row_stats_in = stats, ep.stats_in_slots = slots, ep.ln_eps = 1e-6f;
+    ep.stats_in_pairs = (d % 256 == 0 && slots == d / 64) ? 1 : 0;
     ep.colsum = w.s_qkv, ep.out_lo = (__nv_bfloat16*)e->qkv_lo.p;
     // the fused attention kernels take V in fp16 (their probabilities are fp16; see attention.cuh)
     if (!e->precise && attention_is_fused(e->N, e->D)) ep.f16_from_col = 2 * d;
@@ -759,12 +778,13 @@ static int run_mlp_block(vitb200_engine* e, int l, int B, cudaStream_t st) {
   float* x = (float*)e->x.p;
   __nv_bfloat16* xb = (__nv_bfloat16*)e->xb.p;
   float2* stats = (float2*)e->ln_stats.p;
-  const int slots = d / ln_slot_width(d);
+  const int slots = d / stats_width(M, d);
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_fc1_gelu", st);
     ep.bias = w.bf_fc1, ep.out = e->mlp.p, ep.ldo = c.mlp_dim;
     ep.row_stats_in = stats, ep.stats_in_slots = slots, ep.ln_eps = 1e-6f;
+    ep.stats_in_pairs = (d % 256 == 0 && slots == d / 64) ? 1 : 0;
     ep.colsum = w.s_fc1, ep.out_lo = (__nv_bfloat16*)e->mlp_lo.p;
     VT_TRY(launch_gemm(xb, d, w.w_fc1, M, c.mlp_dim, d, ep, true, false, st, e->xb_lo.p, w.w_fc1_lo));
   }
@@ -1583,6 +1603,7 @@ int vitb200_set_tokens(vitb200_engine* e, const float* tokens_host, int batch) {
   const long rows = (long)batch * e->N;
   rows_bf16_stats_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const float*)e->x.p, (__nv_bfloat16*)e->xb.p,
                                                                               (float2*)e->ln_stats.p, rows, e->cfg.hidden_dim,
+                                                                              stats_width((int)rows, e->cfg.hidden_dim),
                                                                               (__nv_bfloat16*)e->xb_lo.p);
   CU_TRY(cudaGetLastError());
   CU_TRY(cudaStreamSynchronize(st));

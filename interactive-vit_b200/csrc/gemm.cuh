@@ -87,7 +87,8 @@ struct GemmEpilogue {
   // range.)
   int f16_from_col = 0x7fffffff;
   int stats_slots = 0;      // producer side: slots per row of row_stats_out (= N / ln_slot_width(N))
-  int stats_in_slots = 0;   // consumer side: slots per row of row_stats_in (= K / ln_slot_width(K), even)
+  int stats_in_slots = 0;   // consumer side: slots per row of row_stats_in (= K / slot width, even)
+  int stats_in_pairs = 0;   // consumer side: 64-column slots of a K that is a multiple of 256: add adjacent slots first
   float ln_eps = 1e-6f;
 };
 
@@ -381,7 +382,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // lane (2.4 MB per forward pass over the statistics, L2-resident behind the producing GEMM).
     int local = 0;
     const int q = lane & 3, rq = lane >> 2;
-    const int n4 = ep.stats_in_slots >> 1;   // float4 = two slots
+    // stats_in_pairs: the slots are 64 columns wide although K is a multiple of 256 (small batches, see engine.cu:
+    // stats_width): adjacent slots are added first -- exactly the 128-column slot the wide tiles write -- and the rest of
+    // the reduction is the same, so the result does not depend on the slot width.
+    const bool pairs = ep.stats_in_pairs != 0;
+    const int n4 = pairs ? ep.stats_in_slots >> 2 : ep.stats_in_slots >> 1;   // float4 = two (combined) slots
     const float inv_w = 1.0f / static_cast<float>(shape.K);
     for (int unit = slot; unit < num_units; unit += num_slots, ++local) {
       int m_blk, n_blk;
@@ -389,9 +394,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int buf = local & 1;
       ptx::mbar_wait(&ln_empty_bar[buf], ((local >> 1) & 1) ^ 1);
       const int row0 = m_blk * kTileM + static_cast<int>(cta_rank) * BM;
+      if (pairs) {
+        // small batches only.  Same order of additions as below with u = (slot 2i) + (slot 2i+1) in place of the 128-column
+        // slot i; 8 row groups (16 independent 16-byte loads per lane) per L2 round trip
+        constexpr int kG = 8;
+#pragma unroll 1
+        for (int g0 = 0; g0 < BM / 8; g0 += kG) {
+          float s1[kG], s2[kG];
+#pragma unroll
+          for (int g = 0; g < kG; ++g) s1[g] = 0.f, s2[g] = 0.f;
+          for (int j = q; j < n4; j += 4) {
+            float4 lo[kG], hi[kG];
+#pragma unroll
+            for (int g = 0; g < kG; ++g) {
+              const int row = row0 + (g0 + g) * 8 + rq;
+              lo[g] = make_float4(0.f, 0.f, 0.f, 0.f), hi[g] = lo[g];
+              if (row < shape.M) {
+                const float4* sp = reinterpret_cast<const float4*>(ep.row_stats_in + static_cast<long>(row) * ep.stats_in_slots);
+                lo[g] = sp[2 * j], hi[g] = sp[2 * j + 1];
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < kG; ++g)
+              s1[g] += lo[g].x + lo[g].z, s2[g] += lo[g].y + lo[g].w, s1[g] += hi[g].x + hi[g].z, s2[g] += hi[g].y + hi[g].w;
+          }
+#pragma unroll
+          for (int g = 0; g < kG; ++g) {
+            float a = s1[g], b = s2[g];
+            a += __shfl_xor_sync(0xffffffffu, a, 1), b += __shfl_xor_sync(0xffffffffu, b, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2), b += __shfl_xor_sync(0xffffffffu, b, 2);
+            if (q == 0) {
+              const float mean = a * inv_w;
+              const float rstd = rsqrtf(fmaxf(b * inv_w - mean * mean, 0.f) + ep.ln_eps);
+              ln_rows[buf * BM + (g0 + g) * 8 + rq] = make_float2(rstd, -rstd * mean);
+            }
+          }
+        }
+      }
       constexpr int kGroups = 16;            // all 16 row groups (of 8 rows) at once: ONE L2 round trip per tile and j
 #pragma unroll 1
-      for (int g0 = 0; g0 < BM / 8; g0 += kGroups) {
+      for (int g0 = 0; g0 < (pairs ? 0 : BM / 8); g0 += kGroups) {
         float s1[kGroups], s2[kGroups];
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) s1[g] = 0.f, s2[g] = 0.f;
@@ -493,8 +535,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (kLnIn) csum_c[c] = *reinterpret_cast<const float4*>(ep.colsum + col);
         }
       }
-      // producer side of the LayerNorm folding: this lane's row (trow + 4 * tcol of the quarter) summed over the warp's chunks
-      float st1 = 0.f, st2 = 0.f;
+      // producer side of the LayerNorm folding: this lane's row (trow + 4 * tcol of the quarter) summed over the warp's chunks.
+      // A 128-column slot is formed as (chunk 0 + chunk 1) + (chunk 2 + chunk 3), i.e. as the sum of the two 64-column
+      // slots a 128-wide tile would have written: the statistics -- and with them every output of the forward -- are then
+      // bit-identical whichever tile width the engine picked for the batch size (stats_width in engine.cu).
+      float st1 = 0.f, st2 = 0.f, stb1 = 0.f, stb2 = 0.f;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr0 =
@@ -662,7 +707,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float f2 = (b0 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? c2[0] : c2[1], 1);
             // this lane now owns row index tcol of the batch (bit 2 chose rows 4..7, bit 1 rows +2, bit 0 rows +1):
             // chunk sums are added in ascending chunk order
-            st1 += f1, st2 += f2;
+            if (kGroupCols == 128 && c >= 2) stb1 += f1, stb2 += f2;
+            else st1 += f1, st2 += f2;
           }
         }
         __syncwarp();  // slab is rewritten by the next chunk
@@ -677,7 +723,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int g = row / ep.group_rows;
             out_row = static_cast<long>(g) * ep.out_group_stride + ep.out_row_offset + (row - g * ep.group_rows);
           }
-          ep.row_stats_out[out_row * ep.stats_slots + gcol / kGroupCols] = make_float2(st1, st2);
+          ep.row_stats_out[out_row * ep.stats_slots + gcol / kGroupCols] = make_float2(st1 + stb1, st2 + stb2);
         }
       }
     }

@@ -183,16 +183,18 @@ patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, 
 // squares).  One warp per (image, 32-column chunk), one column per lane.
 __global__ void __launch_bounds__(256)
 cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
-                __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int B, int N, int d,
+                __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int B, int N, int d, int sw,
                 __nv_bfloat16* __restrict__ xb_lo = nullptr) {
-  const int sw = ln_slot_width(d), slots = d / sw;
+  const int slots = d / sw;   // sw: columns per statistics slot (64 or 128; the engine picks it per batch size)
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= static_cast<long>(B) * slots) return;
   const int b = static_cast<int>(warp / slots), slot = static_cast<int>(warp % slots);
   const long row = static_cast<long>(b) * N;
-  float p1 = 0.f, p2 = 0.f;
-  for (int c = 0; c < sw; c += 32) {     // chunk sums in ascending order: fixed order, bit-reproducible
+  // chunk sums in a fixed order, bit-reproducible; a 128-column slot is (chunk 0 + chunk 1) + (chunk 2 + chunk 3) = the
+  // sum of its two 64-column halves, like the GEMM epilogues' slots (gemm.cuh)
+  float p1 = 0.f, p2 = 0.f, q1 = 0.f, q2 = 0.f;
+  for (int c = 0; c < sw; c += 32) {
     const int col = slot * sw + c + lane;
     const float v = cls[col] + pos[col];
     x[row * d + col] = v;
@@ -200,32 +202,34 @@ cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, fl
       const __nv_bfloat16 hb = __float2bfloat16_rn(v);
       xb[row * d + col] = hb;
       if (xb_lo != nullptr) xb_lo[row * d + col] = __float2bfloat16_rn(v - __bfloat162float(hb));
-      p1 += warp_sum(v), p2 += warp_sum(v * v);
+      if (c < 64) p1 += warp_sum(v), p2 += warp_sum(v * v);
+      else q1 += warp_sum(v), q2 += warp_sum(v * v);
     }
   }
-  if (xb != nullptr && lane == 0) stats[row * slots + slot] = make_float2(p1, p2);
+  if (xb != nullptr && lane == 0) stats[row * slots + slot] = make_float2(p1 + q1, p2 + q2);
 }
 
 // bf16 copy + partial LayerNorm sums of arbitrary fp32 rows (token streams that enter through the boundary,
 // vitb200_set_tokens): one warp per row.
 __global__ void __launch_bounds__(256)
 rows_bf16_stats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, long rows,
-                       int d, __nv_bfloat16* __restrict__ xb_lo = nullptr) {
+                       int d, int sw, __nv_bfloat16* __restrict__ xb_lo = nullptr) {
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int sw = ln_slot_width(d), slots = d / sw;
+  const int slots = d / sw;
   for (int slot = 0; slot < slots; ++slot) {
-    float p1 = 0.f, p2 = 0.f;
+    float p1 = 0.f, p2 = 0.f, q1 = 0.f, q2 = 0.f;   // (chunk 0 + chunk 1) + (chunk 2 + chunk 3), see cls_rows_kernel
     for (int c = 0; c < sw; c += 32) {
       const int col = slot * sw + c + lane;
       const float v = x[row * d + col];
       const __nv_bfloat16 hb = __float2bfloat16_rn(v);
       xb[row * d + col] = hb;
       if (xb_lo != nullptr) xb_lo[row * d + col] = __float2bfloat16_rn(v - __bfloat162float(hb));
-      p1 += warp_sum(v), p2 += warp_sum(v * v);
+      if (c < 64) p1 += warp_sum(v), p2 += warp_sum(v * v);
+      else q1 += warp_sum(v), q2 += warp_sum(v * v);
     }
-    if (lane == 0) stats[row * slots + slot] = make_float2(p1, p2);
+    if (lane == 0) stats[row * slots + slot] = make_float2(p1 + q1, p2 + q2);
   }
 }
 
