@@ -251,7 +251,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps * kPair);  // one elected lane per epilogue warp (of both CTAs)
-      ptx::mbar_init(&ln_full_bar[a], 1);
+      ptx::mbar_init(&ln_full_bar[a], 2);   // the two statistics warps (roles 2 and 3), 64 rows each
       ptx::mbar_init(&ln_empty_bar[a], kEpiWarps);
     }
     ptx::fence_mbar_init();
@@ -370,7 +370,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       __syncwarp();
     }
-  } else if (kLnIn && warp == 3) {
+  } else if (kLnIn && (warp == 3 || warp == 2)) {
     // ------------------------------------------------------------ LayerNorm row statistics (folded-LN GEMMs)
     // Runs one tile ahead of the epilogue: reduces the partial sums (sum x, sum x^2 per 32-column chunk, written by the
     // GEMM that produced the rows) of the tile's 128 rows (this CTA's) to (rstd, -rstd * mean) and stages them in smem,
@@ -380,7 +380,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // separate row_stats_finalize kernel produced).  With one slot per 128 (64) columns a ViT-B row has 6 slots = 3
     // float4: lanes q < 3 of a row's quad load one each, so a tile costs one L2 round trip of 16 independent loads per
     // lane (2.4 MB per forward pass over the statistics, L2-resident behind the producing GEMM).
+    // (roles 2 and 3 split the tile's 128 rows: with short K -- ViT-S, six k-blocks per tile -- ONE warp reducing all 128
+    //  rows took as long as the tile's main loop and the qkv / fc1 GEMMs ran 50 % / 15 % slower than with round 1's
+    //  separate finalize kernel: measured)
     int local = 0;
+    const int half = warp - 2;
     const int q = lane & 3, rq = lane >> 2;
     // stats_in_pairs: the slots are 64 columns wide although K is a multiple of 256 (small batches, see engine.cu:
     // stats_width): adjacent slots are added first -- exactly the 128-column slot the wide tiles write -- and the rest of
@@ -399,7 +403,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // slot i; 8 row groups (16 independent 16-byte loads per lane) per L2 round trip
         constexpr int kG = 8;
 #pragma unroll 1
-        for (int g0 = 0; g0 < BM / 8; g0 += kG) {
+        for (int g0 = half * (BM / 16); g0 < (half + 1) * (BM / 16); g0 += kG) {
           float s1[kG], s2[kG];
 #pragma unroll
           for (int g = 0; g < kG; ++g) s1[g] = 0.f, s2[g] = 0.f;
@@ -431,9 +435,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
       }
-      constexpr int kGroups = 16;            // all 16 row groups (of 8 rows) at once: ONE L2 round trip per tile and j
+      constexpr int kGroups = 8;             // this warp's 8 row groups (of 8 rows) at once: ONE L2 round trip per tile and j
 #pragma unroll 1
-      for (int g0 = 0; g0 < (pairs ? 0 : BM / 8); g0 += kGroups) {
+      for (int g0 = half * (BM / 16); g0 < (pairs ? 0 : (half + 1) * (BM / 16)); g0 += kGroups) {
         float s1[kGroups], s2[kGroups];
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) s1[g] = 0.f, s2[g] = 0.f;
