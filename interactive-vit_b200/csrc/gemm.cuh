@@ -113,6 +113,7 @@ __host__ __device__ constexpr int epi_warps(bool gelu) { return gelu ? VITB200_G
 constexpr int kSlabStride = 36;                           // floats per slab row: 32 + 4 pad (16-B bank skew)
 constexpr int kSlabBytes = 32 * kSlabStride * 4;          // one warp's 32 x 32 fp32 transpose slab
 constexpr int kResidStageBytes = 32 * 8 * 16;             // one warp's residual prefetch buffer: 8 x 16 B per lane
+constexpr int kLnBufs = 4;                                // folded LayerNorm: the statistics warps run up to three tiles ahead
 template <int BN, int kPair, int kEpiWarps, bool kResidStage = false>
 struct Cfg {
   static constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
@@ -120,11 +121,11 @@ struct Cfg {
   static constexpr int kStageBytesB = (BN / kPair) * BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kResidBytes = kResidStage ? kEpiWarps * kResidStageBytes : 0;
-  static constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - 2 * BM * 8 /*LN rows*/ - kEpiWarps * kSlabBytes - kResidBytes;
+  static constexpr int kSmemBudget = 227 * 1024 - 256 /*barriers*/ - kLnBufs * BM * 8 /*LN rows*/ - kEpiWarps * kSlabBytes - kResidBytes;
   static constexpr int kStagesFit = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
-  static constexpr int kLnBytes = 2 * BM * 8;  // folded LayerNorm: (rstd, -rstd * mean) of the tile's rows, double-buffered
+  static constexpr int kLnBytes = kLnBufs * BM * 8;  // folded LayerNorm: (rstd, -rstd * mean) of the tile's rows, kLnBufs tiles deep
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kSlabBytes + 256 + kLnBytes + kResidBytes;
   static_assert(kSmemBytes <= 227 * 1024, "gemm: shared memory budget");
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -210,9 +211,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* ln_full_bar = tmem_empty_bar + 2;   // [2] (rstd, -rstd * mean) of a tile's rows staged by warp 3
-  uint64_t* ln_empty_bar = ln_full_bar + 2;     // [2] ... and read by every epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_empty_bar + 2);
+  uint64_t* ln_full_bar = tmem_empty_bar + 2;   // [kLnBufs] (rstd, -rstd * mean) of a tile's rows staged by warps 2 and 3
+  uint64_t* ln_empty_bar = ln_full_bar + kLnBufs;     // [kLnBufs] ... and read by every epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_empty_bar + kLnBufs);
+  static_assert((2 * 8 + 4 + 2 * kLnBufs) * 8 + 8 <= 256, "barrier area");
   float2* ln_rows = reinterpret_cast<float2*>(smem + kStages * C::kStageBytes + kEpiWarps * kSlabBytes + 256);  // [2][BM]
   float4* resid_stage = reinterpret_cast<float4*>(smem + kStages * C::kStageBytes + kEpiWarps * kSlabBytes + 256 + C::kLnBytes);
 
@@ -251,6 +253,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps * kPair);  // one elected lane per epilogue warp (of both CTAs)
+    }
+    for (int a = 0; a < kLnBufs; ++a) {
       ptx::mbar_init(&ln_full_bar[a], 2);   // the two statistics warps (roles 2 and 3), 64 rows each
       ptx::mbar_init(&ln_empty_bar[a], kEpiWarps);
     }
@@ -395,8 +399,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int unit = slot; unit < num_units; unit += num_slots, ++local) {
       int m_blk, n_blk;
       work.decode(unit, kPairs, pair_id, m_blk, n_blk);
-      const int buf = local & 1;
-      ptx::mbar_wait(&ln_empty_bar[buf], ((local >> 1) & 1) ^ 1);
+      const int buf = local % kLnBufs;
+      ptx::mbar_wait(&ln_empty_bar[buf], ((local / kLnBufs) & 1) ^ 1);
       const int row0 = m_blk * kTileM + static_cast<int>(cta_rank) * BM;
       if (pairs) {
         // small batches only.  Same order of additions as below with u = (slot 2i) + (slot 2i+1) in place of the 128-column
@@ -518,14 +522,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // folded LayerNorm: scale a = rstd and offset c = -rstd * mean of this thread's 8 rows (trow + 4 i), staged by warp 3
       float ln_a[8], ln_c[8];
       if (kLnIn) {
-        ptx::mbar_wait(&ln_full_bar[acc], acc_phase);
+        const int lbuf = local % kLnBufs;
+        ptx::mbar_wait(&ln_full_bar[lbuf], (local / kLnBufs) & 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float2 v = ln_rows[acc * BM + quarter * 32 + trow + 4 * i];
+          const float2 v = ln_rows[lbuf * BM + quarter * 32 + trow + 4 * i];
           ln_a[i] = v.x, ln_c[i] = v.y;
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ln_empty_bar[acc]);
+        if (lane == 0) ptx::mbar_arrive(&ln_empty_bar[lbuf]);
       }
       // bias (and folded-LayerNorm column sums) of every chunk of this tile, fetched before the accumulator wait: loaded
       // inside the chunk loop their L2 latency was exposed once per chunk (9 % of the epilogue's stall samples)
