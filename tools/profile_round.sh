@@ -9,5 +9,5 @@ cmd="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $cmd > $out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $out/launches_$tag.csv $cmd > $out/ncu_launches_$tag.log 2>&1
 $cmd > $out/plain2_$tag.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'gemm_bf16_kernel|attention_kernel|rollout|row_stats' -s 150 -c 12 -o $out/prof_$tag $cmd > $out/ncu_full_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'gemm_bf16_kernel|attention_pp_kernel|attention_kernel|rollout' -s 150 -c 12 -o $out/prof_$tag $cmd > $out/ncu_full_$tag.log 2>&1
 ls -la $out | tail -8
