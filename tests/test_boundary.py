@@ -432,3 +432,55 @@ def test_pending_tensor_through_the_unmodified_reference_graph_and_encoder():
     assert eng.drains == [3]
     back = M.decode_response(wire)
     assert torch.equal(back[a.index]["o"], vals)
+
+
+def test_response_encoded_in_place_from_a_wire_ready_slab():
+    """message.Response.encode's zero-copy path (engine outputs of one request sit in ONE slab with block-header gaps,
+    engine.VitEngine._host_out): the response is a view of the slab, decodes to the same tensors as the copying encoder's
+    bytes, lists the blocks in slab order whatever the node order, and falls back to the copying encoder when a tensor
+    does not belong to the slab.  Simulated here with an ordinary (unpinned) slab; the GPU suite drives the real one."""
+    import interactive_vit_b200.engine as E
+    from interactive_vit_b200 import message as M
+
+    slab = torch.zeros(1 << 20, dtype=torch.uint8)
+    off = E.VitEngine.PREFIX_GAP
+    made = []
+    for shape in [(7, 5), (3, 4, 2), (11,), (5, 5)]:
+        n = 1
+        for d in shape:
+            n *= d
+        hdr = 8 + 4 * len(shape)
+        o = off + hdr
+        v = slab[o:o + n * 4].view(torch.float32).view(*shape)
+        v.copy_(torch.arange(n, dtype=torch.float32).reshape(shape) + len(made))
+        t = v.as_subclass(E.PendingTensor)
+        t._wire, t._seq, t._engine = (slab, o), len(made) + 1, None
+        made.append(t)
+        off = o + n * 4
+
+    def response(order):
+        r = M.Response.__new__(M.Response)
+        r.outputs = {}
+        for node, ch, idx in order:
+            r.outputs.setdefault(node, {})[ch] = made[idx]
+        return r
+
+    # node order == slab order, and node order != slab order (the scheduler ran node 2 before node 1)
+    for order in ([(0, "o", 0), (1, "o", 1), (1, "attn", 2), (2, "o", 3)], [(0, "o", 0), (2, "o", 1), (2, "attn", 2), (1, "o", 3)]):
+        r = response(order)
+        enc = r.encode()
+        assert isinstance(enc, memoryview) and enc.obj is not None
+        plain = M.Response.__new__(M.Response)
+        plain.outputs = {n: {ch: t.clone().as_subclass(torch.Tensor) for ch, t in chans.items()} for n, chans in r.outputs.items()}
+        joined = plain.encode()
+        assert isinstance(joined, bytes) and len(joined) == len(enc)
+        a, b = M.decode_response(enc), M.decode_response(joined)
+        assert {n: sorted(v) for n, v in a.items()} == {n: sorted(v) for n, v in b.items()}
+        assert all(torch.equal(a[n][ch], b[n][ch]) for n in b for ch in b[n])
+        assert bytes(r.encode()) == bytes(enc)      # idempotent
+    # a tensor from elsewhere, or a missing block of the slab: the copying encoder takes over
+    r = response([(0, "o", 0), (1, "o", 1)])
+    r.outputs[2] = {"o": torch.ones(3)}
+    assert isinstance(r.encode(), bytes)
+    assert isinstance(response([(0, "o", 0), (1, "o", 2)]).encode(), bytes)      # block 1 skipped: not contiguous
+    assert M.decode_response(response([(0, "o", 0), (1, "o", 2)]).encode())[1]["o"].shape == (11,)
