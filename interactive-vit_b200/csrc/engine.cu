@@ -35,6 +35,7 @@
 #include "attention_long.cuh"
 #include "attention_precise.cuh"
 #include "gemm.cuh"
+#include "patch_embed.cuh"
 #include "peer.cuh"
 #include "rowwise.cuh"
 
@@ -103,6 +104,22 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return VITB200_OK;
+}
+
+// Generic tiled tensor map: `rank` dimensions, fastest first; strides in bytes for dimensions 1 .. rank-1 (multiples of 16);
+// swizzle chosen by the caller (the box's innermost extent in bytes must not exceed the swizzle span).
+static int make_tmap_nd(CUtensorMap* tm, CUtensorMapDataType dtype, const void* base, int rank, const cuuint64_t* dims,
+                        const cuuint64_t* strides_bytes, const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(VITB200_ERR_INVALID, "TMA operand must be 16-byte aligned (base %p)", base);
+  for (int i = 0; i + 1 < rank; ++i)
+    if (strides_bytes[i] % 16 != 0) return fail(VITB200_ERR_INVALID, "TMA stride %d (%llu B) must be a multiple of 16", i, (unsigned long long)strides_bytes[i]);
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VITB200_ERR_CUDA, "cuTensorMapEncodeTiled (%d-D) failed with CUresult %d", rank, (int)r);
   return VITB200_OK;
 }
 
@@ -550,6 +567,8 @@ struct vitb200_engine {
   // weights
   bool precise = false;  // fp32x3 mode: every GEMM / attention operand is carried as hi + lo bf16 (cfg.precision == 1)
   __nv_bfloat16* w_patch = nullptr;
+  float* w_patch_f32 = nullptr;   // conv_proj.weight in fp32: the B operand of the TMA-im2col patch embedding (kind::tf32)
+  bool patch_tma = false;         // VITB200_PATCH_TMA=1 at creation: patch_embed.cuh instead of patchify + GEMM
   __nv_bfloat16 *w_patch_lo = nullptr, *w_head_lo = nullptr;
   float* b_patch = nullptr;
   float *cls_token = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
@@ -697,8 +716,69 @@ static void prof_mark(vitb200_engine* e, const char* name, cudaStream_t st) {
 }
 
 // ---- forward stages (all enqueue on `st`, no synchronisation) --------------------------------------
+// Patch embedding with the im2col done by TMA (patch_embed.cuh): bf16 mode, patch 16, width a multiple of 256.  Opt-in
+// (VITB200_PATCH_TMA=1, read when the engine is created): correct and more accurate (tf32 operands: 1.7e-3 against the
+// fp32 oracle where the bf16 patch matrix gives 5.5e-3) but SLOWER than patchify + bf16 GEMM on the B200 -- 0.33 against
+// 0.23 ms per forward at batch 256: with fp32 operands every k-block moves twice the bytes from L2 into shared memory for
+// half the math rate, and the weight tile is re-fetched for every 128-row unit (1.8 GB of L2 -> smem traffic per launch).
+static bool patch_embed_fused(const vitb200_engine* e) {
+  const vitb200_config& c = e->cfg;
+  return e->patch_tma && !e->precise && c.patch_size == 16 && c.hidden_dim % 256 == 0 && e->w_patch_f32 != nullptr &&
+         c.image_size / c.patch_size <= 128;
+}
+
+static int launch_patch_embed(vitb200_engine* e, const float* images_dev, int B, int sw, cudaStream_t st) {
+  using namespace patch_cfg;
+  const vitb200_config& c = e->cfg;
+  const int S = c.image_size, g = S / 16, d = c.hidden_dim;
+  PatchEmbedParams p;
+  p.B = B, p.S = S, p.g = g, p.N = e->N, p.d = d;
+  p.pr = 128 / g, p.groups = (g + p.pr - 1) / p.pr;
+  p.bias = e->b_patch, p.pos = e->pos, p.x = (float*)e->x.p, p.xb = (__nv_bfloat16*)e->xb.p;
+  p.row_stats = (float2*)e->ln_stats.p, p.slot_width = sw;
+  CUtensorMap ti, tw, tx, txb;
+  {   // image [B, 3, S, S] viewed as (kx, px, ky, py, b*3 + c)
+    const cuuint64_t dims[5] = {16, (cuuint64_t)g, 16, (cuuint64_t)g, (cuuint64_t)B * 3};
+    const cuuint64_t str[4] = {64, (cuuint64_t)S * 4, (cuuint64_t)16 * S * 4, (cuuint64_t)S * S * 4};
+    const cuuint32_t box[5] = {16, (cuuint32_t)g, 1, (cuuint32_t)p.pr, 1};
+    VT_TRY(make_tmap_nd(&ti, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, images_dev, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {   // conv_proj.weight [d, 3 * 16 * 16] fp32
+    const cuuint64_t dims[2] = {(cuuint64_t)e->patch_k, (cuuint64_t)d};
+    const cuuint64_t str[1] = {(cuuint64_t)e->patch_k * 4};
+    const cuuint32_t box[2] = {BK, BN};
+    VT_TRY(make_tmap_nd(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, e->w_patch_f32, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {   // token stream [B][N][d] fp32 and its bf16 copy
+    const cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)e->N, (cuuint64_t)B};
+    const cuuint64_t str32[2] = {(cuuint64_t)d * 4, (cuuint64_t)e->N * d * 4};
+    const cuuint64_t str16[2] = {(cuuint64_t)d * 2, (cuuint64_t)e->N * d * 2};
+    const cuuint32_t box[3] = {32, 32, 1};
+    VT_TRY(make_tmap_nd(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, e->x.p, 3, dims, str32, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    VT_TRY(make_tmap_nd(&txb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, e->xb.p, 3, dims, str16, box, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
+  VT_TRY(ensure_func_smem((const void*)patch_embed_kernel, kSmemBytes));
+  const int units = B * p.groups * (d / BN), sms = device_sms();
+  patch_embed_kernel<<<units < sms ? units : sms, kThreads, kSmemBytes, st>>>(ti, tw, tx, txb, p);
+  CU_TRY(cudaGetLastError());
+  return VITB200_OK;
+}
+
 static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStream_t st) {
   const vitb200_config& c = e->cfg;
+  if (patch_embed_fused(e)) {
+    const int sw = stats_width(B * e->N, c.hidden_dim);
+    prof_mark(e, "gemm_patch_embed", st);
+    VT_TRY(launch_patch_embed(e, images_dev, B, sw, st));
+    const long cthreads = (long)B * (c.hidden_dim / sw) * 32;
+    prof_mark(e, "cls_rows", st);
+    cls_rows_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p,
+                                                                        (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B,
+                                                                        e->N, c.hidden_dim, sw, (__nv_bfloat16*)e->xb_lo.p);
+    CU_TRY(cudaGetLastError());
+    e->launches += 2;
+    return VITB200_OK;
+  }
   const long items = (long)B * 3 * c.image_size * (c.image_size / c.patch_size) * (c.patch_size / 8);
   prof_mark(e, "patchify", st);
   patchify_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(images_dev, (__nv_bfloat16*)e->patches.p, B,
@@ -985,7 +1065,7 @@ vitb200_engine::~vitb200_engine() {
                     &patches_lo, &xb_lo, &qkv_lo, &ctx_lo, &mlp_lo, &cls_ln_lo};
   for (Buffer* b : bufs) release(*b);
   auto fr = [](void* p) { if (p) cudaFree(p); };
-  fr(w_patch_lo), fr(w_head_lo);
+  fr(w_patch_lo), fr(w_head_lo), fr(w_patch_f32);
   fr(w_patch), fr(b_patch), fr(cls_token), fr(pos), fr(lnf_g), fr(lnf_b), fr(w_head), fr(b_head);
   for (auto& l : layers) {
     fr(l.ln1_g), fr(l.ln1_b), fr(l.ln2_g), fr(l.ln2_b), fr(l.w_qkv), fr(l.w_o), fr(l.w_fc1), fr(l.w_fc2);
@@ -1046,6 +1126,10 @@ int vitb200_create(const vitb200_config* cfg, vitb200_engine** out) {
   vitb200_engine* e = new vitb200_engine();
   e->cfg = c;
   e->precise = c.precision == 1;
+  {
+    const char* v = getenv("VITB200_PATCH_TMA");
+    e->patch_tma = v && v[0] == '1';
+  }
   e->n = n, e->N = N, e->D = hd, e->KP = KP, e->pitch = KP, e->patch_k = 3 * c.patch_size * c.patch_size;
   e->layers.resize(c.num_layers);
   {
@@ -1144,6 +1228,12 @@ int vitb200_load_weight(vitb200_engine* e, const char* name, const float* data_h
                                                                                     (__nv_bfloat16*)*slot, (long)count);
     }
     CU_TRY(cudaGetLastError());
+    if (key == "conv_proj.weight") {
+      if (e->w_patch_f32) CU_TRY(cudaFree(e->w_patch_f32));
+      e->w_patch_f32 = nullptr;
+      CU_TRY(cudaMalloc(&e->w_patch_f32, count * 4));
+      CU_TRY(cudaMemcpyAsync(e->w_patch_f32, e->stage_f32.p, count * 4, cudaMemcpyDeviceToDevice, e->stream));
+    }
   }
   CU_TRY(cudaStreamSynchronize(e->stream));
   e->loaded[key] = true;

@@ -969,3 +969,35 @@ def test_engines_on_two_devices_in_one_process(E):
         assert torch.equal(outs[0][k], outs[1][k]), k
     for eng in engs:
         eng.close()
+
+
+def test_patch_embedding_with_tma_im2col(E, monkeypatch):
+    """patch_embed.cuh (opt-in, VITB200_PATCH_TMA=1 when the engine is created): the A operand of the patch-embedding GEMM
+    is loaded straight from the fp32 images by one 5-D tiled TMA load per k-block (no patch matrix in HBM), kind::tf32
+    MMAs.  Against the oracle (closer than the bf16 patch matrix: tf32 keeps 10 mantissa bits), against the default
+    path, run to run, and through a whole forward."""
+    from oracle import vit_oracle as O
+
+    for name, batch in (("vit_small_test", 3), ("vit_b_16", 2), ("vit_577_test", 2)):
+        ocfg = O.ORACLE_CONFIGS[name]
+        model = O.build_vit(ocfg, seed=0, init="stress")
+        x = O.synthetic_images(batch, ocfg.image_size)
+        ref = O.embed(model, x)
+        monkeypatch.setenv("VITB200_PATCH_TMA", "1")
+        eng = _engine_for(E, ocfg, model, batch)
+        monkeypatch.delenv("VITB200_PATCH_TMA")
+        base = _engine_for(E, ocfg, model, batch)
+        eng.stage_embed(x)
+        got = eng.get_tokens(batch).clone()
+        eng.stage_embed(x)
+        assert torch.equal(eng.get_tokens(batch), got)
+        base.stage_embed(x)
+        old = base.get_tokens(batch)
+        assert _rel(got, ref) < 1e-3 and _rel(old, ref) < TOL, (name, _rel(got, ref), _rel(old, ref))
+        assert _rel(got, ref) <= _rel(old, ref)
+        full, want = eng.forward_host(x, NO_HEADS), O.forward_with_maps(model, x)
+        for k in ("logits", "avg_maps", "cls_maps", "rollout", "hidden"):
+            assert _rel(full[k], want[k]) < TOL, (name, k, _rel(full[k], want[k]))
+        assert torch.equal(full["logits"].argmax(-1), want["logits"].argmax(-1))
+        eng.close()
+        base.close()
