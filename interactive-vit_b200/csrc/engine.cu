@@ -610,6 +610,24 @@ struct vitb200_engine {
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   uint64_t submitted = 0;  // tickets are submission indices; slot = ticket % 2
 
+  // Deferred node outputs (vitb200_set_deferred) leave on their own stream: in-stream, the next node's kernels queue behind
+  // the PCIe copies of this node's outputs (three per layer node, ~33 us of a ~75 us layer at batch 1).
+  //   side_ev      main stream -> side stream: "everything enqueued so far has run" (recorded lazily, once per node)
+  //   map_ev[l]    side stream -> main stream: the copies of layer l's maps have left; waited for by the NEXT launch that
+  //                rewrites layer l's maps (the next request)
+  //   tok_ring     the token stream is rewritten in place by the next node: snapshot (D2D) into a small ring, copied out
+  //                from there; tok_ev[k] says slot k's previous copy has left
+  cudaStream_t side = nullptr;
+  cudaEvent_t side_ev = nullptr;
+  bool side_stale = true;                 // kernels were enqueued on the main stream since side_ev was last recorded
+  std::vector<cudaEvent_t> map_ev;        // [L], created on first use
+  std::vector<char> map_busy;
+  static constexpr int kTokRing = 4;
+  Buffer tok_ring[kTokRing];
+  cudaEvent_t tok_ev[kTokRing] = {nullptr, nullptr, nullptr, nullptr};
+  bool tok_busy[kTokRing] = {false, false, false, false};
+  int tok_next = 0;
+
   // Bumped whenever an activation buffer is re-allocated (vitb200_workspace_generation): device-resident state a caller
   // believes the engine still holds (token stream, maps, preprocessed images) is gone, and so is every captured graph.
   uint64_t generation = 1;
@@ -972,6 +990,7 @@ static void clear_graphs(vitb200_engine* e) {
 // re-allocation bumps `generation` and drops every graph).
 template <class Body>
 static int run_graphed(vitb200_engine* e, const vitb200_engine::GraphKey& key, cudaStream_t st, Body&& body) {
+  e->side_stale = true;   // kernels go onto the main stream: the side stream has to follow it again before its next copy
   // (the legacy default stream cannot be captured; profiling needs an event in front of every launch)
   if (!e->use_graphs || e->profiling || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return body();
   if (e->graphs_generation != e->generation) {
@@ -1038,6 +1057,12 @@ static int forward_device_locked(vitb200_engine* e, const float* images_dev, int
   VT_TRY(check_batch(e, B));
   // the layer-strided map buffers are addressed with cap_batch: grow first, then never shrink
   VT_TRY(ensure_workspace(e, B > e->cap_batch ? B : e->cap_batch, flags | e->cap_flags));
+  if (e->side)   // a whole forward rewrites every layer's maps: side-stream copies of node outputs must have left
+    for (int l = 0; l < e->cfg.num_layers; ++l)
+      if (e->map_busy[l]) {
+        CU_TRY(cudaStreamWaitEvent(st, e->map_ev[l], 0));
+        e->map_busy[l] = 0;
+      }
   return run_graphed(e, graph_key(e, kGraphForward, 0, B, flags, images_dev), st,
                      [&] { return forward_stages(e, images_dev, B, flags, st); });
 }
@@ -1082,6 +1107,13 @@ vitb200_engine::~vitb200_engine() {
   }
   if (copy_in) cudaStreamDestroy(copy_in);
   if (copy_out) cudaStreamDestroy(copy_out);
+  if (side) cudaStreamDestroy(side);
+  if (side_ev) cudaEventDestroy(side_ev);
+  for (cudaEvent_t ev : map_ev) if (ev) cudaEventDestroy(ev);
+  for (int k = 0; k < kTokRing; ++k) {
+    if (tok_ev[k]) cudaEventDestroy(tok_ev[k]);
+    release(tok_ring[k]);
+  }
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -1582,10 +1614,50 @@ int vitb200_synchronize(vitb200_engine* e) {
   if (!e) return fail(VITB200_ERR_INVALID, "null engine");
   CU_TRY(cudaSetDevice(e->cfg.device));
   CU_TRY(cudaStreamSynchronize(e->stream));
+  if (e->side) CU_TRY(cudaStreamSynchronize(e->side));
   return VITB200_OK;
 }
 
 uint64_t vitb200_launch_count(vitb200_engine* e) { return e ? e->launches : 0; }
+
+// ---- deferred node outputs on a side stream --------------------------------------------------------
+static constexpr size_t kSideMaxBytes = 32u << 20;   // larger outputs (batched requests) keep the in-stream copy
+
+static int side_ready(vitb200_engine* e) {
+  if (e->side) return VITB200_OK;
+  CU_TRY(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&e->side_ev, cudaEventDisableTiming));
+  e->map_ev.assign(e->cfg.num_layers, nullptr);
+  e->map_busy.assign(e->cfg.num_layers, 0);
+  for (auto& ev : e->map_ev) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (int k = 0; k < vitb200_engine::kTokRing; ++k) CU_TRY(cudaEventCreateWithFlags(&e->tok_ev[k], cudaEventDisableTiming));
+  return VITB200_OK;
+}
+// The side stream may start once everything enqueued on the main stream so far has run (one record + wait per node).
+static int side_follow(vitb200_engine* e, cudaStream_t st) {
+  if (!e->side_stale) return VITB200_OK;
+  CU_TRY(cudaEventRecord(e->side_ev, st));
+  CU_TRY(cudaStreamWaitEvent(e->side, e->side_ev, 0));
+  e->side_stale = false;
+  return VITB200_OK;
+}
+// A launch that rewrites layer l's maps waits for their previous copies (normally the previous request's: long gone).
+static int side_guard_maps(vitb200_engine* e, int layer, cudaStream_t st) {
+  if (e->side && e->map_busy[layer]) {
+    CU_TRY(cudaStreamWaitEvent(st, e->map_ev[layer], 0));
+    e->map_busy[layer] = 0;
+  }
+  return VITB200_OK;
+}
+static int side_copy_map(vitb200_engine* e, int layer, float* dst, const float* src, size_t rows, int width, int pitch,
+                         cudaStream_t st) {
+  VT_TRY(side_ready(e));
+  VT_TRY(side_follow(e, st));
+  VT_TRY(copy_rows_to_host(dst, src, rows, width, pitch, e->side));
+  CU_TRY(cudaEventRecord(e->map_ev[layer], e->side));
+  e->map_busy[layer] = 1;
+  return VITB200_OK;
+}
 
 // ---- node-granular stages --------------------------------------------------------------------------
 #define STAGE_PROLOGUE(B, FLAGS)                                                            \
@@ -1596,6 +1668,7 @@ uint64_t vitb200_launch_count(vitb200_engine* e) { return e ? e->launches : 0; }
   VT_TRY(check_batch(e, (B)));                                                              \
   VT_TRY(ensure_workspace(e, (B) > e->cap_batch ? (B) : e->cap_batch, (FLAGS) | e->cap_flags)); \
   cudaStream_t st = e->stream;
+
 
 int vitb200_set_deferred(vitb200_engine* e, int on) {
   if (!e) return fail(VITB200_ERR_INVALID, "null engine");
@@ -1643,6 +1716,7 @@ int vitb200_stage_embed_resident(vitb200_engine* e, int batch) {
 int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags) {
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)
+  VT_TRY(side_guard_maps(e, layer, st));
   VT_TRY(run_graphed(e, graph_key(e, kGraphLayer, layer, batch, flags, nullptr), st,
                      [&] { return run_layer(e, layer, batch, flags, st); }));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
@@ -1652,6 +1726,7 @@ int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags)
 int vitb200_stage_attn_block(vitb200_engine* e, int layer, int batch, uint32_t flags) {
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)
+  VT_TRY(side_guard_maps(e, layer, st));
   VT_TRY(run_graphed(e, graph_key(e, kGraphAttnBlock, layer, batch, flags, nullptr), st,
                      [&] { return run_attn_block(e, layer, batch, flags, st); }));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
@@ -1703,7 +1778,26 @@ int vitb200_set_tokens(vitb200_engine* e, const float* tokens_host, int batch) {
 int vitb200_get_tokens(vitb200_engine* e, float* tokens_host, int batch) {
   if (!tokens_host) return fail(VITB200_ERR_INVALID, "null tokens");
   STAGE_PROLOGUE(batch, 0)
-  CU_TRY(cudaMemcpyAsync(tokens_host, e->x.p, (size_t)batch * e->N * e->cfg.hidden_dim * 4, cudaMemcpyDeviceToHost, st));
+  const size_t bytes = (size_t)batch * e->N * e->cfg.hidden_dim * 4;
+  if (e->deferred && bytes <= kSideMaxBytes) {
+    // the next node rewrites x in place: snapshot it (a few us on the main stream) and copy the snapshot out on the side
+    VT_TRY(side_ready(e));
+    const int k = e->tok_next;
+    e->tok_next = (k + 1) % vitb200_engine::kTokRing;
+    if (e->tok_busy[k]) {   // the slot's previous copy (four token outputs ago) has left
+      CU_TRY(cudaStreamWaitEvent(st, e->tok_ev[k], 0));
+      e->tok_busy[k] = false;
+    }
+    VT_TRY(ensure(e->tok_ring[k], bytes));
+    CU_TRY(cudaMemcpyAsync(e->tok_ring[k].p, e->x.p, bytes, cudaMemcpyDeviceToDevice, st));
+    e->side_stale = true;
+    VT_TRY(side_follow(e, st));
+    CU_TRY(cudaMemcpyAsync(tokens_host, e->tok_ring[k].p, bytes, cudaMemcpyDeviceToHost, e->side));
+    CU_TRY(cudaEventRecord(e->tok_ev[k], e->side));
+    e->tok_busy[k] = true;
+    return VITB200_OK;
+  }
+  CU_TRY(cudaMemcpyAsync(tokens_host, e->x.p, bytes, cudaMemcpyDeviceToHost, st));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
 }
@@ -1724,6 +1818,8 @@ int vitb200_get_avg_map(vitb200_engine* e, int layer, float* map_host, int batch
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, VITB200_EMIT_AVG)
   const float* src = (const float*)e->avg.p + (size_t)layer * e->cap_batch * e->N * e->pitch;
+  if (e->deferred && (size_t)batch * e->N * e->N * 4 <= kSideMaxBytes)
+    return side_copy_map(e, layer, map_host, src, (size_t)batch * e->N, e->N, e->pitch, st);
   VT_TRY(copy_rows_to_host(map_host, src, (size_t)batch * e->N, e->N, e->pitch, st));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
@@ -1734,6 +1830,8 @@ int vitb200_get_cls_map(vitb200_engine* e, int layer, float* map_host, int batch
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, VITB200_EMIT_CLS)
   const float* src = (const float*)e->cls.p + (size_t)layer * e->cap_batch * e->cfg.num_heads * e->N;
+  if (e->deferred && (size_t)batch * e->cfg.num_heads * e->N * 4 <= kSideMaxBytes)
+    return side_copy_map(e, layer, map_host, src, (size_t)batch * e->cfg.num_heads, e->N, e->N, st);
   CU_TRY(cudaMemcpyAsync(map_host, src, (size_t)batch * e->cfg.num_heads * e->N * 4, cudaMemcpyDeviceToHost, st));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
@@ -1745,6 +1843,8 @@ int vitb200_get_cls_grid(vitb200_engine* e, int layer, float* map_host, int batc
   STAGE_PROLOGUE(batch, VITB200_EMIT_CLS)
   // the class token's attention to the PATCH tokens only: column 0 (class -> class) is dropped by the strided copy
   const float* src = (const float*)e->cls.p + (size_t)layer * e->cap_batch * e->cfg.num_heads * e->N + 1;
+  if (e->deferred && (size_t)batch * e->cfg.num_heads * e->N * 4 <= kSideMaxBytes)
+    return side_copy_map(e, layer, map_host, src, (size_t)batch * e->cfg.num_heads, e->N - 1, e->N, st);
   VT_TRY(copy_rows_to_host(map_host, src, (size_t)batch * e->cfg.num_heads, e->N - 1, e->N, st));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
@@ -1755,6 +1855,8 @@ int vitb200_get_head_map(vitb200_engine* e, int layer, float* map_host, int batc
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, VITB200_EMIT_HEADS)
   const float* src = (const float*)e->heads.p + (size_t)layer * e->cap_batch * e->cfg.num_heads * e->N * e->pitch;
+  if (e->deferred && (size_t)batch * e->cfg.num_heads * e->N * e->N * 4 <= kSideMaxBytes)
+    return side_copy_map(e, layer, map_host, src, (size_t)batch * e->cfg.num_heads * e->N, e->N, e->pitch, st);
   VT_TRY(copy_rows_to_host(map_host, src, (size_t)batch * e->cfg.num_heads * e->N, e->N, e->pitch, st));
   if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
   return VITB200_OK;
