@@ -1806,6 +1806,8 @@ int vitb200_set_avg_map(vitb200_engine* e, int layer, const float* map_host, int
   if (!map_host) return fail(VITB200_ERR_INVALID, "null map");
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, VITB200_EMIT_AVG)
+  VT_TRY(side_guard_maps(e, layer, st));   // a side-stream copy of this layer's map may still be reading it
+  e->side_stale = true;
   float* dst = (float*)e->avg.p + (size_t)layer * e->cap_batch * e->N * e->pitch;
   CU_TRY(cudaMemcpy2DAsync(dst, (size_t)e->pitch * 4, map_host, (size_t)e->N * 4, (size_t)e->N * 4, (size_t)batch * e->N,
                            cudaMemcpyHostToDevice, st));
