@@ -184,6 +184,12 @@ int vitb200_stage_transform(vitb200_engine* e, const float* images_host, int bat
                             float* out_host);
 int vitb200_stage_embed_resident(vitb200_engine* e, int batch);
 int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags);        /* TV:110-119 */
+/* One layer node in one call: vitb200_stage_layer (half == 0) or vitb200_stage_attn_block (half == 1) followed by the
+ * copies of its outputs -- the token stream [batch, tokens, width], the head-averaged map [batch, tokens, tokens] and the
+ * class token's per-head attention to the patch tokens [batch, heads, tokens - 1] (vitb200_get_tokens / _get_avg_map /
+ * _get_cls_grid; any pointer may be NULL).  Saves three calls and their stream bookkeeping per node of a request. */
+int vitb200_stage_layer_fetch(vitb200_engine* e, int layer, int batch, uint32_t flags, int half, float* tokens_host,
+                              float* avg_host, float* cls_grid_host);
 /* The two halves of an EncoderBlock as separate nodes (`<model>:layer.<i>.attn`, `<model>:layer.<i>.mlp`; SURVEY.md
  * section 8f-4, finer-grained graphs): attn = x + out_proj(MHA(LN1 x)) with the maps `flags` ask for (TV:112-116),
  * mlp = x + MLP(LN2 x) (TV:118-119).  stage_attn_block followed by stage_mlp_block is stage_layer, bit for bit. */

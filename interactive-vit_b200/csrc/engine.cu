@@ -1723,6 +1723,59 @@ int vitb200_stage_layer(vitb200_engine* e, int layer, int batch, uint32_t flags)
   return VITB200_OK;
 }
 
+int vitb200_stage_layer_fetch(vitb200_engine* e, int layer, int batch, uint32_t flags, int half, float* tokens_host,
+                              float* avg_host, float* cls_grid_host) {
+  if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
+  if ((avg_host && !(flags & VITB200_EMIT_AVG)) || (cls_grid_host && !(flags & VITB200_EMIT_CLS)))
+    return fail(VITB200_ERR_INVALID, "stage_layer_fetch: a map is requested that the flags do not emit");
+  STAGE_PROLOGUE(batch, flags)
+  VT_TRY(side_guard_maps(e, layer, st));
+  if (half == 0)
+    VT_TRY(run_graphed(e, graph_key(e, kGraphLayer, layer, batch, flags, nullptr), st,
+                       [&] { return run_layer(e, layer, batch, flags, st); }));
+  else
+    VT_TRY(run_graphed(e, graph_key(e, kGraphAttnBlock, layer, batch, flags, nullptr), st,
+                       [&] { return run_attn_block(e, layer, batch, flags, st); }));
+  const int N = e->N, H = e->cfg.num_heads;
+  const size_t tok_bytes = (size_t)batch * N * e->cfg.hidden_dim * 4;
+  const float* avg_src = (const float*)e->avg.p + (size_t)layer * e->cap_batch * N * e->pitch;
+  const float* cls_src = (const float*)e->cls.p + (size_t)layer * e->cap_batch * H * N + 1;
+  if (e->deferred && tok_bytes <= kSideMaxBytes && (size_t)batch * N * N * 4 <= kSideMaxBytes) {
+    // every copy of the node on the side stream behind ONE event (see the getters for the individual steps)
+    VT_TRY(side_ready(e));
+    int k = -1;
+    if (tokens_host) {
+      k = e->tok_next;
+      e->tok_next = (k + 1) % vitb200_engine::kTokRing;
+      if (e->tok_busy[k]) {
+        CU_TRY(cudaStreamWaitEvent(st, e->tok_ev[k], 0));
+        e->tok_busy[k] = false;
+      }
+      VT_TRY(ensure(e->tok_ring[k], tok_bytes));
+      CU_TRY(cudaMemcpyAsync(e->tok_ring[k].p, e->x.p, tok_bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    e->side_stale = true;
+    VT_TRY(side_follow(e, st));
+    if (tokens_host) {
+      CU_TRY(cudaMemcpyAsync(tokens_host, e->tok_ring[k].p, tok_bytes, cudaMemcpyDeviceToHost, e->side));
+      CU_TRY(cudaEventRecord(e->tok_ev[k], e->side));
+      e->tok_busy[k] = true;
+    }
+    if (avg_host) VT_TRY(copy_rows_to_host(avg_host, avg_src, (size_t)batch * N, N, e->pitch, e->side));
+    if (cls_grid_host) VT_TRY(copy_rows_to_host(cls_grid_host, cls_src, (size_t)batch * H, N - 1, N, e->side));
+    if (avg_host || cls_grid_host) {
+      CU_TRY(cudaEventRecord(e->map_ev[layer], e->side));
+      e->map_busy[layer] = 1;
+    }
+    return VITB200_OK;
+  }
+  if (tokens_host) CU_TRY(cudaMemcpyAsync(tokens_host, e->x.p, tok_bytes, cudaMemcpyDeviceToHost, st));
+  if (avg_host) VT_TRY(copy_rows_to_host(avg_host, avg_src, (size_t)batch * N, N, e->pitch, st));
+  if (cls_grid_host) VT_TRY(copy_rows_to_host(cls_grid_host, cls_src, (size_t)batch * H, N - 1, N, st));
+  if (!e->deferred) CU_TRY(cudaStreamSynchronize(st));
+  return VITB200_OK;
+}
+
 int vitb200_stage_attn_block(vitb200_engine* e, int layer, int batch, uint32_t flags) {
   if (e && (layer < 0 || layer >= e->cfg.num_layers)) return fail(VITB200_ERR_INVALID, "layer %d out of range", layer);
   STAGE_PROLOGUE(batch, flags)

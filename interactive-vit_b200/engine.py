@@ -90,6 +90,7 @@ SIGNATURES = {
     "vitb200_stage_transform": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "vitb200_stage_embed_resident": (_I, [_P, _I]),
     "vitb200_stage_layer": (_I, [_P, _I, _I, _U32]),
+    "vitb200_stage_layer_fetch": (_I, [_P, _I, _I, _U32, _I, _P, _P, _P]),
     "vitb200_stage_attn_block": (_I, [_P, _I, _I, _U32]),
     "vitb200_stage_mlp_block": (_I, [_P, _I, _I]),
     "vitb200_stage_head": (_I, [_P, _I, _P]),
@@ -520,6 +521,18 @@ class VitEngine:
 
     def stage_layer(self, layer: int, batch: int, flags: int) -> None:
         check(self.lib.vitb200_stage_layer(self._h, layer, batch, flags))
+
+    def stage_layer_fetch(self, layer: int, batch: int, flags: int, half: bool, tok_shape, map_shape, cls_shape):
+        """A whole layer node -- `stage_layer` (or `stage_attn_block` with `half`) and its three host outputs (token
+        stream, head-averaged map, class-token grid; shapes as in the getters) -- in ONE call into the library."""
+        c = self.cfg
+        tok = self._host_out(batch, c.tokens, c.hidden_dim, final=tok_shape)
+        amap = self._host_out(batch, c.tokens, c.tokens, final=map_shape)
+        cls = self._host_out(batch, c.num_heads, c.tokens - 1, final=cls_shape)
+        status = self.lib.vitb200_stage_layer_fetch(self._h, layer, batch, flags, 1 if half else 0, tok.data_ptr(),
+                                                    amap.data_ptr(), cls.data_ptr())
+        self._checked_out(status, tok)
+        return self._issue(tok, tok_shape), self._issue(amap, map_shape), self._issue(cls, cls_shape)
 
     def stage_attn_block(self, layer: int, batch: int, flags: int = EMIT_AVG | EMIT_CLS) -> None:
         """First half of an EncoderBlock on the resident token stream: x <- x + out_proj(MHA(LN1 x)), maps per `flags`."""

@@ -306,16 +306,25 @@ def make_vit_model_class(ModelBase, PinoutCls):
                     want_heads = params is not None and str(params.get("heads", "0")) == "1"
                     flags = E.EMIT_AVG | E.EMIT_CLS | (E.EMIT_HEADS if want_heads else 0)
                     batch = self._bind_tokens(x, flags)
-                    if kind == "layer":
-                        self.engine.stage_layer(i, batch, flags)
-                    else:
-                        self.engine.stage_attn_block(i, batch, flags)
-                    out.set("o", self._emit_tokens(batch, batched))
                     lead = (batch,) if batched else ()
-                    amap = self.engine.get_avg_map(i, batch, lead + (c.tokens, c.tokens))
+                    if hasattr(self.engine, "stage_layer_fetch"):
+                        # the node and its three output copies in one call into the library
+                        tok, amap, cls = self.engine.stage_layer_fetch(
+                            i, batch, flags, kind != "layer", lead + (c.tokens, c.hidden_dim), lead + (c.tokens, c.tokens),
+                            lead + (c.num_heads, g, g))
+                        self._tokens_out, self._tokens_batch = tok, batch
+                    else:
+                        if kind == "layer":
+                            self.engine.stage_layer(i, batch, flags)
+                        else:
+                            self.engine.stage_attn_block(i, batch, flags)
+                        tok = self._emit_tokens(batch, batched)
+                        amap = self.engine.get_avg_map(i, batch, lead + (c.tokens, c.tokens))
+                        cls = self.engine.get_cls_grid(i, batch, lead + (c.num_heads, g, g))
+                    out.set("o", tok)
                     self._maps_out[i] = (amap, batch)
                     out.set("attn", amap)
-                    out.set("cls", self.engine.get_cls_grid(i, batch, lead + (c.num_heads, g, g)))
+                    out.set("cls", cls)
                     if want_heads:
                         out.set("heads", self.engine.get_head_map(i, batch, lead + (c.num_heads, c.tokens, c.tokens)))
                 elif kind == "head":
