@@ -73,6 +73,12 @@ struct AttnParams {
   // TWO CTAs by heads ([0, H/2) and [H/2, H)) whose head-average tiles are combined with a TMA reduce-add into rows the
   // host zeroed.  512 equal items on 148 SMs otherwise leave 80 SMs idle for the whole last round.
   int full_items;
+  // Small launches (every item split: full_items = 0, up to sms / items parts): `split` parts per item; with more than two
+  // parts a reduce-add would depend on arrival order, so part s stores its share of the head average (already scaled by
+  // 1 / H) into image s * part_images + b of a scratch tensor (tmap_avg then describes the scratch) and
+  // avg_parts_sum_kernel adds the parts in index order.
+  int split = 2;
+  int part_images = 0;   // 0: two parts, reduce-add into avg_map
   int one = 1;          // always 1 (attention_pp.cuh: trip count of its scheduling-fence loops)
 };
 
@@ -160,13 +166,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   const int lane = threadIdx.x & 31;
   int item = blockIdx.x, h0 = 0, nh = p.H;
   bool split_cta = false;
+  int avg_img = 0;   // p.part_images > 0: this part's slab of the head-average scratch starts at image avg_img
   if (item >= p.full_items) {
     const int r = item - p.full_items;
-    item = p.full_items + (r >> 1);
-    const int first = p.H >> 1;
-    h0 = (r & 1) ? first : 0;
-    nh = (r & 1) ? p.H - first : first;
+    const int it = r / p.split, part = r - it * p.split;
+    item = p.full_items + it;
+    h0 = part * p.H / p.split;                 // two parts: [0, H / 2) and [H / 2, H)
+    nh = (part + 1) * p.H / p.split - h0;
     split_cta = true;
+    avg_img = part * p.part_images;
   }
   const int b = item / p.q_tiles;
   const int qt = item - b * p.q_tiles;
@@ -637,8 +645,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
       if (warp == kCtrlWarps && ptx::elect_one()) {
         const int nslabs = (KP + 31) >> 5;
         for (int j = 0; j < nslabs; ++j) {
-          if (split_cta) ptx::tma_reduce_add_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, b);
-          else ptx::tma_store_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, b);
+          if (split_cta && p.part_images == 0) ptx::tma_reduce_add_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, b);
+          else ptx::tma_store_3d(&tmap_avg, smem + j * (BM * 128), 32 * j, qt * BM, avg_img + b);
         }
         ptx::tma_store_commit();
       }

@@ -125,13 +125,15 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
   const int lane = threadIdx.x & 31;
   int item = blockIdx.x, h0 = 0, nh = p.H;
   bool split_cta = false;
+  int avg_img = 0;   // p.part_images > 0: this part's slab of the head-average scratch starts at image avg_img
   if (item >= p.full_items) {
     const int r = item - p.full_items;
-    item = p.full_items + (r >> 1);
-    const int first = p.H >> 1;
-    h0 = (r & 1) ? first : 0;
-    nh = (r & 1) ? p.H - first : first;
+    const int it = r / p.split, part = r - it * p.split;
+    item = p.full_items + it;
+    h0 = part * p.H / p.split;                 // two parts: [0, H / 2) and [H / 2, H)
+    nh = (part + 1) * p.H / p.split - h0;
     split_cta = true;
+    avg_img = part * p.part_images;
   }
   const int b = item / p.q_tiles;
   const int qt = item - b * p.q_tiles;
@@ -613,8 +615,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
       if (warp == kCtrlWarps && ptx::elect_one()) {
         constexpr int nslabs = (KP + 31) >> 5;
         for (int s = 0; s < nslabs; ++s) {
-          if (split_cta) ptx::tma_reduce_add_3d(&tmap_avg, smem + s * (BM * 128), 32 * s, qt * BM, b);
-          else ptx::tma_store_3d(&tmap_avg, smem + s * (BM * 128), 32 * s, qt * BM, b);
+          if (split_cta && p.part_images == 0) ptx::tma_reduce_add_3d(&tmap_avg, smem + s * (BM * 128), 32 * s, qt * BM, b);
+          else ptx::tma_store_3d(&tmap_avg, smem + s * (BM * 128), 32 * s, qt * BM, avg_img + b);
         }
         ptx::tma_store_commit();
       }

@@ -176,6 +176,8 @@ struct DeviceCtx {
   float2* op_stats = nullptr;              // scratch of the single-kernel attention entry point (parity tests)
   void* op_qkv = nullptr;                  // ... and its fp16-V copy of the input
   size_t op_qkv_cap = 0;
+  void* op_parts = nullptr;                // ... and the head-average scratch of its head-split small launches
+  size_t op_parts_cap = 0;
   size_t op_stats_cap = 0;
 };
 static std::mutex g_dev_mu;
@@ -474,9 +476,16 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
 static int attention_pitch(int N) { return (N + 15) / 16 * 16; }
 static bool attention_is_fused(int N, int D) { return D == 64 && (N + 15) / 16 * 16 <= attn_cfg::KP_MAX; }
 
+// Images of head-average scratch a small launch can need (launch_attention: parts x batch <= SMs / query tiles).
+static size_t attention_parts_bytes(int N, int pitch) {
+  const int q_tiles = (N + attn_cfg::BM - 1) / attn_cfg::BM;
+  return (size_t)(device_sms() / q_tiles) * N * pitch * sizeof(float);
+}
+
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float* avg, float* cls, float* heads, int B,
                             int N, int H, int D, int pitch, float2* stats, cudaStream_t st,
-                            const __nv_bfloat16* qkv_lo = nullptr, __nv_bfloat16* ctx_lo = nullptr) {
+                            const __nv_bfloat16* qkv_lo = nullptr, __nv_bfloat16* ctx_lo = nullptr,
+                            float* parts = nullptr /* attention_parts_bytes() of scratch, or none */) {
   using namespace attn_cfg;
   if (qkv_lo != nullptr || !attention_is_fused(N, D))
     return launch_attention_long(qkv, ctx, avg, cls, heads, B, N, H, D, pitch, stats, st, qkv_lo, ctx_lo);
@@ -501,17 +510,25 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   // Tail balancing (see AttnParams::full_items): the items of a last, at most half-full round are split by heads.
   const int items = B * p.q_tiles, sms = device_sms();
   const int rem = items % sms;
-  static int split_mode = -1;
-  if (split_mode < 0) {
-    const char* v = getenv("VITB200_ATTN_SPLIT");
-    split_mode = (v && v[0] == '0') ? 0 : 1;
-  }
+  // VITB200_ATTN_SPLIT: 0 = never split an item, 2 = two parts at most (read at every launch: the parity tests compare the
+  // variants in one process)
+  const char* split_env = getenv("VITB200_ATTN_SPLIT");
+  const int split_mode = (split_env && split_env[0] == '0') ? 0 : (split_env && split_env[0] == '2') ? 2 : 1;
   p.full_items = items;
-  // (also when the whole launch is such a round: up to sms / 2 items -- small batches, the single-image request path --
-  // run on twice the SMs.  Two-way only: a + b is commutative, so the reduce-add stays bit-reproducible.)
-  if (split_mode && H >= 2 && rem > 0 && 2 * rem <= sms) p.full_items = items - rem;
-  const int grid = p.full_items + 2 * (items - p.full_items);
-  if (avg && p.full_items < items) {
+  // Small launches (the single-image request, batches up to ~24): every item split over up to H CTAs by heads, so that a
+  // request's attention is not 6 heads in sequence on 4 of 148 SMs.  The parts' head averages go to scratch slabs and
+  // avg_parts_sum_kernel adds them in index order (a reduce-add of more than two parts would not be reproducible).
+  const int S = (split_mode == 1 && (parts || !avg)) ? std::min(H, sms / items) : 1;
+  if (S >= 3) {
+    p.full_items = 0, p.split = S, p.part_images = avg ? B : 0;
+    if (avg) VT_TRY(make_tmap_f32_3d(&tavg, parts, (uint64_t)S * B, N, pitch, pitch, BM));
+  } else if (split_mode && H >= 2 && rem > 0 && 2 * rem <= sms) {
+    // (also when the whole launch is such a round: up to sms / 2 items run on twice the SMs.  Two parts: a + b is
+    // commutative, so the reduce-add into the zeroed rows stays bit-reproducible.)
+    p.full_items = items - rem;
+  }
+  const int grid = p.full_items + p.split * (items - p.full_items);
+  if (avg && p.full_items < items && p.part_images == 0) {
     // the split CTAs reduce-add their halves of the head average: zero the images they touch first (a full CTA of
     // the first such image simply stores over the zeros)
     const int b0 = p.full_items / p.q_tiles;
@@ -533,6 +550,11 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   else if (KP == KP_MAX && full_mode) attention_kernel<false, true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   else attention_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
   CU_TRY(cudaGetLastError());
+  if (avg && p.part_images > 0) {
+    const long n4 = (long)B * N * pitch / 4;
+    avg_parts_sum_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)parts, (float4*)avg, n4, S);
+    CU_TRY(cudaGetLastError());
+  }
   return VITB200_OK;
 }
 
@@ -583,7 +605,7 @@ struct vitb200_engine {
   // activations (sized for cap_batch images)
   int cap_batch = 0;
   uint32_t cap_flags = 0;
-  Buffer images, patches, x, xb, ln_stats, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats;
+  Buffer images, patches, x, xb, ln_stats, qkv, ctx, mlp, cls_ln, logits, avg, cls, heads, hidden, rollout, attn_stats, avg_parts;
   Buffer patches_lo, xb_lo, qkv_lo, ctx_lo, mlp_lo, cls_ln_lo;  // fp32x3 mode: low halves of the bf16 operands
 
   // vitb200_bind_outputs: caller-owned destinations of the small results (typically slices of rank 0's receive
@@ -699,6 +721,7 @@ static int ensure_workspace(vitb200_engine* e, int B, uint32_t flags) {
   VT_TRY(ensure(e->qkv, M * 3 * c.hidden_dim * 2));
   VT_TRY(ensure(e->ctx, M * c.hidden_dim * 2));
   if (e->precise || !attention_is_fused(e->N, e->D)) VT_TRY(ensure(e->attn_stats, M * c.num_heads * sizeof(float2)));
+  else VT_TRY(ensure(e->avg_parts, attention_parts_bytes(e->N, e->pitch)));   // head-split small launches (launch_attention)
   if (e->precise) {
     VT_TRY(ensure(e->patches_lo, (size_t)B * e->n * e->patch_k * 2));
     VT_TRY(ensure(e->xb_lo, M * c.hidden_dim * 2));
@@ -856,7 +879,7 @@ static int run_attn_block(vitb200_engine* e, int l, int B, uint32_t flags, cudaS
   prof_mark(e, "attention", st);
   VT_TRY(launch_attention((const __nv_bfloat16*)e->qkv.p, (__nv_bfloat16*)e->ctx.p, avg, cls, hm, B, e->N, c.num_heads,
                           e->D, e->pitch, (float2*)e->attn_stats.p, st, (const __nv_bfloat16*)e->qkv_lo.p,
-                          (__nv_bfloat16*)e->ctx_lo.p));
+                          (__nv_bfloat16*)e->ctx_lo.p, (float*)e->avg_parts.p));
   {
     GemmEpilogue ep;
     prof_mark(e, "gemm_out_proj", st);
@@ -927,6 +950,27 @@ static int launch_rollout(const float* maps, long layer_stride, int L, int B, in
   if (N > kRolloutThreads * kRolloutMaxCols) return fail(VITB200_ERR_INVALID, "rollout: at most %d tokens", kRolloutThreads * kRolloutMaxCols);
   if (ld % 4 != 0 || ld < N) return fail(VITB200_ERR_INVALID, "rollout: pitch %d must be >= %d and a multiple of 4", ld, N);
   int stages = 8;
+  // Small batches: a cluster of C CTAs per image (rollout_cluster_kernel), so that a single-image request or a 16-image
+  // ViT-H batch does not run its rollout on 1 / 16 of 148 SMs.  VITB200_ROLLOUT_CLUSTER=0 keeps one CTA per image.
+  static const int cluster_mode = [] {
+    const char* v = getenv("VITB200_ROLLOUT_CLUSTER");
+    return (v && v[0] == '0') ? 0 : 1;
+  }();
+  int C = 1;
+  if (cluster_mode) while (C < kRolloutMaxCluster && 2 * C * B <= device_sms()) C *= 2;
+  if (C > 1) {
+    while (stages > 2 && rollout_cluster_smem_bytes(ld, stages, C) > 110 * 1024) --stages;
+    const int smem = rollout_cluster_smem_bytes(ld, stages, C);
+    VT_TRY(ensure_func_smem((const void*)rollout_cluster_kernel, smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * C), cfg.blockDim = dim3(kRolloutThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    CU_TRY(cudaLaunchKernelEx(&cfg, rollout_cluster_kernel, maps, layer_stride, L, N, ld, stages, C, out));
+    return VITB200_OK;
+  }
   while (stages > 2 && rollout_smem_bytes(ld, stages) > 110 * 1024) --stages;
   const int smem = rollout_smem_bytes(ld, stages);
   VT_TRY(ensure_func_smem((const void*)rollout_cls_kernel, smem));
@@ -1086,7 +1130,7 @@ static int copy_rows_to_host(float* dst, const float* src_dev, size_t rows, int 
 
 vitb200_engine::~vitb200_engine() {
   clear_graphs(this);
-  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats,
+  Buffer* bufs[] = {&stage_f32, &images, &patches, &x, &xb, &ln_stats, &qkv, &ctx, &mlp, &cls_ln, &logits, &avg, &cls, &heads, &hidden, &rollout, &attn_stats, &avg_parts,
                     &patches_lo, &xb_lo, &qkv_lo, &ctx_lo, &mlp_lo, &cls_ln_lo};
   for (Buffer* b : bufs) release(*b);
   auto fr = [](void* p) { if (p) cudaFree(p); };
@@ -2027,8 +2071,20 @@ int vitb200_op_attention_ex(const void* qkv, void* ctx, float* avg, float* cls, 
     CU_TRY(cudaGetLastError());
     qkv = tmp;
   }
+  float* parts = nullptr;
+  if (fused && avg) {   // scratch of the head-split small launches (grown on demand; without it they split two ways at most)
+    const size_t bytes = attention_parts_bytes(tokens, pitch);
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    DeviceCtx& dc = dev_ctx_locked();
+    if (bytes > dc.op_parts_cap) {
+      if (dc.op_parts) cudaFree(dc.op_parts);
+      dc.op_parts = nullptr, dc.op_parts_cap = 0;
+      if (cudaMalloc(&dc.op_parts, bytes) == cudaSuccess) dc.op_parts_cap = bytes;
+    }
+    parts = (float*)dc.op_parts;
+  }
   return launch_attention((const __nv_bfloat16*)qkv, (__nv_bfloat16*)ctx, avg, cls, heads, batch, tokens, nheads, head_dim,
-                          pitch, stats, (cudaStream_t)stream);
+                          pitch, stats, (cudaStream_t)stream, nullptr, nullptr, parts);
 }
 
 int vitb200_op_attention(const void* qkv, void* ctx, float* avg, float* cls, float* heads, int batch, int tokens,

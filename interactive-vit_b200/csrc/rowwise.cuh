@@ -490,4 +490,217 @@ rollout_cls_kernel(const float* __restrict__ maps, long layer_stride, int L, int
   for (int j = tid + 1; j < N; j += kRolloutThreads) out[static_cast<long>(b) * (N - 1) + j - 1] = r[j];
 }
 
+
+// Class-token rollout for SMALL batches: the same recurrence as rollout_cls_kernel, one thread-block CLUSTER of C CTAs
+// per image instead of one CTA (a single-image request ran 12 layers x 13 chunks serially on ONE of 148 SMs: 135 us of a
+// 0.92 ms forward; ViT-H at batch 16: 1.3 ms of an 18 ms step on 16 SMs).  CTA `rank` streams the 16-row chunks
+// rank, rank + C, ... of every layer; at the end of a layer each CTA pushes its partial product vector and the w_k of its
+// rows into every peer's shared memory (DSMEM stores), one cluster barrier, and every CTA forms the same
+//     r[j] = 0.5 * (part_0[j] + part_1[j] + ... + part_{C-1}[j]) + 0.5 * w[j]
+// in the same order: bit-reproducible for a given C.  (C depends on the batch size, so the last bits of a rollout differ
+// between batch sizes -- as they already do through the head-averaged maps' split CTAs; see test_bench_size_properties.)
+// Exchange buffers alternate with the layer parity, so one barrier per layer suffices: a CTA can only push layer l - 2's
+// values after barrier l - 1, which every peer enters after it has read layer l's.
+constexpr int kRolloutMaxCluster = 8;
+__host__ __device__ inline int rollout_cluster_smem_bytes(int ld, int stages, int C) {
+  return stages * rollout_stage_bytes(ld) + (1 + 2) * kRolloutMaxCols * kRolloutThreads * 4 /* r, w x 2 */ + kRolloutRows * 4 + 16 * 8 +
+         4 * ld * 4 /* group partials */ + 2 * C * ld * 4 /* peers' partial vectors x 2 */;
+}
+
+__device__ __forceinline__ void st_cluster_f32(float* local_ptr, uint32_t cta, float v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tst.shared::cluster.f32 [ra], %2;\n\t}" ::"r"(
+          static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr))),
+      "r"(cta), "f"(v)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kRolloutThreads)
+rollout_cluster_kernel(const float* __restrict__ maps, long layer_stride, int L, int N, int ld, int stages, int C,
+                       float* __restrict__ out /*[B, N-1]*/) {
+  extern __shared__ __align__(128) uint8_t rsm[];
+  const int stage_bytes = rollout_stage_bytes(ld);
+  constexpr int kVec = kRolloutMaxCols * kRolloutThreads;
+  float* r = reinterpret_cast<float*>(rsm + stages * stage_bytes);   // current row vector
+  float* w2 = r + kVec;                                               // [2 parities][kVec] r_k / rowsum_k of the layer
+  float* wchunk = w2 + 2 * kVec;                                      // the stage's w_k
+  uint64_t* full = reinterpret_cast<uint64_t*>(wchunk + kRolloutRows);
+  float4* scratch = reinterpret_cast<float4*>(wchunk + kRolloutRows + 32);   // [4 row groups][ld] partial products
+  float* xpart = reinterpret_cast<float*>(scratch) + 4 * ld;                 // [2 parities][C][ld] every CTA's partial vector
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int b = blockIdx.x / C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunks_per_layer = (N + kRolloutRows - 1) / kRolloutRows;
+  const int ld4 = ld >> 2;
+  const float* img = maps + static_cast<long>(b) * N * ld;
+  // chunks of a layer that belong to this CTA: rank, rank + C, ... (the top layer has one chunk -- row 0 -- owned by rank 0)
+  auto owned = [&](int layer) {
+    if (layer == L - 1) return rank == 0 ? 1 : 0;
+    return chunks_per_layer > static_cast<int>(rank) ? (chunks_per_layer - static_cast<int>(rank) + C - 1) / C : 0;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&full[s]));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = tid; j < kVec; j += kRolloutThreads) r[j] = (j == 0) ? 1.0f : 0.0f, w2[j] = 0.0f, w2[kVec + j] = 0.0f;
+  __syncthreads();
+  ptx::cluster_sync();   // every CTA's exchange buffers exist before the first remote store
+
+  // producer cursor (thread 0): (layer, i-th owned chunk)
+  int p_layer = L - 1, p_i = 0, p_stage = 0;
+  auto p_skip = [&]() { while (p_layer >= 0 && p_i >= owned(p_layer)) --p_layer, p_i = 0; };
+  auto issue = [&]() {
+    const int chunk = (p_layer == L - 1) ? 0 : static_cast<int>(rank) + p_i * C;
+    const int row0 = chunk * kRolloutRows;
+    const int rows = (p_layer == L - 1) ? 1 : min(kRolloutRows, N - row0);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ld * 4;
+    const float* src = img + p_layer * layer_stride + static_cast<long>(row0) * ld;
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&full[p_stage]));
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(rsm + p_stage * stage_bytes));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+    ++p_i;
+    if (++p_stage == stages) p_stage = 0;
+  };
+  if (tid == 0) {
+    p_skip();
+    for (int q = 0; q < stages && p_layer >= 0; ++q) issue(), p_skip();
+  }
+
+  float4 acc4[kRolloutMaxCols];
+  const int g = tid >> 6, t = tid & 63;   // accumulate pass: row group, float4 column
+  int c_stage = 0;
+  uint32_t c_parity = 0;
+  for (int layer = L - 1; layer >= 0; --layer) {
+    const int par = layer & 1;
+    float* w = w2 + par * kVec;
+#pragma unroll
+    for (int i = 0; i < kRolloutMaxCols; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int mine = owned(layer);
+    for (int ci = 0; ci < mine; ++ci) {
+      const int chunk = (layer == L - 1) ? 0 : static_cast<int>(rank) + ci * C;
+      const int row0 = chunk * kRolloutRows;
+      const int rows = (layer == L - 1) ? 1 : min(kRolloutRows, N - row0);
+      const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&full[c_stage]));
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(c_parity)
+            : "memory");
+      }
+      const float* A = reinterpret_cast<const float*>(rsm + c_stage * stage_bytes);
+      // row sums -> w_k = r_k / (0.5 * rowsum_k + 0.5), as in rollout_cls_kernel; w_k also goes to every peer
+      {
+        const int k0 = warp, k1 = warp + kRolloutThreads / 32;
+        const float4* rowa = reinterpret_cast<const float4*>(A + k0 * ld);
+        const float4* rowb = reinterpret_cast<const float4*>(A + k1 * ld);
+        const bool has_b = k1 < rows;
+        float sa = 0.f, sb = 0.f;
+        if (k0 < rows) {
+          for (int c = lane; c < ld4; c += 32) {
+            float4 va = rowa[c];
+            float4 vb = has_b ? rowb[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int j = 4 * c;
+            if (j + 3 >= N) {
+              if (j >= N) va.x = 0.f, vb.x = 0.f;
+              if (j + 1 >= N) va.y = 0.f, vb.y = 0.f;
+              if (j + 2 >= N) va.z = 0.f, vb.z = 0.f;
+              va.w = 0.f, vb.w = 0.f;
+            }
+            sa += (va.x + va.y) + (va.z + va.w);
+            sb += (vb.x + vb.y) + (vb.z + vb.w);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+          }
+          const float wk0 = __fdividef(r[row0 + k0], 0.5f * sa + 0.5f);
+          const float wk1 = has_b ? __fdividef(r[row0 + k1], 0.5f * sb + 0.5f) : 0.f;
+          if (lane == 0) wchunk[k0] = wk0;
+          if (lane == 0 && has_b) wchunk[k1] = wk1;
+          if (lane < C) {   // lane c stores into CTA c (its own included)
+            st_cluster_f32(&w[row0 + k0], static_cast<uint32_t>(lane), wk0);
+            if (has_b) st_cluster_f32(&w[row0 + k1], static_cast<uint32_t>(lane), wk1);
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kRolloutMaxCols; ++i) {
+        const int c4 = t + 64 * i;
+        if (c4 < ld4) {
+          float4 a = acc4[i];
+#pragma unroll
+          for (int kk = 0; kk < kRolloutRows / 4; ++kk) {
+            const int k = g + 4 * kk;
+            if (k < rows) {
+              const float wk = wchunk[k];
+              const float4 v = reinterpret_cast<const float4*>(A + k * ld)[c4];
+              a.x = fmaf(wk, v.x, a.x), a.y = fmaf(wk, v.y, a.y), a.z = fmaf(wk, v.z, a.z), a.w = fmaf(wk, v.w, a.w);
+            }
+          }
+          acc4[i] = a;
+        }
+      }
+      __syncthreads();  // the stage and wchunk are free again
+      if (tid == 0 && p_layer >= 0) issue(), p_skip();
+      if (++c_stage == stages) c_stage = 0, c_parity ^= 1;
+    }
+    // ---- end of the layer: this CTA's partial product (four row groups, fixed order) -> every CTA
+#pragma unroll
+    for (int i = 0; i < kRolloutMaxCols; ++i) {
+      const int c4 = t + 64 * i;
+      if (c4 < ld4) scratch[g * ld4 + c4] = acc4[i];
+    }
+    __syncthreads();
+    {
+      const float* sc = reinterpret_cast<const float*>(scratch);
+      float* mine_part = xpart + (par * C + static_cast<int>(rank)) * ld;   // slot `rank` of parity `par`, in every CTA
+      for (int j = tid; j < N; j += kRolloutThreads) {
+        const float a = (sc[j] + sc[ld + j]) + (sc[2 * ld + j] + sc[3 * ld + j]);
+        for (int c = 0; c < C; ++c) st_cluster_f32(&mine_part[j], static_cast<uint32_t>(c), a);
+      }
+    }
+    ptx::cluster_sync();   // release / acquire: every CTA's partials and w_k of this layer are visible everywhere
+    {
+      const float* parts = xpart + par * C * ld;
+      for (int j = tid; j < N; j += kRolloutThreads) {
+        float a = parts[j];
+        for (int c = 1; c < C; ++c) a += parts[c * ld + j];
+        r[j] = 0.5f * a + 0.5f * w[j];
+      }
+    }
+    __syncthreads();
+    // (rows the top layer does not touch keep w = 0 in both parity buffers; every later layer rewrites all N rows)
+  }
+  if (rank == 0)
+    for (int j = tid + 1; j < N; j += kRolloutThreads) out[static_cast<long>(b) * (N - 1) + j - 1] = r[j];
+  ptx::cluster_sync();   // no CTA leaves while a peer may still address its shared memory
+}
+
+
+// Head-average maps of a small launch whose (image, query tile) items were split over S > 2 CTAs by heads
+// (attention.cuh AttnParams::split): avg = ((part_0 + part_1) + part_2) + ..., always in index order -- bit-reproducible,
+// which a reduce-add by more than two CTAs is not.  parts: [S][n4] float4, avg: [n4].
+__global__ void __launch_bounds__(256)
+avg_parts_sum_kernel(const float4* __restrict__ parts, float4* __restrict__ avg, long n4, int S) {
+  const long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = parts[i];
+  for (int s = 1; s < S; ++s) {
+    const float4 v = parts[s * n4 + i];
+    a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+  }
+  avg[i] = a;
+}
+
 }  // namespace vitb200

@@ -244,6 +244,35 @@ def test_attention_two_heads_in_flight(E, B, N, H, scale):
     assert torch.equal(ctx, ctx3) and torch.equal(avg, avg3) and torch.equal(cls, cls3)
 
 
+@pytest.mark.parametrize("B,N,H,heads", [(1, 197, 12, False), (1, 197, 12, True), (2, 197, 6, False), (5, 197, 16, False),
+                                         (8, 197, 12, False), (3, 100, 5, False), (24, 197, 12, False), (1, 197, 3, False)])
+def test_attention_head_split_of_small_launches(E, B, N, H, heads):
+    """Launches with at most a third of the SMs' worth of (image, query tile) items split every item over up to H CTAs
+    by heads (engine.cu launch_attention); the parts of the head average meet in index order (avg_parts_sum_kernel).
+    Context, class-token rows and per-head maps must not depend on the split at all, the head average only through
+    the order of its fp32 sum; every variant is bit-reproducible."""
+    torch.manual_seed(B * 100 + H)
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda").bfloat16()
+    outs = {}
+    for mode in ("0", "2", "1"):
+        os.environ["VITB200_ATTN_SPLIT"] = mode
+        try:
+            outs[mode] = E.op_attention(qkv, B, N, H, True, True, heads)
+            again = E.op_attention(qkv, B, N, H, True, True, heads)
+        finally:
+            del os.environ["VITB200_ATTN_SPLIT"]
+        for a, b in zip(outs[mode], again):
+            assert (a is None and b is None) or torch.equal(a, b)
+    ctx0, avg0, cls0, hm0 = outs["0"]
+    _, p = _attn_ref(qkv, B, N, H)
+    for mode in ("2", "1"):
+        ctx, avg, cls, hm = outs[mode]
+        assert torch.equal(ctx, ctx0) and torch.equal(cls, cls0)
+        assert (hm is None and hm0 is None) or torch.equal(hm, hm0)
+        assert (avg - avg0).abs().max() < 1e-6
+        assert _rel(avg, p.mean(1)) < BF16_EPS
+
+
 @pytest.mark.parametrize("B,N,H,D,scale", [(2, 577, 12, 64, 1.0), (2, 577, 16, 80, 1.0), (1, 257, 4, 80, 2.0),
                                            (3, 197, 6, 80, 1.0), (1, 300, 2, 96, 1.0), (1, 129, 2, 128, 1.0),
                                            (2, 209, 3, 64, 3.0), (1, 768, 1, 64, 1.0)])
@@ -276,15 +305,21 @@ def test_attention_masks_padded_keys(E):
     assert torch.equal(ctx_a[:N], ctx_b[:N]) and torch.equal(avg_a[0], avg_b[0])
 
 
-def test_rollout(E):
+# Batch sizes on either side of the cluster switch (engine.cu launch_rollout: clusters of 8 / 4 / 2 CTAs per image up to
+# 74 images on 148 SMs, one CTA per image beyond), both token counts, pad columns poisoned.
+@pytest.mark.parametrize("L,B,N,pitch", [(5, 3, 197, 208), (12, 1, 197, 208), (4, 1, 577, 592), (3, 20, 197, 208),
+                                         (3, 40, 50, 64), (2, 80, 197, 208), (1, 2, 197, 208), (6, 2, 17, 32)])
+def test_rollout(E, L, B, N, pitch):
     from oracle.vit_oracle import rollout_from_avg
 
-    L, B, N, pitch = 5, 3, 197, 208
     torch.manual_seed(2)
     p = torch.softmax(torch.randn(L, B, N, N) * 2, dim=-1)
-    padded = torch.zeros(L, B, N, pitch)
+    padded = torch.full((L, B, N, pitch), float("nan"))
     padded[..., :N] = p
-    got = E.op_rollout(padded.cuda()).cpu()
+    dev = padded.cuda()
+    got = E.op_rollout(dev).cpu()
     ref = rollout_from_avg(list(p))
+    assert torch.isfinite(got).all()
     assert _rel(got, ref) < 1e-5
-    assert (got.sum(-1) + rollout_from_avg(list(p)).new_zeros(B) - ref.sum(-1)).abs().max() < 1e-5
+    assert (got.sum(-1) - ref.sum(-1)).abs().max() < 1e-5
+    assert torch.equal(E.op_rollout(dev).cpu(), got)      # fixed summation order: bit-reproducible
