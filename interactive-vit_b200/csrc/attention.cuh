@@ -230,6 +230,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 128 o
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();   // PDL (ptx.cuh): prologue above overlaps the previous kernel; nothing below runs before it has completed
+  ptx::grid_dep_wait();
 
   const int row0 = b * p.N;  // first token row of this image in the [B*N, 3d] activation
 

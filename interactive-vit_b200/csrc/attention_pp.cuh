@@ -186,6 +186,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmap_q,   // box 64 x 12
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();   // PDL (ptx.cuh): prologue above overlaps the previous kernel; nothing below runs before it has completed
+  ptx::grid_dep_wait();
   const int row0 = b * p.N;
 
   // Context epilogue of one TMEM lane quarter (control role q reads lanes 32 q .. 32 q + 31): O of head hh is final

@@ -200,6 +200,32 @@ static int device_sms() {
   return dev_ctx_locked().sms;
 }
 
+// Programmatic dependent launch (ptx.cuh grid_dep_wait): kernels of the forward are launched so that their prologue may
+// overlap the tail of the previous kernel of the stream.  VITB200_PDL=0 launches them fully serialised (A/B switch;
+// read once).  Only kernels that execute grid_dep_wait() before touching global memory may go through launch_pdl.
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("VITB200_PDL");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_if(bool allow, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = (allow && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_pdl_if(true, kern, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+
 // Raise the dynamic shared-memory limit of `kern` on the CURRENT device (once per device and kernel).
 static int ensure_func_smem(const void* kern, int bytes) {
   std::lock_guard<std::mutex> lock(g_dev_mu);
@@ -229,13 +255,15 @@ static int launch_gemm_t(const CUtensorMap* maps, GemmShape sh, const GemmEpilog
   cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kClusterCtas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   // persistent: one CTA / pair / 4-CTA cluster per scheduler slot; the slots are what the device can co-schedule
   // (4-CTA clusters do not tile every GPC: 148 SMs hold fewer than 37 of them)
   VT_TRY(ensure_func_smem(reinterpret_cast<const void*>(kern), C::kSmemBytes));
@@ -380,7 +408,7 @@ static int launch_layernorm(const float* x, long in_stride, const float* g, cons
   const int blocks = (rows + 7) / 8;  // 8 warps (rows) per 256-thread block
 #define VT_LN_CASE(V)                                                                                \
   case V:                                                                                            \
-    layernorm_f32_bf16_kernel<V><<<blocks, 256, 0, st>>>(x, in_stride, g, b, y, rows, eps, y_lo);    \
+    CU_TRY(launch_pdl(layernorm_f32_bf16_kernel<V>, dim3(blocks), dim3(256), 0, st, x, in_stride, g, b, y, rows, eps, y_lo)); \
     break;
   switch (d / 128) {
     VT_LN_CASE(1) VT_LN_CASE(2) VT_LN_CASE(3) VT_LN_CASE(4) VT_LN_CASE(5) VT_LN_CASE(6) VT_LN_CASE(8) VT_LN_CASE(10)
@@ -518,7 +546,7 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   // Small launches (the single-image request, batches up to ~24): every item split over up to H CTAs by heads, so that a
   // request's attention is not 6 heads in sequence on 4 of 148 SMs.  The parts' head averages go to scratch slabs and
   // avg_parts_sum_kernel adds them in index order (a reduce-add of more than two parts would not be reproducible).
-  const int S = (split_mode == 1 && (parts || !avg)) ? std::min(H, sms / items) : 1;
+  const int S = (split_mode == 1 && (parts || !avg)) ? std::min(std::min(H, kAvgPartsMax), sms / items) : 1;
   if (S >= 3) {
     p.full_items = 0, p.split = S, p.part_images = avg ? B : 0;
     if (avg) VT_TRY(make_tmap_f32_3d(&tavg, parts, (uint64_t)S * B, N, pitch, pitch, BM));
@@ -528,7 +556,9 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
     p.full_items = items - rem;
   }
   const int grid = p.full_items + p.split * (items - p.full_items);
+  bool after_kernel = true;   // the launch directly follows a kernel in the stream (PDL) -- not when a memset sits between
   if (avg && p.full_items < items && p.part_images == 0) {
+    after_kernel = false;
     // the split CTAs reduce-add their halves of the head average: zero the images they touch first (a full CTA of
     // the first such image simply stores over the zeros)
     const int b0 = p.full_items / p.q_tiles;
@@ -545,15 +575,13 @@ static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, float*
   const bool pp_mode = !(pp_env && pp_env[0] == '0');
   if (!heads && pp_mode && KP == KP_MAX && N >= attn_pp_cfg::kMinTokens && N <= attn_pp_cfg::kMaxTokens) {
     VT_TRY(ensure_func_smem((const void*)attention_pp_kernel, attn_pp_cfg::kSmemBytesPP));
-    attention_pp_kernel<<<grid, kThreads, attn_pp_cfg::kSmemBytesPP, st>>>(tq, tkv, tctx, tavg, p);
-  } else if (heads) attention_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
-  else if (KP == KP_MAX && full_mode) attention_kernel<false, true><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
-  else attention_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tctx, tavg, p);
-  CU_TRY(cudaGetLastError());
+    CU_TRY(launch_pdl_if(after_kernel, attention_pp_kernel, dim3(grid), dim3(kThreads), attn_pp_cfg::kSmemBytesPP, st, tq, tkv, tctx, tavg, p));
+  } else if (heads) CU_TRY(launch_pdl_if(after_kernel, attention_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, st, tq, tkv, tctx, tavg, p));
+  else if (KP == KP_MAX && full_mode) CU_TRY(launch_pdl_if(after_kernel, attention_kernel<false, true>, dim3(grid), dim3(kThreads), kSmemBytes, st, tq, tkv, tctx, tavg, p));
+  else CU_TRY(launch_pdl_if(after_kernel, attention_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, st, tq, tkv, tctx, tavg, p));
   if (avg && p.part_images > 0) {
     const long n4 = (long)B * N * pitch / 4;
-    avg_parts_sum_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)parts, (float4*)avg, n4, S);
-    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_pdl(avg_parts_sum_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, (const float4*)parts, (float4*)avg, n4, S));
   }
   return VITB200_OK;
 }
@@ -813,10 +841,9 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
     VT_TRY(launch_patch_embed(e, images_dev, B, sw, st));
     const long cthreads = (long)B * (c.hidden_dim / sw) * 32;
     prof_mark(e, "cls_rows", st);
-    cls_rows_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p,
-                                                                        (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B,
-                                                                        e->N, c.hidden_dim, sw, (__nv_bfloat16*)e->xb_lo.p);
-    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_pdl(cls_rows_kernel, dim3((unsigned)((cthreads + 255) / 256)), dim3(256), 0, st, e->cls_token, e->pos,
+                      (float*)e->x.p, (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B, e->N, c.hidden_dim, sw,
+                      (__nv_bfloat16*)e->xb_lo.p));
     e->launches += 2;
     return VITB200_OK;
   }
@@ -841,10 +868,9 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
                      e->patches_lo.p, e->w_patch_lo));
   const long cthreads = (long)B * (c.hidden_dim / sw) * 32;
   prof_mark(e, "cls_rows", st);
-  cls_rows_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, st>>>(e->cls_token, e->pos, (float*)e->x.p,
-                                                                      (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B,
-                                                                      e->N, c.hidden_dim, sw, (__nv_bfloat16*)e->xb_lo.p);
-  CU_TRY(cudaGetLastError());
+  CU_TRY(launch_pdl(cls_rows_kernel, dim3((unsigned)((cthreads + 255) / 256)), dim3(256), 0, st, e->cls_token, e->pos,
+                    (float*)e->x.p, (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B, e->N, c.hidden_dim, sw,
+                    (__nv_bfloat16*)e->xb_lo.p));
   e->launches += 3;
   return VITB200_OK;
 }
@@ -964,18 +990,19 @@ static int launch_rollout(const float* maps, long layer_stride, int L, int B, in
     VT_TRY(ensure_func_smem((const void*)rollout_cluster_kernel, smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * C), cfg.blockDim = dim3(kRolloutThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
     CU_TRY(cudaLaunchKernelEx(&cfg, rollout_cluster_kernel, maps, layer_stride, L, N, ld, stages, C, out));
     return VITB200_OK;
   }
   while (stages > 2 && rollout_smem_bytes(ld, stages) > 110 * 1024) --stages;
   const int smem = rollout_smem_bytes(ld, stages);
   VT_TRY(ensure_func_smem((const void*)rollout_cls_kernel, smem));
-  rollout_cls_kernel<<<B, kRolloutThreads, smem, st>>>(maps, layer_stride, L, N, ld, stages, out);
-  CU_TRY(cudaGetLastError());
+  CU_TRY(launch_pdl(rollout_cls_kernel, dim3(B), dim3(kRolloutThreads), smem, st, maps, layer_stride, L, N, ld, stages, out));
   return VITB200_OK;
 }
 

@@ -269,6 +269,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::grid_dep_launch();   // PDL: the next kernel's CTAs may take the SMs this grid leaves free / frees at its tail ...
+  ptx::grid_dep_wait();     // ... and everything below waits for the previous kernel's results
 
   // The producer and MMA loops are executed by WHOLE warps with one elected lane issuing: loop counters, smem
   // addresses and descriptors then stay warp-uniform (uniform registers), instead of being moved from vector to

@@ -269,6 +269,17 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still running: its CTAs become resident as SM resources free up, run their prologue (barrier init, TMEM allocation,
+// tensor-map prefetch -- nothing that touches global data) and block in grid_dep_wait() until the predecessor has
+// COMPLETED and its writes are visible.  grid_dep_launch() tells the scheduler that the NEXT kernel of the stream may be
+// made resident from now on (it fires once every CTA of this grid has called it or exited).  Both are no-ops in a kernel
+// launched without the attribute / with no dependent.  Rule in this library: every thread executes grid_dep_wait() right
+// after the prologue, before the first access to global memory.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2) and clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

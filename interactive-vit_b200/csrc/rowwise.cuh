@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cstdint>
+#include "ptx.cuh"
 
 namespace vitb200 {
 
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(256)
 layernorm_f32_bf16_kernel(const float* __restrict__ x, long in_row_stride, const float* __restrict__ gamma,
                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, float eps,
                           __nv_bfloat16* __restrict__ y_lo = nullptr /* fp32x3 mode: low halves */) {
+  ptx::grid_dep_launch(), ptx::grid_dep_wait();   // PDL (ptx.cuh)
   constexpr int d = kVec * 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,6 +146,7 @@ preprocess_kernel(const float* __restrict__ in, float* __restrict__ out, Preproc
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int S, int p,
                 __nv_bfloat16* __restrict__ out_lo = nullptr /* fp32x3 mode: low halves */) {
+  ptx::grid_dep_launch(), ptx::grid_dep_wait();   // PDL (ptx.cuh)
   const int np = S / p;
   const int kx8 = p / 8;                                 // 16-byte groups per patch row
   const long total = static_cast<long>(B) * 3 * S * np * kx8;  // one item per (b, c, y, px, g)
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(256)
 cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                 __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int B, int N, int d, int sw,
                 __nv_bfloat16* __restrict__ xb_lo = nullptr) {
+  ptx::grid_dep_launch(), ptx::grid_dep_wait();   // PDL (ptx.cuh)
   const int slots = d / sw;   // sw: columns per statistics slot (64 or 128; the engine picks it per batch size)
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -385,6 +389,7 @@ rollout_cls_kernel(const float* __restrict__ maps, long layer_stride, int L, int
   }
   for (int j = tid; j < kRolloutMaxCols * kRolloutThreads; j += kRolloutThreads) r[j] = (j == 0) ? 1.0f : 0.0f, w[j] = 0.0f;
   __syncthreads();
+  ptx::grid_dep_launch(), ptx::grid_dep_wait();   // PDL (ptx.cuh): the maps are the previous kernels' output
   RolloutCursor prod{L - 1, 0, 0, 0};   // next chunk to fetch (thread 0)
   if (tid == 0)
     for (int q = 0; q < stages && prod.layer >= 0; ++q) issue(prod), prod.advance(L, chunks_per_layer, stages);
@@ -549,6 +554,7 @@ rollout_cluster_kernel(const float* __restrict__ maps, long layer_stride, int L,
   for (int j = tid; j < kVec; j += kRolloutThreads) r[j] = (j == 0) ? 1.0f : 0.0f, w2[j] = 0.0f, w2[kVec + j] = 0.0f;
   __syncthreads();
   ptx::cluster_sync();   // every CTA's exchange buffers exist before the first remote store
+  ptx::grid_dep_launch(), ptx::grid_dep_wait();   // PDL (ptx.cuh): the maps are the previous kernels' output
 
   // producer cursor (thread 0): (layer, i-th owned chunk)
   int p_layer = L - 1, p_i = 0, p_stage = 0;
@@ -691,15 +697,22 @@ rollout_cluster_kernel(const float* __restrict__ maps, long layer_stride, int L,
 // Head-average maps of a small launch whose (image, query tile) items were split over S > 2 CTAs by heads
 // (attention.cuh AttnParams::split): avg = ((part_0 + part_1) + part_2) + ..., always in index order -- bit-reproducible,
 // which a reduce-add by more than two CTAs is not.  parts: [S][n4] float4, avg: [n4].
+constexpr int kAvgPartsMax = 16;
 __global__ void __launch_bounds__(256)
 avg_parts_sum_kernel(const float4* __restrict__ parts, float4* __restrict__ avg, long n4, int S) {
+  ptx::grid_dep_launch(), ptx::grid_dep_wait();   // PDL (ptx.cuh)
   const long i = static_cast<long>(blockIdx.x) * 256 + threadIdx.x;
   if (i >= n4) return;
-  float4 a = parts[i];
-  for (int s = 1; s < S; ++s) {
-    const float4 v = parts[s * n4 + i];
-    a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
-  }
+  // every part's load in flight before the first add (a loop of dependent load + add pairs cost one L2 round trip per
+  // part: 5.6 us for 12 parts of one image)
+  float4 v[kAvgPartsMax];
+#pragma unroll
+  for (int s = 0; s < kAvgPartsMax; ++s)
+    if (s < S) v[s] = parts[s * n4 + i];
+  float4 a = v[0];
+#pragma unroll
+  for (int s = 1; s < kAvgPartsMax; ++s)
+    if (s < S) a.x += v[s].x, a.y += v[s].y, a.z += v[s].z, a.w += v[s].w;
   avg[i] = a;
 }
 
