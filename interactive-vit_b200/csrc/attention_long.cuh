@@ -101,7 +101,7 @@ __device__ __forceinline__ void issue_qk_long_split(uint32_t tmem_s, uint32_t sq
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool kSplit, bool kCompact = false>
+template <bool kSplit, bool kCompact = false, bool kOnline = true>
 __global__ void __launch_bounds__(attn_long_cfg::kThreads, kCompact ? 2 : 1)
 attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 64 x 128 over qkv viewed as [B][N][3d]
                           const __grid_constant__ CUtensorMap tmap_qkv_lo,  // kSplit: the low halves, same geometry
@@ -114,6 +114,9 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
   constexpr int kVStages = kCompact ? 1 : 2;
   constexpr int kSBufs = kCompact ? 1 : 2;                 // S buffers in TMEM
   constexpr uint32_t kTmemOc = kCompact ? 128 : kTmemO;    // O columns behind the S buffer(s)
+  // kOnline: one O accumulator per 64-key half of the blocks (the two threads of a row keep independent reference
+  // maxima; the halves meet in the epilogue), the second one kOStride columns after the first
+  constexpr uint32_t kOStride = kCompact ? 64 : 128;
   uint8_t* s_q = smem;
   uint8_t* s_k = smem + kOp;                       // 2 stages
   uint8_t* s_v = smem + 3 * kOp;                   // kVStages stages
@@ -170,8 +173,8 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
     };
     if (ptx::elect_one()) load_tile(s_q, q_full, h * D, qt * BM);
     __syncwarp();
-    int it = 0;  // K stage uses: pass A blocks then pass B blocks
-    for (int pass = 0; pass < 2; ++pass) {
+    int it = 0;  // K stage uses: pass A blocks (not kOnline) then pass B blocks
+    for (int pass = kOnline ? 1 : 0; pass < 2; ++pass) {
       for (int blk = 0; blk < nb; ++blk, ++it) {
         const int st = it & 1;
         ptx::mbar_wait(&k_empty[st], ((it >> 1) & 1) ^ 1);
@@ -209,13 +212,15 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
       __syncwarp();
     };
     // pass A: maxima only
-    for (int blk = 0; blk < nb; ++blk) issue_qk(blk);
+    const int it0 = kOnline ? 0 : nb;   // S / K use index of pass B's first block
+    if (!kOnline)
+      for (int blk = 0; blk < nb; ++blk) issue_qk(blk);
     // pass B: Q K^T of block blk+1 is issued before P V of block blk
-    issue_qk(nb);
+    issue_qk(it0);
     const uint32_t idesc_pv0 = ptx::make_idesc_bf16(BM, 64, 0, 1);                       // V columns [0, 64)
     const uint32_t idesc_pv1 = ptx::make_idesc_bf16(BM, static_cast<uint32_t>(two_box ? D - 64 : 16), 0, 1);
     for (int blk = 0; blk < nb; ++blk) {
-      if (blk + 1 < nb) issue_qk(nb + blk + 1);
+      if (blk + 1 < nb) issue_qk(it0 + blk + 1);
       const int vs = kVStages == 2 ? (blk & 1) : 0;
       ptx::mbar_wait(&v_full[vs], kVStages == 2 ? ((blk >> 1) & 1) : (blk & 1));
       ptx::mbar_wait(p_full, blk & 1);
@@ -228,14 +233,16 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
           // A: P K-block ks / 4 (+16 KB), +32 B per 16 keys; B: V rows [16 ks, +16) MN-major, +2 KB per 16 keys
           const uint64_t dp = dp0 + static_cast<uint64_t>((ks >> 2) * (kBoxBytes >> 4) + 2 * (ks & 3));
           const uint64_t dv = dv0 + static_cast<uint64_t>(ks * (2048 >> 4));
-          const uint32_t acc = (blk | ks) != 0 ? 1u : 0u;
-          ptx::umma_bf16_ss(tmem_base + kTmemOc, dp, dv, idesc_pv0, acc);
+          // kOnline: keys [0, 64) of the block (ks < 4) accumulate into O_0, keys [64, 128) into O_1
+          const uint32_t acc = (kOnline ? (blk | (ks & 3)) : (blk | ks)) != 0 ? 1u : 0u;
+          const uint32_t t_o = tmem_base + kTmemOc + (kOnline ? (ks >> 2) * kOStride : 0u);
+          ptx::umma_bf16_ss(t_o, dp, dv, idesc_pv0, acc);
           if (kSplit) {
             // + P_lo V_hi + P_hi V_lo (the P_lo tile sits one 32 KB slot after P_hi, V_lo one box after V_hi)
-            ptx::umma_bf16_ss(tmem_base + kTmemOc, dp + (kTileBytes >> 4), dv, idesc_pv0, 1u);
-            ptx::umma_bf16_ss(tmem_base + kTmemOc, dp, dv + (kBoxBytes >> 4), idesc_pv0, 1u);
+            ptx::umma_bf16_ss(t_o, dp + (kTileBytes >> 4), dv, idesc_pv0, 1u);
+            ptx::umma_bf16_ss(t_o, dp, dv + (kBoxBytes >> 4), idesc_pv0, 1u);
           } else if (two_box) {
-            ptx::umma_bf16_ss(tmem_base + kTmemOc + 64, dp, dv + (kBoxBytes >> 4), idesc_pv1, acc);
+            ptx::umma_bf16_ss(t_o + 64, dp, dv + (kBoxBytes >> 4), idesc_pv1, acc);
           }
         }
         ptx::umma_commit(&v_empty[vs]);
@@ -256,19 +263,25 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
     const int sw = r & 7;
     float* red_max = red;
     float* red_sum = red + 2 * BM;
+    const int it0s = kOnline ? 0 : nb;   // S use index of pass B's first block
 
     uint32_t s[4][16];
-    auto load_s = [&](int it) {
+    // S block `it` -> registers; release = hand the S buffer back to the MMA issuer
+    auto read_s = [&](int it, bool wait) {
       const int st = kSBufs == 2 ? (it & 1) : 0;
-      ptx::mbar_wait(&s_full[st], kSBufs == 2 ? ((it >> 1) & 1) : (it & 1));
+      if (wait) ptx::mbar_wait(&s_full[st], kSBufs == 2 ? ((it >> 1) & 1) : (it & 1));
       ptx::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 4; ++c) ptx::tmem_ld_x16(lane_base + kTmemS + st * BK + half * 64 + c * 16, s[c]);
       ptx::tmem_ld_wait();
+    };
+    auto release_s = [&](int it) {
+      const int st = kSBufs == 2 ? (it & 1) : 0;
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&s_free[st]);
     };
+    auto load_s = [&](int it) { read_s(it, true), release_s(it); };
     auto mask_s = [&](int blk) {
       const int key0 = blk * BK + half * 64;
       if (key0 + 64 > p.N) {
@@ -279,32 +292,77 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
             if (key0 + c * 16 + j >= p.N) s[c][j] = 0xff800000u;
       }
     };
-    // ---- pass A: row maximum
-    float mx = -INFINITY;
-    for (int blk = 0; blk < nb; ++blk) {
-      load_s(blk);
-      mask_s(blk);
+    float mxs, sum = 0.f;   // reference maximum (scaled: log2 units) and the row sum relative to it
+    float a_self = 1.f, a_oth = 0.f;   // kOnline: weights of this half's / the other half's O accumulator in the epilogue
+    if (!kOnline) {
+      // ---- pass A: row maximum
+      float mx = -INFINITY;
+      for (int blk = 0; blk < nb; ++blk) {
+        load_s(blk);
+        mask_s(blk);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) mx = ptx::fmax3(mx, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
+          for (int j = 0; j < 16; j += 2) mx = ptx::fmax3(mx, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
+      }
+      red_max[half * BM + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, red_max[(half ^ 1) * BM + r]);
+      mxs = mx * p.scale_log2;
+    } else {
+      mxs = -INFINITY;
     }
-    red_max[half * BM + r] = mx;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    mx = fmaxf(mx, red_max[(half ^ 1) * BM + r]);
-    const float mxs = mx * p.scale_log2;
-    // ---- pass B: e = exp2(s c - max c) -> row sum, bf16 P tile -> O += P V
-    float sum = 0.f;
+    // ---- pass B: e = exp2(s c - ref) -> row sum, bf16 P tile -> O += P V.  Without pass A (kOnline) `ref` is this
+    //      THREAD's running reference: the maximum of its 64-key half of the first block, raised only when a later block
+    //      exceeds it by more than kLazy (2^8: e stays far inside bf16 / fp32 range), in which case the thread rescales
+    //      its own row of its own O accumulator in TMEM between the P V of the previous block and its next P tile.
+    constexpr float kLazy = 8.0f;
     for (int blk = 0; blk < nb; ++blk) {
-      load_s(nb + blk);
+      if (kOnline) read_s(it0s + blk, true);   // the buffer is handed back below: the rescale path reads the block twice
+      else load_s(it0s + blk);
       mask_s(blk);
+      if (kOnline) {
+        float bm = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) bm = ptx::fmax3(bm, __uint_as_float(s[c][j]), __uint_as_float(s[c][j + 1]));
+        const float bms = bm * p.scale_log2;
+        const bool raise = bms > mxs + kLazy;   // also true for the first unmasked block of the thread (mxs = -inf)
+        if (blk > 0 && __any_sync(0xffffffffu, raise)) {
+          // (warp-uniform branch: tcgen05.ld / st are warp-collective; lanes that keep their reference multiply by 1)
+          const float f = raise ? ptx::ex2_approx(mxs - bms) : 1.0f;   // exp2(-inf) = 0: nothing accumulated yet
+          ptx::mbar_wait(p_free, (blk - 1) & 1);   // O is complete up to the previous block
+          ptx::tc_fence_after();
+          const uint32_t t_o = lane_base + kTmemOc + half * kOStride;
+          for (int c0 = 0; c0 < D; c0 += 16) {
+            uint32_t o[16];
+            ptx::tmem_ld_x16(t_o + c0, o);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+            ptx::tmem_st_x16(t_o + c0, o);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          sum *= f;
+          // (the block is read again instead of being kept in 64 registers across this branch: with it live here the
+          // compact instantiation -- 80 registers, two CTAs per SM -- parked the whole block in local memory on EVERY
+          // iteration)
+          read_s(it0s + blk, false);
+          mask_s(blk);
+        }
+        release_s(it0s + blk);
+        if (raise) mxs = bms;
+      }
       if (blk > 0) ptx::mbar_wait(p_free, (blk - 1) & 1);  // the previous block's P V has read the tile
+      const float ref = (kOnline && mxs == -INFINITY) ? 0.f : mxs;   // a thread whose keys are all masked so far: e = 0
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float e[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          e[j] = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -mxs));
+          e[j] = ptx::ex2_approx(fmaf(__uint_as_float(s[c][j]), p.scale_log2, -ref));
           sum += e[j];
         }
         // keys [16 c, 16 c + 16) of this half: 16-byte chunks 2c, 2c+1 of the row in K-block `half`
@@ -334,34 +392,61 @@ attention_long_ctx_kernel(const __grid_constant__ CUtensorMap tmap_qkv,  // box 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
     }
-    red_sum[half * BM + r] = sum;
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-    sum += red_sum[(half ^ 1) * BM + r];
-    const float inv = 1.0f / sum;
+    float inv;
+    if (!kOnline) {
+      red_sum[half * BM + r] = sum;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      sum += red_sum[(half ^ 1) * BM + r];
+      inv = 1.0f / sum;
+    } else {
+      // the two halves of the row meet: common reference M = max of the two, each half's sum and O weighted by
+      // 2^(own reference - M).  Formed from (half 0, half 1) in that order by both threads: the same bits in both.
+      red_max[half * BM + r] = mxs, red_sum[half * BM + r] = sum;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float m0 = red_max[r], m1 = red_max[BM + r], s0 = red_sum[r], s1 = red_sum[BM + r];
+      const float M = fmaxf(m0, m1);   // finite: key 0 is never masked
+      const float a0 = m0 == -INFINITY ? 0.f : ptx::ex2_approx(m0 - M), a1 = m1 == -INFINITY ? 0.f : ptx::ex2_approx(m1 - M);
+      inv = 1.0f / __fadd_rn(__fmul_rn(s0, a0), __fmul_rn(s1, a1));
+      a_self = half == 0 ? a0 : a1, a_oth = half == 0 ? a1 : a0;
+      mxs = M;
+    }
     if (half == 0 && row_ok) p.stats[(static_cast<size_t>(b) * p.H + h) * p.N + qrow] = make_float2(mxs, inv);
     // ---- context rows: this half owns D / 2 of the D columns (D / 2 is a multiple of 8)
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
     const int cols = D >> 1;
     __nv_bfloat16* op = p.ctx + (static_cast<size_t>(b) * p.N + qrow) * p.d + h * D + half * cols;
+    const float w_self = a_self * inv, w_oth = a_oth * inv;
+    const float inv_e = kOnline ? 1.0f : inv;   // kOnline: 1 / sum is part of the weights
     for (int c0 = 0; c0 < cols; c0 += 8) {
       uint32_t o[8];
-      ptx::tmem_ld_x8(lane_base + kTmemOc + half * cols + c0, o);
-      ptx::tmem_ld_wait();
+      if (!kOnline) {
+        ptx::tmem_ld_x8(lane_base + kTmemOc + half * cols + c0, o);
+        ptx::tmem_ld_wait();
+      } else {
+        // O = (O_half0 2^(m0 - M) + O_half1 2^(m1 - M)) / sum; the scaling by inv below is folded into the weights
+        uint32_t o2[8];
+        ptx::tmem_ld_x8(lane_base + kTmemOc + half * kOStride + half * cols + c0, o);
+        ptx::tmem_ld_x8(lane_base + kTmemOc + (half ^ 1) * kOStride + half * cols + c0, o2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = __float_as_uint(fmaf(__uint_as_float(o2[j]), w_oth, __uint_as_float(o[j]) * w_self));
+      }
       if (row_ok) {
         uint4 v;
-        v.x = pack_bf16x2_f(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-        v.y = pack_bf16x2_f(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-        v.z = pack_bf16x2_f(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-        v.w = pack_bf16x2_f(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        v.x = pack_bf16x2_f(__uint_as_float(o[0]) * inv_e, __uint_as_float(o[1]) * inv_e);
+        v.y = pack_bf16x2_f(__uint_as_float(o[2]) * inv_e, __uint_as_float(o[3]) * inv_e);
+        v.z = pack_bf16x2_f(__uint_as_float(o[4]) * inv_e, __uint_as_float(o[5]) * inv_e);
+        v.w = pack_bf16x2_f(__uint_as_float(o[6]) * inv_e, __uint_as_float(o[7]) * inv_e);
         *reinterpret_cast<uint4*>(op + c0) = v;
         if (kSplit) {
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
           uint4 l;
-          l.x = pack_bf16x2_f(__uint_as_float(o[0]) * inv - __low2float(h[0]), __uint_as_float(o[1]) * inv - __high2float(h[0]));
-          l.y = pack_bf16x2_f(__uint_as_float(o[2]) * inv - __low2float(h[1]), __uint_as_float(o[3]) * inv - __high2float(h[1]));
-          l.z = pack_bf16x2_f(__uint_as_float(o[4]) * inv - __low2float(h[2]), __uint_as_float(o[5]) * inv - __high2float(h[2]));
-          l.w = pack_bf16x2_f(__uint_as_float(o[6]) * inv - __low2float(h[3]), __uint_as_float(o[7]) * inv - __high2float(h[3]));
+          l.x = pack_bf16x2_f(__uint_as_float(o[0]) * inv_e - __low2float(h[0]), __uint_as_float(o[1]) * inv_e - __high2float(h[0]));
+          l.y = pack_bf16x2_f(__uint_as_float(o[2]) * inv_e - __low2float(h[1]), __uint_as_float(o[3]) * inv_e - __high2float(h[1]));
+          l.z = pack_bf16x2_f(__uint_as_float(o[4]) * inv_e - __low2float(h[2]), __uint_as_float(o[5]) * inv_e - __high2float(h[2]));
+          l.w = pack_bf16x2_f(__uint_as_float(o[6]) * inv_e - __low2float(h[3]), __uint_as_float(o[7]) * inv_e - __high2float(h[3]));
           *reinterpret_cast<uint4*>(p.ctx_lo + (op - p.ctx) + c0) = l;
         }
       }

@@ -451,9 +451,12 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
   if (split) VT_TRY(make_tmap_bf16_3d(&tqkv_lo, qkv_lo, B, N, 3 * d, 3 * d, 128, 64));
   {
     const std::pair<const void*, int> kerns[] = {
-        {(const void*)attention_long_ctx_kernel<false>, kSmemCtx},
-        {(const void*)attention_long_ctx_kernel<true>, kSmemCtxSplit},
-        {(const void*)attention_long_ctx_kernel<false, true>, kSmemCtxCompact},
+        {(const void*)attention_long_ctx_kernel<false, false, true>, kSmemCtx},
+        {(const void*)attention_long_ctx_kernel<true, false, true>, kSmemCtxSplit},
+        {(const void*)attention_long_ctx_kernel<false, true, true>, kSmemCtxCompact},
+        {(const void*)attention_long_ctx_kernel<false, false, false>, kSmemCtx},
+        {(const void*)attention_long_ctx_kernel<true, false, false>, kSmemCtxSplit},
+        {(const void*)attention_long_ctx_kernel<false, true, false>, kSmemCtxCompact},
         {(const void*)attention_long_maps_kernel<false, false, true>, kSmemMapsCompact},
         {(const void*)attention_long_maps_kernel<true, false, true>, kSmemMapsCompact},
         {(const void*)attention_long_maps_kernel<false, false>, kSmemMaps},
@@ -473,9 +476,20 @@ static int launch_attention_long(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, f
     const char* v = getenv("VITB200_ATTN_LONG_COMPACT");
     compact_mode = (v && v[0] == '0') ? 0 : 1;
   }
-  if (split) attention_long_ctx_kernel<true><<<B * p.q_tiles * H, kThreads, kSmemCtxSplit, st>>>(tqkv, tqkv_lo, p);
-  else if (D == 64 && compact_mode) attention_long_ctx_kernel<false, true><<<B * p.q_tiles * H, kThreads, kSmemCtxCompact, st>>>(tqkv, tqkv_lo, p);
-  else attention_long_ctx_kernel<false><<<B * p.q_tiles * H, kThreads, kSmemCtx, st>>>(tqkv, tqkv_lo, p);
+  // VITB200_ATTN_LONG_ONLINE=0: the two-pass context kernel (separate maximum pass) instead of the lazily rescaled
+  // single pass (read at every launch: the parity tests compare both)
+  const char* online_env = getenv("VITB200_ATTN_LONG_ONLINE");
+  const bool online = !(online_env && online_env[0] == '0');
+  const unsigned cgrid = (unsigned)(B * p.q_tiles * H);
+  if (online) {
+    if (split) attention_long_ctx_kernel<true, false, true><<<cgrid, kThreads, kSmemCtxSplit, st>>>(tqkv, tqkv_lo, p);
+    else if (D == 64 && compact_mode) attention_long_ctx_kernel<false, true, true><<<cgrid, kThreads, kSmemCtxCompact, st>>>(tqkv, tqkv_lo, p);
+    else attention_long_ctx_kernel<false, false, true><<<cgrid, kThreads, kSmemCtx, st>>>(tqkv, tqkv_lo, p);
+  } else {
+    if (split) attention_long_ctx_kernel<true, false, false><<<cgrid, kThreads, kSmemCtxSplit, st>>>(tqkv, tqkv_lo, p);
+    else if (D == 64 && compact_mode) attention_long_ctx_kernel<false, true, false><<<cgrid, kThreads, kSmemCtxCompact, st>>>(tqkv, tqkv_lo, p);
+    else attention_long_ctx_kernel<false, false, false><<<cgrid, kThreads, kSmemCtx, st>>>(tqkv, tqkv_lo, p);
+  }
   CU_TRY(cudaGetLastError());
   if (avg || cls || heads) {
     const int grid = B * p.q_tiles * p.k_blocks;

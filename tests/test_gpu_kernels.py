@@ -292,6 +292,40 @@ def test_attention_long(E, B, N, H, D, scale):
     assert torch.equal(ctx, ctx2)
 
 
+@pytest.mark.parametrize("B,N,H,D", [(2, 577, 3, 64), (1, 577, 2, 80), (1, 700, 2, 64), (2, 257, 2, 128)])
+def test_attention_long_online_rescale(E, B, N, H, D):
+    """The context kernel of the key-blocked path makes ONE pass over the keys: every thread (query row, 64-key half of a
+    128-key block) keeps its own reference maximum and raises it -- rescaling its row of its O accumulator in TMEM --
+    only when a later block exceeds it by more than 2^8 (attention_long.cuh).  Keys whose scores grow block by block
+    force that path in every block; keys that shrink never take it; both against the fp32 reference and against the
+    two-pass kernel (VITB200_ATTN_LONG_ONLINE=0)."""
+    torch.manual_seed(N + D)
+    d = H * D
+    for growth in (1.35, 1 / 1.35, 1.0):
+        qkv = torch.randn(B, N, 3, H, D, device="cuda")
+        ramp = growth ** (torch.arange(N, device="cuda") // 64).float()           # per 64-key half block
+        qkv[:, :, 1] *= ramp[None, :, None, None] * 2.0
+        qkv[:, :, 0] *= 2.0
+        qkv = qkv.reshape(B * N, 3 * d).bfloat16()
+        ctx, avg, cls, hm = E.op_attention(qkv, B, N, H, True, True, True, head_dim=D)
+        o, p = _attn_ref(qkv, B, N, H, D)
+        assert torch.isfinite(ctx.float()).all()
+        assert _rel(ctx, o) < 2 * BF16_EPS
+        # (scores reach several hundred here: the fp32 rounding of s * c alone is ~1e-5 relative in exp2; the two-pass
+        # kernel measures the same on these inputs)
+        assert _rel(hm, p) < 2e-5 and _rel(avg, p.mean(1)) < 2e-5 and _rel(cls, p[:, :, 0, :]) < 2e-5
+        assert (hm.sum(-1) - 1).abs().max() < 2e-5
+        os.environ["VITB200_ATTN_LONG_ONLINE"] = "0"
+        try:
+            ctx2, avg2, _, _ = E.op_attention(qkv, B, N, H, True, False, False, head_dim=D)
+        finally:
+            del os.environ["VITB200_ATTN_LONG_ONLINE"]
+        assert _rel(ctx, ctx2) < 2 * BF16_EPS and _rel(avg, avg2) < 2e-5
+        assert _rel(avg2, p.mean(1)) < 2e-5
+        ctx3, _, _, _ = E.op_attention(qkv, B, N, H, False, False, False, head_dim=D)
+        assert torch.equal(ctx, ctx3)            # bit-reproducible, independent of the outputs selected
+
+
 def test_attention_masks_padded_keys(E):
     """Keys beyond N come from the next image (or TMA zero fill) and must get probability 0: changing image 1 must
     not change image 0's outputs."""
