@@ -853,7 +853,7 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
     const int sw = stats_width(B * e->N, c.hidden_dim);
     prof_mark(e, "gemm_patch_embed", st);
     VT_TRY(launch_patch_embed(e, images_dev, B, sw, st));
-    const long cthreads = (long)B * (c.hidden_dim / sw) * 32;
+    const long cthreads = (long)B * ((c.hidden_dim + 127) / 128) * 32;   // one warp per (image, 128 columns)
     prof_mark(e, "cls_rows", st);
     CU_TRY(launch_pdl(cls_rows_kernel, dim3((unsigned)((cthreads + 255) / 256)), dim3(256), 0, st, e->cls_token, e->pos,
                       (float*)e->x.p, (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B, e->N, c.hidden_dim, sw,
@@ -880,7 +880,7 @@ static int run_embed(vitb200_engine* e, const float* images_dev, int B, cudaStre
   prof_mark(e, "gemm_patch_embed", st);
   VT_TRY(launch_gemm(e->patches.p, e->patch_k, e->w_patch, B * e->n, c.hidden_dim, e->patch_k, ep, false, true, st,
                      e->patches_lo.p, e->w_patch_lo));
-  const long cthreads = (long)B * (c.hidden_dim / sw) * 32;
+  const long cthreads = (long)B * ((c.hidden_dim + 127) / 128) * 32;   // one warp per (image, 128 columns)
   prof_mark(e, "cls_rows", st);
   CU_TRY(launch_pdl(cls_rows_kernel, dim3((unsigned)((cthreads + 255) / 256)), dim3(256), 0, st, e->cls_token, e->pos,
                     (float*)e->x.p, (__nv_bfloat16*)e->xb.p, (float2*)e->ln_stats.p, B, e->N, c.hidden_dim, sw,

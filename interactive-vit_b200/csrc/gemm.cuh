@@ -649,8 +649,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (kResid) t.x += q[i].x, t.y += q[i].y, t.z += q[i].z, t.w += q[i].w;
             if (kResid && ep.xb != nullptr) {
               // bf16 copy for the next GEMM; this thread's share of the row's partial sums (reduced after the loop)
-              p1[i] = ok[i] ? (t.x + t.y) + (t.z + t.w) : 0.f;
-              p2[i] = ok[i] ? (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w) : 0.f;
+              p1[i] = ok[i] ? quad_sum(t) : 0.f;      // the canonical order of rowwise.cuh ("LayerNorm partial sums")
+              p2[i] = ok[i] ? quad_sumsq(t) : 0.f;
               if (ok[i]) {
                 const __nv_bfloat162 h01 = __floats2bfloat162_rn(t.x, t.y), h23 = __floats2bfloat162_rn(t.z, t.w);
                 uint2 pk;

@@ -181,36 +181,78 @@ patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, 
   }
 }
 
+// ---- LayerNorm partial sums in ONE canonical order -----------------------------------------------------------------
+// The folded LayerNorm (gemm.cuh) reads per-row partial sums (sum x, sum x^2) per 64- or 128-column slot.  Three
+// producers write them: the residual / patch-embedding GEMM epilogues, cls_rows_kernel (class-token rows) and
+// rows_bf16_stats_kernel (token streams that enter through the boundary, vitb200_set_tokens).  All three form a slot in
+// the SAME order, so that a request whose tokens were uploaded again (interleaved requests, a client that edits the
+// tokens) continues bit-identically to one whose tokens stayed resident:
+//   quad   q_k = (x0 + x1) + (x2 + x3)  /  fma(x0, x0, x1 x1) + fma(x2, x2, x3 x3)  over columns 4k .. 4k+3 (explicit
+//          intrinsics: no contraction choice left to the compiler),
+//   chunk  f_c = ((q0 + q4) + (q2 + q6)) + ((q1 + q5) + (q3 + q7))  over the 8 quads of 32 columns (every level is ONE
+//          commutative add of two partners: the result does not depend on which lane holds which),
+//   slot   64 columns: f_0 + f_1;  128 columns: (f_0 + f_1) + (f_2 + f_3).
+__device__ __forceinline__ float quad_sum(const float4& t) { return __fadd_rn(__fadd_rn(t.x, t.y), __fadd_rn(t.z, t.w)); }
+__device__ __forceinline__ float quad_sumsq(const float4& t) {
+  return __fadd_rn(__fmaf_rn(t.x, t.x, __fmul_rn(t.y, t.y)), __fmaf_rn(t.z, t.z, __fmul_rn(t.w, t.w)));
+}
+// Lane l of a warp holds quad (l & 7) of chunk (l >> 3) of 128 consecutive columns: returns the slot sum that covers this
+// lane's chunk (sw = 64: chunks {0,1} / {2,3}; sw = 128: all four), identical on every lane of the slot.
+__device__ __forceinline__ float slot_sum_128(float q, int sw) {
+  q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 4));
+  q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 2));
+  q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 1));    // f_c on the 8 lanes of chunk c
+  q = __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 8));    // f_0 + f_1 | f_2 + f_3
+  const float o = __shfl_xor_sync(0xffffffffu, q, 16);
+  return sw == 128 ? __fadd_rn(q, o) : q;
+}
+// One warp, 128 columns [c0, c0 + 128) of one row: fp32 value v (this lane's 4 columns) -> bf16 copy (+ low halves) and
+// the slot statistics.  Columns at or beyond d contribute nothing.
+__device__ __forceinline__ void row128_bf16_stats(const float4& v, long row, int c0, int d, int sw, int lane,
+                                                  __nv_bfloat16* __restrict__ xb, __nv_bfloat16* __restrict__ xb_lo,
+                                                  float2* __restrict__ stats) {
+  const int col = c0 + 4 * lane;   // lane l: chunk l >> 3, quad l & 7 -> columns c0 + 32 (l >> 3) + 4 (l & 7)
+  const bool ok = col < d;
+  if (ok && xb != nullptr) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h01), pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(xb + row * d + col) = pk;
+    if (xb_lo != nullptr) {
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+      uint2 pl;
+      pl.x = *reinterpret_cast<const uint32_t*>(&l01), pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(xb_lo + row * d + col) = pl;
+    }
+  }
+  const float s1 = slot_sum_128(ok ? quad_sum(v) : 0.f, sw), s2 = slot_sum_128(ok ? quad_sumsq(v) : 0.f, sw);
+  // one writer per slot: the first lane of the slot's first chunk
+  if (ok && stats != nullptr && (lane & (sw == 128 ? 31 : 15)) == 0) stats[row * (d / sw) + col / sw] = make_float2(s1, s2);
+}
+
 // Class-token rows of the token stream: x[b, 0, :] = class_token + pos_embedding[0]  (fp32), plus what the folded
-// LayerNorm of the next GEMM needs for these rows: the bf16 copy and the per-32-column partial sums (sum, sum of
-// squares).  One warp per (image, 32-column chunk), one column per lane.
+// LayerNorm of the next GEMM needs for these rows: the bf16 copy and the per-slot partial sums.  One warp per
+// (image, 128 columns).
 __global__ void __launch_bounds__(256)
 cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
                 __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int B, int N, int d, int sw,
                 __nv_bfloat16* __restrict__ xb_lo = nullptr) {
   ptx::grid_dep_launch(), ptx::grid_dep_wait();   // PDL (ptx.cuh)
-  const int slots = d / sw;   // sw: columns per statistics slot (64 or 128; the engine picks it per batch size)
+  const int groups = (d + 127) / 128;
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= static_cast<long>(B) * slots) return;
-  const int b = static_cast<int>(warp / slots), slot = static_cast<int>(warp % slots);
+  if (warp >= static_cast<long>(B) * groups) return;
+  const int b = static_cast<int>(warp / groups), c0 = static_cast<int>(warp % groups) * 128;
   const long row = static_cast<long>(b) * N;
-  // chunk sums in a fixed order, bit-reproducible; a 128-column slot is (chunk 0 + chunk 1) + (chunk 2 + chunk 3) = the
-  // sum of its two 64-column halves, like the GEMM epilogues' slots (gemm.cuh)
-  float p1 = 0.f, p2 = 0.f, q1 = 0.f, q2 = 0.f;
-  for (int c = 0; c < sw; c += 32) {
-    const int col = slot * sw + c + lane;
-    const float v = cls[col] + pos[col];
-    x[row * d + col] = v;
-    if (xb != nullptr) {
-      const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-      xb[row * d + col] = hb;
-      if (xb_lo != nullptr) xb_lo[row * d + col] = __float2bfloat16_rn(v - __bfloat162float(hb));
-      if (c < 64) p1 += warp_sum(v), p2 += warp_sum(v * v);
-      else q1 += warp_sum(v), q2 += warp_sum(v * v);
-    }
+  const int col = c0 + 4 * lane;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < d) {
+    const float4 a = *reinterpret_cast<const float4*>(cls + col), p = *reinterpret_cast<const float4*>(pos + col);
+    v = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    *reinterpret_cast<float4*>(x + row * d + col) = v;
   }
-  if (xb != nullptr && lane == 0) stats[row * slots + slot] = make_float2(p1 + q1, p2 + q2);
+  row128_bf16_stats(v, row, c0, d, sw, lane, xb, xb_lo, xb != nullptr ? stats : nullptr);
 }
 
 // bf16 copy + partial LayerNorm sums of arbitrary fp32 rows (token streams that enter through the boundary,
@@ -221,19 +263,10 @@ rows_bf16_stats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ 
   const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const int slots = d / sw;
-  for (int slot = 0; slot < slots; ++slot) {
-    float p1 = 0.f, p2 = 0.f, q1 = 0.f, q2 = 0.f;   // (chunk 0 + chunk 1) + (chunk 2 + chunk 3), see cls_rows_kernel
-    for (int c = 0; c < sw; c += 32) {
-      const int col = slot * sw + c + lane;
-      const float v = x[row * d + col];
-      const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-      xb[row * d + col] = hb;
-      if (xb_lo != nullptr) xb_lo[row * d + col] = __float2bfloat16_rn(v - __bfloat162float(hb));
-      if (c < 64) p1 += warp_sum(v), p2 += warp_sum(v * v);
-      else q1 += warp_sum(v), q2 += warp_sum(v * v);
-    }
-    if (lane == 0) stats[row * slots + slot] = make_float2(p1 + q1, p2 + q2);
+  for (int c0 = 0; c0 < d; c0 += 128) {
+    const int col = c0 + 4 * lane;
+    const float4 v = col < d ? *reinterpret_cast<const float4*>(x + row * d + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    row128_bf16_stats(v, row, c0, d, sw, lane, xb, xb_lo, stats);
   }
 }
 

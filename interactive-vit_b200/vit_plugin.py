@@ -346,6 +346,9 @@ def make_vit_model_class(ModelBase, PinoutCls):
                         res = self._maps_out.get(i)
                         if res is None or res[0] is not m or res[1] != batch:   # not (or no longer) resident
                             self.engine.set_avg_map(i, self._host(m).reshape(batch, c.tokens, c.tokens))
+                            # the engine now holds m for layer i, not the map it handed out last: the request that map
+                            # belongs to (interleaved on another thread) must upload it again for ITS rollout
+                            self._maps_out[i] = (m, batch)
                     out.set("o", self.engine.stage_rollout(batch, (batch, g, g) if batched else (g, g)))
             return out
 

@@ -896,6 +896,90 @@ def test_interleaved_requests_with_a_growing_batch(E):
     plug.engine.close()
 
 
+def test_uploaded_tokens_continue_bit_identically(E):
+    """A node whose input tokens are not the engine's resident stream (another request ran in between, or the client
+    edited them) uploads them and recomputes what the folded LayerNorm reads -- the bf16 copy and the per-slot partial
+    sums (`rows_bf16_stats_kernel`).  Those sums are formed in the same order as in the GEMM epilogues and in
+    `cls_rows_kernel` (rowwise.cuh, "LayerNorm partial sums"), so every later output is bit-identical to the resident
+    path -- for the class-token row too."""
+    from interactive_vit_b200.graph import Pinout
+    from oracle import vit_oracle as O
+
+    for name in ("vit_small_test", "vit_tiny_test"):
+        ocfg = O.ORACLE_CONFIGS[name]
+        module = O.build_vit(ocfg, seed=0, init="stress")
+        plug, ctx = _plugin_context(E, name, ocfg, module, max_batch=2)
+        L = ocfg.num_layers
+        x = O.synthetic_images(2, ocfg.image_size, seed=5)
+
+        def call(node, **chans):
+            p = Pinout()
+            for k, v in chans.items():
+                p.set(k, v)
+            return plug.compute(f"{name}:{node}", p)
+
+        def run(images, upload):
+            t = call("embed", o=images).get("o")
+            outs = []
+            for i in range(L):
+                if upload:
+                    t = torch.as_tensor(t).clone()      # a different object: not the resident stream any more
+                r = call(f"layer.{i}", o=t)
+                t = r.get("o")
+                outs += [torch.as_tensor(t).clone(), torch.as_tensor(r.get("attn")).clone(), torch.as_tensor(r.get("cls")).clone()]
+            if upload:
+                t = torch.as_tensor(t).clone()
+            outs.append(torch.as_tensor(call("head", o=t).get("o")).clone())
+            return outs
+
+        for images in (x[0], x[1], x):
+            for a, b in zip(run(images, False), run(images, True)):
+                assert torch.equal(a, b)
+        plug.engine.close()
+
+
+def test_concurrent_requests_from_two_threads(E):
+    """The reference serves every request on its own thread against ONE process-wide Context with no locking
+    (`ref:main/context.py:149-152`, Django's thread-per-request dev server): node calls of different requests interleave
+    at node granularity.  Two threads push different images through decode -> Context.compute -> encode at the same
+    time; every response must equal the response of the same image served alone, bit for bit."""
+    import threading
+
+    from oracle import vit_oracle as O
+
+    name = "vit_small_test"
+    ocfg = O.ORACLE_CONFIGS[name]
+    module = O.build_vit(ocfg, seed=0, init="stress")
+    plug, ctx = _plugin_context(E, name, ocfg, module)
+    L = ocfg.num_layers
+    images = O.synthetic_images(6, ocfg.image_size, seed=5)
+    alone = [_wire_request(ctx, name, L, images[i]) for i in range(6)]
+    results, errors = {}, []
+    start = threading.Barrier(2)
+
+    def serve(tid):
+        try:
+            start.wait()
+            for rep in range(4):
+                for i in range(tid, 6, 2):
+                    results[(tid, rep, i)] = _wire_request(ctx, name, L, images[i])
+        except Exception as e:   # surfaced below: an exception in a thread must fail the test
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=serve, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    assert len(results) == 2 * 4 * 3
+    for (tid, rep, i), got in results.items():
+        for node in alone[i]:
+            for ch in alone[i][node]:
+                assert torch.equal(got[node][ch], alone[i][node][ch]), (tid, rep, i, node, ch)
+    plug.engine.close()
+
+
 def test_graph_replay_equals_eager_launches(E):
     """CUDA-graph replay (from the second call with the same batch / flags / input address) is bit-identical to launching
     the kernels one by one, for the whole forward and for the node-granular stages; a different batch or a re-allocated
