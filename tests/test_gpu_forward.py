@@ -980,6 +980,82 @@ def test_concurrent_requests_from_two_threads(E):
     plug.engine.close()
 
 
+def test_concurrent_mixed_requests(E):
+    """Three request shapes at once on one plugin and one Context: single images through the block-granular graph, a
+    batch of two through the same graph, and the half-block graph with a logit-lens head tapping every block (server-side
+    fan-out) plus per-head maps from one layer.  The interleaving makes nodes re-upload tokens and maps, switch batch
+    sizes between node calls and replay / re-capture stage graphs; every response must equal the one served alone."""
+    import threading
+
+    from interactive_vit_b200 import message as M, vit_plugin as P
+    from oracle import vit_oracle as O
+
+    name = "vit_small_test"
+    ocfg = O.ORACLE_CONFIGS[name]
+    module = O.build_vit(ocfg, seed=0, init="stress")
+    plug, ctx = _plugin_context(E, name, ocfg, module, max_batch=2)   # registers the half-block nodes too
+    L = ocfg.num_layers
+    x = O.synthetic_images(6, ocfg.image_size, seed=9)
+
+    def lens_request(image):
+        nodes = [{"endpoint": f"{name}:embed", "params": {}}]
+        for i in range(L):
+            nodes += [{"endpoint": f"{name}:layer.{i}.attn", "params": {"heads": "1"} if i == 1 else {}},
+                      {"endpoint": f"{name}:layer.{i}.mlp", "params": {}}]
+        lens0 = len(nodes)
+        nodes += [{"endpoint": f"{name}:head", "params": {}} for _ in range(L)]
+        nodes.append({"endpoint": f"{name}:rollout", "params": {}})
+        edges = [{"tensor": 0, "out_port": {"node": 0, "channel": "o"}}]
+        for i in range(1, 2 * L + 1):
+            edges.append({"in_port": {"node": i - 1, "channel": "o"}, "out_port": {"node": i, "channel": "o"}})
+        for i in range(L):
+            edges.append({"in_port": {"node": 2 + 2 * i, "channel": "o"}, "out_port": {"node": lens0 + i, "channel": "o"}})
+            edges.append({"in_port": {"node": 1 + 2 * i, "channel": "attn"},
+                          "out_port": {"node": len(nodes) - 1, "channel": f"a{i}"}})
+        return M.encode_request(nodes, edges, [image]), True
+
+    def plain_request(image):
+        return M.encode_request(*P.vit_graph_request(name, L, image)), False
+
+    def serve(blob, fan_out):
+        req = M.Request(fan_out=True) if fan_out else M.Request()
+        req.decode(blob)
+        ctx.compute(req.graph)
+        return M.decode_response(M.Response(req.graph).encode())
+
+    jobs = {0: [plain_request(x[0]), plain_request(x[1])], 1: [plain_request(x[2:4]), plain_request(x[4:6])],
+            2: [lens_request(x[0]), lens_request(x[5])]}
+    alone = {t: [serve(*job) for job in js] for t, js in jobs.items()}
+    results, errors = {}, []
+    start = threading.Barrier(len(jobs))
+
+    def worker(t):
+        try:
+            start.wait()
+            for rep in range(3):
+                for k, job in enumerate(jobs[t]):
+                    results[(t, rep, k)] = serve(*job)
+        except Exception:
+            import traceback
+            errors.append(traceback.format_exc())
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in jobs]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(180)
+    assert not errors, errors
+    assert len(results) == 3 * 3 * 2
+    for (t, rep, k), got in results.items():
+        want = alone[t][k]
+        assert {n: sorted(v) for n, v in got.items()} == {n: sorted(v) for n, v in want.items()}
+        for node in want:
+            for ch in want[node]:
+                assert torch.equal(got[node][ch], want[node][ch]), (t, rep, k, node, ch,
+                                                                   (got[node][ch] - want[node][ch]).abs().max().item())
+    plug.engine.close()
+
+
 def test_graph_replay_equals_eager_launches(E):
     """CUDA-graph replay (from the second call with the same batch / flags / input address) is bit-identical to launching
     the kernels one by one, for the whole forward and for the node-granular stages; a different batch or a re-allocated
