@@ -387,6 +387,11 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
   VT_TRY(make_tmap_bf16(&maps[1], w, N, K, K, mode == 4 ? 64 : bn / pair, gemm_cfg::BK));
   maps[2] = maps[0], maps[3] = maps[1];
   GemmShape sh{M, N, K};
+  static const int prefetch_w = [] {   // VITB200_GEMM_PREFETCH_W=0: no L2 prefetch of the weight panel in small launches
+    const char* v = getenv("VITB200_GEMM_PREFETCH_W");
+    return (v && v[0] == '0') ? 0 : 1;
+  }();
+  sh.prefetch_w = prefetch_w;
   if (a_lo != nullptr) {
     VT_TRY(make_tmap_bf16(&maps[2], a_lo, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
     VT_TRY(make_tmap_bf16(&maps[3], w_lo, N, K, K, mode == 4 ? 64 : bn / pair, gemm_cfg::BK));

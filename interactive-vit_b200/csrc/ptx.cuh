@@ -277,6 +277,10 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // made resident from now on (it fires once every CTA of this grid has called it or exited).  Both are no-ops in a kernel
 // launched without the attribute / with no dependent.  Rule in this library: every thread executes grid_dep_wait() right
 // after the prologue, before the first access to global memory.
+// TMA prefetch of one box of a tiled tensor into L2 (no shared memory, no barrier).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
