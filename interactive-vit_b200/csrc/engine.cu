@@ -381,6 +381,16 @@ static int launch_gemm(const void* a, int lda, const void* w, int M, int N, int 
   if (ep.row_stats_out != nullptr && ep.stats_slots > 0 && mode != 4) bn = (N / ep.stats_slots == 64) ? 128 : 256;
   if (small_mode && mode == 2 && N % 128 == 0 && (ep.row_stats_out == nullptr || bn == 128) && gemm_small(M, N))
     pair = 1, bn = 128;
+  // ... except where ONE 256-row pair tile covers all rows and the output is narrow (patch embedding, out_proj, fc2 of
+  // a single image: N = d): pairs of the same 128-wide tiles give the same number of CTAs, and each CTA streams half
+  // of the W panel -- at B = 1 a GEMM is bound by what one SM can keep in flight (VITB200_GEMM_SMALL_PAIR=0 disables;
+  // same k order, same statistics slots: bit-identical).  Measured at B = 1: 0.659 -> 0.631 ms per forward (fc2 alone:
+  // 0.638).
+  static const int small_pair = [] {
+    const char* v = getenv("VITB200_GEMM_SMALL_PAIR");
+    return (v && v[0] == '0') ? 0 : 1;
+  }();
+  if (small_pair && pair == 1 && bn == 128 && M <= 256 && M > 128 && ep.row_stats_out != nullptr) pair = 2;
   if ((a_lo == nullptr) != (w_lo == nullptr)) return fail(VITB200_ERR_INVALID, "gemm: split-bf16 needs both low operands");
   CUtensorMap maps[4];  // A, W, A_lo, W_lo (the low maps alias the high ones when the operands are plain bf16)
   VT_TRY(make_tmap_bf16(&maps[0], a, M, K, lda, mode == 4 ? 64 : gemm_cfg::BM, gemm_cfg::BK));
