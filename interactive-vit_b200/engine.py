@@ -457,7 +457,7 @@ class VitEngine:
             # view is created in its final shape straight away
             v = self._slab_f32.as_strided(fs, strides[::-1], off >> 2)
             self._slab_off = off + n * 4
-            self._wire_pending[v.data_ptr()] = (self._slab, off)
+            self._wire_pending[v.data_ptr()] = (self._slab, off, fs)   # fs: the handed-out shape, cached for the encoder
         return v
 
     def _checked_out(self, status: int, out: torch.Tensor) -> None:
@@ -485,7 +485,10 @@ class VitEngine:
             self._issued += 1
             t._seq, t._engine = self._issued, self
             self._keep.append((t._seq, out))
-            t._wire = self._wire_pending.pop(out.data_ptr(), None)   # (slab, payload offset): message.Response.encode
+            # (slab, payload offset, shape): message.Response.encode and the plugin read these instead of calling
+            # tensor methods -- every metadata call on a PendingTensor goes through __torch_function__ (~1 us; ~350 of
+            # them per single-image request before)
+            t._wire = self._wire_pending.pop(out.data_ptr(), None)
         return t
 
     def _drain(self, seq: int) -> None:

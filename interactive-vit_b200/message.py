@@ -131,30 +131,37 @@ class Response:
     @staticmethod
     def _encode_in_place(index: List[Dict], tensors: List[torch.Tensor]):
         """Zero-copy path: the tensors are the consecutive wire blocks of one pinned request slab (each carries
-        `_wire = (slab, payload offset)` from the engine).  The blocks are listed in SLAB order -- the order the nodes
+        `_wire = (slab, payload offset, shape)` from the engine).  The blocks are listed in SLAB order -- the order the nodes
         ran in, which the scheduler's visit order can make differ from the node order (graph.py) -- and the JSON index
         names them in that order: a decoder goes by the index (net_node.js:235-297).  None if anything differs."""
         if not tensors:
             return None
         items = []
         for ent, t in zip(index, tensors):
+            # engine outputs carry (slab, payload offset, shape); CPU fp32 contiguous by construction (engine._host_out).
+            # No tensor method is called here: on the deferred outputs every one of them is a __torch_function__ trip.
             w = getattr(t, "_wire", None)
-            if w is None or t.dtype != torch.float32 or t.device.type != "cpu" or not t.is_contiguous():
+            if w is None:
                 return None
-            items.append((w[1], ent, t, w[0]))
+            items.append((w[1], ent, t, w[0], w[2]))
         items.sort(key=lambda it: it[0])
         json_utf8 = json.dumps([it[1] for it in items]).encode()
         pad = align_next(16 + len(json_utf8), 4) - 16 - len(json_utf8)
         prefix = 16 + len(json_utf8) + pad
         slab = items[0][3]
-        start = items[0][0] - (8 + 4 * items[0][2].dim()) - prefix
+        start = items[0][0] - (8 + 4 * len(items[0][4])) - prefix
         if start < 0:
             return None
         expect = start + prefix
-        for off, _, t, s in items:
-            if s is not slab or off - (8 + 4 * t.dim()) != expect:
+        sizes = []
+        for off, _, t, s, dims in items:
+            if s is not slab or off - (8 + 4 * len(dims)) != expect:
                 return None
-            expect = off + t.numel() * 4
+            n = 4
+            for d in dims:
+                n *= d
+            sizes.append(n)
+            expect = off + n
         last = items[-1][2]
         if hasattr(last, "wait"):
             last.wait()          # stream order: every earlier copy of the request has landed as well
@@ -163,9 +170,8 @@ class Response:
         buf[start + 16:start + 16 + len(json_utf8)] = json_utf8
         if pad:
             buf[start + 16 + len(json_utf8):start + prefix] = b"\0" * pad
-        for off, _, t, _s in items:
-            dims = list(t.shape)
-            struct.pack_into(f"<II{len(dims)}I", buf, off - 8 - 4 * len(dims), 8 + 4 * len(dims) + t.numel() * 4, len(dims), *dims)
+        for (off, _, t, _s, dims), n in zip(items, sizes):
+            struct.pack_into(f"<II{len(dims)}I", buf, off - 8 - 4 * len(dims), 8 + 4 * len(dims) + n, len(dims), *dims)
         return buf[start:expect]
 
 

@@ -239,12 +239,20 @@ def make_vit_model_class(ModelBase, PinoutCls):
                     self._maps_out.clear()
                     self._images_out = None
 
+        @staticmethod
+        def _shape(x) -> tuple:
+            """Shape of a node input.  Engine outputs carry it as a plain tuple (`_wire`, engine._issue): a metadata call
+            on a deferred output is a `__torch_function__` trip (~1 us each, several per node call)."""
+            w = getattr(x, "_wire", None)
+            return w[2] if w is not None else tuple(x.shape)
+
         def _bind_tokens(self, x: torch.Tensor, flags: int = 0) -> int:
             """Make the engine's token stream equal to `x` ([N,d] or [B,N,d]); returns the batch size."""
             c = self.cfg
-            if x.dim() not in (2, 3) or tuple(x.shape[-2:]) != (c.tokens, c.hidden_dim):
-                raise Exception(f"expected tokens of shape [{c.tokens}, {c.hidden_dim}] (optionally batched), got {list(x.shape)}")
-            batch = 1 if x.dim() == 2 else x.shape[0]
+            shp = self._shape(x)
+            if len(shp) not in (2, 3) or shp[-2:] != (c.tokens, c.hidden_dim):
+                raise Exception(f"expected tokens of shape [{c.tokens}, {c.hidden_dim}] (optionally batched), got {list(shp)}")
+            batch = 1 if len(shp) == 2 else shp[0]
             self._reserve(batch, flags)
             if x is self._tokens_out and batch == self._tokens_batch:
                 return batch  # still resident from the previous node of this request
@@ -295,14 +303,14 @@ def make_vit_model_class(ModelBase, PinoutCls):
                 elif kind == "mlp_block":
                     i = self._layer_index(node_name)
                     x = self._need(pinin, "o")
-                    batched = x.dim() == 3
+                    batched = len(self._shape(x)) == 3
                     batch = self._bind_tokens(x)
                     self.engine.stage_mlp_block(i, batch)
                     out.set("o", self._emit_tokens(batch, batched))
                 elif kind in ("layer", "attn_block"):
                     i = self._layer_index(node_name)
                     x = self._need(pinin, "o")
-                    batched = x.dim() == 3
+                    batched = len(self._shape(x)) == 3
                     want_heads = params is not None and str(params.get("heads", "0")) == "1"
                     flags = E.EMIT_AVG | E.EMIT_CLS | (E.EMIT_HEADS if want_heads else 0)
                     batch = self._bind_tokens(x, flags)
@@ -329,18 +337,19 @@ def make_vit_model_class(ModelBase, PinoutCls):
                         out.set("heads", self.engine.get_head_map(i, batch, lead + (c.num_heads, c.tokens, c.tokens)))
                 elif kind == "head":
                     x = self._need(pinin, "o")
-                    batched = x.dim() == 3
+                    batched = len(self._shape(x)) == 3
                     batch = self._bind_tokens(x)
                     out.set("o", self.engine.stage_head(batch, (batch, c.num_classes) if batched else (c.num_classes,)))
                 else:  # rollout
                     maps = [self._need(pinin, f"a{i}") for i in range(c.num_layers)]
-                    batched = maps[0].dim() == 3
-                    batch = maps[0].shape[0] if batched else 1
-                    for i, m in enumerate(maps):
-                        if (tuple(m.shape[-2:]) != (c.tokens, c.tokens) or (m.dim() == 3) != batched
-                                or (batched and m.shape[0] != batch)):
+                    shapes = [self._shape(m) for m in maps]
+                    batched = len(shapes[0]) == 3
+                    batch = shapes[0][0] if batched else 1
+                    for i, ms in enumerate(shapes):
+                        if (ms[-2:] != (c.tokens, c.tokens) or (len(ms) == 3) != batched
+                                or (batched and ms[0] != batch)):
                             raise Exception(f"a{i}: expected a [{c.tokens}, {c.tokens}] map"
-                                            f"{f' for each of {batch} images' if batched else ''}, got {list(m.shape)}")
+                                            f"{f' for each of {batch} images' if batched else ''}, got {list(ms)}")
                     self._reserve(batch, E.EMIT_AVG | E.EMIT_ROLLOUT)
                     for i, m in enumerate(maps):
                         res = self._maps_out.get(i)

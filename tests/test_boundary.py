@@ -454,7 +454,7 @@ def test_response_encoded_in_place_from_a_wire_ready_slab():
         v = slab[o:o + n * 4].view(torch.float32).view(*shape)
         v.copy_(torch.arange(n, dtype=torch.float32).reshape(shape) + len(made))
         t = v.as_subclass(E.PendingTensor)
-        t._wire, t._seq, t._engine = (slab, o), len(made) + 1, None
+        t._wire, t._seq, t._engine = (slab, o, tuple(shape)), len(made) + 1, None
         made.append(t)
         off = o + n * 4
 
