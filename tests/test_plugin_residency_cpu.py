@@ -46,7 +46,16 @@ class ModelEngine:
         pass
 
     # stages
+    def stage_transform(self, images, resize):
+        self.images = O.preprocess(images, self.ocfg.image_size, resize)      # stays "on the device" for the embed node
+        return self.images.clone()
+
+    def stage_embed_resident(self, batch):
+        self.x = O.embed(self.module, self.images[:batch])
+
     def stage_embed(self, images):
+        self.uploads["images"] = self.uploads.get("images", 0) + 1
+        self.images = images.clone()
         self.x = O.embed(self.module, images)
 
     def set_tokens(self, tokens):
@@ -100,10 +109,10 @@ def _plugin(name="vit_tiny_test"):
     return P.VitB200Model(name, cfg, module, 0, 1, engine=eng), eng, ocfg, module
 
 
-def _steps(name, L, image, half_blocks=False):
+def _steps(name, L, image, half_blocks=False, transform=False):
     """The node calls of one request, in scheduler order, as (node, input channels -> source step / image)."""
-    steps = [("embed", {"o": ("image", image)})]
-    prev = 0
+    steps = [("transform", {"o": ("image", image)}), ("embed", {"o": ("step", 0, "o")})] if transform else [("embed", {"o": ("image", image)})]
+    prev = len(steps) - 1
     map_src = []
     for i in range(L):
         if half_blocks:
@@ -190,9 +199,12 @@ def test_undisturbed_request_uploads_nothing():
     name, L = "vit_tiny_test", ocfg.num_layers
     img = O.synthetic_images(1, ocfg.image_size, seed=4)[0]
     _serve_alone(plug, name, _steps(name, L, img))
-    assert eng.uploads == {"tokens": 0, "maps": 0}
+    assert eng.uploads == {"tokens": 0, "maps": 0, "images": 1}
     _serve_alone(plug, name, _steps(name, L, img, half_blocks=True))
-    assert eng.uploads == {"tokens": 0, "maps": 0}
+    assert eng.uploads == {"tokens": 0, "maps": 0, "images": 2}
+    raw = torch.rand(3, 80, 72)
+    _serve_alone(plug, name, _steps(name, L, raw, transform=True))      # preprocessed on the device: embed takes it from there
+    assert eng.uploads == {"tokens": 0, "maps": 0, "images": 2}
 
 
 def test_growing_batch_forgets_resident_state():
@@ -212,3 +224,22 @@ def test_growing_batch_forgets_resident_state():
         a.step()
     assert _same(a.result(), want)
     assert eng.uploads["maps"] == L and eng.uploads["tokens"] >= 1
+
+
+def test_transform_nodes_of_interleaved_requests():
+    """`<model>:transform` leaves the preprocessed image on the device for the embed node; another request's transform or
+    embed in between must make the embed node upload its own image again."""
+    plug, eng, ocfg, _ = _plugin()
+    name, L = "vit_tiny_test", ocfg.num_layers
+    g = torch.Generator().manual_seed(11)
+    raw = [torch.rand(3, 90, 70, generator=g), torch.rand(3, 66, 100, generator=g)]
+    plans = [_steps(name, L, raw[0], transform=True), _steps(name, L, raw[1], transform=True),
+             _steps(name, L, O.synthetic_images(1, ocfg.image_size, seed=6)[0])]
+    alone = [_serve_alone(plug, name, p) for p in plans]
+    for a, b in itertools.permutations(range(3), 2):
+        for lead in (1, 2):           # B's nodes start after A's transform / after A's embed
+            reqs = {a: _Request(plug, name, plans[a]), b: _Request(plug, name, plans[b])}
+            order = [a] * lead + [b] * 2 + [a] * (len(plans[a]) - lead) + [b] * (len(plans[b]) - 2)
+            for who in order:
+                reqs[who].step()
+            assert _same(reqs[a].result(), alone[a]) and _same(reqs[b].result(), alone[b]), (a, b, lead)
