@@ -1029,6 +1029,17 @@ static int launch_rollout(const float* maps, long layer_stride, int L, int B, in
     CU_TRY(cudaLaunchKernelEx(&cfg, rollout_cluster_kernel, maps, layer_stride, L, N, ld, stages, C, out));
     return VITB200_OK;
   }
+  static const int warp_mode = [] {   // VITB200_ROLLOUT_WARP=0: the block-synchronous kernel
+    const char* v = getenv("VITB200_ROLLOUT_WARP");
+    return (v && v[0] == '0') ? 0 : 1;
+  }();
+  if (warp_mode) {
+    while (stages > 2 && rollout_warp_smem_bytes(ld, stages) > 110 * 1024) --stages;
+    const int smem = rollout_warp_smem_bytes(ld, stages);
+    VT_TRY(ensure_func_smem((const void*)rollout_warp_kernel, smem));
+    CU_TRY(launch_pdl(rollout_warp_kernel, dim3(B), dim3(kRolloutWarpThreads), smem, st, maps, layer_stride, L, N, ld, stages, out));
+    return VITB200_OK;
+  }
   while (stages > 2 && rollout_smem_bytes(ld, stages) > 110 * 1024) --stages;
   const int smem = rollout_smem_bytes(ld, stages);
   VT_TRY(ensure_func_smem((const void*)rollout_cls_kernel, smem));

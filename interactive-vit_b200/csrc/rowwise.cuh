@@ -529,6 +529,167 @@ rollout_cls_kernel(const float* __restrict__ maps, long layer_stride, int L, int
 }
 
 
+// Warp-autonomous variant of rollout_cls_kernel (the default for one-CTA-per-image launches; VITB200_ROLLOUT_WARP=0 keeps
+// the block-synchronous kernel above).  That kernel meets at two __syncthreads per 16-row chunk (row sums -> w_k ->
+// accumulate), ~2,000 cycles per 13 KB chunk where the arithmetic needs ~300: 160-260 us for 503 MB at batch 256 (HBM
+// floor 78 us).  Here every consumer warp owns rows w and w + 8 of EVERY chunk outright: it sums them, forms w_k and adds
+// w_k * row into accumulators of its own (lane l: float4 columns l, l + 32, ...), with no block-wide meeting inside a
+// layer; a chunk goes back to the producer warp through an `empty` mbarrier (8 arrivals).  The eight partial vectors meet
+// once per layer in a fixed tree: bit-reproducible.  9 warps: 8 consumers + 1 producer.
+constexpr int kRolloutWarpThreads = 288;
+constexpr int kRolloutLaneCols = 6;     // float4 columns per lane: ld / 4 <= 192
+__host__ __device__ inline int rollout_warp_smem_bytes(int ld, int stages) {
+  return stages * rollout_stage_bytes(ld) + 2 * kRolloutMaxCols * kRolloutThreads * 4 /* r, w */ + 2 * 16 * 8 /* barriers */ +
+         8 * ld * 4 /* the warps' partial vectors */;
+}
+
+__global__ void __launch_bounds__(kRolloutWarpThreads, 2)
+rollout_warp_kernel(const float* __restrict__ maps, long layer_stride, int L, int N, int ld, int stages,
+                    float* __restrict__ out /*[B, N-1]*/) {
+  extern __shared__ __align__(128) uint8_t rsm[];
+  const int stage_bytes = rollout_stage_bytes(ld);
+  constexpr int kVec = kRolloutMaxCols * kRolloutThreads;
+  float* r = reinterpret_cast<float*>(rsm + stages * stage_bytes);
+  float* w = r + kVec;
+  uint64_t* full = reinterpret_cast<uint64_t*>(w + kVec);
+  uint64_t* empty = full + 16;
+  float* part = reinterpret_cast<float*>(empty + 16);    // [8 warps][ld]
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunks_per_layer = (N + kRolloutRows - 1) / kRolloutRows;
+  const int ld4 = ld >> 2;
+  const float* img = maps + static_cast<long>(b) * N * ld;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&full[s]))) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&empty[s]))) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = tid; j < kVec; j += kRolloutWarpThreads) r[j] = (j == 0) ? 1.0f : 0.0f, w[j] = 0.0f;
+  __syncthreads();
+  ptx::grid_dep_launch(), ptx::grid_dep_wait();   // PDL (ptx.cuh): the maps are the previous kernels' output
+
+  auto wait_bar = [](uint64_t* barp, uint32_t parity) {
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(barp));
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
+  };
+
+  if (warp == 8) {
+    // ------------------------------------------------------------ producer: every chunk of every layer, top layer first
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t parity = 0;
+      for (int layer = L - 1; layer >= 0; --layer) {
+        const int nchunks = (layer == L - 1) ? 1 : chunks_per_layer;   // r = e_0 at the top: only row 0 matters
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+          wait_bar(&empty[stage], parity ^ 1);
+          const int row0 = chunk * kRolloutRows;
+          const int rows = (layer == L - 1) ? 1 : min(kRolloutRows, N - row0);
+          const uint32_t bytes = static_cast<uint32_t>(rows) * ld * 4;
+          const float* src = img + layer * layer_stride + static_cast<long>(row0) * ld;
+          const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&full[stage]));
+          const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(rsm + stage * stage_bytes));
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                       "l"(src), "r"(bytes), "r"(bar)
+                       : "memory");
+          if (++stage == stages) stage = 0, parity ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- consumers (warps 0..7)
+  int stage = 0;
+  uint32_t parity = 0;
+  for (int layer = L - 1; layer >= 0; --layer) {
+    float4 acc[kRolloutLaneCols];
+#pragma unroll
+    for (int i = 0; i < kRolloutLaneCols; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nchunks = (layer == L - 1) ? 1 : chunks_per_layer;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      const int row0 = chunk * kRolloutRows;
+      const int rows = (layer == L - 1) ? 1 : min(kRolloutRows, N - row0);
+      wait_bar(&full[stage], parity);
+      const float* A = reinterpret_cast<const float*>(rsm + stage * stage_bytes);
+      const int k0 = warp, k1 = warp + 8;
+      if (k0 < rows) {
+        const bool has_b = k1 < rows;
+        const float4* rowa = reinterpret_cast<const float4*>(A + k0 * ld);
+        const float4* rowb = reinterpret_cast<const float4*>(A + k1 * ld);
+        float4 va[kRolloutLaneCols], vb[kRolloutLaneCols];
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int i = 0; i < kRolloutLaneCols; ++i) {
+          const int c = lane + 32 * i;
+          va[i] = make_float4(0.f, 0.f, 0.f, 0.f), vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < ld4) {
+            va[i] = rowa[c];
+            if (has_b) vb[i] = rowb[c];
+            const int j = 4 * c;
+            if (j + 3 >= N) {   // the float4 that straddles column N and the pad columns behind it (may hold anything)
+              if (j >= N) va[i].x = 0.f, vb[i].x = 0.f;
+              if (j + 1 >= N) va[i].y = 0.f, vb[i].y = 0.f;
+              if (j + 2 >= N) va[i].z = 0.f, vb[i].z = 0.f;
+              va[i].w = 0.f, vb[i].w = 0.f;
+            }
+            sa += (va[i].x + va[i].y) + (va[i].z + va[i].w);
+            sb += (vb[i].x + vb[i].y) + (vb[i].z + vb[i].w);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        const float wk0 = __fdividef(r[row0 + k0], 0.5f * sa + 0.5f);
+        const float wk1 = has_b ? __fdividef(r[row0 + k1], 0.5f * sb + 0.5f) : 0.f;
+        if (lane == 0) {
+          w[row0 + k0] = wk0;
+          if (has_b) w[row0 + k1] = wk1;
+        }
+#pragma unroll
+        for (int i = 0; i < kRolloutLaneCols; ++i) {   // (masked pad columns contribute w_k * 0)
+          acc[i].x = fmaf(wk0, va[i].x, acc[i].x), acc[i].y = fmaf(wk0, va[i].y, acc[i].y);
+          acc[i].z = fmaf(wk0, va[i].z, acc[i].z), acc[i].w = fmaf(wk0, va[i].w, acc[i].w);
+          acc[i].x = fmaf(wk1, vb[i].x, acc[i].x), acc[i].y = fmaf(wk1, vb[i].y, acc[i].y);
+          acc[i].z = fmaf(wk1, vb[i].z, acc[i].z), acc[i].w = fmaf(wk1, vb[i].w, acc[i].w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&empty[stage]))) : "memory");
+      if (++stage == stages) stage = 0, parity ^= 1;
+    }
+    // ---- end of the layer: the eight warps' partial vectors meet in a fixed tree
+    float4* mine = reinterpret_cast<float4*>(part + warp * ld);
+#pragma unroll
+    for (int i = 0; i < kRolloutLaneCols; ++i) {
+      const int c = lane + 32 * i;
+      if (c < ld4) mine[c] = acc[i];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int j = tid; j < N; j += 256) {
+      const float a = ((part[j] + part[ld + j]) + (part[2 * ld + j] + part[3 * ld + j])) +
+                      ((part[4 * ld + j] + part[5 * ld + j]) + (part[6 * ld + j] + part[7 * ld + j]));
+      r[j] = 0.5f * a + 0.5f * w[j];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // (w needs no reset: rows 1.. of the top layer keep their initial 0, later layers rewrite every row)
+  }
+  for (int j = tid + 1; j < N; j += 256) out[static_cast<long>(b) * (N - 1) + j - 1] = r[j];
+}
+
 // Class-token rollout for SMALL batches: the same recurrence as rollout_cls_kernel, one thread-block CLUSTER of C CTAs
 // per image instead of one CTA (a single-image request ran 12 layers x 13 chunks serially on ONE of 148 SMs: 135 us of a
 // 0.92 ms forward; ViT-H at batch 16: 1.3 ms of an 18 ms step on 16 SMs).  CTA `rank` streams the 16-row chunks
